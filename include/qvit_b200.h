@@ -1,0 +1,188 @@
+/* libqvit_b200 - C ABI of the B200-native (sm_100a) quantized Conv2d/Linear hot path.
+ *
+ * The reference (LongAoTianxia/Quantized_ViT) is pure Python/PyTorch and has NO FFI: its "operator
+ * interface" for this path is a set of nn.Module / autograd.Function classes.  Each entry point below
+ * therefore names the reference function whose ATen op chain it replaces (file:line relative to the
+ * reference root; QL = QViT_with_GETA/only_train_once/quantization/quant_layers.py,
+ * QU = "4-bit quantization/quant_ultra.py", QZ = "4-bit quantization/quantization.py",
+ * MEM = "4-bit quantization/qnn_mem_process.py").  The Python binding a reference maintainer would add is
+ * shown in INTEGRATION.md and implemented in quantized_vit_b200/_lib.py (ctypes).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless stated; the caller (PyTorch) owns all memory;
+ *  - quantizer parameters (d_quant, q_m, t_quant) are passed as device pointers to the (1,) fp32
+ *    nn.Parameter storage, so no call ever synchronises with the host;
+ *  - `stream` is a cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); functions only enqueue
+ *    work, never synchronise, never allocate -> they are CUDA-graph capturable;
+ *  - return value: 0 = ok, otherwise an error code; the message is qvit_last_error() (thread-local);
+ *  - `flags` (optional, may be NULL) is an int32 device word that kernels OR bits into:
+ *      QVIT_FLAG_NAN (1)       a NaN reached a quantizer (the reference would propagate NaN, QL:160)
+ *      QVIT_FLAG_OVERFLOW (2)  a code magnitude exceeded 127 (int8 pipe not applicable)
+ *      QVIT_FLAG_NAN_GRAD (4)  NaN in a reduced gradient (reference raises NanInGradientError, QL:189-204)
+ */
+#ifndef QVIT_B200_H_
+#define QVIT_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QVIT_ABI_VERSION 1
+
+#define QVIT_OK 0
+#define QVIT_ERR_INVALID 1
+#define QVIT_ERR_CUDA 2
+#define QVIT_ERR_UNSUPPORTED 3
+
+#define QVIT_FLAG_NAN 1
+#define QVIT_FLAG_OVERFLOW 2
+#define QVIT_FLAG_NAN_GRAD 4
+
+typedef void* qvit_stream_t; /* cudaStream_t */
+
+/* ------------------------------------------------------------------ library */
+int qvit_abi_version(void);
+const char* qvit_last_error(void);
+/* SM count and compute capability of the current device (host call). */
+int qvit_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ------------------------------------------------------------------ GETA symmetric quantizers
+ * Replaces SymQuantizerLinear.forward (QL:136-161) when t == NULL and SymQuantizerNonLinear.forward
+ * (QL:40-69) otherwise.  x is a [rows, cols] fp32 matrix with row pitch ld_x (elements).            */
+
+/* integer codes: codes[r*ld_codes + c] = sign(x) * |round(p/d)| (saturated to round(r/d) where |x| >= q_m),
+ * int8; columns cols..ld_codes-1 of every row are written as 0 (GEMM K padding).                      */
+int qvit_quantize_sym(const float* x, int64_t rows, int64_t cols, int64_t ld_x,
+                      const float* d, const float* q_m, const float* t /* NULL = linear */,
+                      int8_t* codes, int64_t ld_codes, int32_t* flags, qvit_stream_t stream);
+
+/* fake-quantized fp32 values, bit-for-bit what the reference autograd.Function returns (n elements). */
+int qvit_fake_quantize_sym(const float* x, int64_t n, const float* d, const float* q_m, const float* t,
+                           float* out, qvit_stream_t stream);
+
+/* Backward of both Functions (QL:163-205 / QL:71-125) in ONE pass over (x, g):
+ *   grad_x[i]      = g[i] if clip_lo < x[i] < clip_hi else 0            (STE through saturation)
+ *   grad_scalars[0] += sum g*sign(x)*(round(p/d) - p/d | saturated residual | 0)      (d_quant)
+ *   grad_scalars[1] += sum g*sign(x)*[|x| > q_m] (* t*exp((t-1)log(|q_m|+1e-6)))      (q_m)
+ *   grad_scalars[2] += sum g*sign(x)*(p*log|x| | r*log(|q_m|+1e-6) | 0)   (t_quant; only if t != NULL)
+ * grad_scalars must be zeroed by the caller; block partials are combined with fp32 atomics after an fp32
+ * warp-shuffle/shared-memory tree.  NaN in a reduced scalar sets QVIT_FLAG_NAN_GRAD in *flags.
+ * grad_x may be NULL (weight-side call when only the scalars and a masked copy are wanted separately).   */
+int qvit_sym_backward(const float* x, const float* g, int64_t n,
+                      const float* d, const float* q_m, const float* t,
+                      float clip_lo, float clip_hi,
+                      float* grad_x, float* grad_scalars, int32_t* flags, qvit_stream_t stream);
+
+/* max|x| over n elements -> out[0] (initialize_quant_layer, QL:423: q_m = max|W|).  out is overwritten. */
+int qvit_absmax(const float* x, int64_t n, float* out, qvit_stream_t stream);
+
+/* ------------------------------------------------------------------ conv lowering
+ * QuantizeConv2d.forward (QL:575-587): activation quantize (as qvit_quantize_sym) fused with im2col.
+ * x is NCHW fp32; cols is [B*OH*OW, ld_cols] int8 with K = C*kh*kw ordered (c, kh, kw) =
+ * weight.reshape(O, -1); zero padding and columns K..ld_cols-1 get code 0.                            */
+int qvit_im2col_quantize_sym(const float* x, int B, int C, int H, int W,
+                             int kh, int kw, int sh, int sw, int ph, int pw, int dh, int dw,
+                             const float* d, const float* q_m, const float* t,
+                             int8_t* cols, int64_t ld_cols, int32_t* flags, qvit_stream_t stream);
+
+/* ------------------------------------------------------------------ UltraNet (DoReFa) quantizers */
+/* max|tanh(w)| -> out[0]  (weight_quantize_fn.forward, QU:50-53). */
+int qvit_ultra_tanh_absmax(const float* w, int64_t n, float* out, qvit_stream_t stream);
+/* codes = round(tanh(w)/max * (2^(w_bit-1)-1)) (sign() at w_bit == 2, QU:15-16); 2 <= w_bit <= 8. */
+int qvit_ultra_quantize_weight(const float* w, int64_t n, int w_bit, const float* max_tanh,
+                               int8_t* codes, qvit_stream_t stream);
+/* activation_quantize_fn.forward (QU:66-73): codes = round(clamp(x,0,1) * (2^a_bit-1)), uint8;
+ * values = codes / (2^a_bit-1) written to out_values if non-NULL (either output may be NULL).        */
+int qvit_ultra_quantize_act(const float* x, int64_t n, int a_bit, uint8_t* codes, float* out_values,
+                            qvit_stream_t stream);
+/* Conv2d_Q.forward (QU:85-89) with arbitrary fp32 input: y = conv2d(x, codes / w_levels) + bias, NCHW fp32,
+ * groups == 1, w_levels = 2^(w_bit-1)-1 (the fp32 quotient codes/w_levels is bit-for-bit the reference's w_q,
+ * QU:18-19).  The input is NOT quantised by the reference layer (the first UltraNet layer sees the image). */
+int qvit_conv2d_f32_wcodes(const float* x, int B, int C, int H, int W,
+                           const int8_t* w_codes, int O, int kh, int kw,
+                           int sh, int sw, int ph, int pw, int dh, int dw,
+                           float w_levels, const float* bias, float* y, qvit_stream_t stream);
+/* One fused integer UltraNet layer (MM:71-125 pattern conv -> BatchNorm2d(eval) -> act-quant [-> 2x2 max-pool]):
+ * in_codes  [B, H, W, C]  uint8 NHWC activation codes (0..2^a_bit-1)
+ * w_codes   [O, kh, kw, C] int8 (K ordered (kh, kw, c) - the order MEM:152-154 exports)
+ * y = acc * acc_scale * bn_scale[o] + bn_bias[o];  out_codes = round(clamp(y,0,1) * out_levels), max-pooled 2x2
+ * if pool != 0 (pooling commutes with the monotone code map).  out_codes [B, OH, OW, O] uint8.
+ * If out_f32 != NULL the un-quantised y is written there instead as NCHW fp32 (last layer, MM:123).   */
+int qvit_ultra_conv_bn_act(const uint8_t* in_codes, int B, int H, int W, int C,
+                           const int8_t* w_codes, int O, int kh, int kw, int pad,
+                           float acc_scale, const float* bn_scale, const float* bn_bias,
+                           int out_levels, int pool, uint8_t* out_codes, float* out_f32,
+                           qvit_stream_t stream);
+
+/* ------------------------------------------------------------------ BN fold / pack (one-time)
+ * mode 0: nn.BatchNorm2d eval  scale = gamma/sqrt(var+eps),   bias = beta - mean*scale   (MM:74.. + F.batch_norm)
+ * mode 1: export fold          scale = gamma/(sqrt(var)+eps), bias = beta - mean/(sqrt(var)+eps)*gamma (QZ:34-46) */
+int qvit_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps,
+                 int mode, int C, float* scale, float* bias, qvit_stream_t stream);
+/* bn_act_quantize_int (QZ:68-89): int32 (inc, bias) thresholds.  The NumPy reference computes in the dtype of
+ * the arrays it is handed (float32 from an .npz export, float64 in its own demo): is_f64 selects which; the
+ * four inputs are device arrays of that dtype.                                                         */
+int qvit_bn_act_quantize_int(const void* gamma, const void* beta, const void* mean, const void* var, int is_f64,
+                             double eps, int w_bit, int in_bit, int out_bit, int l_shift, int C,
+                             int32_t* inc, int32_t* bias, qvit_stream_t stream);
+/* 4-bit pack, element i of a run in bits [4i, 4i+4), two's complement (array_to_string, MEM:11-24).
+ * n must be even; packed has n/2 bytes.                                                               */
+int qvit_pack_int4(const int8_t* codes, int64_t n, uint8_t* packed, qvit_stream_t stream);
+int qvit_unpack_int4(const uint8_t* packed, int64_t n, int is_signed, int8_t* codes, qvit_stream_t stream);
+
+/* ------------------------------------------------------------------ QuantLinear GEMM
+ * Replaces nn.functional.linear(x_q, w_q, bias) on fake-quant values (QL:499, QU:220) by the exact integer
+ * contraction  acc[m,n] = sum_k A[m,k] * Wc[n,k]  (int8 x int8 -> int32, tcgen05.mma kind::i8, TMEM
+ * accumulators) and a fused epilogue.  A is [M, lda] int8 (or uint8 if a_unsigned), Wc is [N, ldw] int8,
+ * both K-major; lda, ldw multiples of 16 and base pointers 16-byte aligned for the tensor-core backend. */
+enum {
+  QVIT_OUT_I32 = 0,   /* raw accumulators (parity tests)                           out: int32  [M, ldo] */
+  QVIT_OUT_F32 = 1,   /* y                                                       out: fp32   [M, ldo] */
+  QVIT_OUT_BF16 = 2,  /* y rounded to bf16                                         out: bf16   [M, ldo] */
+  QVIT_OUT_I8 = 3     /* y re-quantised with (next_d, next_qm[, next_t]) -> int8 codes  out: int8 [M, ldo] */
+};
+enum { QVIT_ACT_NONE = 0, QVIT_ACT_GELU = 1, QVIT_ACT_RELU = 2 };
+enum { QVIT_GEMM_AUTO = 0, QVIT_GEMM_TCGEN05 = 1, QVIT_GEMM_SIMT = 2 };
+
+typedef struct qvit_epilogue {
+  int32_t out_kind;        /* QVIT_OUT_*                                                              */
+  int32_t act;             /* QVIT_ACT_* applied to y before residual / requant                        */
+  const float* scale_a;    /* (1,) device: |.| is taken  (d_quant_act)  or NULL = 1                    */
+  const float* scale_w;    /* (1,) device: |.| is taken  (d_quant_wt)   or NULL = 1                    */
+  float scale_const;       /* host multiplier (1.0; 1/(7*15) for UltraNet codes)                      */
+  const float* col_scale;  /* [N] per-output-channel multiplier (folded BN) or NULL                    */
+  const float* bias;       /* [N] or NULL                                                              */
+  const float* residual;   /* [M, ld_res] fp32 added after act, or NULL                                */
+  int64_t ld_res;
+  const float* next_d;     /* QVIT_OUT_I8: quantizer of the consumer layer                             */
+  const float* next_qm;
+  const float* next_t;     /* NULL = linear                                                            */
+  int32_t* flags;          /* optional                                                                 */
+} qvit_epilogue_t;
+/* y = act( float(acc) * (|scale_a|*|scale_w|*scale_const) * col_scale[n] + bias[n] ) + residual[m,n]  */
+
+int qvit_gemm_i8(const void* a, int64_t lda, int a_unsigned,
+                 const int8_t* w, int64_t ldw,
+                 int M, int N, int K,
+                 void* out, int64_t ldo,
+                 const qvit_epilogue_t* epi, int backend, qvit_stream_t stream);
+
+/* ------------------------------------------------------------------ glue fused with the quantizer
+ * ("next" rows of SURVEY.md section 8f, built on the same quantizer device function)
+ * LayerNorm (vit_model.py:206-207, eps inside sqrt, biased variance) followed by the consumer layer's
+ * activation quantizer: codes = Q(LN(x) * gamma + beta).  x [rows, cols] fp32 contiguous.             */
+int qvit_layernorm_quantize(const float* x, int64_t rows, int cols, const float* gamma, const float* beta,
+                            float eps, const float* d, const float* q_m, const float* t,
+                            int8_t* codes, int64_t ld_codes, float* ln_out /* optional fp32 copy */,
+                            int32_t* flags, qvit_stream_t stream);
+/* bf16 -> codes (attention output feeding `proj`): same quantizer on bf16 input widened to fp32. */
+int qvit_quantize_sym_bf16(const void* x_bf16, int64_t rows, int64_t cols, int64_t ld_x,
+                           const float* d, const float* q_m, const float* t,
+                           int8_t* codes, int64_t ld_codes, int32_t* flags, qvit_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QVIT_B200_H_ */

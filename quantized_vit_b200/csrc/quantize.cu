@@ -1,0 +1,428 @@
+// K1/K2: GETA symmetric quantizers -> int8 codes / fp32 fake-quant values; im2col+quantize;
+// LayerNorm+quantize; bf16 quantize; absmax; int4 pack/unpack.
+//
+// All of these are HBM-bound elementwise/row kernels (roofline: 4 B read + 1 B written per element
+// for fp32 -> int8).  Layout rule: one warp owns 512 consecutive elements per step; lane l loads the
+// float4 at element 128*j + 4*l (j = 0..3) so every load instruction is a fully coalesced 512 B
+// request, and stores one packed 4-code word per j (128 B coalesced per store instruction).
+// Grids are sized as multiples of the SM count (148 on B200) with grid-stride loops.
+#include "common.cuh"
+
+namespace qvit {
+
+constexpr int kThreads = 256;
+constexpr int kWarpElems = 512;                        // elements one warp converts per step
+constexpr int kBlockElems = kWarpElems * (kThreads / 32);
+
+static inline int stream_grid(int64_t work_items, int per_block, int ctas_per_sm = 8) {
+  int64_t blocks = (work_items + per_block - 1) / per_block;
+  int64_t cap = (int64_t)sm_count() * ctas_per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+// ------------------------------------------------------------------------------------------------
+// flat fp32 -> int8 codes, n % 512 handled by a scalar tail
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+quantize_sym_flat_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ d,
+                         const float* __restrict__ qm, const float* __restrict__ t,
+                         int8_t* __restrict__ codes, int32_t* __restrict__ flags) {
+  const SymParams p = load_sym_params(d, qm, t);
+  int fl = 0;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const int64_t warp_stride = (int64_t)gridDim.x * (kThreads / 32);
+  const int64_t full = n / kWarpElems;
+  for (int64_t w = warp_global; w < full; w += warp_stride) {
+    const float* src = x + w * kWarpElems;
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = ldg_stream4(src + j * 128 + lane * 4);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(codes + w * kWarpElems);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      dst[j * 32 + lane] = pack4_i8(sym_code(v[j].x, p, fl), sym_code(v[j].y, p, fl),
+                                    sym_code(v[j].z, p, fl), sym_code(v[j].w, p, fl));
+    }
+  }
+  // tail (< 512 elements): first warp of block 0
+  if (warp_global == 0) {
+    for (int64_t i = full * kWarpElems + lane; i < n; i += 32) codes[i] = (int8_t)sym_code(x[i], p, fl);
+  }
+  fl = warp_or(fl);
+  if (fl && flags && lane == 0) atomicOr(flags, fl);
+}
+
+// general 2-D form with row pitches and zero padding of columns cols..ld_codes-1
+__global__ void __launch_bounds__(kThreads)
+quantize_sym_rows_kernel(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld_x,
+                         const float* __restrict__ d, const float* __restrict__ qm, const float* __restrict__ t,
+                         int8_t* __restrict__ codes, int64_t ld_codes, int32_t* __restrict__ flags) {
+  const SymParams p = load_sym_params(d, qm, t);
+  int fl = 0;
+  const int64_t total = rows * ld_codes;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / ld_codes, c = i - r * ld_codes;
+    codes[i] = (c < cols) ? (int8_t)sym_code(x[r * ld_x + c], p, fl) : (int8_t)0;
+  }
+  fl = warp_or(fl);
+  if (fl && flags && (threadIdx.x & 31) == 0) atomicOr(flags, fl);
+}
+
+__global__ void __launch_bounds__(kThreads)
+fake_quantize_sym_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ d,
+                         const float* __restrict__ qm, const float* __restrict__ t, float* __restrict__ out) {
+  const SymParams p = load_sym_params(d, qm, t);
+  const int64_t n4 = n >> 2;
+  const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  if (aligned) {
+    for (int64_t i = tid; i < n4; i += stride) {
+      float4 v = ldg_stream4(x + i * 4);
+      float4 o = make_float4(sym_value(v.x, p), sym_value(v.y, p), sym_value(v.z, p), sym_value(v.w, p));
+      reinterpret_cast<float4*>(out)[i] = o;
+    }
+    for (int64_t i = n4 * 4 + tid; i < n; i += stride) out[i] = sym_value(x[i], p);
+  } else {
+    for (int64_t i = tid; i < n; i += stride) out[i] = sym_value(x[i], p);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// bf16 -> codes (flat or rows)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+quantize_sym_bf16_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows, int64_t cols, int64_t ld_x,
+                              const float* __restrict__ d, const float* __restrict__ qm, const float* __restrict__ t,
+                              int8_t* __restrict__ codes, int64_t ld_codes, int32_t* __restrict__ flags) {
+  const SymParams p = load_sym_params(d, qm, t);
+  int fl = 0;
+  // one thread = 8 consecutive columns (16 B in, 8 B out) when everything is 8-aligned
+  const bool vec = (cols % 8 == 0) && (ld_x % 8 == 0) && (ld_codes % 8 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(codes) & 7) == 0);
+  if (vec) {
+    const int64_t groups_per_row = ld_codes / 8;
+    const int64_t total = rows * groups_per_row;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = i / groups_per_row, g = i - r * groups_per_row;
+      uint2 o = make_uint2(0u, 0u);
+      if (g * 8 < cols) {
+        const uint4 raw = *reinterpret_cast<const uint4*>(x + r * ld_x + g * 8);
+        const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+        int c[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          c[2 * j] = sym_code(__uint_as_float(w[j] << 16), p, fl);
+          c[2 * j + 1] = sym_code(__uint_as_float(w[j] & 0xffff0000u), p, fl);
+        }
+        o.x = pack4_i8(c[0], c[1], c[2], c[3]);
+        o.y = pack4_i8(c[4], c[5], c[6], c[7]);
+      }
+      *reinterpret_cast<uint2*>(codes + r * ld_codes + g * 8) = o;
+    }
+  } else {
+    const int64_t total = rows * ld_codes;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = i / ld_codes, c = i - r * ld_codes;
+      codes[i] = (c < cols) ? (int8_t)sym_code(__bfloat162float(x[r * ld_x + c]), p, fl) : (int8_t)0;
+    }
+  }
+  fl = warp_or(fl);
+  if (fl && flags && (threadIdx.x & 31) == 0) atomicOr(flags, fl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// im2col + quantize (NCHW fp32 -> [B*OH*OW, ld_cols] int8, K ordered (c, kh, kw))
+// ------------------------------------------------------------------------------------------------
+struct ConvGeom {
+  int B, C, H, W, kh, kw, sh, sw, ph, pw, dh, dw, OH, OW, K;
+};
+
+__global__ void __launch_bounds__(kThreads)
+im2col_quantize_kernel(const float* __restrict__ x, ConvGeom g, const float* __restrict__ d,
+                       const float* __restrict__ qm, const float* __restrict__ t,
+                       int8_t* __restrict__ cols, int64_t ld_cols, int32_t* __restrict__ flags) {
+  const SymParams p = load_sym_params(d, qm, t);
+  int fl = 0;
+  const int64_t words_per_row = ld_cols / 4;            // ld_cols % 4 == 0 enforced by the host
+  const int64_t rows = (int64_t)g.B * g.OH * g.OW;
+  const int64_t total = rows * words_per_row;
+  const int khw = g.kh * g.kw;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / words_per_row;
+    const int k0 = (int)(i - r * words_per_row) * 4;
+    const int ow = (int)(r % g.OW);
+    const int oh = (int)((r / g.OW) % g.OH);
+    const int b = (int)(r / ((int64_t)g.OW * g.OH));
+    int c4[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + j;
+      int code = 0;
+      if (k < g.K) {
+        const int c = k / khw;
+        const int rem = k - c * khw;
+        const int ki = rem / g.kw, kj = rem - ki * g.kw;
+        const int ih = oh * g.sh - g.ph + ki * g.dh;
+        const int iw = ow * g.sw - g.pw + kj * g.dw;
+        if (ih >= 0 && ih < g.H && iw >= 0 && iw < g.W)
+          code = sym_code(__ldg(x + (((int64_t)b * g.C + c) * g.H + ih) * g.W + iw), p, fl);
+      }
+      c4[j] = code;
+    }
+    reinterpret_cast<uint32_t*>(cols)[i] = pack4_i8(c4[0], c4[1], c4[2], c4[3]);
+  }
+  fl = warp_or(fl);
+  if (fl && flags && (threadIdx.x & 31) == 0) atomicOr(flags, fl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm + quantize: one warp per row, the row lives in registers (cols = 128 * V, V <= 16)
+// ------------------------------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(kThreads)
+layernorm_quantize_kernel(const float* __restrict__ x, int64_t rows, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, float eps, const float* __restrict__ d,
+                          const float* __restrict__ qm, const float* __restrict__ t,
+                          int8_t* __restrict__ codes, int64_t ld_codes, float* __restrict__ ln_out,
+                          int32_t* __restrict__ flags) {
+  constexpr int cols = V * 128;
+  const SymParams p = load_sym_params(d, qm, t);
+  int fl = 0;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const int64_t warp_stride = (int64_t)gridDim.x * (kThreads / 32);
+  float4 gm[V], bt[V];
+#pragma unroll
+  for (int j = 0; j < V; ++j) {
+    gm[j] = __ldg(reinterpret_cast<const float4*>(gamma) + j * 32 + lane);
+    bt[j] = __ldg(reinterpret_cast<const float4*>(beta) + j * 32 + lane);
+  }
+  for (int64_t r = warp_global; r < rows; r += warp_stride) {
+    const float* src = x + r * cols;
+    float4 v[V];
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      v[j] = ldg_stream4(src + j * 128 + lane * 4);
+      s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    const float mean = warp_sum(s) * (1.0f / cols);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      const float a = v[j].x - mean, b = v[j].y - mean, c = v[j].z - mean, e = v[j].w - mean;
+      q += (a * a + b * b) + (c * c + e * e);
+    }
+    const float rstd = rsqrtf(warp_sum(q) * (1.0f / cols) + eps);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(codes + r * ld_codes);
+#pragma unroll
+    for (int j = 0; j < V; ++j) {
+      float4 y;
+      y.x = (v[j].x - mean) * rstd * gm[j].x + bt[j].x;
+      y.y = (v[j].y - mean) * rstd * gm[j].y + bt[j].y;
+      y.z = (v[j].z - mean) * rstd * gm[j].z + bt[j].z;
+      y.w = (v[j].w - mean) * rstd * gm[j].w + bt[j].w;
+      if (ln_out) reinterpret_cast<float4*>(ln_out + r * cols)[j * 32 + lane] = y;
+      dst[j * 32 + lane] = pack4_i8(sym_code(y.x, p, fl), sym_code(y.y, p, fl), sym_code(y.z, p, fl), sym_code(y.w, p, fl));
+    }
+    // zero the K padding, if any
+    for (int64_t c = cols + lane; c < ld_codes; c += 32) codes[r * ld_codes + c] = 0;
+  }
+  fl = warp_or(fl);
+  if (fl && flags && lane == 0) atomicOr(flags, fl);
+}
+
+// generic width: one warp per row, three passes over the (L1/L2-resident) row
+__global__ void __launch_bounds__(kThreads)
+layernorm_quantize_generic_kernel(const float* __restrict__ x, int64_t rows, int cols, const float* __restrict__ gamma,
+                                  const float* __restrict__ beta, float eps, const float* __restrict__ d,
+                                  const float* __restrict__ qm, const float* __restrict__ t,
+                                  int8_t* __restrict__ codes, int64_t ld_codes, float* __restrict__ ln_out,
+                                  int32_t* __restrict__ flags) {
+  const SymParams p = load_sym_params(d, qm, t);
+  int fl = 0;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp_global = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
+  const int64_t warp_stride = (int64_t)gridDim.x * (kThreads / 32);
+  for (int64_t r = warp_global; r < rows; r += warp_stride) {
+    const float* src = x + r * cols;
+    float s = 0.f;
+    for (int c = lane; c < cols; c += 32) s += src[c];
+    const float mean = warp_sum(s) / (float)cols;
+    float q = 0.f;
+    for (int c = lane; c < cols; c += 32) { const float a = src[c] - mean; q += a * a; }
+    const float rstd = rsqrtf(warp_sum(q) / (float)cols + eps);
+    for (int c = lane; c < ld_codes; c += 32) {
+      int code = 0;
+      if (c < cols) {
+        const float y = (src[c] - mean) * rstd * gamma[c] + beta[c];
+        if (ln_out) ln_out[r * cols + c] = y;
+        code = sym_code(y, p, fl);
+      }
+      codes[r * ld_codes + c] = (int8_t)code;
+    }
+  }
+  fl = warp_or(fl);
+  if (fl && flags && lane == 0) atomicOr(flags, fl);
+}
+
+// ------------------------------------------------------------------------------------------------
+// absmax, int4 pack / unpack
+// ------------------------------------------------------------------------------------------------
+__global__ void zero_word_kernel(uint32_t* p) { *p = 0u; }
+
+__global__ void __launch_bounds__(kThreads)
+absmax_kernel(const float* __restrict__ x, int64_t n, uint32_t* __restrict__ out_bits) {
+  float m = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    m = fmaxf(m, fabsf(x[i]));
+  m = warp_max(m);
+  __shared__ float sm[kThreads / 32];
+  if ((threadIdx.x & 31) == 0) sm[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = threadIdx.x < kThreads / 32 ? sm[threadIdx.x] : 0.f;
+    m = warp_max(m);
+    if (threadIdx.x == 0) atomicMax(out_bits, __float_as_uint(m));   // non-negative floats order like uints
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+pack_int4_kernel(const int8_t* __restrict__ codes, int64_t nbytes, uint8_t* __restrict__ packed) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += (int64_t)gridDim.x * blockDim.x) {
+    const int lo = codes[2 * i], hi = codes[2 * i + 1];
+    packed[i] = (uint8_t)((lo & 0xF) | ((hi & 0xF) << 4));
+  }
+}
+
+__global__ void __launch_bounds__(kThreads)
+unpack_int4_kernel(const uint8_t* __restrict__ packed, int64_t nbytes, int is_signed, int8_t* __restrict__ codes) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += (int64_t)gridDim.x * blockDim.x) {
+    int lo = packed[i] & 0xF, hi = (packed[i] >> 4) & 0xF;
+    if (is_signed) { lo = (lo ^ 8) - 8; hi = (hi ^ 8) - 8; }
+    codes[2 * i] = (int8_t)lo;
+    codes[2 * i + 1] = (int8_t)hi;
+  }
+}
+
+}  // namespace qvit
+
+using namespace qvit;
+
+extern "C" {
+
+int qvit_quantize_sym(const float* x, int64_t rows, int64_t cols, int64_t ld_x, const float* d, const float* q_m,
+                      const float* t, int8_t* codes, int64_t ld_codes, int32_t* flags, qvit_stream_t stream) {
+  QVIT_REQUIRE(x && d && q_m && codes, "qvit_quantize_sym: null pointer");
+  QVIT_REQUIRE(rows >= 0 && cols >= 0 && ld_x >= cols && ld_codes >= cols, "qvit_quantize_sym: bad shape");
+  if (rows == 0 || ld_codes == 0) return QVIT_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const bool flat = (ld_x == cols) && (ld_codes == cols) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(codes) & 3) == 0);
+  if (flat) {
+    const int64_t n = rows * cols;
+    quantize_sym_flat_kernel<<<stream_grid(n, kBlockElems), kThreads, 0, s>>>(x, n, d, q_m, t, codes, flags);
+  } else {
+    const int64_t n = rows * ld_codes;
+    quantize_sym_rows_kernel<<<stream_grid(n, kThreads * 4), kThreads, 0, s>>>(x, rows, cols, ld_x, d, q_m, t, codes,
+                                                                             ld_codes, flags);
+  }
+  return check_launch("qvit_quantize_sym");
+}
+
+int qvit_fake_quantize_sym(const float* x, int64_t n, const float* d, const float* q_m, const float* t, float* out,
+                           qvit_stream_t stream) {
+  QVIT_REQUIRE(x && d && q_m && out && n >= 0, "qvit_fake_quantize_sym: bad argument");
+  if (n == 0) return QVIT_OK;
+  fake_quantize_sym_kernel<<<stream_grid(n, kThreads * 4), kThreads, 0, (cudaStream_t)stream>>>(x, n, d, q_m, t, out);
+  return check_launch("qvit_fake_quantize_sym");
+}
+
+int qvit_quantize_sym_bf16(const void* x, int64_t rows, int64_t cols, int64_t ld_x, const float* d, const float* q_m,
+                           const float* t, int8_t* codes, int64_t ld_codes, int32_t* flags, qvit_stream_t stream) {
+  QVIT_REQUIRE(x && d && q_m && codes, "qvit_quantize_sym_bf16: null pointer");
+  QVIT_REQUIRE(rows >= 0 && cols >= 0 && ld_x >= cols && ld_codes >= cols, "qvit_quantize_sym_bf16: bad shape");
+  if (rows == 0 || ld_codes == 0) return QVIT_OK;
+  const int64_t n = rows * ld_codes;
+  quantize_sym_bf16_rows_kernel<<<stream_grid(n, kThreads * 8), kThreads, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const __nv_bfloat16*>(x), rows, cols, ld_x, d, q_m, t, codes, ld_codes, flags);
+  return check_launch("qvit_quantize_sym_bf16");
+}
+
+int qvit_im2col_quantize_sym(const float* x, int B, int C, int H, int W, int kh, int kw, int sh, int sw, int ph,
+                             int pw, int dh, int dw, const float* d, const float* q_m, const float* t, int8_t* cols,
+                             int64_t ld_cols, int32_t* flags, qvit_stream_t stream) {
+  QVIT_REQUIRE(x && d && q_m && cols, "qvit_im2col_quantize_sym: null pointer");
+  QVIT_REQUIRE(B > 0 && C > 0 && H > 0 && W > 0 && kh > 0 && kw > 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0 &&
+                   ph >= 0 && pw >= 0, "qvit_im2col_quantize_sym: bad geometry");
+  ConvGeom g{B, C, H, W, kh, kw, sh, sw, ph, pw, dh, dw, 0, 0, C * kh * kw};
+  g.OH = (H + 2 * ph - dh * (kh - 1) - 1) / sh + 1;
+  g.OW = (W + 2 * pw - dw * (kw - 1) - 1) / sw + 1;
+  QVIT_REQUIRE(g.OH > 0 && g.OW > 0, "qvit_im2col_quantize_sym: empty output");
+  QVIT_REQUIRE(ld_cols >= g.K && ld_cols % 4 == 0 && (reinterpret_cast<uintptr_t>(cols) & 3) == 0,
+               "qvit_im2col_quantize_sym: ld_cols must be >= C*kh*kw and a multiple of 4");
+  const int64_t words = (int64_t)B * g.OH * g.OW * (ld_cols / 4);
+  im2col_quantize_kernel<<<stream_grid(words, kThreads * 2), kThreads, 0, (cudaStream_t)stream>>>(x, g, d, q_m, t, cols,
+                                                                                                  ld_cols, flags);
+  return check_launch("qvit_im2col_quantize_sym");
+}
+
+int qvit_layernorm_quantize(const float* x, int64_t rows, int cols, const float* gamma, const float* beta, float eps,
+                            const float* d, const float* q_m, const float* t, int8_t* codes, int64_t ld_codes,
+                            float* ln_out, int32_t* flags, qvit_stream_t stream) {
+  QVIT_REQUIRE(x && gamma && beta && d && q_m && codes, "qvit_layernorm_quantize: null pointer");
+  QVIT_REQUIRE(rows >= 0 && cols > 0 && ld_codes >= cols, "qvit_layernorm_quantize: bad shape");
+  if (rows == 0) return QVIT_OK;
+  cudaStream_t s = (cudaStream_t)stream;
+  const int grid = stream_grid(rows, kThreads / 32, 8);
+  const bool fast = (cols % 128 == 0) && (cols / 128 <= 8) && (ld_codes % 4 == 0) &&
+                    ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(codes) & 3) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0) && ((reinterpret_cast<uintptr_t>(beta) & 15) == 0) &&
+                    (!ln_out || (reinterpret_cast<uintptr_t>(ln_out) & 15) == 0);
+#define QVIT_LN_CASE(V)                                                                                            \
+  case V:                                                                                                          \
+    layernorm_quantize_kernel<V><<<grid, kThreads, 0, s>>>(x, rows, gamma, beta, eps, d, q_m, t, codes, ld_codes,  \
+                                                           ln_out, flags);                                         \
+    break;
+  if (fast) {
+    switch (cols / 128) {
+      QVIT_LN_CASE(1) QVIT_LN_CASE(2) QVIT_LN_CASE(3) QVIT_LN_CASE(4) QVIT_LN_CASE(5) QVIT_LN_CASE(6) QVIT_LN_CASE(7)
+      QVIT_LN_CASE(8)
+    }
+  } else {
+    layernorm_quantize_generic_kernel<<<grid, kThreads, 0, s>>>(x, rows, cols, gamma, beta, eps, d, q_m, t, codes,
+                                                                ld_codes, ln_out, flags);
+  }
+#undef QVIT_LN_CASE
+  return check_launch("qvit_layernorm_quantize");
+}
+
+int qvit_absmax(const float* x, int64_t n, float* out, qvit_stream_t stream) {
+  QVIT_REQUIRE(x && out && n >= 0, "qvit_absmax: bad argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  zero_word_kernel<<<1, 1, 0, s>>>(reinterpret_cast<uint32_t*>(out));
+  if (n > 0)
+    absmax_kernel<<<stream_grid(n, kThreads * 8, 4), kThreads, 0, s>>>(x, n, reinterpret_cast<uint32_t*>(out));
+  return check_launch("qvit_absmax");
+}
+
+int qvit_pack_int4(const int8_t* codes, int64_t n, uint8_t* packed, qvit_stream_t stream) {
+  QVIT_REQUIRE(codes && packed && n >= 0 && n % 2 == 0, "qvit_pack_int4: n must be even");
+  if (n == 0) return QVIT_OK;
+  pack_int4_kernel<<<stream_grid(n / 2, kThreads * 4), kThreads, 0, (cudaStream_t)stream>>>(codes, n / 2, packed);
+  return check_launch("qvit_pack_int4");
+}
+
+int qvit_unpack_int4(const uint8_t* packed, int64_t n, int is_signed, int8_t* codes, qvit_stream_t stream) {
+  QVIT_REQUIRE(codes && packed && n >= 0 && n % 2 == 0, "qvit_unpack_int4: n must be even");
+  if (n == 0) return QVIT_OK;
+  unpack_int4_kernel<<<stream_grid(n / 2, kThreads * 4), kThreads, 0, (cudaStream_t)stream>>>(packed, n / 2, is_signed,
+                                                                                             codes);
+  return check_launch("qvit_unpack_int4");
+}
+
+}  // extern "C"

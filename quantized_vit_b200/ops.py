@@ -1,0 +1,353 @@
+"""Tensor-level wrappers over the C ABI (include/qvit_b200.h).
+
+PyTorch is plumbing here: it owns device memory (``torch.empty``) and the current stream; every function
+below only validates arguments, allocates outputs and forwards raw device pointers to libqvit_b200.
+All inputs must live on a CUDA device - there is no CPU path (the reference's CPU semantics live in
+``oracle/`` and are used by tests only).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import (QVIT_ACT_GELU, QVIT_ACT_NONE, QVIT_ACT_RELU, QVIT_GEMM_AUTO, QVIT_GEMM_SIMT, QVIT_GEMM_TCGEN05,
+                   QVIT_OUT_BF16, QVIT_OUT_F32, QVIT_OUT_I8, QVIT_OUT_I32)
+
+__all__ = ["pad16", "quantize_sym", "fake_quantize_sym", "sym_backward", "absmax", "im2col_quantize_sym", "gemm_i8",
+           "layernorm_quantize", "ultra_weight_codes", "ultra_act", "conv2d_f32_wcodes", "ultra_conv_bn_act", "bn_fold",
+           "bn_act_quantize_int", "pack_int4", "unpack_int4", "new_flags", "QVIT_OUT_I32", "QVIT_OUT_F32",
+           "QVIT_OUT_BF16", "QVIT_OUT_I8", "QVIT_ACT_NONE", "QVIT_ACT_GELU", "QVIT_ACT_RELU", "QVIT_GEMM_AUTO",
+           "QVIT_GEMM_TCGEN05", "QVIT_GEMM_SIMT"]
+
+_OUT_DTYPE = {QVIT_OUT_I32: torch.int32, QVIT_OUT_F32: torch.float32, QVIT_OUT_BF16: torch.bfloat16,
+              QVIT_OUT_I8: torch.int8}
+
+
+def pad16(k: int) -> int:
+    """Row pitch (bytes) of an int8 code matrix: TMA needs global strides that are multiples of 16 bytes."""
+    return (int(k) + 15) // 16 * 16
+
+
+def _f32c(t: torch.Tensor, what: str) -> torch.Tensor:
+    _lib.require_cuda(t)
+    if t.dtype != torch.float32:
+        raise TypeError(f"{what}: expected float32, got {t.dtype}")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _scalar_param(t, dev, what: str) -> torch.Tensor:
+    """(1,) fp32 device tensor for a quantizer parameter (nn.Parameter, tensor or Python number)."""
+    if isinstance(t, torch.Tensor):
+        if t.device != dev or t.dtype != torch.float32:
+            t = t.detach().to(device=dev, dtype=torch.float32)     # the reference does .to(device) too (QL:148-151)
+        if t.numel() != 1:
+            raise ValueError(f"{what}: quantizer parameters are per-tensor scalars of shape (1,)")
+        return t.detach().contiguous()
+    return torch.tensor([float(t)], dtype=torch.float32, device=dev)
+
+
+def new_flags(device) -> torch.Tensor:
+    return torch.zeros(1, dtype=torch.int32, device=device)
+
+
+# ------------------------------------------------------------------------------------------ GETA quantizers
+def quantize_sym(x: torch.Tensor, d, q_m, t=None, ld_codes: Optional[int] = None, flags: Optional[torch.Tensor] = None,
+                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """int8 codes of SymQuantizerLinear/NonLinear.forward (QL:136-161 / QL:40-69) for x viewed as [rows, cols]
+    (cols = last dim).  Returns [rows, ld_codes] int8, padding columns zero."""
+    if x.dtype == torch.bfloat16:
+        _lib.require_cuda(x)
+        x2 = x.reshape(-1, x.shape[-1]) if x.dim() > 1 else x.reshape(1, -1)
+        x2 = x2 if x2.stride(-1) == 1 else x2.contiguous()
+        fn = _lib.lib().qvit_quantize_sym_bf16
+    else:
+        x = _f32c(x, "quantize_sym")
+        x2 = x.reshape(-1, x.shape[-1]) if x.dim() > 1 else x.reshape(1, -1)
+        fn = _lib.lib().qvit_quantize_sym
+    rows, cols = x2.shape
+    ld = cols if ld_codes is None else int(ld_codes)
+    if ld < cols:
+        raise ValueError("ld_codes < cols")
+    dev = x2.device
+    d_, q_ = _scalar_param(d, dev, "d_quant"), _scalar_param(q_m, dev, "q_m")
+    t_ = None if t is None else _scalar_param(t, dev, "t_quant")
+    if out is None:
+        out = torch.empty((rows, ld), dtype=torch.int8, device=dev)
+    elif out.shape != (rows, ld) or out.dtype != torch.int8 or not out.is_contiguous():
+        raise ValueError("quantize_sym: bad `out`")
+    _lib.check(fn(_lib.ptr(x2), rows, cols, x2.stride(0) if rows > 1 else max(cols, x2.stride(0)), _lib.ptr(d_),
+                  _lib.ptr(q_), _lib.ptr(t_), _lib.ptr(out), ld, _lib.ptr(flags), _lib.stream()), "qvit_quantize_sym")
+    return out
+
+
+def fake_quantize_sym(x: torch.Tensor, d, q_m, t=None) -> torch.Tensor:
+    """fp32 fake-quant values, bit-for-bit the reference Function output (sign(x) * d * round(p/d))."""
+    x = _f32c(x, "fake_quantize_sym")
+    dev = x.device
+    d_, q_ = _scalar_param(d, dev, "d_quant"), _scalar_param(q_m, dev, "q_m")
+    t_ = None if t is None else _scalar_param(t, dev, "t_quant")
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().qvit_fake_quantize_sym(_lib.ptr(x), x.numel(), _lib.ptr(d_), _lib.ptr(q_), _lib.ptr(t_),
+                                                 _lib.ptr(out), _lib.stream()), "qvit_fake_quantize_sym")
+    return out
+
+
+def sym_backward(x: torch.Tensor, g: torch.Tensor, d, q_m, t=None, clip: Tuple[float, float] = (-2.0, 2.0),
+                 want_grad_x: bool = True, flags: Optional[torch.Tensor] = None):
+    """One fused pass: (grad_x | None, scalars[3] = grad_d, grad_qm, grad_t).  QL:163-205 / QL:71-125."""
+    x = _f32c(x, "sym_backward x")
+    g = _f32c(g, "sym_backward g")
+    if g.shape != x.shape:
+        raise ValueError("sym_backward: grad_output shape mismatch")
+    dev = x.device
+    d_, q_ = _scalar_param(d, dev, "d_quant"), _scalar_param(q_m, dev, "q_m")
+    t_ = None if t is None else _scalar_param(t, dev, "t_quant")
+    grad_x = torch.empty_like(x) if want_grad_x else None
+    scalars = torch.zeros(3, dtype=torch.float32, device=dev)
+    _lib.check(_lib.lib().qvit_sym_backward(_lib.ptr(x), _lib.ptr(g), x.numel(), _lib.ptr(d_), _lib.ptr(q_), _lib.ptr(t_),
+                                            float(clip[0]), float(clip[1]), _lib.ptr(grad_x), _lib.ptr(scalars),
+                                            _lib.ptr(flags), _lib.stream()), "qvit_sym_backward")
+    return grad_x, scalars
+
+
+def absmax(x: torch.Tensor) -> torch.Tensor:
+    """max|x| as a (1,) device tensor (initialize_quant_layer, QL:423) - no host sync."""
+    x = _f32c(x, "absmax")
+    out = torch.empty(1, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().qvit_absmax(_lib.ptr(x), x.numel(), _lib.ptr(out), _lib.stream()), "qvit_absmax")
+    return out
+
+
+def im2col_quantize_sym(x: torch.Tensor, kernel, stride, padding, dilation, d, q_m, t=None,
+                        flags: Optional[torch.Tensor] = None):
+    """Activation quantizer fused with im2col: NCHW fp32 -> ([B*OH*OW, pad16(C*kh*kw)] int8, OH, OW)."""
+    x = _f32c(x, "im2col_quantize_sym")
+    B, Cc, H, W = x.shape
+    kh, kw = kernel
+    sh, sw = stride
+    ph, pw = padding
+    dh, dw = dilation
+    OH = (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1
+    OW = (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+    if OH <= 0 or OW <= 0:
+        raise ValueError("im2col_quantize_sym: empty output")
+    K = Cc * kh * kw
+    ld = pad16(K)
+    dev = x.device
+    d_, q_ = _scalar_param(d, dev, "d_quant"), _scalar_param(q_m, dev, "q_m")
+    t_ = None if t is None else _scalar_param(t, dev, "t_quant")
+    cols = torch.empty((B * OH * OW, ld), dtype=torch.int8, device=dev)
+    _lib.check(_lib.lib().qvit_im2col_quantize_sym(_lib.ptr(x), B, Cc, H, W, kh, kw, sh, sw, ph, pw, dh, dw, _lib.ptr(d_),
+                                                   _lib.ptr(q_), _lib.ptr(t_), _lib.ptr(cols), ld, _lib.ptr(flags),
+                                                   _lib.stream()), "qvit_im2col_quantize_sym")
+    return cols, OH, OW
+
+
+def layernorm_quantize(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float, d, q_m, t=None,
+                       ld_codes: Optional[int] = None, want_ln: bool = False, flags: Optional[torch.Tensor] = None):
+    """codes = Q(LayerNorm(x)) for x [rows, cols] (vit_model.py:206-207 feeding QL:356-381).  Returns (codes, ln|None)."""
+    x = _f32c(x, "layernorm_quantize")
+    x2 = x.reshape(-1, x.shape[-1])
+    rows, cols = x2.shape
+    ld = pad16(cols) if ld_codes is None else int(ld_codes)
+    dev = x.device
+    gamma, beta = _f32c(gamma, "gamma"), _f32c(beta, "beta")
+    d_, q_ = _scalar_param(d, dev, "d_quant"), _scalar_param(q_m, dev, "q_m")
+    t_ = None if t is None else _scalar_param(t, dev, "t_quant")
+    codes = torch.empty((rows, ld), dtype=torch.int8, device=dev)
+    ln = torch.empty_like(x2) if want_ln else None
+    _lib.check(_lib.lib().qvit_layernorm_quantize(_lib.ptr(x2), rows, cols, _lib.ptr(gamma), _lib.ptr(beta), float(eps),
+                                                  _lib.ptr(d_), _lib.ptr(q_), _lib.ptr(t_), _lib.ptr(codes), ld,
+                                                  _lib.ptr(ln), _lib.ptr(flags), _lib.stream()), "qvit_layernorm_quantize")
+    return codes, ln
+
+
+# ------------------------------------------------------------------------------------------ GEMM
+def gemm_i8(a: torch.Tensor, w: torch.Tensor, K: int, N: Optional[int] = None, *, out_kind: int = QVIT_OUT_F32,
+            act: int = QVIT_ACT_NONE, scale_a=None, scale_w=None, scale_const: float = 1.0,
+            col_scale: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+            residual: Optional[torch.Tensor] = None, next_q=None, flags: Optional[torch.Tensor] = None,
+            backend: int = QVIT_GEMM_AUTO, out: Optional[torch.Tensor] = None, ldo: Optional[int] = None) -> torch.Tensor:
+    """acc = A[M, :K] @ W[N, :K]^T (int8/uint8 x int8 -> int32) + fused epilogue (include/qvit_b200.h).
+
+    a: [M, lda] int8 or uint8 codes, w: [N, ldw] int8 codes; both row-major with the pitch as second dim.
+    next_q = (d, q_m, t|None) of the consumer layer for QVIT_OUT_I8."""
+    _lib.require_cuda(a, w)
+    if a.dtype not in (torch.int8, torch.uint8) or w.dtype != torch.int8:
+        raise TypeError("gemm_i8: a must be int8/uint8 and w int8")
+    if a.dim() != 2 or w.dim() != 2 or a.stride(1) != 1 or w.stride(1) != 1:
+        raise ValueError("gemm_i8: operands must be 2-D with unit inner stride")
+    M = a.shape[0]
+    N = w.shape[0] if N is None else int(N)
+    lda, ldw = (a.stride(0) if M > 1 else a.shape[1]), (w.stride(0) if w.shape[0] > 1 else w.shape[1])
+    if K > a.shape[1] or K > w.shape[1]:
+        raise ValueError("gemm_i8: K exceeds the operand width")
+    dev = a.device
+    if out is None:
+        ldo = N if ldo is None else int(ldo)
+        out = torch.empty((M, ldo), dtype=_OUT_DTYPE[out_kind], device=dev)
+        if ldo > N and out_kind == QVIT_OUT_I8:
+            out[:, N:].zero_()
+    else:
+        if out.dtype != _OUT_DTYPE[out_kind] or out.dim() != 2 or out.shape[0] != M or out.stride(1) != 1:
+            raise ValueError("gemm_i8: bad `out`")
+        ldo = out.stride(0) if M > 1 else out.shape[1]
+    epi = _lib.Epilogue()
+    epi.out_kind, epi.act, epi.scale_const = out_kind, act, float(scale_const)
+    keep = []
+
+    def sp(v, what):
+        if v is None:
+            return None
+        t_ = _scalar_param(v, dev, what)
+        keep.append(t_)
+        return t_.data_ptr()
+
+    epi.scale_a, epi.scale_w = sp(scale_a, "scale_a"), sp(scale_w, "scale_w")
+    if col_scale is not None:
+        col_scale = _f32c(col_scale, "col_scale")
+        if col_scale.numel() != N:
+            raise ValueError("gemm_i8: col_scale must have N elements")
+    if bias is not None:
+        bias = _f32c(bias.detach(), "bias")
+        if bias.numel() != N:
+            raise ValueError("gemm_i8: bias must have N elements")
+    epi.col_scale, epi.bias = _lib.ptr(col_scale), _lib.ptr(bias)
+    if residual is not None:
+        residual = _f32c(residual, "residual")
+        if residual.dim() != 2 or residual.shape[0] != M or residual.shape[1] < N:
+            raise ValueError("gemm_i8: residual must be [M, >=N] fp32")
+        epi.residual, epi.ld_res = residual.data_ptr(), residual.stride(0) if M > 1 else residual.shape[1]
+    if out_kind == QVIT_OUT_I8:
+        if next_q is None:
+            raise ValueError("gemm_i8: QVIT_OUT_I8 needs next_q=(d, q_m, t)")
+        epi.next_d, epi.next_qm = sp(next_q[0], "next_d"), sp(next_q[1], "next_qm")
+        epi.next_t = sp(next_q[2], "next_t") if len(next_q) > 2 else None
+    epi.flags = _lib.ptr(flags)
+    _lib.check(_lib.lib().qvit_gemm_i8(_lib.ptr(a), lda, 1 if a.dtype == torch.uint8 else 0, _lib.ptr(w), ldw, M, N, int(K),
+                                       _lib.ptr(out), ldo, C.byref(epi), backend, _lib.stream()), "qvit_gemm_i8")
+    return out
+
+
+# ------------------------------------------------------------------------------------------ UltraNet (DoReFa)
+def ultra_weight_codes(w: torch.Tensor, w_bit: int) -> torch.Tensor:
+    """int8 codes of weight_quantize_fn(w_bit).forward (QU:38-56), same shape as w; values = codes / (2^(b-1)-1)."""
+    w = _f32c(w.detach(), "ultra_weight_codes")
+    mx = torch.empty(1, dtype=torch.float32, device=w.device)
+    codes = torch.empty(w.shape, dtype=torch.int8, device=w.device)
+    L = _lib.lib()
+    _lib.check(L.qvit_ultra_tanh_absmax(_lib.ptr(w), w.numel(), _lib.ptr(mx), _lib.stream()), "qvit_ultra_tanh_absmax")
+    _lib.check(L.qvit_ultra_quantize_weight(_lib.ptr(w), w.numel(), int(w_bit), _lib.ptr(mx), _lib.ptr(codes),
+                                            _lib.stream()), "qvit_ultra_quantize_weight")
+    return codes
+
+
+def ultra_act(x: torch.Tensor, a_bit: int, want_codes: bool = True, want_values: bool = False):
+    """activation_quantize_fn(a_bit).forward (QU:66-73): (uint8 codes | None, fp32 values | None)."""
+    x = _f32c(x, "ultra_act")
+    codes = torch.empty(x.shape, dtype=torch.uint8, device=x.device) if want_codes else None
+    vals = torch.empty_like(x) if want_values else None
+    _lib.check(_lib.lib().qvit_ultra_quantize_act(_lib.ptr(x), x.numel(), int(a_bit), _lib.ptr(codes), _lib.ptr(vals),
+                                                  _lib.stream()), "qvit_ultra_quantize_act")
+    return codes, vals
+
+
+def conv2d_f32_wcodes(x, w_codes, w_levels: float, bias, stride, padding, dilation) -> torch.Tensor:
+    """Conv2d_Q.forward (QU:85-89) on a raw fp32 input, weights as integer codes (groups == 1)."""
+    x = _f32c(x, "conv2d_f32_wcodes")
+    _lib.require_cuda(w_codes)
+    B, Cc, H, W = x.shape
+    O, Ci, kh, kw = w_codes.shape
+    if Ci != Cc:
+        raise ValueError("conv2d_f32_wcodes: channel mismatch (groups must be 1)")
+    sh, sw = stride
+    ph, pw = padding
+    dh, dw = dilation
+    OH = (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1
+    OW = (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
+    y = torch.empty((B, O, OH, OW), dtype=torch.float32, device=x.device)
+    b = None if bias is None else _f32c(bias.detach(), "bias")
+    _lib.check(_lib.lib().qvit_conv2d_f32_wcodes(_lib.ptr(x), B, Cc, H, W, _lib.ptr(w_codes.contiguous()), O, kh, kw, sh, sw,
+                                                 ph, pw, dh, dw, float(w_levels), _lib.ptr(b), _lib.ptr(y), _lib.stream()),
+               "qvit_conv2d_f32_wcodes")
+    return y
+
+
+def ultra_conv_bn_act(in_codes: torch.Tensor, w_codes_ohwi: torch.Tensor, pad: int, acc_scale: float,
+                      bn_scale: Optional[torch.Tensor], bn_bias: Optional[torch.Tensor], out_levels: int, pool: bool,
+                      f32_out: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One fused integer UltraNet layer.  in_codes [B,H,W,C] uint8, w_codes [O,kh,kw,C] int8.
+    Returns uint8 NHWC codes (pooled 2x2 if `pool`) or, with f32_out, the un-quantised NCHW fp32 map."""
+    _lib.require_cuda(in_codes, w_codes_ohwi)
+    if in_codes.dtype != torch.uint8 or w_codes_ohwi.dtype != torch.int8:
+        raise TypeError("ultra_conv_bn_act: uint8 activations and int8 weights expected")
+    in_codes, w_codes_ohwi = in_codes.contiguous(), w_codes_ohwi.contiguous()
+    B, H, W, Cc = in_codes.shape
+    O, kh, kw, Ci = w_codes_ohwi.shape
+    if Ci != Cc:
+        raise ValueError("ultra_conv_bn_act: channel mismatch")
+    OH, OW = H + 2 * pad - kh + 1, W + 2 * pad - kw + 1
+    dev = in_codes.device
+    if f32_out:
+        if out is None:
+            out = torch.empty((B, O, OH, OW), dtype=torch.float32, device=dev)
+        oc, of = None, out
+    else:
+        if out is None:
+            out = torch.empty((B, OH // 2, OW // 2, O) if pool else (B, OH, OW, O), dtype=torch.uint8, device=dev)
+        oc, of = out, None
+    _lib.check(_lib.lib().qvit_ultra_conv_bn_act(_lib.ptr(in_codes), B, H, W, Cc, _lib.ptr(w_codes_ohwi), O, kh, kw, int(pad),
+                                                 float(acc_scale), _lib.ptr(bn_scale), _lib.ptr(bn_bias), int(out_levels),
+                                                 1 if pool else 0, _lib.ptr(oc), _lib.ptr(of), _lib.stream()),
+               "qvit_ultra_conv_bn_act")
+    return out
+
+
+def bn_fold(gamma, beta, mean, var, eps: float, mode: int = 0):
+    """(scale, bias) of an eval BatchNorm.  mode 0: nn.BatchNorm2d (eps inside sqrt); mode 1: QZ:34-46 (eps outside)."""
+    gamma, beta, mean, var = (_f32c(t.detach(), "bn_fold") for t in (gamma, beta, mean, var))
+    Cn = gamma.numel()
+    scale, bias = torch.empty_like(gamma), torch.empty_like(gamma)
+    _lib.check(_lib.lib().qvit_bn_fold(_lib.ptr(gamma), _lib.ptr(beta), _lib.ptr(mean), _lib.ptr(var), float(eps), int(mode), Cn,
+                                       _lib.ptr(scale), _lib.ptr(bias), _lib.stream()), "qvit_bn_fold")
+    return scale, bias
+
+
+def bn_act_quantize_int(gamma, beta, mean, var, eps: float, w_bit=2, in_bit=4, out_bit=4, l_shift=4):
+    """bn_act_quantize_int (QZ:68-89) -> (inc, bias) int32, computed in the dtype of the inputs (fp32 or fp64)."""
+    ts = [gamma, beta, mean, var]
+    _lib.require_cuda(*ts)
+    is64 = all(t.dtype == torch.float64 for t in ts)
+    if not is64:
+        ts = [t.to(torch.float32) for t in ts]
+    ts = [t.contiguous() for t in ts]
+    Cn = ts[0].numel()
+    inc = torch.empty(Cn, dtype=torch.int32, device=ts[0].device)
+    bias = torch.empty(Cn, dtype=torch.int32, device=ts[0].device)
+    _lib.check(_lib.lib().qvit_bn_act_quantize_int(*[_lib.ptr(t) for t in ts], 1 if is64 else 0, float(eps), int(w_bit),
+                                                   int(in_bit), int(out_bit), int(l_shift), Cn, _lib.ptr(inc),
+                                                   _lib.ptr(bias), _lib.stream()), "qvit_bn_act_quantize_int")
+    return inc, bias
+
+
+def pack_int4(codes: torch.Tensor) -> torch.Tensor:
+    """Little-endian nibble pack (array_to_string, qnn_mem_process.py:11-24): last dim must be even."""
+    _lib.require_cuda(codes)
+    codes = codes.to(torch.int8).contiguous()
+    if codes.shape[-1] % 2:
+        raise ValueError("pack_int4: last dimension must be even")
+    out = torch.empty((*codes.shape[:-1], codes.shape[-1] // 2), dtype=torch.uint8, device=codes.device)
+    _lib.check(_lib.lib().qvit_pack_int4(_lib.ptr(codes), codes.numel(), _lib.ptr(out), _lib.stream()), "qvit_pack_int4")
+    return out
+
+
+def unpack_int4(packed: torch.Tensor, signed: bool = True) -> torch.Tensor:
+    _lib.require_cuda(packed)
+    packed = packed.to(torch.uint8).contiguous()
+    out = torch.empty((*packed.shape[:-1], packed.shape[-1] * 2), dtype=torch.int8, device=packed.device)
+    _lib.check(_lib.lib().qvit_unpack_int4(_lib.ptr(packed), out.numel(), 1 if signed else 0, _lib.ptr(out), _lib.stream()),
+               "qvit_unpack_int4")
+    return out

@@ -1,0 +1,467 @@
+"""Drop-in replacements for the reference's GETA quantized layers, running on hand-written sm_100a kernels.
+
+Mirrors ``QViT_with_GETA/only_train_once/quantization/quant_layers.py`` (reference file:line cited per symbol):
+same class names, constructor arguments, parameter names, ``state_dict`` layout, enums and error
+behaviour, so ``model_to_quantize_model`` / GETA / checkpoints keep working unchanged.  What changes is what runs:
+
+* inference (no autograd): activations -> int8 codes (``qvit_quantize_sym``), weights -> int8 codes cached per
+  parameter version, exact integer contraction on the tcgen05 ``kind::i8`` pipe with TMEM int32 accumulators and
+  a fused dequant + bias epilogue (``qvit_gemm_i8``).  The reference runs ~11 elementwise ATen kernels per
+  quantizer and an fp32 GEMM on fake-quant values (QL:495-499).
+* training (autograd): fake-quant values from ONE fused kernel per quantizer and the fused STE/step-size
+  backward (``qvit_sym_backward``); the two fp32 gradient GEMMs stay on cuBLAS (their ``grad_output`` operand is
+  never quantized by the reference).
+* configurations the int8 pipe cannot carry (weight-only mode, > 8-bit codes, grouped conv) use the same
+  fused quantizer kernels and a library fp32 GEMM/conv on the GPU.  There is no CPU path.
+"""
+from __future__ import annotations
+
+import logging
+import math
+from enum import Enum
+from typing import Optional, Tuple, Union
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .. import ops
+
+logger = logging.getLogger(__name__)
+
+
+class NanInGradientError(Exception):
+    """QL:10-13."""
+
+    def __init__(self, message):
+        self.message = message
+        super().__init__(self.message)
+
+
+class QuantizationType(Enum):          # QL:20-24
+    SYMMETRIC_LINEAR = "symmetric+linear"
+    SYMMETRIC_NONLINEAR = "symmetric+nonlinear"
+    DGE = "dge"
+
+
+class QuantizationMode(Enum):          # QL:27-29
+    WEIGHT_ONLY = "weight_only"
+    WEIGHT_AND_ACTIVATION = "weight_and_activation"
+
+
+# ---------------------------------------------------------------------------------------------------
+# NaN-in-gradient reporting without a per-layer host sync: kernels OR a bit into a per-device flag word; it
+# is polled once per step by check_nan_flags() (or eagerly when QVIT_EAGER_NAN_CHECK is set by a test).
+# ---------------------------------------------------------------------------------------------------
+_flag_words = {}
+EAGER_NAN_CHECK = False
+
+
+def _flags_for(device: torch.device) -> torch.Tensor:
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    w = _flag_words.get(key)
+    if w is None:
+        w = ops.new_flags(device)
+        _flag_words[key] = w
+    return w
+
+
+def check_nan_flags(raise_error: bool = True) -> int:
+    """Poll (one host sync) and clear the device flag words.  Raises NanInGradientError if a fused backward saw a
+    NaN in the reduced step-size gradient - the deferred equivalent of QL:189-204 / QL:107-123."""
+    bits = 0
+    for w in _flag_words.values():
+        bits |= int(w.item())
+        w.zero_()
+    if raise_error and bits & ops._lib.QVIT_FLAG_NAN_GRAD:
+        raise NanInGradientError("Error: NaN appears in gradient! (reported by the fused quantizer backward)")
+    return bits
+
+
+def _clip_pair(clip_val) -> Tuple[float, float]:
+    if isinstance(clip_val, torch.Tensor):
+        lo, hi = clip_val.detach().flatten().tolist()[:2]      # reference API passes a tensor (QL:334); host read
+        return float(lo), float(hi)
+    return float(clip_val[0]), float(clip_val[1])
+
+
+def _sym_forward(ctx, input, d_quant, q_m, t_quant, clip_val):
+    dev = input.device
+    ops._lib.require_cuda(input)
+    d_quant, q_m = d_quant.to(dev), q_m.to(dev)                 # QL:148-151
+    t_quant = None if t_quant is None else t_quant.to(dev)
+    x = input.contiguous()
+    ctx.clip = _clip_pair(clip_val)
+    ctx.save_for_backward(x, d_quant, q_m) if t_quant is None else ctx.save_for_backward(x, d_quant, q_m, t_quant)
+    return ops.fake_quantize_sym(x, d_quant, q_m, t_quant)
+
+
+def _sym_backward(ctx, grad_output, nonlinear: bool):
+    if nonlinear:
+        x, d_quant, q_m, t_quant = ctx.saved_tensors
+    else:
+        (x, d_quant, q_m), t_quant = ctx.saved_tensors, None
+    flags = _flags_for(x.device)
+    grad_x, s = ops.sym_backward(x, grad_output.contiguous(), d_quant, q_m, t_quant, ctx.clip,
+                                 want_grad_x=ctx.needs_input_grad[0], flags=flags)
+    if EAGER_NAN_CHECK:
+        check_nan_flags()
+    return grad_x, s[0:1], s[1:2], s[2:3]
+
+
+class SymQuantizerNonLinear(torch.autograd.Function):
+    """QL:33-125.  forward: sign(x) * d * round(exp(t*log|x|) / d) with zero / saturation overrides;
+    backward: STE inside clip_val + fused reductions for d, q_m, t."""
+
+    @staticmethod
+    def forward(ctx, input, d_quant, q_m, t_quant, clip_val, q_s):
+        return _sym_forward(ctx, input, d_quant, q_m, t_quant, clip_val)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        gx, gd, gq, gt = _sym_backward(ctx, grad_output, True)
+        return gx, gd, gq, gt, None, None
+
+
+class SymQuantizerLinear(torch.autograd.Function):
+    """QL:128-205."""
+
+    @staticmethod
+    def forward(ctx, input, d_quant, q_m, clip_val, q_s):
+        return _sym_forward(ctx, input, d_quant, q_m, None, clip_val)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        gx, gd, gq, _ = _sym_backward(ctx, grad_output, False)
+        return gx, gd, gq, None, None
+
+
+class DGEQuantizer(torch.autograd.Function):
+    """QL:207-290 ("experimental WIP, not used" upstream).  Forward = the linear quantizer kernel; backward reuses
+    the fused kernel for the d / q_m reductions and applies the DGE factor (1/k)|x - d/2|^(1/k-1), clamp +-3."""
+
+    @staticmethod
+    def forward(ctx, input, d_quant, q_m, clip_val, q_s, num_bits):
+        ctx.k = 5.0 * (4.0 / float(num_bits))                    # QL:236
+        return _sym_forward(ctx, input, d_quant, q_m, None, clip_val)
+
+    @staticmethod
+    def backward(ctx, grad_output):
+        x, d_quant, q_m = ctx.saved_tensors
+        gx, gd, gq, _ = _sym_backward(ctx, grad_output, False)
+        k = ctx.k
+        scale = (1.0 / k) * torch.pow(torch.abs(x - d_quant / 2), 1.0 / k - 1.0)     # QL:259-261
+        gx = torch.clamp(gx * scale, -3.0, 3.0)                                     # QL:262-265
+        if EAGER_NAN_CHECK and torch.isnan(gx).any():
+            raise NanInGradientError("NaN in gradient computation")
+        return gx, gd, gq, None, None, None
+
+
+def _get_quantizer(qtype: QuantizationType):
+    """QL:292-300."""
+    if qtype == QuantizationType.SYMMETRIC_LINEAR:
+        return SymQuantizerLinear
+    elif qtype == QuantizationType.SYMMETRIC_NONLINEAR:
+        return SymQuantizerNonLinear
+    elif qtype == QuantizationType.DGE:
+        return DGEQuantizer
+    else:
+        raise NotImplementedError
+
+
+class _QuantCache:
+    """Integer weight codes + saturation levels, valid for one (parameter identity, version) tuple.
+
+    OTO pruning replaces ``module.weight`` with a new sliced Parameter (operator.py:481-499) and optimizers may
+    write through ``.data`` without bumping ``_version``; the key therefore includes data_ptr/shape, and
+    ``train()`` / ``load_state_dict`` / ``invalidate_quant_cache()`` drop the cache."""
+    __slots__ = ("key", "w_codes", "w_sat", "a_sat", "w_q")
+
+    def __init__(self):
+        self.key = None
+        self.w_codes = None
+        self.w_sat = None
+        self.a_sat = None
+        self.w_q = None
+
+
+def _bit_width(d: float, qmax: float, t: float) -> int:
+    return round(math.log2(math.exp(t * math.log(qmax)) / abs(d) + 1) + 1)      # QL:394
+
+
+class QuantizeMixin:
+    """QL:303-410: owns d_quant_*/q_m_*/t_quant_* (each an nn.Parameter of shape (1,))."""
+
+    def init_quantization(self, d_quant_init: float = 1.0, t_quant_init: float = 1.0, q_m_init: float = 1.0,
+                          quant_type: QuantizationType = QuantizationType.SYMMETRIC_LINEAR,
+                          quant_mode: QuantizationMode = QuantizationMode.WEIGHT_ONLY,
+                          weight_clip_val: Tuple[float, float] = (-2.0, 2.0),
+                          act_clip_val: Tuple[float, float] = (-2.0, 2.0)):
+        self.d_quant_wt = nn.Parameter(torch.tensor([d_quant_init]))
+        self.q_m_wt = nn.Parameter(torch.tensor([q_m_init]))
+        if quant_type == QuantizationType.SYMMETRIC_NONLINEAR:
+            self.t_quant_wt = nn.Parameter(torch.tensor([t_quant_init]))
+        if quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION:
+            self.d_quant_act = nn.Parameter(torch.tensor([d_quant_init]))
+            self.q_m_act = nn.Parameter(torch.tensor([q_m_init]))
+            if quant_type == QuantizationType.SYMMETRIC_NONLINEAR:
+                self.t_quant_act = nn.Parameter(torch.tensor([t_quant_init]))
+        self.quant_type = quant_type
+        self.quant_mode = quant_mode
+        self.weight_clip_val = weight_clip_val
+        self.act_clip_val = act_clip_val
+        self.__dict__["_qcache"] = _QuantCache()      # plain attribute: never in state_dict, not a buffer
+
+    # ---- reference API -------------------------------------------------------------------------
+    def quantize_weight(self, weight: torch.Tensor) -> torch.Tensor:
+        """QL:332-354: fake-quantized weight (autograd-aware)."""
+        quantizer = _get_quantizer(self.quant_type)
+        if self.quant_type == QuantizationType.SYMMETRIC_LINEAR:
+            return quantizer.apply(weight, self.d_quant_wt, self.q_m_wt, self.weight_clip_val, 0.0)
+        # the reference passes t_quant_wt for every non-linear type (a DGE module has none -> AttributeError, QL:346-354)
+        return quantizer.apply(weight, self.d_quant_wt, self.q_m_wt, self.t_quant_wt, self.weight_clip_val, 0.0)
+
+    def quantize_act(self, activation: torch.Tensor) -> torch.Tensor:
+        """QL:356-381."""
+        if self.quant_mode != QuantizationMode.WEIGHT_AND_ACTIVATION:
+            return activation
+        quantizer = _get_quantizer(self.quant_type)
+        if self.quant_type == QuantizationType.SYMMETRIC_LINEAR:
+            return quantizer.apply(activation, self.d_quant_act, self.q_m_act, self.act_clip_val, 0.0)
+        return quantizer.apply(activation, self.d_quant_act, self.q_m_act, self.t_quant_act, self.act_clip_val, 0.0)
+
+    @property
+    def weight_bit(self) -> int:
+        """QL:383-394."""
+        d = self.d_quant_wt.item()
+        qmax = abs(self.q_m_wt.item())
+        if self.quant_type == QuantizationType.SYMMETRIC_LINEAR:
+            t = 1.0
+        elif self.quant_type == QuantizationType.SYMMETRIC_NONLINEAR:
+            t = self.t_quant_wt.item()
+        else:
+            raise NotImplementedError
+        return _bit_width(d, qmax, t)
+
+    @property
+    def activation_bit(self) -> int:
+        """QL:396-410."""
+        if self.quant_mode != QuantizationMode.WEIGHT_AND_ACTIVATION:
+            return 32
+        d = self.d_quant_act.item()
+        qmax = abs(self.q_m_act.item())
+        if self.quant_type == QuantizationType.SYMMETRIC_LINEAR:
+            t = 1.0
+        elif self.quant_type == QuantizationType.SYMMETRIC_NONLINEAR:
+            t = self.t_quant_act.item()
+        else:
+            raise NotImplementedError
+        return _bit_width(d, qmax, t)
+
+    # ---- integer-path plumbing -----------------------------------------------------------------
+    def invalidate_quant_cache(self) -> None:
+        self.__dict__["_qcache"] = _QuantCache()
+
+    def _wt_qparams(self):
+        return self.d_quant_wt, self.q_m_wt, getattr(self, "t_quant_wt", None)
+
+    def _act_qparams(self):
+        return self.d_quant_act, self.q_m_act, getattr(self, "t_quant_act", None)
+
+    def _cache_key(self):
+        ps = [self.weight, *[p for p in self._wt_qparams() if p is not None]]
+        if self.quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION:
+            ps += [p for p in self._act_qparams() if p is not None]
+        return tuple((p.data_ptr(), p._version, tuple(p.shape), str(p.device)) for p in ps)
+
+    @staticmethod
+    def _sat_level(d, q_m, t) -> float:
+        """round(r/d): largest code magnitude (QL:159 / QL:67), evaluated in fp32 like the kernels."""
+        with torch.no_grad():
+            r = torch.abs(q_m.detach().float())
+            if t is not None:
+                r = torch.exp(t.detach().float() * torch.log(r + 1e-6))
+            v = torch.abs(torch.round(r / torch.abs(d.detach().float()))).item()      # one host read per parameter change
+        return v if math.isfinite(v) else float("inf")
+
+    def _refresh_cache(self) -> _QuantCache:
+        c = self.__dict__.get("_qcache")
+        if c is None:
+            c = self.__dict__["_qcache"] = _QuantCache()
+        key = self._cache_key()
+        if c.key == key:
+            return c
+        c.key, c.w_codes, c.w_q = key, None, None
+        d, q, t = self._wt_qparams()
+        c.w_sat = self._sat_level(d, q, t)
+        c.a_sat = None
+        if self.quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION:
+            c.a_sat = self._sat_level(*self._act_qparams())
+        return c
+
+    def _int8_ok(self, c: _QuantCache) -> bool:
+        return (self.quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION and self.quant_type != QuantizationType.DGE
+                and c.w_sat <= 127 and c.a_sat is not None and c.a_sat <= 127)
+
+    def _weight_codes(self, c: _QuantCache) -> torch.Tensor:
+        """[out, pad16(K)] int8 codes, K = in_features or C*kh*kw ordered (c, kh, kw) = weight.reshape(O, -1)."""
+        if c.w_codes is None:
+            w2 = self.weight.detach().reshape(self.weight.shape[0], -1)
+            d, q, t = self._wt_qparams()
+            c.w_codes = ops.quantize_sym(w2, d, q, t, ld_codes=ops.pad16(w2.shape[1]))
+        return c.w_codes
+
+    def _weight_fake(self, c: _QuantCache) -> torch.Tensor:
+        if c.w_q is None:
+            d, q, t = self._wt_qparams()
+            c.w_q = ops.fake_quantize_sym(self.weight.detach(), d, q, t)
+        return c.w_q
+
+    def _needs_autograd(self, input_: torch.Tensor) -> bool:
+        if not torch.is_grad_enabled():
+            return False
+        return input_.requires_grad or any(p.requires_grad for p in self.parameters(recurse=False))
+
+    def train(self, mode: bool = True):
+        self.invalidate_quant_cache()
+        return super().train(mode)
+
+    def _load_from_state_dict(self, *args, **kwargs):
+        self.invalidate_quant_cache()
+        return super()._load_from_state_dict(*args, **kwargs)
+
+    def __getstate__(self):
+        st = self.__dict__.copy()
+        st["_qcache"] = None          # whole-model pickles (pruning_compression.py:34) never carry device caches
+        return st
+
+
+def initialize_quant_layer(layer, num_bits: int = 16, quant_type: QuantizationType = QuantizationType.SYMMETRIC_LINEAR,
+                           quant_mode: QuantizationMode = QuantizationMode.WEIGHT_ONLY) -> None:
+    """QL:413-440: q_m = max|W|, d = q_m / (2^(b-1)-1); the activation quantizer gets the SAME values."""
+    if not isinstance(layer, (QuantizeConv2d, QuantizeLinear)):
+        return
+    num_bits = float(num_bits)
+    with torch.no_grad():
+        w = layer.weight.detach()
+        if w.is_cuda:
+            qm = ops.absmax(w)[0]                  # warp-shuffle reduction on the device, no host sync
+        else:
+            qm = torch.max(torch.abs(w))           # module construction on the host happens before .to(device)
+        d = (qm - 0.0) / (2 ** (num_bits - 1) - 1)
+        layer.d_quant_wt.fill_(d)
+        layer.q_m_wt.fill_(qm)
+        if quant_type == QuantizationType.SYMMETRIC_NONLINEAR:
+            layer.t_quant_wt.fill_(1.0)
+        if quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION:
+            layer.d_quant_act.fill_(d)
+            layer.q_m_act.fill_(qm)
+            if quant_type == QuantizationType.SYMMETRIC_NONLINEAR:
+                layer.t_quant_act.fill_(1.0)
+    layer.invalidate_quant_cache()
+
+
+class QuantizeLinear(QuantizeMixin, nn.Linear):
+    """QL:443-499.  (MRO note: the mixin comes first so its train()/_load_from_state_dict hooks run; the
+    reference lists nn.Linear first, which only matters for attribute lookup of names both define - none.)"""
+
+    def __init__(self, in_features, out_features, bias=True, d_quant_init=1.0, t_quant_init=1.0, q_m_init=1.0,
+                 quant_type=QuantizationType.SYMMETRIC_LINEAR, quant_mode=QuantizationMode.WEIGHT_ONLY):
+        nn.Linear.__init__(self, in_features, out_features, bias)
+        self.init_quantization(d_quant_init, t_quant_init, q_m_init, quant_type, quant_mode)
+
+    @staticmethod
+    def from_module(module=None, d_quant_init=1.0, t_quant_init=1.0, q_m_init=1.0,
+                    quant_type=QuantizationType.SYMMETRIC_LINEAR, quant_mode=QuantizationMode.WEIGHT_ONLY,
+                    quant_init_by_module=True, num_bits=8):
+        """QL:460-493."""
+        q = QuantizeLinear(in_features=module.in_features, out_features=module.out_features,
+                           bias=module.bias is not None, d_quant_init=d_quant_init, t_quant_init=t_quant_init,
+                           q_m_init=q_m_init, quant_type=quant_type, quant_mode=quant_mode)
+        q.to(module.weight.device)
+        q.weight.data.copy_(module.weight.data)
+        if module.bias is not None:
+            q.bias.data.copy_(module.bias.data)
+        if quant_init_by_module:
+            initialize_quant_layer(q, num_bits=num_bits, quant_type=quant_type, quant_mode=quant_mode)
+        return q
+
+    def forward(self, input_: torch.Tensor) -> torch.Tensor:
+        """QL:495-499."""
+        ops._lib.require_cuda(input_, self.weight)
+        if self._needs_autograd(input_):
+            weight = self.quantize_weight(self.weight)
+            if self.quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION:
+                input_ = self.quantize_act(input_)
+            return F.linear(input_, weight, self.bias)
+        c = self._refresh_cache()
+        if self._int8_ok(c) and input_.dtype == torch.float32:
+            K, N = self.in_features, self.out_features
+            flags = _flags_for(input_.device)
+            d_a, q_a, t_a = self._act_qparams()
+            a_codes = ops.quantize_sym(input_, d_a, q_a, t_a, ld_codes=ops.pad16(K), flags=flags)
+            y = ops.gemm_i8(a_codes, self._weight_codes(c), K, N, out_kind=ops.QVIT_OUT_F32, scale_a=d_a,
+                            scale_w=self.d_quant_wt, bias=self.bias, flags=flags)
+            return y.reshape(*input_.shape[:-1], N)
+        # wide path: codes do not fit int8 (or weight-only mode) -> fused quantizer kernels + library fp32 GEMM
+        x = input_
+        if self.quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION:
+            x = ops.fake_quantize_sym(input_, *self._act_qparams())
+        return F.linear(x, self._weight_fake(c), self.bias)
+
+
+class QuantizeConv2d(QuantizeMixin, nn.Conv2d):
+    """QL:502-587 (defaults padding=1, bias=False as upstream)."""
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=1, dilation=1, groups=1, bias=False,
+                 d_quant_init=1.0, t_quant_init=1.0, q_m_init=1.0, quant_type=QuantizationType.SYMMETRIC_LINEAR,
+                 quant_mode=QuantizationMode.WEIGHT_ONLY):
+        nn.Conv2d.__init__(self, in_channels, out_channels, kernel_size, stride, padding, dilation, groups, bias=bias)
+        self.init_quantization(d_quant_init, t_quant_init, q_m_init, quant_type, quant_mode)
+
+    @staticmethod
+    def from_module(module=None, d_quant_init=1.0, t_quant_init=1.0, q_m_init=1.0,
+                    quant_type=QuantizationType.SYMMETRIC_LINEAR, quant_mode=QuantizationMode.WEIGHT_ONLY,
+                    quant_init_by_module=True, num_bits=8):
+        """QL:534-573."""
+        q = QuantizeConv2d(in_channels=module.in_channels, out_channels=module.out_channels,
+                           kernel_size=module.kernel_size, stride=module.stride, padding=module.padding,
+                           dilation=module.dilation, groups=module.groups, bias=module.bias is not None,
+                           d_quant_init=d_quant_init, t_quant_init=t_quant_init, q_m_init=q_m_init,
+                           quant_type=quant_type, quant_mode=quant_mode)
+        q.to(module.weight.device)
+        q.weight.data.copy_(module.weight.data)
+        if module.bias is not None:
+            q.bias.data.copy_(module.bias.data)
+        if quant_init_by_module:
+            initialize_quant_layer(q, num_bits=num_bits, quant_type=quant_type, quant_mode=quant_mode)
+        return q
+
+    def forward(self, input_: torch.Tensor) -> torch.Tensor:
+        """QL:575-587."""
+        ops._lib.require_cuda(input_, self.weight)
+        if self._needs_autograd(input_):
+            weight = self.quantize_weight(self.weight)
+            if self.quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION:
+                input_ = self.quantize_act(input_)
+            return F.conv2d(input_, weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+        c = self._refresh_cache()
+        if (self._int8_ok(c) and self.groups == 1 and input_.dtype == torch.float32 and input_.dim() == 4
+                and not isinstance(self.padding, str) and self.padding_mode == "zeros"):
+            flags = _flags_for(input_.device)
+            d_a, q_a, t_a = self._act_qparams()
+            cols, OH, OW = ops.im2col_quantize_sym(input_, self.kernel_size, self.stride, self.padding, self.dilation,
+                                                   d_a, q_a, t_a, flags=flags)
+            K = self.in_channels * self.kernel_size[0] * self.kernel_size[1]
+            y = ops.gemm_i8(cols, self._weight_codes(c), K, self.out_channels, out_kind=ops.QVIT_OUT_F32, scale_a=d_a,
+                            scale_w=self.d_quant_wt, bias=self.bias, flags=flags)
+            # [B*OH*OW, O] is NHWC memory; hand back the NCHW view (PatchEmbed's flatten(2).transpose(1,2),
+            # vit_model.py:100, turns it into the contiguous token matrix without a copy)
+            return y.view(input_.shape[0], OH, OW, self.out_channels).permute(0, 3, 1, 2)
+        x = input_
+        if self.quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION:
+            x = ops.fake_quantize_sym(input_, *self._act_qparams())
+        return F.conv2d(x, self._weight_fake(c), self.bias, self.stride, self.padding, self.dilation, self.groups)
+
+
+LAYER_TO_QUANTLAYER = {"Linear": QuantizeLinear, "Conv2d": QuantizeConv2d}     # QL:590

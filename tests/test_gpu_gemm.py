@@ -1,0 +1,130 @@
+"""GPU parity of the integer GEMM (K3): int32 accumulators must EQUAL the oracle's exact int64 contraction, for
+both the tcgen05 tensor-core kernel and the CUDA-core dp4a kernel, on aligned, ragged and tiny shapes; the fused
+epilogue variants are checked against a plain fp32 restatement."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from quantized_vit_b200 import ops
+    return ops
+
+
+def _codes(M, K, lo, hi, seed, ld=None):
+    g = torch.Generator().manual_seed(seed)
+    ld = ld or (K + 15) // 16 * 16
+    a = torch.zeros(M, ld, dtype=torch.int8)
+    a[:, :K] = torch.randint(lo, hi + 1, (M, K), generator=g, dtype=torch.int64).to(torch.int8)
+    return a
+
+
+SHAPES = [(128, 256, 128), (197, 2304, 768), (394, 768, 3072), (1, 1000, 768), (50, 37, 50), (300, 136, 200),
+          (129, 257, 129), (1024, 3072, 768), (2000, 768, 768)]
+
+
+@pytest.mark.parametrize("backend", ["tcgen05", "simt"])
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_accumulators_bit_exact(ops, backend, M, N, K):
+    a = _codes(M, K, -127, 127, 1)
+    w = _codes(N, K, -7, 7, 2)
+    want = a[:, :K].to(torch.int64) @ w[:, :K].to(torch.int64).t()
+    be = ops.QVIT_GEMM_TCGEN05 if backend == "tcgen05" else ops.QVIT_GEMM_SIMT
+    got = ops.gemm_i8(a.cuda(), w.cuda(), K, N, out_kind=ops.QVIT_OUT_I32, backend=be)
+    torch.cuda.synchronize()
+    assert torch.equal(got.cpu().to(torch.int64), want)
+
+
+@pytest.mark.parametrize("backend", ["tcgen05", "simt"])
+def test_unsigned_activations(ops, backend):
+    M, N, K = 260, 64, 576
+    g = torch.Generator().manual_seed(3)
+    a = torch.randint(0, 256, (M, K), generator=g, dtype=torch.int64)
+    w = _codes(N, K, -7, 7, 4)
+    want = a @ w[:, :K].to(torch.int64).t()
+    be = ops.QVIT_GEMM_TCGEN05 if backend == "tcgen05" else ops.QVIT_GEMM_SIMT
+    got = ops.gemm_i8(a.to(torch.uint8).cuda(), w.cuda(), K, N, out_kind=ops.QVIT_OUT_I32, backend=be)
+    assert torch.equal(got.cpu().to(torch.int64), want)
+
+
+def test_many_tiles_persistent_schedule(ops):
+    # > 148 tiles per CTA wave, both accumulator buffers and every smem stage phase are exercised
+    M, N, K = 128 * 40, 1024, 256 + 128 * 5
+    a = _codes(M, K, -127, 127, 5)
+    w = _codes(N, K, -127, 127, 6)
+    want = a[:, :K].to(torch.int64) @ w[:, :K].to(torch.int64).t()
+    got = ops.gemm_i8(a.cuda(), w.cuda(), K, N, out_kind=ops.QVIT_OUT_I32, backend=ops.QVIT_GEMM_TCGEN05)
+    assert torch.equal(got.cpu().to(torch.int64), want)
+
+
+@pytest.mark.parametrize("backend", ["tcgen05", "simt"])
+def test_fused_epilogues(ops, backend):
+    from oracle import ref_geta
+    be = ops.QVIT_GEMM_TCGEN05 if backend == "tcgen05" else ops.QVIT_GEMM_SIMT
+    M, N, K = 333, 200, 320
+    a = _codes(M, K, -7, 7, 7)
+    w = _codes(N, K, -7, 7, 8)
+    acc = (a[:, :K].to(torch.int64) @ w[:, :K].to(torch.int64).t()).to(torch.float32)
+    g = torch.Generator().manual_seed(9)
+    bias = torch.randn(N, generator=g) * 0.1
+    res = torch.randn(M, N, generator=g)
+    colsc = torch.rand(N, generator=g) + 0.5
+    d_a, d_w = torch.tensor([0.31]), torch.tensor([-0.0123])          # |.| is taken
+    scale = d_a.abs() * d_w.abs()
+    base = acc * scale
+    kw = dict(scale_a=d_a.cuda(), scale_w=d_w.cuda(), backend=be)
+    # fp32 + bias
+    y = ops.gemm_i8(a.cuda(), w.cuda(), K, N, out_kind=ops.QVIT_OUT_F32, bias=bias.cuda(), **kw).cpu()
+    assert torch.allclose(y, base + bias, rtol=1e-6, atol=1e-6)
+    # col_scale + bias + relu + residual
+    y = ops.gemm_i8(a.cuda(), w.cuda(), K, N, out_kind=ops.QVIT_OUT_F32, bias=bias.cuda(), col_scale=colsc.cuda(),
+                    act=ops.QVIT_ACT_RELU, residual=res.cuda(), **kw).cpu()
+    assert torch.allclose(y, torch.relu(base * colsc + bias) + res, rtol=1e-6, atol=1e-6)
+    # GELU(erf) -> bf16
+    y = ops.gemm_i8(a.cuda(), w.cuda(), K, N, out_kind=ops.QVIT_OUT_BF16, bias=bias.cuda(), act=ops.QVIT_ACT_GELU, **kw).cpu()
+    want = torch.nn.functional.gelu(base + bias)
+    assert torch.allclose(y.float(), want, rtol=1e-2, atol=1e-2)
+    # GELU -> requantise with the consumer's quantizer: codes equal the oracle quantizer applied to the fp32 epilogue value
+    nd, nq = 1.7 / 7, 1.7
+    yf = ops.gemm_i8(a.cuda(), w.cuda(), K, N, out_kind=ops.QVIT_OUT_F32, bias=bias.cuda(), act=ops.QVIT_ACT_GELU, **kw).cpu()
+    yc = ops.gemm_i8(a.cuda(), w.cuda(), K, N, out_kind=ops.QVIT_OUT_I8, bias=bias.cuda(), act=ops.QVIT_ACT_GELU,
+                     next_q=(nd, nq, None), ldo=208, **kw).cpu()
+    assert yc.shape == (M, 208)
+    assert torch.equal(yc[:, :N].to(torch.int64), ref_geta.sym_codes(yf, nd, nq))
+    assert int(yc[:, N:].abs().sum()) == 0
+
+
+def test_backends_agree_on_random_epilogue(ops):
+    M, N, K = 517, 392, 1000 // 16 * 16
+    a = _codes(M, K, -127, 127, 11)
+    w = _codes(N, K, -7, 7, 12)
+    bias = torch.randn(N).cuda()
+    outs = [ops.gemm_i8(a.cuda(), w.cuda(), K, N, out_kind=ops.QVIT_OUT_F32, bias=bias, scale_a=0.02, scale_w=0.003,
+                        act=ops.QVIT_ACT_GELU, backend=be) for be in (ops.QVIT_GEMM_TCGEN05, ops.QVIT_GEMM_SIMT)]
+    assert torch.equal(outs[0], outs[1])
+
+
+def test_k_zero_and_empty(ops):
+    a = torch.zeros(4, 16, dtype=torch.int8).cuda()
+    w = torch.zeros(8, 16, dtype=torch.int8).cuda()
+    bias = torch.arange(8, dtype=torch.float32).cuda()
+    y = ops.gemm_i8(a, w, 0, 8, out_kind=ops.QVIT_OUT_F32, bias=bias)
+    assert torch.equal(y.cpu(), bias.cpu().expand(4, 8))
+    y = ops.gemm_i8(a[:0], w, 16, 8, out_kind=ops.QVIT_OUT_F32)
+    assert y.shape == (0, 8)
+
+
+def test_unaligned_pitch_falls_back_to_simt_and_tc_refuses(ops):
+    M, N, K = 40, 24, 50
+    g = torch.Generator().manual_seed(13)
+    a = torch.randint(-7, 8, (M, K), generator=g, dtype=torch.int64).to(torch.int8)      # pitch 50: not 16-aligned
+    w = torch.randint(-7, 8, (N, K), generator=g, dtype=torch.int64).to(torch.int8)
+    want = a.to(torch.int64) @ w.to(torch.int64).t()
+    got = ops.gemm_i8(a.cuda(), w.cuda(), K, N, out_kind=ops.QVIT_OUT_I32)
+    assert torch.equal(got.cpu().to(torch.int64), want)
+    with pytest.raises(RuntimeError, match="tcgen05"):
+        ops.gemm_i8(a.cuda(), w.cuda(), K, N, out_kind=ops.QVIT_OUT_I32, backend=ops.QVIT_GEMM_TCGEN05)
