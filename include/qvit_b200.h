@@ -90,13 +90,22 @@ int qvit_im2col_quantize_sym(const float* x, int B, int C, int H, int W,
 /* ------------------------------------------------------------------ UltraNet (DoReFa) quantizers */
 /* max|tanh(w)| -> out[0]  (weight_quantize_fn.forward, QU:50-53). */
 int qvit_ultra_tanh_absmax(const float* w, int64_t n, float* out, qvit_stream_t stream);
-/* codes = round(tanh(w)/max * (2^(w_bit-1)-1)) (sign() at w_bit == 2, QU:15-16); 2 <= w_bit <= 8. */
-int qvit_ultra_quantize_weight(const float* w, int64_t n, int w_bit, const float* max_tanh,
+/* codes = round(tanh(w)/max * (2^(w_bit-1)-1)); 2 <= w_bit <= 8.  export_rounding = 0: the torch forward
+ * (uniform_quantize(k=1) is sign() at w_bit == 2, QU:15-16); 1: the NumPy export, which always rounds (QZ:24-31). */
+int qvit_ultra_quantize_weight(const float* w, int64_t n, int w_bit, int export_rounding, const float* max_tanh,
                                int8_t* codes, qvit_stream_t stream);
 /* activation_quantize_fn.forward (QU:66-73): codes = round(clamp(x,0,1) * (2^a_bit-1)), uint8;
  * values = codes / (2^a_bit-1) written to out_values if non-NULL (either output may be NULL).        */
 int qvit_ultra_quantize_act(const float* x, int64_t n, int a_bit, uint8_t* codes, float* out_values,
                             qvit_stream_t stream);
+/* uniform_quantize(k).forward (QU:12-20): identity (k = 32), sign (k = 1), else round(x*n)/n with n = 2^k-1
+ * (k = 0 gives n = 0 -> NaN, the reference's own 1-bit-weight quirk, QU:36 with QU:18-19).             */
+int qvit_uniform_quantize(const float* x, int64_t n, int k, float* out, qvit_stream_t stream);
+/* nn.BatchNorm2d(eval) as (scale, bias) + activation_quantize_fn + optional 2x2 max-pool (MM:74-76) on an NCHW
+ * fp32 map, written as NHWC uint8 codes with channel pitch ldc (padding channels are NOT written).
+ * scale = bias = NULL: codes = round(clamp(x,0,1)*levels) only (image -> 8-bit input codes).           */
+int qvit_ultra_bn_act_pool_nchw(const float* x, int B, int C, int H, int W, const float* scale, const float* bias,
+                                int levels, int pool, uint8_t* out_codes, int ldc, qvit_stream_t stream);
 /* Conv2d_Q.forward (QU:85-89) with arbitrary fp32 input: y = conv2d(x, codes / w_levels) + bias, NCHW fp32,
  * groups == 1, w_levels = 2^(w_bit-1)-1 (the fp32 quotient codes/w_levels is bit-for-bit the reference's w_q,
  * QU:18-19).  The input is NOT quantised by the reference layer (the first UltraNet layer sees the image). */

@@ -43,8 +43,10 @@ PROTOTYPES = {
     "qvit_absmax": (_i, [_p, _i64, _p, _p]),
     "qvit_im2col_quantize_sym": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _p, _p]),
     "qvit_ultra_tanh_absmax": (_i, [_p, _i64, _p, _p]),
-    "qvit_ultra_quantize_weight": (_i, [_p, _i64, _i, _p, _p, _p]),
+    "qvit_ultra_quantize_weight": (_i, [_p, _i64, _i, _i, _p, _p, _p]),
     "qvit_ultra_quantize_act": (_i, [_p, _i64, _i, _p, _p, _p]),
+    "qvit_uniform_quantize": (_i, [_p, _i64, _i, _p, _p]),
+    "qvit_ultra_bn_act_pool_nchw": (_i, [_p, _i, _i, _i, _i, _p, _p, _i, _i, _p, _i, _p]),
     "qvit_conv2d_f32_wcodes": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p]),
     "qvit_ultra_conv_bn_act": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _f, _p, _p, _i, _i, _p, _p, _p]),
     "qvit_bn_fold": (_i, [_p, _p, _p, _p, _f, _i, _i, _p, _p, _p]),

@@ -41,7 +41,7 @@ __device__ __forceinline__ float epi_value(const EpiParams& e, int acc, float sc
   if (e.bias) y += __ldg(e.bias + n);
   if (e.act == QVIT_ACT_GELU) y = gelu_erf(y);
   else if (e.act == QVIT_ACT_RELU) y = fmaxf(y, 0.0f);
-  if (e.residual) y += __ldg(e.residual + m * e.ld_res + n);
+  if (e.residual) y += e.residual[m * e.ld_res + n];
   return y;
 }
 
@@ -109,7 +109,7 @@ __device__ __forceinline__ void epi_store_chunk32(const EpiParams& e, const SymP
       const float* r = e.residual + m * e.ld_res + n0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 c = ldg_stream4(r + 4 * j);
+        const float4 c = *reinterpret_cast<const float4*>(r + 4 * j);   // plain load: `out` may alias `residual`
         y[4 * j] += c.x; y[4 * j + 1] += c.y; y[4 * j + 2] += c.z; y[4 * j + 3] += c.w;
       }
     }

@@ -40,14 +40,14 @@ tanh_absmax_kernel(const float* __restrict__ w, int64_t n, uint32_t* __restrict_
 __global__ void zero_u32_kernel(uint32_t* p) { *p = 0u; }
 
 __global__ void __launch_bounds__(kUT)
-ultra_quantize_weight_kernel(const float* __restrict__ w, int64_t n, int w_bit, const float* __restrict__ max_tanh,
-                             int8_t* __restrict__ codes) {
+ultra_quantize_weight_kernel(const float* __restrict__ w, int64_t n, int w_bit, int export_rounding,
+                             const float* __restrict__ max_tanh, int8_t* __restrict__ codes) {
   const float mx = __ldg(max_tanh);
   const float levels = (float)((1 << (w_bit - 1)) - 1);
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float v = __fdiv_rn(tanhf(w[i]), mx);            // QU:50-53
     float c;
-    if (w_bit == 2) c = (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f);   // uniform_quantize(k=1) = sign  (QU:15-16)
+    if (w_bit == 2 && !export_rounding) c = (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f);   // uniform_quantize(k=1) = sign  (QU:15-16)
     else c = rintf(v * levels);                            // QU:18
     if (!(c == c)) c = 0.f;
     codes[i] = (int8_t)(int)c;
@@ -74,31 +74,81 @@ struct ConvF32Geom {
   int B, C, H, W, O, kh, kw, sh, sw, ph, pw, dh, dw, OH, OW;
 };
 
+// grid = (pixel blocks, O): one CTA = one output channel x 256 output pixels.  The channel's fake-quant weights
+// w_q = code / levels (bit-for-bit the reference's round(v*n)/n, QU:18-19) are expanded to fp32 in shared memory
+// once, so the inner loop is one broadcast LDS + one coalesced LDG + one FFMA per tap.
 __global__ void __launch_bounds__(kUT)
 conv2d_f32_wcodes_kernel(const float* __restrict__ x, const int8_t* __restrict__ wc, ConvF32Geom g, float w_levels,
                          const float* __restrict__ bias, float* __restrict__ y) {
-  const int64_t total = (int64_t)g.B * g.O * g.OH * g.OW;
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+  extern __shared__ float s_wq[];
+  const int o = blockIdx.y;
+  const int taps = g.C * g.kh * g.kw;
+  for (int i = threadIdx.x; i < taps; i += blockDim.x)
+    s_wq[i] = __fdiv_rn((float)__ldg(wc + (int64_t)o * taps + i), w_levels);
+  __syncthreads();
+  const int64_t npix = (int64_t)g.B * g.OH * g.OW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < npix; i += (int64_t)gridDim.x * blockDim.x) {
     const int ow = (int)(i % g.OW);
     const int oh = (int)((i / g.OW) % g.OH);
-    const int o = (int)((i / ((int64_t)g.OW * g.OH)) % g.O);
-    const int b = (int)(i / ((int64_t)g.OW * g.OH * g.O));
+    const int b = (int)(i / ((int64_t)g.OW * g.OH));
     float acc = 0.f;
     for (int c = 0; c < g.C; ++c) {
+      const float* xc = x + ((int64_t)b * g.C + c) * g.H * g.W;
+      const float* wq = s_wq + c * g.kh * g.kw;
       for (int ki = 0; ki < g.kh; ++ki) {
         const int ih = oh * g.sh - g.ph + ki * g.dh;
         if (ih < 0 || ih >= g.H) continue;
         for (int kj = 0; kj < g.kw; ++kj) {
           const int iw = ow * g.sw - g.pw + kj * g.dw;
           if (iw < 0 || iw >= g.W) continue;
-          // the reference multiplies by w_q = round(v*n)/n (QU:18-19): the same fp32 quotient here
-          const float wq = __fdiv_rn((float)__ldg(wc + (((int64_t)o * g.C + c) * g.kh + ki) * g.kw + kj), w_levels);
-          acc = fmaf(__ldg(x + (((int64_t)b * g.C + c) * g.H + ih) * g.W + iw), wq, acc);
+          acc = fmaf(__ldg(xc + (int64_t)ih * g.W + iw), wq[ki * g.kw + kj], acc);
         }
       }
     }
     if (bias) acc += __ldg(bias + o);
-    y[i] = acc;
+    y[(((int64_t)b * g.O + o) * g.OH + oh) * g.OW + ow] = acc;
+  }
+}
+
+// ---------------------------------------------------------------- uniform_quantize(k) forward (QU:12-20)
+__global__ void __launch_bounds__(kUT)
+uniform_quantize_kernel(const float* __restrict__ x, int64_t n, int k, float* __restrict__ out) {
+  const float levels = (k >= 1 && k < 32) ? (float)((1u << k) - 1u) : 0.0f;      // k = 0 -> n = 0 (NaN, as upstream)
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float v = x[i];
+    float o;
+    if (k == 32) o = v;
+    else if (k == 1) o = (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : ((v == 0.f) ? 0.f : v));
+    else o = __fdiv_rn(rintf(v * levels), levels);
+    out[i] = o;
+  }
+}
+
+// ---------------------------------------------------------------- BN(eval) + act-quant (+ 2x2 max-pool): NCHW fp32 -> NHWC codes
+// Used after the fp32 first-layer conv (MM:73-76) and, with scale = bias = NULL, to turn an image into 8-bit codes.
+__global__ void __launch_bounds__(kUT)
+bn_act_pool_nchw_kernel(const float* __restrict__ x, int B, int C, int H, int W, const float* __restrict__ scale,
+                        const float* __restrict__ bias, int levels, int pool, uint8_t* __restrict__ out, int ldc) {
+  const int OH = pool ? H / 2 : H, OW = pool ? W / 2 : W;
+  const int64_t total = (int64_t)B * C * OH * OW;
+  const float lv = (float)levels;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int ow = (int)(i % OW);
+    const int oh = (int)((i / OW) % OH);
+    const int c = (int)((i / ((int64_t)OW * OH)) % C);
+    const int b = (int)(i / ((int64_t)OW * OH * C));
+    const float s = scale ? __ldg(scale + c) : 1.0f, bb = bias ? __ldg(bias + c) : 0.0f;
+    const float* src = x + ((int64_t)b * C + c) * H * W;
+    int best = 0;
+    const int reps = pool ? 2 : 1;
+    for (int dy = 0; dy < reps; ++dy)
+      for (int dx = 0; dx < reps; ++dx) {
+        const float v = src[(int64_t)(oh * reps + dy) * W + (ow * reps + dx)];
+        const float yv = scale ? (v * s + bb) : v;
+        const int code = (int)rintf(fminf(fmaxf(yv, 0.0f), 1.0f) * lv);
+        best = max(best, code);
+      }
+    out[(((int64_t)b * OH + oh) * OW + ow) * ldc + c] = (uint8_t)best;
   }
 }
 
@@ -313,12 +363,13 @@ int qvit_ultra_tanh_absmax(const float* w, int64_t n, float* out, qvit_stream_t 
   return check_launch("qvit_ultra_tanh_absmax");
 }
 
-int qvit_ultra_quantize_weight(const float* w, int64_t n, int w_bit, const float* max_tanh, int8_t* codes,
-                               qvit_stream_t stream) {
+int qvit_ultra_quantize_weight(const float* w, int64_t n, int w_bit, int export_rounding, const float* max_tanh,
+                               int8_t* codes, qvit_stream_t stream) {
   QVIT_REQUIRE(w && max_tanh && codes && n >= 0, "qvit_ultra_quantize_weight: bad argument");
   QVIT_REQUIRE(w_bit >= 2 && w_bit <= 8, "qvit_ultra_quantize_weight: w_bit must be in [2, 8] (got %d)", w_bit);
   if (n == 0) return QVIT_OK;
-  ultra_quantize_weight_kernel<<<ultra_grid(n, kUT * 4), kUT, 0, (cudaStream_t)stream>>>(w, n, w_bit, max_tanh, codes);
+  ultra_quantize_weight_kernel<<<ultra_grid(n, kUT * 4), kUT, 0, (cudaStream_t)stream>>>(w, n, w_bit, export_rounding, max_tanh,
+                                                                                         codes);
   return check_launch("qvit_ultra_quantize_weight");
 }
 
@@ -341,8 +392,14 @@ int qvit_conv2d_f32_wcodes(const float* x, int B, int C, int H, int W, const int
   g.OH = (H + 2 * ph - dh * (kh - 1) - 1) / sh + 1;
   g.OW = (W + 2 * pw - dw * (kw - 1) - 1) / sw + 1;
   QVIT_REQUIRE(g.OH > 0 && g.OW > 0, "qvit_conv2d_f32_wcodes: empty output");
-  const int64_t total = (int64_t)B * O * g.OH * g.OW;
-  conv2d_f32_wcodes_kernel<<<ultra_grid(total, kUT), kUT, 0, (cudaStream_t)stream>>>(x, w_codes, g, w_levels, bias, y);
+  const int64_t npix = (int64_t)B * g.OH * g.OW;
+  const size_t smem = sizeof(float) * (size_t)C * kh * kw;
+  QVIT_REQUIRE(smem <= 48 * 1024 && O <= 65535, "qvit_conv2d_f32_wcodes: C*kh*kw <= 12288 and O <= 65535");
+  int gx = (int)((npix + kUT - 1) / kUT);
+  const int cap = (sm_count() * 8 + O - 1) / O;
+  if (gx > cap) gx = cap < 1 ? 1 : cap;
+  conv2d_f32_wcodes_kernel<<<dim3((unsigned)gx, (unsigned)O), kUT, smem, (cudaStream_t)stream>>>(x, w_codes, g, w_levels,
+                                                                                                bias, y);
   return check_launch("qvit_conv2d_f32_wcodes");
 }
 
@@ -377,6 +434,25 @@ int qvit_ultra_conv_bn_act(const uint8_t* in_codes, int B, int H, int W, int C, 
       in_codes, B, H, W, C, w_codes, O, kh, kw, pad, acc_scale, bn_scale, bn_bias, out_levels, pool, out_codes, out_f32,
       tiles_x, tiles_y, TH);
   return check_launch("qvit_ultra_conv_bn_act");
+}
+
+int qvit_uniform_quantize(const float* x, int64_t n, int k, float* out, qvit_stream_t stream) {
+  QVIT_REQUIRE(x && out && n >= 0 && k >= 0 && k <= 32, "qvit_uniform_quantize: bad argument");
+  if (n == 0) return QVIT_OK;
+  uniform_quantize_kernel<<<ultra_grid(n, kUT * 4), kUT, 0, (cudaStream_t)stream>>>(x, n, k, out);
+  return check_launch("qvit_uniform_quantize");
+}
+
+int qvit_ultra_bn_act_pool_nchw(const float* x, int B, int C, int H, int W, const float* scale, const float* bias,
+                                int levels, int pool, uint8_t* out_codes, int ldc, qvit_stream_t stream) {
+  QVIT_REQUIRE(x && out_codes && B > 0 && C > 0 && H > 0 && W > 0 && ldc >= C, "qvit_ultra_bn_act_pool_nchw: bad argument");
+  QVIT_REQUIRE(levels >= 1 && levels <= 255, "qvit_ultra_bn_act_pool_nchw: levels in [1,255]");
+  QVIT_REQUIRE((scale == nullptr) == (bias == nullptr), "qvit_ultra_bn_act_pool_nchw: scale and bias go together");
+  const int64_t total = (int64_t)B * C * (pool ? H / 2 : H) * (pool ? W / 2 : W);
+  if (total == 0) return QVIT_OK;
+  bn_act_pool_nchw_kernel<<<ultra_grid(total, kUT * 2), kUT, 0, (cudaStream_t)stream>>>(x, B, C, H, W, scale, bias, levels,
+                                                                                       pool, out_codes, ldc);
+  return check_launch("qvit_ultra_bn_act_pool_nchw");
 }
 
 int qvit_bn_fold(const float* gamma, const float* beta, const float* mean, const float* var, float eps, int mode, int C,

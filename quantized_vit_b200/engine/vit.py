@@ -1,0 +1,172 @@
+"""Fused inference engine for the GETA-quantized VisionTransformer (callers of the hot path:
+``QViT_with_GETA/vit_model.py`` PatchEmbed :94-103, ViTAttention :125-153, Mlp :170-177, Block :202-208,
+VisionTransformer.forward :290-328 with every Linear/Conv2d swapped by ``model_to_quantize_model``).
+
+What is fused around the integer GEMMs (per Block):
+    LayerNorm1 + quantize(qkv)            one kernel   (qvit_layernorm_quantize)
+    qkv GEMM + bias                       tcgen05 int8 (qvit_gemm_i8, fp32 or bf16 out)
+    softmax(QK^T)V                        library fused attention (NOT quantized upstream; out of the hot path)
+    quantize(proj)                        one kernel   (qvit_quantize_sym / _bf16)
+    proj GEMM + bias + residual           tcgen05 int8, residual added in the epilogue, in place on the stream
+    LayerNorm2 + quantize(fc1)            one kernel
+    fc1 GEMM + bias + GELU + quantize(fc2)  tcgen05 int8 -> int8 codes straight out of the epilogue
+    fc2 GEMM + bias + residual            tcgen05 int8, in place
+The patch embedding is quantize+im2col (non-overlapping patches) -> the same GEMM.
+
+The engine works on a plain ``state_dict`` with the reference's key names (weights + d_quant_*/q_m_*[/t_quant_*]),
+so it accepts ``model.state_dict()`` of a converted reference model or of our drop-in modules alike.
+Requires a WEIGHT_AND_ACTIVATION configuration whose codes fit int8 (e.g. W4A4, W4A8, W8A8).
+"""
+from __future__ import annotations
+
+import math
+from typing import Dict, Optional
+
+import torch
+import torch.nn.functional as F
+
+from .. import ops
+
+VIT_CONFIGS = {
+    # vit_model.py:351-433
+    "vit_base_patch16_224": dict(img_size=224, patch_size=16, embed_dim=768, depth=12, num_heads=12),
+    "vit_large_patch16_224": dict(img_size=224, patch_size=16, embed_dim=1024, depth=24, num_heads=16),
+}
+
+
+class _QLayer:
+    __slots__ = ("w_codes", "bias", "d_wt", "d_act", "qm_act", "t_act", "K", "N")
+
+
+class ViTInferenceEngine:
+    def __init__(self, state_dict: Dict[str, torch.Tensor], *, depth: int, num_heads: int, patch_size: int = 16,
+                 ln_eps: float = 1e-6, device="cuda", precision: str = "fp32"):
+        """precision: "fp32" keeps every non-quantized tensor (residual stream, qkv, attention) in fp32 like the
+        reference; "bf16" stores qkv / attention output in bf16 (the integer GEMMs and the residual stream are
+        unaffected) - faster, slightly outside exact-reference numerics."""
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("ViTInferenceEngine runs on CUDA (sm_100a) only - there is no CPU fallback")
+        self.depth, self.num_heads, self.patch, self.eps, self.precision = depth, num_heads, patch_size, ln_eps, precision
+        sd = {k: v.detach().to(self.device) for k, v in state_dict.items()}
+        self.sd = sd
+        self.flags = ops.new_flags(self.device)
+        self.embed_dim = sd["cls_token"].shape[-1]
+        self.layers: Dict[str, _QLayer] = {}
+        names = ["patch_embed.proj", "head"]
+        for i in range(depth):
+            names += [f"blocks.{i}.attn.qkv", f"blocks.{i}.attn.proj", f"blocks.{i}.mlp.fc1", f"blocks.{i}.mlp.fc2"]
+        for n in names:
+            self.layers[n] = self._prepare(n)
+        self.pos = sd["pos_embed"].float().contiguous()
+        self.cls = sd["cls_token"].float().contiguous()
+        self._graphs = {}
+
+    # ------------------------------------------------------------------ one-time weight quantization (K1 + pack)
+    def _prepare(self, name: str) -> _QLayer:
+        sd = self.sd
+        if f"{name}.d_quant_act" not in sd:
+            raise ValueError(f"{name}: the engine needs quant_mode=weight_and_activation parameters in the state_dict")
+        L = _QLayer()
+        w = sd[f"{name}.weight"].float()
+        w2 = w.reshape(w.shape[0], -1).contiguous()
+        L.N, L.K = w2.shape
+        d, q, t = sd[f"{name}.d_quant_wt"].float(), sd[f"{name}.q_m_wt"].float(), sd.get(f"{name}.t_quant_wt")
+        for (dd, qq, tt, what) in ((d, q, t, "weight"), (sd[f"{name}.d_quant_act"], sd[f"{name}.q_m_act"],
+                                                        sd.get(f"{name}.t_quant_act"), "activation")):
+            r = qq.float().abs()
+            if tt is not None:
+                r = torch.exp(tt.float() * torch.log(r + 1e-6))
+            sat = torch.abs(torch.round(r / dd.float().abs())).item()
+            if not (sat <= 127):
+                raise ValueError(f"{name}: {what} codes reach {sat} > 127 - not representable on the int8 pipe")
+        flags = ops.new_flags(self.device)
+        L.w_codes = ops.quantize_sym(w2, d, q, t, ld_codes=ops.pad16(L.K), flags=flags)
+        L.bias = sd[f"{name}.bias"].float().contiguous() if f"{name}.bias" in sd else None
+        L.d_wt = d.reshape(1).contiguous()
+        L.d_act = sd[f"{name}.d_quant_act"].float().reshape(1).contiguous()
+        L.qm_act = sd[f"{name}.q_m_act"].float().reshape(1).contiguous()
+        t_act = sd.get(f"{name}.t_quant_act")
+        L.t_act = None if t_act is None else t_act.float().reshape(1).contiguous()
+        return L
+
+    def weight_bytes(self) -> int:
+        return sum(L.w_codes.numel() for L in self.layers.values())
+
+    # ------------------------------------------------------------------ forward
+    def _gemm(self, a_codes, L: _QLayer, **kw):
+        return ops.gemm_i8(a_codes, L.w_codes, L.K, L.N, scale_a=L.d_act, scale_w=L.d_wt, bias=L.bias, flags=self.flags, **kw)
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        """x: [B, 3, H, W] fp32 on the engine's device -> logits [B, classes] fp32."""
+        ops._lib.require_cuda(x)
+        sd, D, H = self.sd, self.embed_dim, self.num_heads
+        B = x.shape[0]
+        p = self.patch
+        pe = self.layers["patch_embed.proj"]
+        cols, OH, OW = ops.im2col_quantize_sym(x, (p, p), (p, p), (0, 0), (1, 1), pe.d_act, pe.qm_act, pe.t_act,
+                                               flags=self.flags)
+        tok = self._gemm(cols, pe, out_kind=ops.QVIT_OUT_F32)                     # [B*OH*OW, D]
+        NT = OH * OW + 1
+        h = torch.empty((B, NT, D), dtype=torch.float32, device=x.device)
+        h[:, 0] = self.cls[0, 0] + self.pos[0, 0]                                 # vit_model.py:295-305
+        torch.add(tok.view(B, OH * OW, D), self.pos[:, 1:], out=h[:, 1:])
+        h2 = h.view(B * NT, D)
+        hd = D // H
+        bf16 = self.precision == "bf16"
+        for i in range(self.depth):
+            pre = f"blocks.{i}"
+            qkv_l, proj_l = self.layers[f"{pre}.attn.qkv"], self.layers[f"{pre}.attn.proj"]
+            fc1_l, fc2_l = self.layers[f"{pre}.mlp.fc1"], self.layers[f"{pre}.mlp.fc2"]
+            c1, _ = ops.layernorm_quantize(h2, sd[f"{pre}.norm1.weight"], sd[f"{pre}.norm1.bias"], self.eps, qkv_l.d_act,
+                                           qkv_l.qm_act, qkv_l.t_act, flags=self.flags)
+            qkv = self._gemm(c1, qkv_l, out_kind=ops.QVIT_OUT_BF16 if bf16 else ops.QVIT_OUT_F32)
+            qkv = qkv.view(B, NT, 3, H, hd)
+            q, k, v = (qkv[:, :, j].transpose(1, 2) for j in range(3))            # [B, H, NT, hd] views
+            o = F.scaled_dot_product_attention(q, k, v)                           # vit_model.py:141-149 (not quantized)
+            o = o.transpose(1, 2).reshape(B * NT, D)
+            cp = ops.quantize_sym(o, proj_l.d_act, proj_l.qm_act, proj_l.t_act, ld_codes=ops.pad16(D), flags=self.flags)
+            self._gemm(cp, proj_l, out_kind=ops.QVIT_OUT_F32, residual=h2, out=h2)  # h += proj(o)   (vit_model.py:206)
+            c2, _ = ops.layernorm_quantize(h2, sd[f"{pre}.norm2.weight"], sd[f"{pre}.norm2.bias"], self.eps, fc1_l.d_act,
+                                           fc1_l.qm_act, fc1_l.t_act, flags=self.flags)
+            c3 = self._gemm(c2, fc1_l, out_kind=ops.QVIT_OUT_I8, act=ops.QVIT_ACT_GELU,
+                            next_q=(fc2_l.d_act, fc2_l.qm_act, fc2_l.t_act), ldo=ops.pad16(fc1_l.N))
+            self._gemm(c3, fc2_l, out_kind=ops.QVIT_OUT_F32, residual=h2, out=h2)   # h += fc2(gelu(fc1))  (vit_model.py:207)
+        head = self.layers["head"]
+        cls_tok = h[:, 0].contiguous()                                            # vit_model.py:309-312
+        ch, _ = ops.layernorm_quantize(cls_tok, sd["norm.weight"], sd["norm.bias"], self.eps, head.d_act, head.qm_act,
+                                       head.t_act, flags=self.flags)
+        return self._gemm(ch, head, out_kind=ops.QVIT_OUT_F32)
+
+    __call__ = forward
+
+    # ------------------------------------------------------------------ CUDA-graph replay for a fixed batch size
+    def capture(self, batch: int, img: int = 224):
+        """Capture forward() for [batch, 3, img, img] into a CUDA graph; returns (static_input, static_output, graph)."""
+        key = (batch, img)
+        if key in self._graphs:
+            return self._graphs[key]
+        x = torch.zeros((batch, 3, img, img), dtype=torch.float32, device=self.device)
+        s = torch.cuda.Stream(device=self.device)
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            for _ in range(2):
+                self.forward(x)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            y = self.forward(x)
+        self._graphs[key] = (x, y, g)
+        return self._graphs[key]
+
+    def gemm_ops_per_image(self, img: int = 224) -> float:
+        """2*M*K*N over the quantized layers for one image."""
+        n_patch = (img // self.patch) ** 2
+        total = 0.0
+        for name, L in self.layers.items():
+            rows = n_patch if name == "patch_embed.proj" else (1 if name == "head" else n_patch + 1)
+            total += 2.0 * rows * L.K * L.N
+        return total

@@ -17,7 +17,7 @@ from ._lib import (QVIT_ACT_GELU, QVIT_ACT_NONE, QVIT_ACT_RELU, QVIT_GEMM_AUTO, 
                    QVIT_OUT_BF16, QVIT_OUT_F32, QVIT_OUT_I8, QVIT_OUT_I32)
 
 __all__ = ["pad16", "quantize_sym", "fake_quantize_sym", "sym_backward", "absmax", "im2col_quantize_sym", "gemm_i8",
-           "layernorm_quantize", "ultra_weight_codes", "ultra_act", "conv2d_f32_wcodes", "ultra_conv_bn_act", "bn_fold",
+           "layernorm_quantize", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "bn_fold",
            "bn_act_quantize_int", "pack_int4", "unpack_int4", "new_flags", "QVIT_OUT_I32", "QVIT_OUT_F32",
            "QVIT_OUT_BF16", "QVIT_OUT_I8", "QVIT_ACT_NONE", "QVIT_ACT_GELU", "QVIT_ACT_RELU", "QVIT_GEMM_AUTO",
            "QVIT_GEMM_TCGEN05", "QVIT_GEMM_SIMT"]
@@ -233,14 +233,14 @@ def gemm_i8(a: torch.Tensor, w: torch.Tensor, K: int, N: Optional[int] = None, *
 
 
 # ------------------------------------------------------------------------------------------ UltraNet (DoReFa)
-def ultra_weight_codes(w: torch.Tensor, w_bit: int) -> torch.Tensor:
+def ultra_weight_codes(w: torch.Tensor, w_bit: int, export_rounding: bool = False) -> torch.Tensor:
     """int8 codes of weight_quantize_fn(w_bit).forward (QU:38-56), same shape as w; values = codes / (2^(b-1)-1)."""
     w = _f32c(w.detach(), "ultra_weight_codes")
     mx = torch.empty(1, dtype=torch.float32, device=w.device)
     codes = torch.empty(w.shape, dtype=torch.int8, device=w.device)
     L = _lib.lib()
     _lib.check(L.qvit_ultra_tanh_absmax(_lib.ptr(w), w.numel(), _lib.ptr(mx), _lib.stream()), "qvit_ultra_tanh_absmax")
-    _lib.check(L.qvit_ultra_quantize_weight(_lib.ptr(w), w.numel(), int(w_bit), _lib.ptr(mx), _lib.ptr(codes),
+    _lib.check(L.qvit_ultra_quantize_weight(_lib.ptr(w), w.numel(), int(w_bit), 1 if export_rounding else 0, _lib.ptr(mx), _lib.ptr(codes),
                                             _lib.stream()), "qvit_ultra_quantize_weight")
     return codes
 
@@ -253,6 +253,30 @@ def ultra_act(x: torch.Tensor, a_bit: int, want_codes: bool = True, want_values:
     _lib.check(_lib.lib().qvit_ultra_quantize_act(_lib.ptr(x), x.numel(), int(a_bit), _lib.ptr(codes), _lib.ptr(vals),
                                                   _lib.stream()), "qvit_ultra_quantize_act")
     return codes, vals
+
+
+def uniform_quantize(x: torch.Tensor, k: int) -> torch.Tensor:
+    """uniform_quantize(k).forward (QU:12-20)."""
+    x = _f32c(x, "uniform_quantize")
+    out = torch.empty_like(x)
+    _lib.check(_lib.lib().qvit_uniform_quantize(_lib.ptr(x), x.numel(), int(k), _lib.ptr(out), _lib.stream()),
+               "qvit_uniform_quantize")
+    return out
+
+
+def ultra_bn_act_pool_nchw(x: torch.Tensor, scale, bias, levels: int, pool: bool, ldc: Optional[int] = None) -> torch.Tensor:
+    """NCHW fp32 -> NHWC uint8 codes round(clamp(x*scale+bias, 0, 1) * levels), optionally 2x2 max-pooled.
+    Channel pitch ldc >= C; padding channels are zero."""
+    x = _f32c(x, "ultra_bn_act_pool_nchw")
+    B, Cc, H, W = x.shape
+    ldc = Cc if ldc is None else int(ldc)
+    OH, OW = (H // 2, W // 2) if pool else (H, W)
+    alloc = torch.zeros if ldc > Cc else torch.empty
+    out = alloc((B, OH, OW, ldc), dtype=torch.uint8, device=x.device)
+    _lib.check(_lib.lib().qvit_ultra_bn_act_pool_nchw(_lib.ptr(x), B, Cc, H, W, _lib.ptr(scale), _lib.ptr(bias), int(levels),
+                                                      1 if pool else 0, _lib.ptr(out), ldc, _lib.stream()),
+               "qvit_ultra_bn_act_pool_nchw")
+    return out
 
 
 def conv2d_f32_wcodes(x, w_codes, w_levels: float, bias, stride, padding, dilation) -> torch.Tensor:

@@ -59,7 +59,7 @@ def test_invalid_arguments_are_rejected_without_a_gpu(built_lib):
     assert L.qvit_pack_int4(1, 3, 1, None) == 1                                                # odd n
     assert L.qvit_bn_fold(1, 1, 1, 1, 1e-5, 7, 4, 1, 1, None) == 1                              # bad mode
     assert L.qvit_gemm_i8(None, 16, 0, None, 16, 4, 4, 16, None, 4, None, 0, None) == 1         # NULL epilogue
-    assert L.qvit_ultra_quantize_weight(1, 4, 9, 1, 1, None) == 1                               # w_bit > 8
+    assert L.qvit_ultra_quantize_weight(1, 4, 9, 0, 1, 1, None) == 1                               # w_bit > 8
 
 
 def test_product_refuses_cpu_tensors():
