@@ -1,0 +1,280 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: ViT-B/16 W4A4 inference (BASELINE.json configs[1]) through the fused engine.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one forward pass of ViT-B/16 (quantized patch-embed + 48 QuantizeLinear + head, W4A4 symmetric-linear,
+weight_and_activation) over one batch of 256 synthetic 224x224 images PER GPU (weak scaling: batch-sharded
+replicas, no collective on the forward path - SURVEY.md section 8e).  `value` is whole-job images/s with the
+batch resident in HBM (CUDA-graph replay, device-timed with CUDA events, max over ranks); `e2e` is the same metric
+through the public host-facing call `ViTInferenceEngine.infer()` with host<->device copies inside the timed region.
+`roofline` describes the dominant kernel (the tcgen05 int8 GEMM): algorithmic 2*M*K*N ops of the quantized layers
+divided by the summed CUDA-event duration of the GEMM launches of a step, against 2x the measured dense-bf16 peak
+(MEASURED_PEAKS.json has no int8 entry; int8 tensor throughput is nominally 2x bf16 - DESIGN.md "peaks").
+`cpu_baseline` is the oracle port of the reference's PyTorch-CPU path timed on this host on a bounded sub-batch.
+`--impl reference` times that CPU path alone (the reference is pure Python and cannot travel; oracle/ restates it).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "ViT-B/16 W4A4 inference throughput"
+UNIT = "img/s"
+BATCH = 256
+IMG = 224
+CFG = dict(embed_dim=768, depth=12, num_heads=12, patch=16, img=IMG, classes=1000)
+
+
+def workload_config(n_gpus: int, extra=None):
+    c = {"workload": "ViT-B/16 W4A4 (GETA symmetric-linear, weight_and_activation, num_bits=4; 50 quantized layers) "
+                     "inference, 224x224 synthetic images, random-init weights, activation ranges as initialised "
+                     "(q_m_act = max|W|)",
+         "batch_per_gpu": BATCH, "global_batch": BATCH * n_gpus, "parallelism": f"batch-sharded replicas x{n_gpus}, no collective",
+         "l2": "activations of one step (155 MB per [M,768] fp32 tensor) exceed the 126 MB L2; no explicit flush"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ---------------------------------------------------------------------------------------------- clocks sampler
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------- CPU reference arm
+def cpu_reference_throughput(sub_batch: int, repeats: int, warmup: int = 1):
+    """images/s of the oracle port of the reference's PyTorch-CPU forward (oracle/ref_models.vit_forward) on all host
+    cores, on a sub-batch of the same synthetic workload."""
+    import torch
+    from oracle import ref_geta, ref_models
+    torch.set_num_threads(os.cpu_count() or 1)
+    g = torch.Generator().manual_seed(0)
+    D, depth, hid, classes, patch = CFG["embed_dim"], CFG["depth"], 4 * CFG["embed_dim"], CFG["classes"], CFG["patch"]
+    sd = {"cls_token": torch.randn(1, 1, D, generator=g) * 0.02, "pos_embed": torch.randn(1, (IMG // patch) ** 2 + 1, D, generator=g) * 0.02,
+          "patch_embed.proj.weight": torch.randn(D, 3, patch, patch, generator=g) * 0.02, "patch_embed.proj.bias": torch.zeros(D),
+          "norm.weight": torch.ones(D), "norm.bias": torch.zeros(D),
+          "head.weight": torch.randn(classes, D, generator=g) * 0.02, "head.bias": torch.zeros(classes)}
+    for i in range(depth):
+        p = f"blocks.{i}"
+        for n in ("norm1", "norm2"):
+            sd[f"{p}.{n}.weight"], sd[f"{p}.{n}.bias"] = torch.ones(D), torch.zeros(D)
+        for n, (o, k) in {"attn.qkv": (3 * D, D), "attn.proj": (D, D), "mlp.fc1": (hid, D), "mlp.fc2": (D, hid)}.items():
+            sd[f"{p}.{n}.weight"], sd[f"{p}.{n}.bias"] = torch.randn(o, k, generator=g) * 0.02, torch.zeros(o)
+    for name in [k[:-7] for k in list(sd) if k.endswith(".weight") and sd[k].dim() >= 2]:
+        d, qm = ref_geta.init_quant_params(sd[name + ".weight"], 4)
+        sd[name + ".d_quant_wt"], sd[name + ".q_m_wt"] = d, qm
+        sd[name + ".d_quant_act"], sd[name + ".q_m_act"] = d.clone(), qm.clone()
+    x = torch.randn(sub_batch, 3, IMG, IMG, generator=g)
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + repeats):
+            t0 = time.perf_counter()
+            ref_models.vit_forward(sd, x, depth, CFG["num_heads"], patch)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    return sub_batch / statistics.median(times), statistics.median(times), torch.get_num_threads()
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    sub = 8
+    t0 = time.perf_counter()
+    ips, sec, threads = cpu_reference_throughput(sub, repeats=max(1, args.steps), warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (fake-quant values through F.linear/F.conv2d on the host CPU)", "data": "synthetic",
+            "config": workload_config(args.gpus, {"cpu_sample": f"each step = one forward of a {sub}-image sub-batch"}),
+            "cpu_baseline": {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{sub}-image sub-batch of the 256-image step, median of {max(1, args.steps)} forwards "
+                                       f"({time.perf_counter() - t0:.0f} s of CPU work)"},
+            "e2e": {"value": ips, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- our arm
+def run_ours(args, rank: int, local_rank: int, world: int):
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device - the hot path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    from quantized_vit_b200 import _lib
+    from quantized_vit_b200.engine import ViTInferenceEngine
+    from quantized_vit_b200.engine.synthetic import vit_state_dict
+    _lib.lib()          # fail loudly here if libqvit_b200.so is missing
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sd = vit_state_dict(**CFG, num_bits=4, seed=0, device=dev)
+    eng = ViTInferenceEngine(sd, depth=CFG["depth"], num_heads=CFG["num_heads"], patch_size=CFG["patch"], device=dev,
+                             precision="fp32")
+    g = torch.Generator(device="cpu").manual_seed(1 + rank)
+    x_host = torch.randn(BATCH, 3, IMG, IMG, generator=g).pin_memory()
+    xs, ys, graph = eng.capture(BATCH, IMG)
+    xs.copy_(x_host)
+    # launches of OUR kernels per step (C-ABI calls of one eager forward; the graph replays exactly these)
+    c0 = _lib.CALLS
+    eng.forward(xs)
+    calls_per_step = _lib.CALLS - c0
+    for _ in range(max(args.warmup, 3)):
+        graph.replay()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        graph.replay()
+    e1.record()
+    barrier()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1)
+
+    # end to end through the public host-facing API
+    for _ in range(2):
+        eng.infer(x_host)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        logits_host = eng.infer(x_host)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    flags = int(eng.flags.item())
+
+    # per-kernel timing of the dominant kernel (eager pass, events on the launching stream)
+    eng.gemm_events = []
+    for _ in range(2):
+        eng.gemm_events.clear()
+        eng.forward(xs)
+    torch.cuda.synchronize()
+    gemm_ms = sum(a.elapsed_time(b) for _, _, a, b in eng.gemm_events)
+    gemm_ops = sum(o for _, o, _, _ in eng.gemm_events)
+    n_gemm = len(eng.gemm_events)
+    eng.gemm_events = None
+
+    t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, e2e_ms = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    bf16_sust = peaks.get("bf16_tflops_sustained")
+    peak_tops = 2.0 * bf16_sust if bf16_sust else 2.0 * 1400.0
+    achieved = gemm_ops / (gemm_ms * 1e-3) / 1e12
+    value = world * BATCH * args.steps / (ms * 1e-3)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        tc = time.perf_counter()
+        ips, sec, threads = cpu_reference_throughput(8, repeats=2, warmup=1)
+        cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"8-image sub-batch of the 256-image step, median of 2 forwards ({time.perf_counter() - tc:.0f} s of CPU work)"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "int8 codes x int8 codes -> int32 (tcgen05 kind::i8); fp32 epilogues, LayerNorm, residual stream and attention",
+            "data": "synthetic", "config": workload_config(world),
+            "e2e": {"value": world * BATCH * args.steps / (e2e_ms * 1e-3), "unit": UNIT,
+                    "h2d_bytes_per_step": x_host.numel() * 4, "d2h_bytes_per_step": logits_host.numel() * 4,
+                    "api": "ViTInferenceEngine.infer(pinned host batch) -> host logits"},
+            "gpu_launches": calls_per_step * args.steps,
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tops, "unit": "TOP/s", "frac": achieved / peak_tops,
+                         "traffic": None, "kernel": "gemm_i8_tc_kernel", "launches_per_step": n_gemm,
+                         "kernel_ms_per_step": gemm_ms, "kernel_share_of_step": gemm_ms / (ms / args.steps),
+                         "peak_source": ("2 x bf16_tflops_sustained of MEASURED_PEAKS.json (measured)" if bf16_sust else
+                                         "2 x 1.4 PFLOP/s (fallback)") + "; nominal int8 dense 4500"},
+            "cpu_baseline": cpu, "clocks": clocks, "quantizer_flags": flags,
+            "gemm_top_per_image": eng.gemm_ops_per_image(IMG) / 1e12}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    elif args.gpus > 1:
+        raise SystemExit("bench.py --gpus N>1 must be launched with torch.distributed.run (one process per GPU)")
+    try:
+        run_ours(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -150,7 +150,8 @@ enum {
   QVIT_OUT_I32 = 0,   /* raw accumulators (parity tests)                           out: int32  [M, ldo] */
   QVIT_OUT_F32 = 1,   /* y                                                       out: fp32   [M, ldo] */
   QVIT_OUT_BF16 = 2,  /* y rounded to bf16                                         out: bf16   [M, ldo] */
-  QVIT_OUT_I8 = 3     /* y re-quantised with (next_d, next_qm[, next_t]) -> int8 codes  out: int8 [M, ldo] */
+  QVIT_OUT_I8 = 3,    /* y re-quantised with (next_d, next_qm[, next_t]) -> int8 codes  out: int8 [M, ldo] */
+  QVIT_OUT_NONE = 4   /* nothing is stored (out may be NULL): times the TMA/MMA main loop alone (bench only)  */
 };
 enum { QVIT_ACT_NONE = 0, QVIT_ACT_GELU = 1, QVIT_ACT_RELU = 2 };
 enum { QVIT_GEMM_AUTO = 0, QVIT_GEMM_TCGEN05 = 1, QVIT_GEMM_SIMT = 2 };

@@ -94,6 +94,8 @@ def vit_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, depth: int, num_he
     B = h.shape[0]
     h = torch.cat((sd["cls_token"].expand(B, -1, -1), h), dim=1) + sd["pos_embed"]   # VIT:295-305
     D = h.shape[-1]
+    if taps is not None:
+        taps["embed"] = h
     for i in range(depth):
         p = f"blocks.{i}"
         y = F.layer_norm(h, (D,), sd[f"{p}.norm1.weight"], sd[f"{p}.norm1.bias"], ln_eps)

@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqvit_b200.so")
 
-QVIT_OUT_I32, QVIT_OUT_F32, QVIT_OUT_BF16, QVIT_OUT_I8 = 0, 1, 2, 3
+QVIT_OUT_I32, QVIT_OUT_F32, QVIT_OUT_BF16, QVIT_OUT_I8, QVIT_OUT_NONE = 0, 1, 2, 3, 4
 QVIT_ACT_NONE, QVIT_ACT_GELU, QVIT_ACT_RELU = 0, 1, 2
 QVIT_GEMM_AUTO, QVIT_GEMM_TCGEN05, QVIT_GEMM_SIMT = 0, 1, 2
 QVIT_FLAG_NAN, QVIT_FLAG_OVERFLOW, QVIT_FLAG_NAN_GRAD = 1, 2, 4
@@ -87,7 +87,12 @@ def lib() -> C.CDLL:
     return _lib
 
 
+CALLS = 0     # number of successful C-ABI compute calls (each enqueues >= 1 of our kernels); read by bench.py
+
+
 def check(status: int, what: str = "") -> None:
+    global CALLS
+    CALLS += 1
     if status != 0:
         msg = lib().qvit_last_error()
         raise RuntimeError(f"libqvit_b200 {what} failed (status {status}): {msg.decode() if msg else ''}")

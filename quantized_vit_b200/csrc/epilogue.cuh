@@ -48,6 +48,7 @@ __device__ __forceinline__ float epi_value(const EpiParams& e, int acc, float sc
 // scalar store of one element (any kind)
 __device__ __forceinline__ void epi_store_one(const EpiParams& e, const SymParams* nq, int acc, float scale, int64_t m,
                                               int n, int& fl) {
+  if (e.out_kind == QVIT_OUT_NONE) return;
   if (e.out_kind == QVIT_OUT_I32) {
     reinterpret_cast<int32_t*>(e.out)[m * e.ldo + n] = acc;
     return;

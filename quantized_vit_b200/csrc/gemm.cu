@@ -109,9 +109,10 @@ extern "C" int qvit_gemm_i8(const void* a, int64_t lda, int a_unsigned, const in
   QVIT_REQUIRE(epi != nullptr, "qvit_gemm_i8: epilogue descriptor is NULL");
   QVIT_REQUIRE(M >= 0 && N >= 0 && K >= 0, "qvit_gemm_i8: negative dimension");
   if (M == 0 || N == 0) return QVIT_OK;
-  QVIT_REQUIRE(out != nullptr && ldo >= N, "qvit_gemm_i8: bad output (ldo=%lld < N=%d?)", (long long)ldo, N);
+  QVIT_REQUIRE(epi->out_kind == QVIT_OUT_NONE || (out != nullptr && ldo >= N), "qvit_gemm_i8: bad output (ldo=%lld < N=%d?)",
+               (long long)ldo, N);
   QVIT_REQUIRE(K == 0 || (a != nullptr && w != nullptr && lda >= K && ldw >= K), "qvit_gemm_i8: bad operands");
-  QVIT_REQUIRE(epi->out_kind >= QVIT_OUT_I32 && epi->out_kind <= QVIT_OUT_I8, "qvit_gemm_i8: bad out_kind %d", epi->out_kind);
+  QVIT_REQUIRE(epi->out_kind >= QVIT_OUT_I32 && epi->out_kind <= QVIT_OUT_NONE, "qvit_gemm_i8: bad out_kind %d", epi->out_kind);
   QVIT_REQUIRE(epi->act >= QVIT_ACT_NONE && epi->act <= QVIT_ACT_RELU, "qvit_gemm_i8: bad act %d", epi->act);
   QVIT_REQUIRE(epi->out_kind != QVIT_OUT_I8 || (epi->next_d && epi->next_qm), "qvit_gemm_i8: QVIT_OUT_I8 needs next_d/next_qm");
   QVIT_REQUIRE(!epi->residual || epi->ld_res >= N, "qvit_gemm_i8: ld_res < N");
@@ -134,6 +135,10 @@ extern "C" int qvit_gemm_i8(const void* a, int64_t lda, int a_unsigned, const in
   ep.M = M;
   ep.N = N;
   cudaStream_t s = (cudaStream_t)stream;
+  if (epi->out_kind == QVIT_OUT_NONE && backend != QVIT_GEMM_TCGEN05) {
+    set_error("qvit_gemm_i8: QVIT_OUT_NONE is a tensor-core benchmark mode (backend must be QVIT_GEMM_TCGEN05)");
+    return QVIT_ERR_INVALID;
+  }
   if (K == 0) {
     gemm_k0_kernel<<<div_up((int64_t)M * N, 256) > 1184 ? 1184 : div_up((int64_t)M * N, 256), 256, 0, s>>>(ep);
     return check_launch("gemm_k0_kernel");

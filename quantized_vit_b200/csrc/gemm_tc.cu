@@ -26,22 +26,79 @@ namespace qvit {
 constexpr int kBM = 128;          // rows of A per tile (= UMMA M, = TMEM lanes)
 constexpr int kBK = 128;          // bytes (= int8 elements) of K per stage = one 128B swizzle atom
 constexpr int kUmmaK = 32;        // K per tcgen05.mma for 8-bit operands
-constexpr int kGemmThreads = 192; // 6 warps
+constexpr int kEpiWarps = 8;      // two warps per TMEM lane quarter, each owning half of the tile's columns
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kBoxBytes = kBM * 128;                // one TMA-store box: 128 rows x 128 B (128B-swizzled)
 
 template <int BN>
 struct GemmSmem {
-  static constexpr int kStages = (BN == 256) ? 4 : 6;
+  static constexpr int kStages = (BN == 256) ? 3 : 5;
   static constexpr int kABytes = kBM * kBK;
   static constexpr int kBBytes = BN * kBK;
   static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kOutBytes = 4 * kBoxBytes;     // 2 quads x 2 buffers
   static constexpr int kBarBytes = 256;
-  static constexpr int kTotal = kStages * kStageBytes + kBarBytes + 1024;   // +1024 for manual alignment
+  static constexpr int kTotal = kStages * kStageBytes + kOutBytes + kBarBytes + 1024;   // +1024 for manual alignment
 };
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// y[32] for columns [n0, n0+32) of row m (dequant, col-scale, bias, activation, residual); guarded when ragged.
+__device__ __forceinline__ void epi_compute32(const EpiParams& e, const uint32_t (&acc)[32], float scale, int64_t m, int n0,
+                                              bool row_ok, float (&y)[32]) {
+  const bool full = (n0 + 32 <= e.N);
+  const bool vec_in = full && row_ok && (!e.bias || ((reinterpret_cast<uintptr_t>(e.bias + n0) & 15) == 0)) &&
+                      (!e.col_scale || ((reinterpret_cast<uintptr_t>(e.col_scale + n0) & 15) == 0)) &&
+                      (!e.residual || ((reinterpret_cast<uintptr_t>(e.residual + m * e.ld_res + n0) & 15) == 0));
+  if (vec_in) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) y[j] = (float)(int32_t)acc[j] * scale;
+    if (e.col_scale) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(e.col_scale + n0) + j);
+        y[4 * j] *= c.x; y[4 * j + 1] *= c.y; y[4 * j + 2] *= c.z; y[4 * j + 3] *= c.w;
+      }
+    }
+    if (e.bias) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(e.bias + n0) + j);
+        y[4 * j] += c.x; y[4 * j + 1] += c.y; y[4 * j + 2] += c.z; y[4 * j + 3] += c.w;
+      }
+    }
+    if (e.act == QVIT_ACT_GELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) y[j] = gelu_erf(y[j]);
+    } else if (e.act == QVIT_ACT_RELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
+    }
+    if (e.residual) {
+      const float* r = e.residual + m * e.ld_res + n0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float4 c = *reinterpret_cast<const float4*>(r + 4 * j);   // plain load: `out` may alias `residual`
+        y[4 * j] += c.x; y[4 * j + 1] += c.y; y[4 * j + 2] += c.z; y[4 * j + 3] += c.w;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      y[j] = (row_ok && n0 + j < e.N) ? epi_value(e, (int32_t)acc[j], scale, m, n0 + j) : 0.0f;
+  }
+}
 
 template <int BN>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                  const EpiParams ep, const int K, const uint32_t idesc) {
+                  const __grid_constant__ CUtensorMap tmap_out, const EpiParams ep, const int K, const uint32_t idesc,
+                  const int tma_store) {
   using S = GemmSmem<BN>;
   constexpr int kStages = S::kStages;
   constexpr int kTmemCols = 2 * BN;   // 256 or 512: a power of two >= 32
@@ -50,12 +107,14 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   // SWIZZLE_128B tiles need 1024-byte alignment
   const uint32_t smem_base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem_gen = smem_raw + (smem_base - ptx::smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + kStages * S::kStageBytes;
+  const uint32_t out_base = smem_base + kStages * S::kStageBytes;
+  const uint32_t bar_base = out_base + S::kOutBytes;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * S::kStageBytes + 8 * (2 * kStages + 4));
+  volatile uint32_t* tmem_slot =
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * S::kStageBytes + S::kOutBytes + 8 * (2 * kStages + 4));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -68,6 +127,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_w);
+    if (tma_store) ptx::prefetch_tmap(&tmap_out);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -77,7 +137,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       for (int a = 0; a < 2; ++a) {
         ptx::mbar_init(tfull_bar(a), 1);
-        ptx::mbar_init(tempty_bar(a), 4);      // one arrive per epilogue warp
+        ptx::mbar_init(tempty_bar(a), kEpiWarps);      // one arrive per epilogue warp
       }
       ptx::fence_mbar_init();
     }
@@ -140,33 +200,101 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    // ------------------------------------------------------------------ epilogue (warps 2..9)
     const int lane_grp = warp & 3;                           // TMEM lanes [32*lane_grp, +32) are this warp's
+    const int quad = (warp - 2) >> 2;                        // 0/1: which half of the tile's columns
+    const int row = lane_grp * 32 + lane;                    // row inside the tile
+    const bool leader = (lane_grp == 2 && lane == 0);        // warps 2 and 6: first warp of each quad
+    constexpr int kChunksPerQuad = BN / 64;                  // 32-column chunks per quad and tile
     const float scale = epi_scale(ep);
     SymParams nq;
     if (ep.out_kind == QVIT_OUT_I8) nq = load_sym_params(ep.next_d, ep.next_qm, ep.next_t);
+    const int esz = (ep.out_kind == QVIT_OUT_BF16) ? 2 : ((ep.out_kind == QVIT_OUT_I8) ? 1 : 4);
+    const int chunks_per_box = (esz == 4) ? 1 : ((esz == 2) ? 2 : 4);   // 32 columns * esz * chunks = 128 B
     int fl = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
+    uint32_t box_count = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
-      const int64_t m = (int64_t)m_blk * kBM + lane_grp * 32 + lane;
+      const int64_t m = (int64_t)m_blk * kBM + row;
+      const bool row_ok = m < ep.M;
       const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
+      for (int cq = 0; cq < kChunksPerQuad; ++cq) {
+        const int c = quad * kChunksPerQuad + cq;            // chunk index inside the tile
+        const int n0 = n_blk * BN + c * 32;
         uint32_t r[32];
         ptx::tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
         ptx::tmem_ld_wait();
-        if (m < ep.M) epi_store_chunk32(ep, &nq, r, scale, m, n_blk * BN + c * 32, fl);
+        if (cq == kChunksPerQuad - 1) {                      // all TMEM reads of this warp for this tile are done
+          ptx::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+        }
+        if (ep.out_kind == QVIT_OUT_NONE) continue;          // main-loop benchmark mode
+        if (!tma_store) {
+          if (row_ok) epi_store_chunk32(ep, &nq, r, scale, m, n0, fl);
+          continue;
+        }
+        const int in_box = cq % chunks_per_box;
+        const uint32_t buf = out_base + (uint32_t)((quad * 2 + (box_count & 1)) * kBoxBytes);
+        if (in_box == 0) {
+          // the TMA store issued two boxes ago (same buffer) must have finished reading shared memory
+          if (leader) ptx::tma_store_wait_read<1>();
+          named_bar_sync(1 + quad, 128);
+        }
+        const uint32_t row_addr = buf + (uint32_t)(row * 128);
+        const uint32_t sw = (uint32_t)(row & 7);
+        if (ep.out_kind == QVIT_OUT_I32) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            sts_v4(row_addr + ((((uint32_t)j) ^ sw) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+        } else {
+          float y[32];
+          epi_compute32(ep, r, scale, m, n0, row_ok, y);
+          if (ep.out_kind == QVIT_OUT_F32) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              sts_v4(row_addr + ((((uint32_t)j) ^ sw) << 4), __float_as_uint(y[4 * j]), __float_as_uint(y[4 * j + 1]),
+                     __float_as_uint(y[4 * j + 2]), __float_as_uint(y[4 * j + 3]));
+          } else if (ep.out_kind == QVIT_OUT_BF16) {
+            uint32_t w[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const __nv_bfloat162 p2 = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
+              w[j] = *reinterpret_cast<const uint32_t*>(&p2);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              sts_v4(row_addr + ((((uint32_t)(in_box * 4 + j)) ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+          } else {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              w[j] = pack4_i8(sym_code(y[4 * j], nq, fl), sym_code(y[4 * j + 1], nq, fl), sym_code(y[4 * j + 2], nq, fl),
+                              sym_code(y[4 * j + 3], nq, fl));
+            sts_v4(row_addr + ((((uint32_t)(in_box * 2))     ^ sw) << 4), w[0], w[1], w[2], w[3]);
+            sts_v4(row_addr + ((((uint32_t)(in_box * 2 + 1)) ^ sw) << 4), w[4], w[5], w[6], w[7]);
+          }
+        }
+        if (in_box == chunks_per_box - 1) {
+          ptx::fence_proxy_async_smem();                     // generic-proxy writes -> visible to the TMA engine
+          named_bar_sync(1 + quad, 128);
+          if (leader) {
+            const int box_n0 = n_blk * BN + (c - in_box) * 32;
+            ptx::tma_store_2d(&tmap_out, buf, box_n0, m_blk * kBM);
+            ptx::tma_store_commit();
+          }
+          ++box_count;
+        }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
+    if (tma_store && leader) ptx::tma_store_wait<0>();
     fl = warp_or(fl);
     if (fl && ep.flags && lane == 0) atomicOr(ep.flags, fl);
   }
@@ -224,6 +352,32 @@ static int make_tmap_bytes(CUtensorMap* map, const void* base, int64_t rows, int
   return QVIT_OK;
 }
 
+// output matrix [M, N] of `esz`-byte elements with row pitch ldo (elements): box = 128 rows x 128 B, 128B swizzle
+static int make_tmap_out(CUtensorMap* map, void* base, int64_t M, int64_t N, int64_t ldo, int out_kind) {
+  EncodeTiledFn enc = get_encode_fn();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled not available from the driver");
+    return QVIT_ERR_CUDA;
+  }
+  CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  int esz = 4;
+  if (out_kind == QVIT_OUT_I32) dt = CU_TENSOR_MAP_DATA_TYPE_INT32;
+  else if (out_kind == QVIT_OUT_BF16) { dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; esz = 2; }
+  else if (out_kind == QVIT_OUT_I8) { dt = CU_TENSOR_MAP_DATA_TYPE_UINT8; esz = 1; }
+  cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
+  cuuint64_t strides[1] = {(cuuint64_t)(ldo * esz)};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)kBM};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(out) failed (CUresult %d) M=%lld N=%lld ldo=%lld", (int)r, (long long)M, (long long)N,
+              (long long)ldo);
+    return QVIT_ERR_CUDA;
+  }
+  return QVIT_OK;
+}
+
 bool gemm_tc_supported(const void* a, int64_t lda, const void* w, int64_t ldw, int M, int N, int K) {
   if (M <= 0 || N <= 0 || K <= 0) return false;
   if ((reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(w) & 15)) return false;
@@ -235,8 +389,8 @@ bool gemm_tc_supported(const void* a, int64_t lda, const void* w, int64_t ldw, i
 }
 
 template <int BN>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tw, const EpiParams& ep, int K, bool a_unsigned,
-                     int max_ctas, cudaStream_t s) {
+static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, int tma_store, const EpiParams& ep,
+                     int K, bool a_unsigned, int max_ctas, cudaStream_t s) {
   using S = GemmSmem<BN>;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -253,7 +407,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tw, const EpiPara
   int grid = m_tiles * n_tiles;
   if (grid > max_ctas) grid = max_ctas;
   const uint32_t idesc = ptx::make_idesc_i8(kBM, BN, !a_unsigned, true);
-  gemm_i8_tc_kernel<BN><<<grid, kGemmThreads, S::kTotal, s>>>(ta, tw, ep, K, idesc);
+  gemm_i8_tc_kernel<BN><<<grid, kGemmThreads, S::kTotal, s>>>(ta, tw, to, ep, K, idesc, tma_store);
   return check_launch("gemm_i8_tc_kernel");
 }
 
@@ -268,13 +422,25 @@ int gemm_tc_launch(const void* a, int64_t lda, int a_unsigned, const int8_t* w, 
     const int64_t t256 = (int64_t)((M + kBM - 1) / kBM) * ((N + 255) / 256);
     if (t256 < sms) bn = 128;
   }
-  CUtensorMap ta, tw;
+  CUtensorMap ta, tw, to;
   int rc = make_tmap_bytes(&ta, a, M, K, lda, kBM);
   if (rc) return rc;
   rc = make_tmap_bytes(&tw, w, N, K, ldw, bn);
   if (rc) return rc;
-  if (bn == 256) return launch_tc<256>(ta, tw, ep, K, a_unsigned != 0, sms, s);
-  return launch_tc<128>(ta, tw, ep, K, a_unsigned != 0, sms, s);
+  // Coalesced output through shared memory + TMA store when the output matrix is TMA-addressable and the
+  // quad's column share is a whole number of 128-byte boxes; predicated per-thread vector stores otherwise.
+  const int esz = (ep.out_kind == QVIT_OUT_BF16) ? 2 : ((ep.out_kind == QVIT_OUT_I8) ? 1 : 4);
+  const int chunks_per_box = (esz == 4) ? 1 : ((esz == 2) ? 2 : 4);
+  int tma_store = (ep.out_kind != QVIT_OUT_NONE) && ((reinterpret_cast<uintptr_t>(ep.out) & 15) == 0) &&
+                  (((ep.ldo * esz) & 15) == 0) && (((bn / 64) % chunks_per_box) == 0);
+  if (tma_store) {
+    rc = make_tmap_out(&to, ep.out, M, N, ep.ldo, ep.out_kind);
+    if (rc) return rc;
+  } else {
+    to = ta;
+  }
+  if (bn == 256) return launch_tc<256>(ta, tw, to, tma_store, ep, K, a_unsigned != 0, sms, s);
+  return launch_tc<128>(ta, tw, to, tma_store, ep, K, a_unsigned != 0, sms, s);
 }
 
 }  // namespace qvit

@@ -40,7 +40,7 @@ class _QLayer:
 
 class ViTInferenceEngine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], *, depth: int, num_heads: int, patch_size: int = 16,
-                 ln_eps: float = 1e-6, device="cuda", precision: str = "fp32"):
+                 ln_eps: float = 1e-6, device="cuda", precision: str = "fp32", attention: str = "sdpa"):
         """precision: "fp32" keeps every non-quantized tensor (residual stream, qkv, attention) in fp32 like the
         reference; "bf16" stores qkv / attention output in bf16 (the integer GEMMs and the residual stream are
         unaffected) - faster, slightly outside exact-reference numerics."""
@@ -50,6 +50,9 @@ class ViTInferenceEngine:
         if self.device.type != "cuda":
             raise RuntimeError("ViTInferenceEngine runs on CUDA (sm_100a) only - there is no CPU fallback")
         self.depth, self.num_heads, self.patch, self.eps, self.precision = depth, num_heads, patch_size, ln_eps, precision
+        if attention not in ("sdpa", "math"):
+            raise ValueError("attention must be 'sdpa' (library fused kernel) or 'math' (explicit fp32 matmul/softmax)")
+        self.attention = attention
         sd = {k: v.detach().to(self.device) for k, v in state_dict.items()}
         self.sd = sd
         self.flags = ops.new_flags(self.device)
@@ -63,6 +66,8 @@ class ViTInferenceEngine:
         self.pos = sd["pos_embed"].float().contiguous()
         self.cls = sd["cls_token"].float().contiguous()
         self._graphs = {}
+        self._pinned = {}
+        self.gemm_events = None       # set to [] to record (layer, 2*M*K*N, start_event, end_event) per GEMM launch
 
     # ------------------------------------------------------------------ one-time weight quantization (K1 + pack)
     def _prepare(self, name: str) -> _QLayer:
@@ -97,11 +102,19 @@ class ViTInferenceEngine:
 
     # ------------------------------------------------------------------ forward
     def _gemm(self, a_codes, L: _QLayer, **kw):
-        return ops.gemm_i8(a_codes, L.w_codes, L.K, L.N, scale_a=L.d_act, scale_w=L.d_wt, bias=L.bias, flags=self.flags, **kw)
+        if self.gemm_events is None:
+            return ops.gemm_i8(a_codes, L.w_codes, L.K, L.N, scale_a=L.d_act, scale_w=L.d_wt, bias=L.bias, flags=self.flags, **kw)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        y = ops.gemm_i8(a_codes, L.w_codes, L.K, L.N, scale_a=L.d_act, scale_w=L.d_wt, bias=L.bias, flags=self.flags, **kw)
+        e1.record()
+        self.gemm_events.append((L, 2.0 * a_codes.shape[0] * L.K * L.N, e0, e1))
+        return y
 
     @torch.no_grad()
-    def forward(self, x: torch.Tensor) -> torch.Tensor:
-        """x: [B, 3, H, W] fp32 on the engine's device -> logits [B, classes] fp32."""
+    def forward(self, x: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
+        """x: [B, 3, H, W] fp32 on the engine's device -> logits [B, classes] fp32.
+        ``taps`` (debug/tests): receives copies of intermediate tensors keyed like oracle.ref_models.vit_forward."""
         ops._lib.require_cuda(x)
         sd, D, H = self.sd, self.embed_dim, self.num_heads
         B = x.shape[0]
@@ -115,6 +128,8 @@ class ViTInferenceEngine:
         h[:, 0] = self.cls[0, 0] + self.pos[0, 0]                                 # vit_model.py:295-305
         torch.add(tok.view(B, OH * OW, D), self.pos[:, 1:], out=h[:, 1:])
         h2 = h.view(B * NT, D)
+        if taps is not None:
+            taps["embed"] = h.clone()
         hd = D // H
         bf16 = self.precision == "bf16"
         for i in range(self.depth):
@@ -126,8 +141,13 @@ class ViTInferenceEngine:
             qkv = self._gemm(c1, qkv_l, out_kind=ops.QVIT_OUT_BF16 if bf16 else ops.QVIT_OUT_F32)
             qkv = qkv.view(B, NT, 3, H, hd)
             q, k, v = (qkv[:, :, j].transpose(1, 2) for j in range(3))            # [B, H, NT, hd] views
-            o = F.scaled_dot_product_attention(q, k, v)                           # vit_model.py:141-149 (not quantized)
+            if self.attention == "math":                                          # vit_model.py:141-149, op for op
+                o = ((q @ k.transpose(-2, -1)) * (hd ** -0.5)).softmax(dim=-1) @ v
+            else:
+                o = F.scaled_dot_product_attention(q, k, v)                       # library fused attention (not quantized)
             o = o.transpose(1, 2).reshape(B * NT, D)
+            if taps is not None:
+                taps[f"{pre}.attn.proj.in"] = o.float().view(B, NT, D).clone()
             cp = ops.quantize_sym(o, proj_l.d_act, proj_l.qm_act, proj_l.t_act, ld_codes=ops.pad16(D), flags=self.flags)
             self._gemm(cp, proj_l, out_kind=ops.QVIT_OUT_F32, residual=h2, out=h2)  # h += proj(o)   (vit_model.py:206)
             c2, _ = ops.layernorm_quantize(h2, sd[f"{pre}.norm2.weight"], sd[f"{pre}.norm2.bias"], self.eps, fc1_l.d_act,
@@ -135,6 +155,8 @@ class ViTInferenceEngine:
             c3 = self._gemm(c2, fc1_l, out_kind=ops.QVIT_OUT_I8, act=ops.QVIT_ACT_GELU,
                             next_q=(fc2_l.d_act, fc2_l.qm_act, fc2_l.t_act), ldo=ops.pad16(fc1_l.N))
             self._gemm(c3, fc2_l, out_kind=ops.QVIT_OUT_F32, residual=h2, out=h2)   # h += fc2(gelu(fc1))  (vit_model.py:207)
+            if taps is not None:
+                taps[f"{pre}.out"] = h.clone()
         head = self.layers["head"]
         cls_tok = h[:, 0].contiguous()                                            # vit_model.py:309-312
         ch, _ = ops.layernorm_quantize(cls_tok, sd["norm.weight"], sd["norm.bias"], self.eps, head.d_act, head.qm_act,
@@ -161,6 +183,23 @@ class ViTInferenceEngine:
             y = self.forward(x)
         self._graphs[key] = (x, y, g)
         return self._graphs[key]
+
+    def infer(self, x_host: torch.Tensor) -> torch.Tensor:
+        """Public end-to-end call: HOST images in -> HOST logits out.  Copies the batch host->device, replays the
+        captured forward and copies the logits back; pinned staging buffers are reused across calls."""
+        if x_host.is_cuda:
+            raise ValueError("infer() takes a host tensor; use forward() for device-resident inputs")
+        B, _, H, W = x_host.shape
+        xs, ys, graph = self.capture(B, H)
+        key = (B, ys.shape[1])
+        out = self._pinned.get(key)
+        if out is None:
+            out = self._pinned[key] = torch.empty(ys.shape, dtype=ys.dtype, pin_memory=True)
+        xs.copy_(x_host, non_blocking=True)
+        graph.replay()
+        out.copy_(ys, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return out
 
     def gemm_ops_per_image(self, img: int = 224) -> float:
         """2*M*K*N over the quantized layers for one image."""

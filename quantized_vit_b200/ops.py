@@ -14,12 +14,12 @@ import torch
 
 from . import _lib
 from ._lib import (QVIT_ACT_GELU, QVIT_ACT_NONE, QVIT_ACT_RELU, QVIT_GEMM_AUTO, QVIT_GEMM_SIMT, QVIT_GEMM_TCGEN05,
-                   QVIT_OUT_BF16, QVIT_OUT_F32, QVIT_OUT_I8, QVIT_OUT_I32)
+                   QVIT_OUT_BF16, QVIT_OUT_F32, QVIT_OUT_I8, QVIT_OUT_I32, QVIT_OUT_NONE)
 
 __all__ = ["pad16", "quantize_sym", "fake_quantize_sym", "sym_backward", "absmax", "im2col_quantize_sym", "gemm_i8",
            "layernorm_quantize", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "bn_fold",
            "bn_act_quantize_int", "pack_int4", "unpack_int4", "new_flags", "QVIT_OUT_I32", "QVIT_OUT_F32",
-           "QVIT_OUT_BF16", "QVIT_OUT_I8", "QVIT_ACT_NONE", "QVIT_ACT_GELU", "QVIT_ACT_RELU", "QVIT_GEMM_AUTO",
+           "QVIT_OUT_BF16", "QVIT_OUT_I8", "QVIT_OUT_NONE", "QVIT_ACT_NONE", "QVIT_ACT_GELU", "QVIT_ACT_RELU", "QVIT_GEMM_AUTO",
            "QVIT_GEMM_TCGEN05", "QVIT_GEMM_SIMT"]
 
 _OUT_DTYPE = {QVIT_OUT_I32: torch.int32, QVIT_OUT_F32: torch.float32, QVIT_OUT_BF16: torch.bfloat16,
@@ -186,7 +186,9 @@ def gemm_i8(a: torch.Tensor, w: torch.Tensor, K: int, N: Optional[int] = None, *
     if K > a.shape[1] or K > w.shape[1]:
         raise ValueError("gemm_i8: K exceeds the operand width")
     dev = a.device
-    if out is None:
+    if out_kind == QVIT_OUT_NONE:
+        out, ldo = None, N
+    elif out is None:
         ldo = N if ldo is None else int(ldo)
         out = torch.empty((M, ldo), dtype=_OUT_DTYPE[out_kind], device=dev)
         if ldo > N and out_kind == QVIT_OUT_I8:

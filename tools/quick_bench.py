@@ -25,17 +25,19 @@ def timeit(fn, iters=20, warm=3, flush=None):
 def gemm_sweep():
     flush = torch.empty(256 << 20, dtype=torch.int8, device="cuda")
     for (K, N) in [(768, 2304), (768, 3072), (3072, 768), (768, 768), (1024, 4096)]:
-        for B in (1, 16, 64, 256):
+        for B in (16, 256):
             M = 197 * B
             a = torch.randint(-7, 8, (M, K), dtype=torch.int8, device="cuda")
             w = torch.randint(-7, 8, (N, K), dtype=torch.int8, device="cuda")
             bias = torch.randn(N, device="cuda")
-            for kind, nm in ((ops.QVIT_OUT_I8, "i8"), (ops.QVIT_OUT_BF16, "bf16"), (ops.QVIT_OUT_F32, "f32")):
+            for kind, nm in ((ops.QVIT_OUT_NONE, "none"), (ops.QVIT_OUT_I8, "i8"), (ops.QVIT_OUT_BF16, "bf16"), (ops.QVIT_OUT_F32, "f32")):
                 kw = dict(out_kind=kind, bias=bias, scale_a=0.1, scale_w=0.01)
                 if kind == ops.QVIT_OUT_I8:
                     kw.update(next_q=(0.3, 2.1, None), act=ops.QVIT_ACT_GELU)
-                out = ops.gemm_i8(a, w, K, N, **kw)
-                kw["out"] = out
+                if kind == ops.QVIT_OUT_NONE:
+                    kw["backend"] = ops.QVIT_GEMM_TCGEN05
+                else:
+                    kw["out"] = ops.gemm_i8(a, w, K, N, **kw)
                 med, best = timeit(lambda: ops.gemm_i8(a, w, K, N, **kw), flush=flush if M * K < (64 << 20) else None)
                 tops = 2.0 * M * K * N / (med * 1e-3) / 1e12
                 print(f"gemm M={M:6d} K={K:4d} N={N:4d} out={nm:4s} med {med*1e3:8.1f} us best {best*1e3:8.1f} us  {tops:8.1f} TOPS", flush=True)
