@@ -73,10 +73,12 @@ def _qparams(sd, prefix: str, which: str) -> Optional[Dict[str, torch.Tensor]]:
     return q
 
 
-def _qlinear(sd, prefix: str, x: torch.Tensor) -> torch.Tensor:
+def _qlinear(sd, prefix: str, x: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
     r = ref_geta.quantize_linear_forward(x, sd[f"{prefix}.weight"], sd.get(f"{prefix}.bias"),
                                          _qparams(sd, prefix, "wt"), _qparams(sd, prefix, "act"),
                                          want_int=False)
+    if taps is not None and taps.get("__layers__"):
+        taps[f"{prefix}.in"], taps[f"{prefix}.y"] = x, r["y"]
     return r["y"]
 
 
@@ -99,7 +101,7 @@ def vit_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, depth: int, num_he
     for i in range(depth):
         p = f"blocks.{i}"
         y = F.layer_norm(h, (D,), sd[f"{p}.norm1.weight"], sd[f"{p}.norm1.bias"], ln_eps)
-        qkv = _qlinear(sd, f"{p}.attn.qkv", y)                              # VIT:133
+        qkv = _qlinear(sd, f"{p}.attn.qkv", y, taps)                              # VIT:133
         N = qkv.shape[1]
         qkv = qkv.reshape(B, N, 3, num_heads, -1).permute(2, 0, 3, 1, 4)
         q, k, v = qkv[0], qkv[1], qkv[2]
@@ -108,14 +110,14 @@ def vit_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, depth: int, num_he
         y = (attn @ v).transpose(1, 2).reshape(B, N, -1)                    # VIT:149
         if taps is not None:
             taps[f"{p}.attn.proj.in"] = y
-        h = h + _qlinear(sd, f"{p}.attn.proj", y)                           # VIT:151, 206
+        h = h + _qlinear(sd, f"{p}.attn.proj", y, taps)                           # VIT:151, 206
         y = F.layer_norm(h, (D,), sd[f"{p}.norm2.weight"], sd[f"{p}.norm2.bias"], ln_eps)
-        y = F.gelu(_qlinear(sd, f"{p}.mlp.fc1", y))                         # VIT:172-173
-        h = h + _qlinear(sd, f"{p}.mlp.fc2", y)                             # VIT:175, 207
+        y = F.gelu(_qlinear(sd, f"{p}.mlp.fc1", y, taps))                         # VIT:172-173
+        h = h + _qlinear(sd, f"{p}.mlp.fc2", y, taps)                             # VIT:175, 207
         if taps is not None:
             taps[f"{p}.out"] = h
     h = F.layer_norm(h, (D,), sd["norm.weight"], sd["norm.bias"], ln_eps)   # VIT:309
-    return _qlinear(sd, "head", h[:, 0])                                    # VIT:312, 327
+    return _qlinear(sd, "head", h[:, 0], taps)                                    # VIT:312, 327
 
 
 # ------------------------------------------------------------------------------------------

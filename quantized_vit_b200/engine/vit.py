@@ -111,6 +111,45 @@ class ViTInferenceEngine:
         self.gemm_events.append((L, 2.0 * a_codes.shape[0] * L.K * L.N, e0, e1))
         return y
 
+    def _block(self, i: int, h: torch.Tensor, taps: Optional[dict] = None) -> None:
+        """Block i (vit_model.py:202-208) applied IN PLACE to the residual stream h [B, NT, D] fp32."""
+        sd, D, H = self.sd, self.embed_dim, self.num_heads
+        B, NT = h.shape[0], h.shape[1]
+        h2 = h.view(B * NT, D)
+        hd = D // H
+        bf16 = self.precision == "bf16"
+        pre = f"blocks.{i}"
+        qkv_l, proj_l = self.layers[f"{pre}.attn.qkv"], self.layers[f"{pre}.attn.proj"]
+        fc1_l, fc2_l = self.layers[f"{pre}.mlp.fc1"], self.layers[f"{pre}.mlp.fc2"]
+        c1, _ = ops.layernorm_quantize(h2, sd[f"{pre}.norm1.weight"], sd[f"{pre}.norm1.bias"], self.eps, qkv_l.d_act,
+                                       qkv_l.qm_act, qkv_l.t_act, flags=self.flags)
+        qkv = self._gemm(c1, qkv_l, out_kind=ops.QVIT_OUT_BF16 if bf16 else ops.QVIT_OUT_F32)
+        qkv = qkv.view(B, NT, 3, H, hd)
+        q, k, v = (qkv[:, :, j].transpose(1, 2) for j in range(3))            # [B, H, NT, hd] views
+        if self.attention == "math":                                          # vit_model.py:141-149, op for op
+            o = ((q @ k.transpose(-2, -1)) * (hd ** -0.5)).softmax(dim=-1) @ v
+        else:
+            o = F.scaled_dot_product_attention(q, k, v)                       # library fused attention (not quantized)
+        o = o.transpose(1, 2).reshape(B * NT, D)
+        if taps is not None:
+            taps[f"{pre}.attn.proj.in"] = o.float().view(B, NT, D).clone()
+        cp = ops.quantize_sym(o, proj_l.d_act, proj_l.qm_act, proj_l.t_act, ld_codes=ops.pad16(D), flags=self.flags)
+        self._gemm(cp, proj_l, out_kind=ops.QVIT_OUT_F32, residual=h2, out=h2)  # h += proj(o)   (vit_model.py:206)
+        c2, _ = ops.layernorm_quantize(h2, sd[f"{pre}.norm2.weight"], sd[f"{pre}.norm2.bias"], self.eps, fc1_l.d_act,
+                                       fc1_l.qm_act, fc1_l.t_act, flags=self.flags)
+        c3 = self._gemm(c2, fc1_l, out_kind=ops.QVIT_OUT_I8, act=ops.QVIT_ACT_GELU,
+                        next_q=(fc2_l.d_act, fc2_l.qm_act, fc2_l.t_act), ldo=ops.pad16(fc1_l.N))
+        self._gemm(c3, fc2_l, out_kind=ops.QVIT_OUT_F32, residual=h2, out=h2)   # h += fc2(gelu(fc1))  (vit_model.py:207)
+        if taps is not None:
+            taps[f"{pre}.out"] = h.clone()
+
+    @torch.no_grad()
+    def block_forward(self, i: int, h_in: torch.Tensor) -> torch.Tensor:
+        """Teacher-forced evaluation of one Block on a given input (parity tests): returns a new tensor."""
+        h = h_in.detach().to(self.device, torch.float32).clone().contiguous()
+        self._block(i, h, None)
+        return h
+
     @torch.no_grad()
     def forward(self, x: torch.Tensor, taps: Optional[dict] = None) -> torch.Tensor:
         """x: [B, 3, H, W] fp32 on the engine's device -> logits [B, classes] fp32.
@@ -130,33 +169,8 @@ class ViTInferenceEngine:
         h2 = h.view(B * NT, D)
         if taps is not None:
             taps["embed"] = h.clone()
-        hd = D // H
-        bf16 = self.precision == "bf16"
         for i in range(self.depth):
-            pre = f"blocks.{i}"
-            qkv_l, proj_l = self.layers[f"{pre}.attn.qkv"], self.layers[f"{pre}.attn.proj"]
-            fc1_l, fc2_l = self.layers[f"{pre}.mlp.fc1"], self.layers[f"{pre}.mlp.fc2"]
-            c1, _ = ops.layernorm_quantize(h2, sd[f"{pre}.norm1.weight"], sd[f"{pre}.norm1.bias"], self.eps, qkv_l.d_act,
-                                           qkv_l.qm_act, qkv_l.t_act, flags=self.flags)
-            qkv = self._gemm(c1, qkv_l, out_kind=ops.QVIT_OUT_BF16 if bf16 else ops.QVIT_OUT_F32)
-            qkv = qkv.view(B, NT, 3, H, hd)
-            q, k, v = (qkv[:, :, j].transpose(1, 2) for j in range(3))            # [B, H, NT, hd] views
-            if self.attention == "math":                                          # vit_model.py:141-149, op for op
-                o = ((q @ k.transpose(-2, -1)) * (hd ** -0.5)).softmax(dim=-1) @ v
-            else:
-                o = F.scaled_dot_product_attention(q, k, v)                       # library fused attention (not quantized)
-            o = o.transpose(1, 2).reshape(B * NT, D)
-            if taps is not None:
-                taps[f"{pre}.attn.proj.in"] = o.float().view(B, NT, D).clone()
-            cp = ops.quantize_sym(o, proj_l.d_act, proj_l.qm_act, proj_l.t_act, ld_codes=ops.pad16(D), flags=self.flags)
-            self._gemm(cp, proj_l, out_kind=ops.QVIT_OUT_F32, residual=h2, out=h2)  # h += proj(o)   (vit_model.py:206)
-            c2, _ = ops.layernorm_quantize(h2, sd[f"{pre}.norm2.weight"], sd[f"{pre}.norm2.bias"], self.eps, fc1_l.d_act,
-                                           fc1_l.qm_act, fc1_l.t_act, flags=self.flags)
-            c3 = self._gemm(c2, fc1_l, out_kind=ops.QVIT_OUT_I8, act=ops.QVIT_ACT_GELU,
-                            next_q=(fc2_l.d_act, fc2_l.qm_act, fc2_l.t_act), ldo=ops.pad16(fc1_l.N))
-            self._gemm(c3, fc2_l, out_kind=ops.QVIT_OUT_F32, residual=h2, out=h2)   # h += fc2(gelu(fc1))  (vit_model.py:207)
-            if taps is not None:
-                taps[f"{pre}.out"] = h.clone()
+            self._block(i, h, taps)
         head = self.layers["head"]
         cls_tok = h[:, 0].contiguous()                                            # vit_model.py:309-312
         ch, _ = ops.layernorm_quantize(cls_tok, sd["norm.weight"], sd["norm.bias"], self.eps, head.d_act, head.qm_act,
