@@ -71,6 +71,54 @@ __device__ __forceinline__ int sym_code(float x, const SymParams& p, int& flags)
   return x < 0.0f ? -c : (x > 0.0f ? c : 0);
 }
 
+// Same code, ~4x fewer instructions for the hot epilogue: k = rint(y * (1/d)) agrees with rint(RN(y/d)) unless the
+// quotient lies within 2^-21 relative of a rounding boundary, in which case the exact IEEE division decides.
+// (|RN(y * RN(1/d)) - RN(y/d)| <= 1.5 * 2^-23 |q|, so the 2^-21 guard band is conservative.)  Saturation:
+// for q_m > 0, "|y| >= q_m -> sat" equals clamping to +-sat because RN division and rint are monotone.
+struct FastQ {
+  float inv_d, d, sat;
+  int generic;     // non-linear quantizer, q_m <= 0 or codes beyond int8: use the general path
+};
+__device__ __forceinline__ FastQ make_fastq(const SymParams& p) {
+  FastQ f;
+  f.d = p.d;
+  f.inv_d = __fdiv_rn(1.0f, p.d);
+  f.sat = p.sat;
+  f.generic = (p.nonlinear || !(p.qm > 0.0f) || !(p.sat <= 127.0f) || !(p.d > 0.0f)) ? 1 : 0;
+  return f;
+}
+// branch-free fast code; `doubt` is OR-ed with 1 when the exact division has to decide (caller redoes the element)
+__device__ __forceinline__ int sym_code_fast(float y, const FastQ& f, int& doubt) {
+  const float q = y * f.inv_d;
+  float k = rintf(q);
+  const float t = fabsf(q - k);
+  doubt |= (0.5f - t <= fabsf(q) * 4.8e-7f) ? 1 : 0;
+  doubt |= (y != y) ? 1 : 0;
+  k = fminf(fmaxf(k, -f.sat), f.sat);
+  return __float2int_rn(k);
+}
+
+// four codes packed little-endian into one word: fast path + exact redo when any of the four is in doubt
+__device__ __forceinline__ uint32_t pack4_i8_fwd(int a, int b, int c, int d);
+__device__ __forceinline__ uint32_t sym_codes4(float x0, float x1, float x2, float x3, const SymParams& p, const FastQ& f,
+                                               int& flags) {
+  int doubt = f.generic;
+  int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+  if (!f.generic) {
+    c0 = sym_code_fast(x0, f, doubt);
+    c1 = sym_code_fast(x1, f, doubt);
+    c2 = sym_code_fast(x2, f, doubt);
+    c3 = sym_code_fast(x3, f, doubt);
+  }
+  if (doubt) {
+    c0 = sym_code(x0, p, flags);
+    c1 = sym_code(x1, p, flags);
+    c2 = sym_code(x2, p, flags);
+    c3 = sym_code(x3, p, flags);
+  }
+  return pack4_i8_fwd(c0, c1, c2, c3);
+}
+
 // fake-quantized value exactly as the reference returns it: sign(x) * (d * round(p/d))
 __device__ __forceinline__ float sym_value(float x, const SymParams& p) {
   float k = sym_mag(x, p);
@@ -119,6 +167,8 @@ __device__ __forceinline__ void stg_v8_b32(void* p, const uint32_t* r) {   // 32
 __device__ __forceinline__ uint32_t pack4_i8(int a, int b, int c, int d) {
   return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) | ((uint32_t)(d & 0xff) << 24);
 }
+
+__device__ __forceinline__ uint32_t pack4_i8_fwd(int a, int b, int c, int d) { return pack4_i8(a, b, c, d); }
 
 inline int div_up(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 int sm_count();

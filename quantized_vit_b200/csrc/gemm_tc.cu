@@ -26,9 +26,9 @@ namespace qvit {
 constexpr int kBM = 128;          // rows of A per tile (= UMMA M, = TMEM lanes)
 constexpr int kBK = 128;          // bytes (= int8 elements) of K per stage = one 128B swizzle atom
 constexpr int kUmmaK = 32;        // K per tcgen05.mma for 8-bit operands
-constexpr int kEpiWarps = 8;      // two warps per TMEM lane quarter, each owning half of the tile's columns
-constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
-constexpr int kBoxBytes = kBM * 128;                // one TMA-store box: 128 rows x 128 B (128B-swizzled)
+constexpr int kEpiWarps = 16;     // four warps per TMEM lane quarter ("quads"), each quad owns a quarter of the columns
+constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
+constexpr int kBoxBytes = kBM * 128;                // staging buffer of one quad: 128 rows x (<=128) B, swizzled
 
 template <int BN>
 struct GemmSmem {
@@ -36,10 +36,18 @@ struct GemmSmem {
   static constexpr int kABytes = kBM * kBK;
   static constexpr int kBBytes = BN * kBK;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kOutBytes = 4 * kBoxBytes;     // 2 quads x 2 buffers
+  static constexpr int kOutBytes = 4 * kBoxBytes;     // one buffer per quad
   static constexpr int kBarBytes = 256;
   static constexpr int kTotal = kStages * kStageBytes + kOutBytes + kBarBytes + 1024;   // +1024 for manual alignment
 };
+
+__host__ __device__ constexpr int out_elem_size(int out_kind) {
+  return out_kind == QVIT_OUT_BF16 ? 2 : (out_kind == QVIT_OUT_I8 ? 1 : 4);
+}
+// bytes one quad contributes per output row and tile, capped at the 128 B of a swizzle atom: the TMA-store box width
+__host__ __device__ constexpr int out_box_bytes(int bn, int out_kind) {
+  return (bn / 4) * out_elem_size(out_kind) > 128 ? 128 : (bn / 4) * out_elem_size(out_kind);
+}
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -49,8 +57,9 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, ui
 }
 
 // y[32] for columns [n0, n0+32) of row m (dequant, col-scale, bias, activation, residual); guarded when ragged.
-__device__ __forceinline__ void epi_compute32(const EpiParams& e, const uint32_t (&acc)[32], float scale, int64_t m, int n0,
-                                              bool row_ok, float (&y)[32]) {
+__device__ __forceinline__ void epi_compute32(EpiParams e, const uint32_t (&acc)[32], float scale, int64_t m, int n0,
+                                              bool row_ok, float (&y)[32], bool skip_residual) {
+  if (skip_residual) e.residual = nullptr;                  // the caller adds it from the TMA-staged tile
   const bool full = (n0 + 32 <= e.N);
   const bool vec_in = full && row_ok && (!e.bias || ((reinterpret_cast<uintptr_t>(e.bias + n0) & 15) == 0)) &&
                       (!e.col_scale || ((reinterpret_cast<uintptr_t>(e.col_scale + n0) & 15) == 0)) &&
@@ -94,11 +103,11 @@ __device__ __forceinline__ void epi_compute32(const EpiParams& e, const uint32_t
   }
 }
 
-template <int BN>
+template <int BN, int OUT>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                  const __grid_constant__ CUtensorMap tmap_out, const EpiParams ep, const int K, const uint32_t idesc,
-                  const int tma_store) {
+                  const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
+                  const EpiParams ep, const int K, const uint32_t idesc, const int tma_store, const int res_tma) {
   using S = GemmSmem<BN>;
   constexpr int kStages = S::kStages;
   constexpr int kTmemCols = 2 * BN;   // 256 or 512: a power of two >= 32
@@ -113,8 +122,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
+  auto res_bar = [&](int q) { return bar_base + 8u * (2 * kStages + 4 + q); };
   volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * S::kStageBytes + S::kOutBytes + 8 * (2 * kStages + 4));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * S::kStageBytes + S::kOutBytes + 8 * (2 * kStages + 8));
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -128,6 +138,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     ptx::prefetch_tmap(&tmap_a);
     ptx::prefetch_tmap(&tmap_w);
     if (tma_store) ptx::prefetch_tmap(&tmap_out);
+    if (res_tma) ptx::prefetch_tmap(&tmap_res);
   }
   if (warp == 1) {
     if (lane == 0) {
@@ -139,6 +150,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         ptx::mbar_init(tfull_bar(a), 1);
         ptx::mbar_init(tempty_bar(a), kEpiWarps);      // one arrive per epilogue warp
       }
+      for (int q = 0; q < 4; ++q) ptx::mbar_init(res_bar(q), 1);
       ptx::fence_mbar_init();
     }
     __syncwarp();
@@ -200,21 +212,32 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..9)
+    // ------------------------------------------------------------------ epilogue (warps 2..17)
     const int lane_grp = warp & 3;                           // TMEM lanes [32*lane_grp, +32) are this warp's
-    const int quad = (warp - 2) >> 2;                        // 0/1: which half of the tile's columns
+    const int quad = (warp - 2) >> 2;                        // 0..3: which quarter of the tile's columns
     const int row = lane_grp * 32 + lane;                    // row inside the tile
-    const bool leader = (lane_grp == 2 && lane == 0);        // warps 2 and 6: first warp of each quad
-    constexpr int kChunksPerQuad = BN / 64;                  // 32-column chunks per quad and tile
+    const bool leader = (lane_grp == 2 && lane == 0);        // first warp of each quad (warps 2, 6, 10, 14)
+    constexpr int kChunksPerQuad = BN / 128;                 // 32-column chunks per quad and tile (2 or 1)
+    constexpr int kEsz = out_elem_size(OUT);
+    constexpr int kBoxW = out_box_bytes(BN, OUT);            // 128, 64 or 32 bytes per staged row
+    constexpr int kChunkBytes = 32 * kEsz;
+    constexpr int kChunksPerBox = kBoxW / kChunkBytes;       // 1 or 2
+    constexpr uint32_t kSwzMask = kBoxW / 16 - 1;            // TMA swizzle: 16B-chunk index ^= (byte offset >> 7) & mask
     const float scale = epi_scale(ep);
     SymParams nq;
-    if (ep.out_kind == QVIT_OUT_I8) nq = load_sym_params(ep.next_d, ep.next_qm, ep.next_t);
-    const int esz = (ep.out_kind == QVIT_OUT_BF16) ? 2 : ((ep.out_kind == QVIT_OUT_I8) ? 1 : 4);
-    const int chunks_per_box = (esz == 4) ? 1 : ((esz == 2) ? 2 : 4);   // 32 columns * esz * chunks = 128 B
+    FastQ fq;
+    if (OUT == QVIT_OUT_I8) {
+      nq = load_sym_params(ep.next_d, ep.next_qm, ep.next_t);
+      fq = make_fastq(nq);
+    }
     int fl = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
-    uint32_t box_count = 0;
+    uint32_t res_phase = 0;
+    const bool use_res_tma = (OUT == QVIT_OUT_F32) && res_tma;   // residual tile staged by TMA into the output buffer
+    const uint32_t buf = out_base + (uint32_t)(quad * kBoxBytes);
+    const uint32_t row_off = (uint32_t)(row * kBoxW);
+    const uint32_t sw = (row_off >> 7) & kSwzMask;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
@@ -222,10 +245,16 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       const int64_t m = (int64_t)m_blk * kBM + row;
       const bool row_ok = m < ep.M;
       const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll 1
+#pragma unroll
       for (int cq = 0; cq < kChunksPerQuad; ++cq) {
         const int c = quad * kChunksPerQuad + cq;            // chunk index inside the tile
         const int n0 = n_blk * BN + c * 32;
+        if (use_res_tma && leader) {
+          // buffer free again -> fetch the [128 x 32] fp32 residual tile (coalesced, async) while the math runs
+          ptx::tma_store_wait_read<0>();
+          ptx::mbar_expect_tx(res_bar(quad), (uint32_t)(kBM * 128));
+          ptx::tma_load_2d(buf, &tmap_res, res_bar(quad), n0, m_blk * kBM);
+        }
         uint32_t r[32];
         ptx::tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
         ptx::tmem_ld_wait();
@@ -234,53 +263,67 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           __syncwarp();
           if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
         }
-        if (ep.out_kind == QVIT_OUT_NONE) continue;          // main-loop benchmark mode
+        if (OUT == QVIT_OUT_NONE) continue;                  // main-loop benchmark mode
         if (!tma_store) {
           if (row_ok) epi_store_chunk32(ep, &nq, r, scale, m, n0, fl);
           continue;
         }
-        const int in_box = cq % chunks_per_box;
-        const uint32_t buf = out_base + (uint32_t)((quad * 2 + (box_count & 1)) * kBoxBytes);
-        if (in_box == 0) {
-          // the TMA store issued two boxes ago (same buffer) must have finished reading shared memory
-          if (leader) ptx::tma_store_wait_read<1>();
-          named_bar_sync(1 + quad, 128);
-        }
-        const uint32_t row_addr = buf + (uint32_t)(row * 128);
-        const uint32_t sw = (uint32_t)(row & 7);
-        if (ep.out_kind == QVIT_OUT_I32) {
+        // ---- math first (registers only), so that the previous TMA store of this quad drains meanwhile
+        uint32_t w[kChunkBytes / 4];
+        if (OUT == QVIT_OUT_I32) {
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            sts_v4(row_addr + ((((uint32_t)j) ^ sw) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          for (int j = 0; j < 32; ++j) w[j % (kChunkBytes / 4)] = r[j];      // kChunkBytes/4 == 32 here
         } else {
           float y[32];
-          epi_compute32(ep, r, scale, m, n0, row_ok, y);
-          if (ep.out_kind == QVIT_OUT_F32) {
+          epi_compute32(ep, r, scale, m, n0, row_ok, y, use_res_tma);
+          if (use_res_tma) {
+            ptx::mbar_wait(res_bar(quad), res_phase);
+            res_phase ^= 1u;
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              sts_v4(row_addr + ((((uint32_t)j) ^ sw) << 4), __float_as_uint(y[4 * j]), __float_as_uint(y[4 * j + 1]),
-                     __float_as_uint(y[4 * j + 2]), __float_as_uint(y[4 * j + 3]));
-          } else if (ep.out_kind == QVIT_OUT_BF16) {
-            uint32_t w[16];
+            for (int j = 0; j < 8; ++j) {
+              float4 rv;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                           : "=f"(rv.x), "=f"(rv.y), "=f"(rv.z), "=f"(rv.w)
+                           : "r"(buf + row_off + ((((uint32_t)j) ^ sw) << 4)));
+              y[4 * j] += rv.x; y[4 * j + 1] += rv.y; y[4 * j + 2] += rv.z; y[4 * j + 3] += rv.w;
+            }
+          }
+          if (OUT == QVIT_OUT_F32) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) w[j % (kChunkBytes / 4)] = __float_as_uint(y[j]);
+          } else if (OUT == QVIT_OUT_BF16) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const __nv_bfloat162 p2 = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
-              w[j] = *reinterpret_cast<const uint32_t*>(&p2);
+              w[j % (kChunkBytes / 4)] = *reinterpret_cast<const uint32_t*>(&p2);
             }
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-              sts_v4(row_addr + ((((uint32_t)(in_box * 4 + j)) ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
           } else {
-            uint32_t w[8];
+            int doubt = fq.generic;
+            if (!fq.generic) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              w[j] = pack4_i8(sym_code(y[4 * j], nq, fl), sym_code(y[4 * j + 1], nq, fl), sym_code(y[4 * j + 2], nq, fl),
-                              sym_code(y[4 * j + 3], nq, fl));
-            sts_v4(row_addr + ((((uint32_t)(in_box * 2))     ^ sw) << 4), w[0], w[1], w[2], w[3]);
-            sts_v4(row_addr + ((((uint32_t)(in_box * 2 + 1)) ^ sw) << 4), w[4], w[5], w[6], w[7]);
+              for (int j = 0; j < 8; ++j)
+                w[j % (kChunkBytes / 4)] = pack4_i8(sym_code_fast(y[4 * j], fq, doubt), sym_code_fast(y[4 * j + 1], fq, doubt),
+                                                    sym_code_fast(y[4 * j + 2], fq, doubt), sym_code_fast(y[4 * j + 3], fq, doubt));
+            }
+            if (doubt) {                                     // rare: an element sits on a rounding boundary (or generic quantizer)
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                w[j % (kChunkBytes / 4)] = pack4_i8(sym_code(y[4 * j], nq, fl), sym_code(y[4 * j + 1], nq, fl),
+                                                    sym_code(y[4 * j + 2], nq, fl), sym_code(y[4 * j + 3], nq, fl));
+            }
           }
         }
-        if (in_box == chunks_per_box - 1) {
+        const int in_box = cq % kChunksPerBox;
+        if (in_box == 0 && !use_res_tma) {
+          if (leader) ptx::tma_store_wait_read<0>();         // the quad's previous box has left shared memory
+          named_bar_sync(1 + quad, 128);
+        }
+#pragma unroll
+        for (int j = 0; j < kChunkBytes / 16; ++j) {
+          const uint32_t chunk16 = (uint32_t)(in_box * (kChunkBytes / 16) + j);
+          sts_v4(buf + row_off + ((chunk16 ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+        }
+        if (in_box == kChunksPerBox - 1) {
           ptx::fence_proxy_async_smem();                     // generic-proxy writes -> visible to the TMA engine
           named_bar_sync(1 + quad, 128);
           if (leader) {
@@ -288,7 +331,6 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             ptx::tma_store_2d(&tmap_out, buf, box_n0, m_blk * kBM);
             ptx::tma_store_commit();
           }
-          ++box_count;
         }
       }
       acc ^= 1;
@@ -352,23 +394,25 @@ static int make_tmap_bytes(CUtensorMap* map, const void* base, int64_t rows, int
   return QVIT_OK;
 }
 
-// output matrix [M, N] of `esz`-byte elements with row pitch ldo (elements): box = 128 rows x 128 B, 128B swizzle
-static int make_tmap_out(CUtensorMap* map, void* base, int64_t M, int64_t N, int64_t ldo, int out_kind) {
+// output matrix [M, N] with row pitch ldo (elements): box = 128 rows x box_bytes, swizzle mode = box width
+static int make_tmap_out(CUtensorMap* map, void* base, int64_t M, int64_t N, int64_t ldo, int out_kind, int box_bytes) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
     return QVIT_ERR_CUDA;
   }
   CUtensorMapDataType dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
-  int esz = 4;
+  const int esz = out_elem_size(out_kind);
   if (out_kind == QVIT_OUT_I32) dt = CU_TENSOR_MAP_DATA_TYPE_INT32;
-  else if (out_kind == QVIT_OUT_BF16) { dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16; esz = 2; }
-  else if (out_kind == QVIT_OUT_I8) { dt = CU_TENSOR_MAP_DATA_TYPE_UINT8; esz = 1; }
+  else if (out_kind == QVIT_OUT_BF16) dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  else if (out_kind == QVIT_OUT_I8) dt = CU_TENSOR_MAP_DATA_TYPE_UINT8;
+  const CUtensorMapSwizzle swz = box_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                                  : (box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
   cuuint64_t strides[1] = {(cuuint64_t)(ldo * esz)};
-  cuuint32_t box[2] = {(cuuint32_t)(128 / esz), (cuuint32_t)kBM};
+  cuuint32_t box[2] = {(cuuint32_t)(box_bytes / esz), (cuuint32_t)kBM};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  CUresult r = enc(map, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled(out) failed (CUresult %d) M=%lld N=%lld ldo=%lld", (int)r, (long long)M, (long long)N,
@@ -388,15 +432,19 @@ bool gemm_tc_supported(const void* a, int64_t lda, const void* w, int64_t ldw, i
   return maj == 10 && get_encode_fn() != nullptr;
 }
 
-template <int BN>
-static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tw, const CUtensorMap& to, int tma_store, const EpiParams& ep,
-                     int K, bool a_unsigned, int max_ctas, cudaStream_t s) {
+struct TcMaps {
+  CUtensorMap a, w, out, res;
+  int tma_store, res_tma;
+};
+
+template <int BN, int OUT>
+static int launch_tc(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsigned, int max_ctas, cudaStream_t s) {
   using S = GemmSmem<BN>;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel<BN, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(smem=%d): %s", S::kTotal, cudaGetErrorString(e));
       return QVIT_ERR_CUDA;
@@ -407,8 +455,20 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tw, const CUtenso
   int grid = m_tiles * n_tiles;
   if (grid > max_ctas) grid = max_ctas;
   const uint32_t idesc = ptx::make_idesc_i8(kBM, BN, !a_unsigned, true);
-  gemm_i8_tc_kernel<BN><<<grid, kGemmThreads, S::kTotal, s>>>(ta, tw, to, ep, K, idesc, tma_store);
+  gemm_i8_tc_kernel<BN, OUT><<<grid, kGemmThreads, S::kTotal, s>>>(tm.a, tm.w, tm.out, tm.res, ep, K, idesc, tm.tma_store,
+                                                                   tm.res_tma);
   return check_launch("gemm_i8_tc_kernel");
+}
+
+template <int BN>
+static int launch_tc_kind(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsigned, int max_ctas, cudaStream_t s) {
+  switch (ep.out_kind) {
+    case QVIT_OUT_I32: return launch_tc<BN, QVIT_OUT_I32>(tm, ep, K, a_unsigned, max_ctas, s);
+    case QVIT_OUT_F32: return launch_tc<BN, QVIT_OUT_F32>(tm, ep, K, a_unsigned, max_ctas, s);
+    case QVIT_OUT_BF16: return launch_tc<BN, QVIT_OUT_BF16>(tm, ep, K, a_unsigned, max_ctas, s);
+    case QVIT_OUT_I8: return launch_tc<BN, QVIT_OUT_I8>(tm, ep, K, a_unsigned, max_ctas, s);
+    default: return launch_tc<BN, QVIT_OUT_NONE>(tm, ep, K, a_unsigned, max_ctas, s);
+  }
 }
 
 int gemm_tc_launch(const void* a, int64_t lda, int a_unsigned, const int8_t* w, int64_t ldw, const EpiParams& ep, int K,
@@ -422,25 +482,31 @@ int gemm_tc_launch(const void* a, int64_t lda, int a_unsigned, const int8_t* w, 
     const int64_t t256 = (int64_t)((M + kBM - 1) / kBM) * ((N + 255) / 256);
     if (t256 < sms) bn = 128;
   }
-  CUtensorMap ta, tw, to;
-  int rc = make_tmap_bytes(&ta, a, M, K, lda, kBM);
+  TcMaps tm;
+  int rc = make_tmap_bytes(&tm.a, a, M, K, lda, kBM);
   if (rc) return rc;
-  rc = make_tmap_bytes(&tw, w, N, K, ldw, bn);
+  rc = make_tmap_bytes(&tm.w, w, N, K, ldw, bn);
   if (rc) return rc;
-  // Coalesced output through shared memory + TMA store when the output matrix is TMA-addressable and the
-  // quad's column share is a whole number of 128-byte boxes; predicated per-thread vector stores otherwise.
-  const int esz = (ep.out_kind == QVIT_OUT_BF16) ? 2 : ((ep.out_kind == QVIT_OUT_I8) ? 1 : 4);
-  const int chunks_per_box = (esz == 4) ? 1 : ((esz == 2) ? 2 : 4);
-  int tma_store = (ep.out_kind != QVIT_OUT_NONE) && ((reinterpret_cast<uintptr_t>(ep.out) & 15) == 0) &&
-                  (((ep.ldo * esz) & 15) == 0) && (((bn / 64) % chunks_per_box) == 0);
-  if (tma_store) {
-    rc = make_tmap_out(&to, ep.out, M, N, ep.ldo, ep.out_kind);
+  // Coalesced output through shared memory + TMA store when the output matrix is TMA-addressable;
+  // predicated per-thread vector stores otherwise.
+  const int esz = out_elem_size(ep.out_kind);
+  tm.tma_store = (ep.out_kind != QVIT_OUT_NONE) && ((reinterpret_cast<uintptr_t>(ep.out) & 15) == 0) &&
+                 (((ep.ldo * esz) & 15) == 0);
+  tm.out = tm.a;
+  tm.res = tm.a;
+  if (tm.tma_store) {
+    rc = make_tmap_out(&tm.out, ep.out, M, N, ep.ldo, ep.out_kind, out_box_bytes(bn, ep.out_kind));
     if (rc) return rc;
-  } else {
-    to = ta;
   }
-  if (bn == 256) return launch_tc<256>(ta, tw, to, tma_store, ep, K, a_unsigned != 0, sms, s);
-  return launch_tc<128>(ta, tw, to, tma_store, ep, K, a_unsigned != 0, sms, s);
+  // fp32 residual (Block.forward's "x + ...", vit_model.py:206-207) staged tile-wise by TMA instead of per-thread row reads
+  tm.res_tma = tm.tma_store && ep.out_kind == QVIT_OUT_F32 && ep.residual != nullptr &&
+               ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0) && (((ep.ld_res * 4) & 15) == 0);
+  if (tm.res_tma) {
+    rc = make_tmap_out(&tm.res, const_cast<float*>(ep.residual), M, N, ep.ld_res, QVIT_OUT_F32, 128);
+    if (rc) return rc;
+  }
+  if (bn == 256) return launch_tc_kind<256>(tm, ep, K, a_unsigned != 0, sms, s);
+  return launch_tc_kind<128>(tm, ep, K, a_unsigned != 0, sms, s);
 }
 
 }  // namespace qvit

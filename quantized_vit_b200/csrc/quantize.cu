@@ -30,6 +30,7 @@ quantize_sym_flat_kernel(const float* __restrict__ x, int64_t n, const float* __
                          const float* __restrict__ qm, const float* __restrict__ t,
                          int8_t* __restrict__ codes, int32_t* __restrict__ flags) {
   const SymParams p = load_sym_params(d, qm, t);
+  const FastQ fq = make_fastq(p);
   int fl = 0;
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -43,8 +44,7 @@ quantize_sym_flat_kernel(const float* __restrict__ x, int64_t n, const float* __
     uint32_t* dst = reinterpret_cast<uint32_t*>(codes + w * kWarpElems);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      dst[j * 32 + lane] = pack4_i8(sym_code(v[j].x, p, fl), sym_code(v[j].y, p, fl),
-                                    sym_code(v[j].z, p, fl), sym_code(v[j].w, p, fl));
+      dst[j * 32 + lane] = sym_codes4(v[j].x, v[j].y, v[j].z, v[j].w, p, fq, fl);
     }
   }
   // tail (< 512 elements): first warp of block 0
@@ -99,6 +99,7 @@ quantize_sym_bf16_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows,
                               const float* __restrict__ d, const float* __restrict__ qm, const float* __restrict__ t,
                               int8_t* __restrict__ codes, int64_t ld_codes, int32_t* __restrict__ flags) {
   const SymParams p = load_sym_params(d, qm, t);
+  const FastQ fq = make_fastq(p);
   int fl = 0;
   // one thread = 8 consecutive columns (16 B in, 8 B out) when everything is 8-aligned
   const bool vec = (cols % 8 == 0) && (ld_x % 8 == 0) && (ld_codes % 8 == 0) &&
@@ -112,14 +113,14 @@ quantize_sym_bf16_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows,
       if (g * 8 < cols) {
         const uint4 raw = *reinterpret_cast<const uint4*>(x + r * ld_x + g * 8);
         const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
-        int c[8];
+        float f[8];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          c[2 * j] = sym_code(__uint_as_float(w[j] << 16), p, fl);
-          c[2 * j + 1] = sym_code(__uint_as_float(w[j] & 0xffff0000u), p, fl);
+          f[2 * j] = __uint_as_float(w[j] << 16);
+          f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
         }
-        o.x = pack4_i8(c[0], c[1], c[2], c[3]);
-        o.y = pack4_i8(c[4], c[5], c[6], c[7]);
+        o.x = sym_codes4(f[0], f[1], f[2], f[3], p, fq, fl);
+        o.y = sym_codes4(f[4], f[5], f[6], f[7], p, fq, fl);
       }
       *reinterpret_cast<uint2*>(codes + r * ld_codes + g * 8) = o;
     }
@@ -191,16 +192,13 @@ layernorm_quantize_kernel(const float* __restrict__ x, int64_t rows, const float
                           int32_t* __restrict__ flags) {
   constexpr int cols = V * 128;
   const SymParams p = load_sym_params(d, qm, t);
+  const FastQ fq = make_fastq(p);
   int fl = 0;
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   const int64_t warp_stride = (int64_t)gridDim.x * (kThreads / 32);
-  float4 gm[V], bt[V];
-#pragma unroll
-  for (int j = 0; j < V; ++j) {
-    gm[j] = __ldg(reinterpret_cast<const float4*>(gamma) + j * 32 + lane);
-    bt[j] = __ldg(reinterpret_cast<const float4*>(beta) + j * 32 + lane);
-  }
+  const float4* g4 = reinterpret_cast<const float4*>(gamma);
+  const float4* b4 = reinterpret_cast<const float4*>(beta);
   for (int64_t r = warp_global; r < rows; r += warp_stride) {
     const float* src = x + r * cols;
     float4 v[V];
@@ -221,13 +219,14 @@ layernorm_quantize_kernel(const float* __restrict__ x, int64_t rows, const float
     uint32_t* dst = reinterpret_cast<uint32_t*>(codes + r * ld_codes);
 #pragma unroll
     for (int j = 0; j < V; ++j) {
+      const float4 gm = __ldg(g4 + j * 32 + lane), bt = __ldg(b4 + j * 32 + lane);   // L1-resident, shared by all rows
       float4 y;
-      y.x = (v[j].x - mean) * rstd * gm[j].x + bt[j].x;
-      y.y = (v[j].y - mean) * rstd * gm[j].y + bt[j].y;
-      y.z = (v[j].z - mean) * rstd * gm[j].z + bt[j].z;
-      y.w = (v[j].w - mean) * rstd * gm[j].w + bt[j].w;
+      y.x = (v[j].x - mean) * rstd * gm.x + bt.x;
+      y.y = (v[j].y - mean) * rstd * gm.y + bt.y;
+      y.z = (v[j].z - mean) * rstd * gm.z + bt.z;
+      y.w = (v[j].w - mean) * rstd * gm.w + bt.w;
       if (ln_out) reinterpret_cast<float4*>(ln_out + r * cols)[j * 32 + lane] = y;
-      dst[j * 32 + lane] = pack4_i8(sym_code(y.x, p, fl), sym_code(y.y, p, fl), sym_code(y.z, p, fl), sym_code(y.w, p, fl));
+      dst[j * 32 + lane] = sym_codes4(y.x, y.y, y.z, y.w, p, fq, fl);
     }
     // zero the K padding, if any
     for (int64_t c = cols + lane; c < ld_codes; c += 32) codes[r * ld_codes + c] = 0;

@@ -35,7 +35,7 @@ def uniform_quantize(k):
         def backward(ctx, grad_output):
             return grad_output.clone()
 
-    return qfn().apply
+    return qfn.apply
 
 
 class weight_quantize_fn(nn.Module):
@@ -62,7 +62,8 @@ class weight_quantize_fn(nn.Module):
 
     def values_from_codes(self, codes: torch.Tensor) -> torch.Tensor:
         """codes / (2^(b-1)-1): bit-for-bit round(v*n)/n of QU:18-19 (sign() at w_bit == 2)."""
-        n = float(2 ** (self.w_bit - 1) - 1)
+        # tensor / tensor is an IEEE division on CUDA (tensor / python-scalar is rewritten to a reciprocal multiply)
+        n = torch.full((), float(2 ** (self.w_bit - 1) - 1), dtype=torch.float32, device=codes.device)
         return codes.to(torch.float32) / n
 
 

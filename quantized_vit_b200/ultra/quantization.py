@@ -18,8 +18,8 @@ def weight_quantize_int(weight: torch.Tensor, bit: int) -> torch.Tensor:
 
 def weight_quantize_float(weight: torch.Tensor, bit: int) -> torch.Tensor:
     """QZ:13-19."""
-    n = float(2 ** (bit - 1) - 1)
-    return weight_quantize_int(weight, bit).to(torch.float32) / n
+    codes = weight_quantize_int(weight, bit).to(torch.float32)
+    return codes / torch.full((), float(2 ** (bit - 1) - 1), dtype=torch.float32, device=codes.device)
 
 
 def bn_act_w_bias_float(gamma, beta, mean, var, eps):
