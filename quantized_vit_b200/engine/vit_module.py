@@ -1,0 +1,86 @@
+"""A compact nn.Module VisionTransformer with the reference's parameter names (cls_token, pos_embed,
+patch_embed.proj, blocks.N.{norm1,attn.qkv,attn.proj,norm2,mlp.fc1,mlp.fc2}, norm, head) so that state_dicts are
+interchangeable with ``QViT_with_GETA/vit_model.py`` and ``model_to_quantize_model`` swaps its Linear/Conv2d layers.
+It is the CALLER of the hot path used for the QAT configuration (autograd through the drop-in modules); inference
+throughput goes through ``ViTInferenceEngine`` instead.  Structure follows vit_model.py:46-328 (no dist token, no
+pre-logits, dropout / drop-path 0 as in the reference defaults)."""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+
+class PatchEmbed(nn.Module):
+    def __init__(self, img_size, patch_size, in_c, embed_dim):
+        super().__init__()
+        self.img_size, self.patch_size = img_size, patch_size
+        self.proj = nn.Conv2d(in_c, embed_dim, kernel_size=patch_size, stride=patch_size)
+
+    def forward(self, x):
+        return self.proj(x).flatten(2).transpose(1, 2)          # vit_model.py:100
+
+
+class ViTAttention(nn.Module):
+    def __init__(self, dim, num_heads):
+        super().__init__()
+        self.num_heads = num_heads
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+    def forward(self, x):
+        B, N, C = x.shape
+        qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+        o = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])      # softmax(q k^T / sqrt(d)) v, vit_model.py:141-149
+        return self.proj(o.transpose(1, 2).reshape(B, N, C))
+
+
+class Mlp(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.fc1, self.act, self.fc2 = nn.Linear(dim, hidden), nn.GELU(), nn.Linear(hidden, dim)
+
+    def forward(self, x):
+        return self.fc2(self.act(self.fc1(x)))
+
+
+class Block(nn.Module):
+    def __init__(self, dim, num_heads, mlp_ratio=4.0):
+        super().__init__()
+        self.norm1, self.attn = nn.LayerNorm(dim, eps=1e-6), ViTAttention(dim, num_heads)
+        self.norm2, self.mlp = nn.LayerNorm(dim, eps=1e-6), Mlp(dim, int(dim * mlp_ratio))
+
+    def forward(self, x):
+        x = x + self.attn(self.norm1(x))
+        return x + self.mlp(self.norm2(x))
+
+
+class VisionTransformer(nn.Module):
+    def __init__(self, img_size=224, patch_size=16, in_c=3, num_classes=1000, embed_dim=768, depth=12, num_heads=12,
+                 mlp_ratio=4.0):
+        super().__init__()
+        self.num_classes, self.embed_dim = num_classes, embed_dim
+        self.patch_embed = PatchEmbed(img_size, patch_size, in_c, embed_dim)
+        n = (img_size // patch_size) ** 2
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.pos_embed = nn.Parameter(torch.zeros(1, n + 1, embed_dim))
+        self.blocks = nn.Sequential(*[Block(embed_dim, num_heads, mlp_ratio) for _ in range(depth)])
+        self.norm = nn.LayerNorm(embed_dim, eps=1e-6)
+        self.head = nn.Linear(embed_dim, num_classes)
+        nn.init.trunc_normal_(self.pos_embed, std=0.02)
+        nn.init.trunc_normal_(self.cls_token, std=0.02)
+        for m in self.modules():                                 # vit_model.py:330-346
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.01)
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out")
+                if m.bias is not None:
+                    nn.init.zeros_(m.bias)
+
+    def forward(self, x):
+        x = self.patch_embed(x)
+        x = torch.cat((self.cls_token.expand(x.shape[0], -1, -1), x), dim=1) + self.pos_embed
+        x = self.norm(self.blocks(x))
+        return self.head(x[:, 0])

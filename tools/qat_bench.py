@@ -1,0 +1,68 @@
+"""Config 3: ViT-B/16 4-bit QAT forward+backward through the drop-in modules, gradient + step-size
+all-reduce over NCCL.  Single process or torchrun; global batch 128 split evenly.  Prints one JSON line (rank 0)."""
+import json, os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.distributed as dist
+from quantized_vit_b200 import parallel
+from quantized_vit_b200.engine.vit_module import VisionTransformer
+from quantized_vit_b200.quantization import model_to_quantize_model, check_nan_flags
+
+
+def main():
+    rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    qtype = sys.argv[1] if len(sys.argv) > 1 else "symmetric+linear"
+    global_batch, steps = 128, int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    torch.manual_seed(0)
+    model = VisionTransformer(num_classes=1000)
+    model = model_to_quantize_model(model, num_bits=4, quant_type=qtype, quant_mode="weight_and_activation").cuda().train()
+    with torch.no_grad():                    # calibrated-ish activation ranges so that gradients are informative
+        for m in model.modules():
+            if hasattr(m, "q_m_act"):
+                m.q_m_act.fill_(2.5); m.d_quant_act.fill_(2.5 / 7)
+    red = parallel.GradientAllReducer(model.named_parameters())
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(global_batch, 3, 224, 224, generator=g)
+    y = torch.randint(0, 1000, (global_batch,), generator=torch.Generator().manual_seed(2))
+    xs, ys = parallel.shard_batch(x, rank, world).cuda(), parallel.shard_batch(y, rank, world).cuda()
+    crit = torch.nn.CrossEntropyLoss()
+
+    def step():
+        model.zero_grad(set_to_none=True)
+        loss = crit(model(xs), ys) / 1.0
+        loss.backward()
+        red.reduce()
+        parallel.clip_gradients_(model.parameters(), 1.0)
+        return loss
+
+    for _ in range(2):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda")
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    flags = check_nan_flags(raise_error=False)
+    gn = torch.sqrt(sum((p.grad.float() ** 2).sum() for p in model.parameters() if p.grad is not None))
+    dq = model.blocks[0].attn.qkv.d_quant_act.grad.item()
+    if rank == 0:
+        print(json.dumps({"config": "ViT-B/16 4-bit QAT fwd+bwd+allreduce+clip", "quant_type": qtype, "n_gpus": world,
+                          "global_batch": global_batch, "ms_per_step": float(ms), "img_per_s": global_batch / float(ms) * 1e3,
+                          "loss": float(loss), "grad_norm_after_clip": float(gn), "grad_d_quant_act_block0_qkv": dq,
+                          "nan_flags": flags}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
