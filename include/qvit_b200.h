@@ -192,6 +192,17 @@ int qvit_quantize_sym_bf16(const void* x_bf16, int64_t rows, int64_t cols, int64
                            const float* d, const float* q_m, const float* t,
                            int8_t* codes, int64_t ld_codes, int32_t* flags, qvit_stream_t stream);
 
+/* softmax(Q K^T * scale) V of ViTAttention.forward (vit_model.py:141-149; NOT quantized by the reference, fp32) in
+ * fp32-equivalent precision on the tensor cores (3xTF32 split, tcgen05 kind::tf32, fp32 accumulation in TMEM).
+ * qkv: [B, T, 3, H, head_dim] fp32 contiguous (the output of the qkv QuantizeLinear, vit_model.py:133);
+ * out: [B, T, H*head_dim] fp32 (the layout `proj` consumes, vit_model.py:149).  head_dim == 64 and T <= 208.   */
+int qvit_attention_f32(const float* qkv, int B, int T, int H, int head_dim, float scale, float* out,
+                       qvit_stream_t stream);
+/* test hook: same, and dumps raw scores (cols 0..207) and un-normalised probabilities (cols 208..415) of every query
+ * row into dbg [B, H, 256, 512] fp32 (caller-zeroed; cols 416..479 raw O, 480..482 row sums and 1/sum).                                                            */
+int qvit_attention_f32_debug(const float* qkv, int B, int T, int H, int head_dim, float scale, float* out,
+                             float* dbg, int diag, qvit_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

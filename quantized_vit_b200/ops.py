@@ -17,7 +17,7 @@ from ._lib import (QVIT_ACT_GELU, QVIT_ACT_NONE, QVIT_ACT_RELU, QVIT_GEMM_AUTO, 
                    QVIT_OUT_BF16, QVIT_OUT_F32, QVIT_OUT_I8, QVIT_OUT_I32, QVIT_OUT_NONE)
 
 __all__ = ["pad16", "quantize_sym", "fake_quantize_sym", "sym_backward", "absmax", "im2col_quantize_sym", "gemm_i8",
-           "layernorm_quantize", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "bn_fold",
+           "layernorm_quantize", "attention_f32", "attention_f32_supported", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "bn_fold",
            "bn_act_quantize_int", "pack_int4", "unpack_int4", "new_flags", "QVIT_OUT_I32", "QVIT_OUT_F32",
            "QVIT_OUT_BF16", "QVIT_OUT_I8", "QVIT_OUT_NONE", "QVIT_ACT_NONE", "QVIT_ACT_GELU", "QVIT_ACT_RELU", "QVIT_GEMM_AUTO",
            "QVIT_GEMM_TCGEN05", "QVIT_GEMM_SIMT"]
@@ -163,6 +163,25 @@ def layernorm_quantize(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
                                                   _lib.ptr(d_), _lib.ptr(q_), _lib.ptr(t_), _lib.ptr(codes), ld,
                                                   _lib.ptr(ln), _lib.ptr(flags), _lib.stream()), "qvit_layernorm_quantize")
     return codes, ln
+
+
+def attention_f32(qkv: torch.Tensor, num_heads: int, scale: Optional[float] = None) -> torch.Tensor:
+    """softmax(q k^T * scale) v for qkv [B, T, 3*H*64] fp32 (ViTAttention.forward, vit_model.py:133-149) -> [B, T, H*64] fp32.
+    3xTF32 on tcgen05: fp32-equivalent accuracy.  Requires head_dim == 64 and T <= 208."""
+    qkv = _f32c(qkv, "attention_f32")
+    B, T, C3 = qkv.shape
+    hd = C3 // (3 * num_heads)
+    if hd * 3 * num_heads != C3:
+        raise ValueError("attention_f32: last dim must be 3 * num_heads * head_dim")
+    out = torch.empty((B, T, num_heads * hd), dtype=torch.float32, device=qkv.device)
+    sc = float(hd) ** -0.5 if scale is None else float(scale)
+    _lib.check(_lib.lib().qvit_attention_f32(_lib.ptr(qkv), B, T, num_heads, hd, sc, _lib.ptr(out), _lib.stream()),
+               "qvit_attention_f32")
+    return out
+
+
+def attention_f32_supported(T: int, head_dim: int) -> bool:
+    return head_dim == 64 and T <= 208
 
 
 # ------------------------------------------------------------------------------------------ GEMM
