@@ -223,6 +223,52 @@ class ViTInferenceEngine:
         torch.cuda.current_stream().synchronize()
         return out
 
+    def infer_many(self, host_batches) -> list:
+        """Pipelined end-to-end inference over a sequence of pinned HOST batches of one shape: the host->device copy
+        of batch i+1 (copy stream, double-buffered staging) and the device->host copy of the logits of batch i-1 run
+        while the captured forward of batch i executes.  Returns one host logits tensor per batch."""
+        batches = list(host_batches)
+        if not batches:
+            return []
+        B, _, Hh, _ = batches[0].shape
+        xs, ys, graph = self.capture(B, Hh)
+        key = ("pipe", B, Hh)
+        st = self._pinned.get(key)
+        if st is None:
+            st = self._pinned[key] = {
+                "stage": [torch.empty_like(xs) for _ in range(2)], "h2d": torch.cuda.Stream(device=self.device),
+                "d2h": torch.cuda.Stream(device=self.device), "ydev": [torch.empty_like(ys) for _ in range(2)]}
+        outs = [torch.empty(ys.shape, dtype=ys.dtype, pin_memory=True) for _ in batches]
+        main = torch.cuda.current_stream()
+        copied = [torch.cuda.Event() for _ in range(2)]      # staging[j] filled
+        consumed = [torch.cuda.Event() for _ in range(2)]    # staging[j] read by the compute stream
+        ydone = [torch.cuda.Event() for _ in range(2)]       # ydev[j] written by the compute stream
+        yfree = [torch.cuda.Event() for _ in range(2)]       # ydev[j] copied out
+        st["h2d"].wait_stream(main)
+        st["d2h"].wait_stream(main)
+        for i, xb in enumerate(batches):
+            j = i & 1
+            with torch.cuda.stream(st["h2d"]):
+                if i >= 2:
+                    st["h2d"].wait_event(consumed[j])
+                st["stage"][j].copy_(xb, non_blocking=True)
+                copied[j].record(st["h2d"])
+            main.wait_event(copied[j])
+            xs.copy_(st["stage"][j], non_blocking=True)
+            consumed[j].record(main)
+            graph.replay()
+            if i >= 2:
+                main.wait_event(yfree[j])
+            st["ydev"][j].copy_(ys, non_blocking=True)
+            ydone[j].record(main)
+            with torch.cuda.stream(st["d2h"]):
+                st["d2h"].wait_event(ydone[j])
+                outs[i].copy_(st["ydev"][j], non_blocking=True)
+                yfree[j].record(st["d2h"])
+        main.wait_stream(st["d2h"])
+        main.synchronize()
+        return outs
+
     def gemm_ops_per_image(self, img: int = 224) -> float:
         """2*M*K*N over the quantized layers for one image."""
         n_patch = (img // self.patch) ** 2
