@@ -1,20 +1,21 @@
-// softmax(Q K^T * scale) V in fp32-equivalent precision on the tcgen05 tensor cores ("3xTF32").
+// softmax(Q K^T * scale) V in fp32-equivalent precision on the tcgen05 tensor cores ("3 x BF16" split).
 //
 // This is glue BESIDE the hot path: the reference never quantizes the attention core
-// (vit_model.py:141-149) and runs it in fp32, and the 4-bit quantizer that follows (`proj`) turns any 1e-4-level
-// error of its input into flipped activation codes.  A bf16 or single-pass TF32 kernel is therefore not usable;
-// instead every fp32 operand x is split exactly into x = hi + lo (hi = upper 19 bits, a valid TF32 number;
-// lo = x - hi, again truncated to TF32) and each product a*b is evaluated as a_hi*b_hi + a_lo*b_hi + a_hi*b_lo with
-// fp32 accumulation in TMEM: relative error ~2^-21, at tensor-core speed.
+// (vit_model.py:141-149) and runs it in fp32, and the 4-bit quantizer that follows (`proj`) turns any 1e-5-level
+// error of its input into flipped activation codes, so bf16 / single-pass TF32 attention is not usable.
+// Instead every fp32 operand is split EXACTLY into three bf16 numbers x = b1 + b2 + b3 (8 + 8 + 8 mantissa bits)
+// and each product is evaluated as b1*b1' + b1*b2' + b2*b1' + b2*b2' + b1*b3' + b3*b1' with fp32 accumulation in
+// TMEM (dropped terms <= 2^-24 relative): fp32-level accuracy at tensor-core speed, same MMA count as 3xTF32.
 //
 // One CTA = one (batch, head) and one tile of 128 queries; keys/values of the whole sequence (T <= 208) are resident.
-//   phase 1  TMA loads Q [128 x 64] and K [208 x 64] fp32 (128B-swizzled 32-float sub-tiles, rows beyond T zero-filled)
-//   phase 2  all threads split Q, K into hi / lo planes in shared memory
-//   phase 3  S = Q K^T: 8 k-steps x 3 terms of tcgen05.mma kind::tf32 (M=128, N=208, K=8), SS mode, accumulator in TMEM
-//   phase 4  softmax over the row held by each thread (thread = query row, two warps share a row's columns);
-//            P = exp2((S - max) * scale * log2e) is written back to TMEM as P_hi (over S) and P_lo;
-//            meanwhile TMA loads the raw V tile into the (dead) Q buffers
-//   phase 5  transpose + split V into K-major V^T planes; O = P V: 26 k-steps x 3 terms, A = P from TMEM (TS mode)
+//   phase 1  TMA loads the raw fp32 K tile [208 x 64]; meanwhile all threads read the Q tile from global memory and
+//            write its three bf16 planes (K-major, 128B swizzle: one 128-byte row = the 64 head-dim values)
+//   phase 2  raw K -> three bf16 planes
+//   phase 3  S = Q K^T: 4 k-steps x 6 terms of tcgen05.mma kind::f16 (M=128, N=208, K=16), accumulator in TMEM
+//   phase 4  softmax over the row held by each thread (thread = query row; two warps share a row's columns);
+//            P = exp2((S - max) * scale * log2e) goes back to TMEM as three packed-bf16 planes (A operand of phase 5);
+//            meanwhile TMA loads the raw V tile
+//   phase 5  raw V -> three TRANSPOSED bf16 planes V^T [64 x keys] (K-major); O = P V: 13 k-steps x 6 terms, A from TMEM
 //   phase 6  O / rowsum -> global [B, T, H*64]
 #include <cuda.h>
 
@@ -23,46 +24,38 @@
 
 namespace qvit {
 
-constexpr int kAttHd = 64;            // head dim (floats): 2 sub-tiles of 32 floats = 128 B rows
+constexpr int kAttHd = 64;            // head dim
 constexpr int kAttMQ = 128;           // queries per CTA
 constexpr int kAttNK = 208;           // keys per CTA (13 x 16): UMMA N of the S tile, K extent of the PV product
 constexpr int kAttThreads = 256;
-constexpr int kQSub = kAttMQ * 128;   // bytes of one Q sub-tile  [128 rows x 128 B]
-constexpr int kKSub = kAttNK * 128;   // bytes of one K/V sub-tile [208 rows x 128 B] (26 KiB, multiple of 1024)
-constexpr int kVtSub = kAttHd * 128;  // bytes of one V^T sub-tile [64 head-dim rows x 32 keys]
-constexpr int kVtSubs = 7;            // 7 x 32 = 224 >= 208 keys
-constexpr int kPlane = kVtSubs * kVtSub;              // 56 KiB: holds a K plane (52 KiB) or a V^T plane
-constexpr int kAttSmem = 4 * kQSub + 2 * kPlane + 4096 + 1024;  // Q hi/lo | K or V^T hi | lo | misc | alignment slack
-static_assert(2 * kKSub <= kPlane && 2 * kKSub <= 4 * kQSub, "plane sizes");
+constexpr int kQPlane = kAttMQ * 128;             // bf16 Q plane   [128 rows x 64 bf16]            16 KiB
+constexpr int kKVPlane = 4 * kAttHd * 128;        // bf16 K plane [208 x 64] (26 KiB) or V^T plane: 4 sub-tiles [64 x 64 keys] 32 KiB
+constexpr int kVtSub = kAttHd * 128;               // one V^T sub-tile of one plane: [64 head-dim rows x 64 keys] 8 KiB
+constexpr int kRawSub = kAttNK * 128;             // raw fp32 sub-tile [208 rows x 32 floats]        26 KiB
+constexpr int kAttSmem = 3 * kQPlane + 3 * kKVPlane + 2 * kRawSub + 4096 + 1024;
+constexpr int kPCols = kAttNK / 2;                // TMEM columns of one packed-bf16 P plane (104)
+constexpr int kOCol = 320;                        // TMEM columns [320, 512): three partial O accumulators of 64 columns
 
-// round-to-nearest TF32 (10-bit mantissa) and the exact remainder, itself rounded to TF32
-__device__ __forceinline__ uint32_t tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
-__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
-  hi = tf32_rna(x);
-  lo = tf32_rna(x - __uint_as_float(hi));
-}
-
-// tcgen05.mma kind::tf32, A and B from shared memory
-__device__ __forceinline__ void mma_tf32_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+// tcgen05.mma kind::f16 (bf16 inputs, fp32 accumulate), A and B from shared memory
+__device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
       ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
       : "memory");
 }
-// A from tensor memory (lane = row, column = k), B from shared memory
-__device__ __forceinline__ void mma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+// A from tensor memory (lane = row, two bf16 k-values per 32-bit column), B from shared memory
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
   asm volatile(
       "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
       ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
       : "memory");
 }
-__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+template <int N>
+__device__ __forceinline__ void tmem_st_n(uint32_t taddr, const uint32_t* r);
+template <>
+__device__ __forceinline__ void tmem_st_n<32>(uint32_t taddr, const uint32_t* r) {
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
       "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
@@ -73,9 +66,19 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
-__device__ __forceinline__ void tmem_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+template <>
+__device__ __forceinline__ void tmem_st_n<16>(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_st_n<4>(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
                : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
@@ -94,90 +97,66 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint
       : "memory");
 }
 
-// MN-major operand (V: keys = K dimension are the rows, head-dim floats contiguous), 128B swizzle.
-// LBO = byte distance between the two 32-float column atoms, SBO = byte distance between 8-row (K) atoms.
-__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
-  return d;
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+  return (1u << 4) /*D = f32*/ | (1u << 7) /*A = bf16*/ | (1u << 10) /*B = bf16*/ | ((uint32_t)(N >> 3) << 17) |
+         ((uint32_t)(M >> 4) << 24);
 }
 
-__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N, bool b_mn_major) {
-  return (1u << 4) /*D = f32*/ | (2u << 7) /*A = tf32*/ | (2u << 10) /*B = tf32*/ | ((b_mn_major ? 1u : 0u) << 16) |
-         ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
 }
 
-// hi/lo split of a plane of fp32 values in shared memory (position preserving, so the TMA swizzle is irrelevant)
-__device__ __forceinline__ void split_plane(uint8_t* hi_plane, uint8_t* lo_plane, int bytes) {
-  for (int off = threadIdx.x * 16; off < bytes; off += kAttThreads * 16) {
-    const float4 v = *reinterpret_cast<const float4*>(hi_plane + off);
-    uint4 h, l;
-    tf32_split(v.x, h.x, l.x);
-    tf32_split(v.y, h.y, l.y);
-    tf32_split(v.z, h.z, l.z);
-    tf32_split(v.w, h.w, l.w);
-    *reinterpret_cast<uint4*>(hi_plane + off) = h;
-    *reinterpret_cast<uint4*>(lo_plane + off) = l;
-  }
+// exact three-way split of two fp32 values into packed bf16 pairs (low half = first value)
+__device__ __forceinline__ void split3_pair(float x, float y, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(x, y);
+  const float2 af = __bfloat1622float2(a);
+  const float rx = x - af.x, ry = y - af.y;                    // exact
+  const __nv_bfloat162 b = __floats2bfloat162_rn(rx, ry);
+  const float2 bf = __bfloat1622float2(b);
+  const __nv_bfloat162 c = __floats2bfloat162_rn(rx - bf.x, ry - bf.y);   // exact remainder, <= 8 significant bits
+  p1 = *reinterpret_cast<const uint32_t*>(&a);
+  p2 = *reinterpret_cast<const uint32_t*>(&b);
+  p3 = *reinterpret_cast<const uint32_t*>(&c);
 }
 
-// V arrives as [key rows x 64 floats] (two 128B-swizzled sub-tiles of 32 floats); the PV product wants B = V^T K-major:
-// [64 head-dim rows x keys], as 128B-swizzled sub-tiles of 32 keys.  A warp owns 32 head-dim rows and 4 consecutive
-// keys per step: the four reads each sweep one (permuted) 128-byte row, the 128-bit writes hit 8 distinct 16-byte
-// chunks per quarter warp - both free of bank conflicts.
-__device__ __forceinline__ void transpose_split_v(const uint8_t* raw, uint8_t* hi_plane, uint8_t* lo_plane) {
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int item = warp; item < 2 * (kAttNK / 4); item += kAttThreads / 32) {
-    const int hsub = item / (kAttNK / 4), kg = item - hsub * (kAttNK / 4);
-    const int hd = hsub * 32 + lane;
-    uint4 h, l;
-    uint32_t* hp = &h.x;
-    uint32_t* lp = &l.x;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int key = 4 * kg + i;
-      const float x = *reinterpret_cast<const float*>(raw + hsub * kKSub + key * 128 + (((lane >> 2) ^ (key & 7)) << 4) +
-                                                      ((lane & 3) << 2));
-      tf32_split(x, hp[i], lp[i]);
-    }
-    const int off = (kg >> 3) * kVtSub + hd * 128 + (((kg & 7) ^ (hd & 7)) << 4);
-    *reinterpret_cast<uint4*>(hi_plane + off) = h;
-    *reinterpret_cast<uint4*>(lo_plane + off) = l;
-  }
+// 8 consecutive fp32 -> one 16-byte chunk (8 bf16) per plane
+__device__ __forceinline__ void split3_chunk(const float4& u, const float4& v, uint4& c1, uint4& c2, uint4& c3) {
+  split3_pair(u.x, u.y, c1.x, c2.x, c3.x);
+  split3_pair(u.z, u.w, c1.y, c2.y, c3.y);
+  split3_pair(v.x, v.y, c1.z, c2.z, c3.z);
+  split3_pair(v.z, v.w, c1.w, c2.w, c3.w);
 }
+
+// the six product terms kept (plane of A, plane of B): all pairs with index sum <= 2 plus (1,1)
+__device__ __constant__ const int kTermA[6] = {0, 0, 1, 1, 0, 2};
+__device__ __constant__ const int kTermB[6] = {0, 1, 0, 1, 2, 0};
 
 __global__ void __launch_bounds__(kAttThreads, 1)
-attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
-                     float* __restrict__ out, int T, int H, float scale_log2e, float* __restrict__ dbg, int diag) {
+attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* __restrict__ qkv, float* __restrict__ out,
+                     int T, int H, int total_work, float scale_log2e, float* __restrict__ dbg, int dump) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
-  // layout: Q_hi (2 sub-tiles) | Q_lo (2) | plane_hi | plane_lo | misc.  The planes hold K (hi/lo) for S = Q K^T and
-  // later V^T (hi/lo) for O = P V; the raw V tile lands in the (by then dead) Q region.
-  const uint32_t q_hi = base, q_lo = base + 2 * kQSub, kv_hi = base + 4 * kQSub, kv_lo = kv_hi + kPlane;
-  uint8_t* g_q_hi = gen;
-  uint8_t* g_q_lo = gen + 2 * kQSub;
-  uint8_t* g_kv_hi = gen + 4 * kQSub;
-  uint8_t* g_kv_lo = g_kv_hi + kPlane;
-  uint8_t* misc = g_kv_lo + kPlane;
-  const uint32_t misc_a = kv_lo + kPlane;
-  const uint32_t bar_qk = misc_a, bar_v = misc_a + 8, bar_s = misc_a + 16, bar_o = misc_a + 24;
+  // layout: Q planes (3 x 16 KiB) | K / V^T planes (3 x 32 KiB) | raw fp32 K or V tile (2 x 26 KiB) | misc
+  const uint32_t q_pl = base, kv_pl = base + 3 * kQPlane, raw = kv_pl + 3 * kKVPlane, misc_a = raw + 2 * kRawSub;
+  uint8_t* g_q = gen;
+  uint8_t* g_kv = gen + 3 * kQPlane;
+  uint8_t* g_raw = g_kv + 3 * kKVPlane;
+  uint8_t* misc = g_raw + 2 * kRawSub;
+  const uint32_t bar_k = misc_a, bar_v = misc_a + 8, bar_s = misc_a + 16, bar_o = misc_a + 24;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc + 32);
   float* red_max = reinterpret_cast<float*>(misc + 64);          // [2][128]
   float* red_sum = red_max + 2 * kAttMQ;                         // [2][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_tile = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
-  const int q0 = q_tile * kAttMQ;
+  const int64_t row_floats = 3ll * H * kAttHd;
+  const int q_tiles = (T + kAttMQ - 1) / kAttMQ;
 
   if (threadIdx.x == 0) {
-    ptx::prefetch_tmap(&tmap_q);
     ptx::prefetch_tmap(&tmap_kv);
-    ptx::mbar_init(bar_qk, 1);
+    ptx::mbar_init(bar_k, 1);
     ptx::mbar_init(bar_v, 1);
     ptx::mbar_init(bar_s, 1);
     ptx::mbar_init(bar_o, 1);
@@ -191,172 +170,225 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t t_s = tmem, t_plo = tmem + kAttNK, t_o = tmem + 2 * kAttNK;
+  const uint32_t t_s = tmem, t_o = tmem + kOCol;
 
-  // ---- phase 1: Q and K tiles (column index in floats: q at (0*H + h)*64, k at (1*H + h)*64, v at (2*H + h)*64)
-  if (threadIdx.x == 0) {
-    ptx::mbar_expect_tx(bar_qk, 2 * kQSub + 2 * kKSub);
-    for (int s = 0; s < 2; ++s) {
-      tma_load_3d(q_hi + s * kQSub, &tmap_q, bar_qk, (0 * H + h) * kAttHd + s * 32, q0, b);
-      tma_load_3d(kv_hi + s * kKSub, &tmap_kv, bar_qk, (1 * H + h) * kAttHd + s * 32, 0, b);
+  // persistent over (batch, head, query tile); the raw K tile of the NEXT work item is prefetched during phase 5/6
+  auto issue_k = [&](int w) {
+    const int hh = (w / q_tiles) % H, bb = w / (q_tiles * H);
+    ptx::mbar_expect_tx(bar_k, 2 * kRawSub);
+    for (int s = 0; s < 2; ++s) tma_load_3d(raw + s * kRawSub, &tmap_kv, bar_k, (1 * H + hh) * kAttHd + s * 32, 0, bb);
+  };
+  // Q tile of work item w: global fp32 -> three bf16 planes (K-major, 128B swizzle).  All eight 16-byte loads are
+  // issued before the first use: one memory round trip.
+  auto convert_q = [&](int w) {
+    const int qt = w % q_tiles, hh = (w / q_tiles) % H, bb = w / (q_tiles * H);
+    float4 u[4], v[4];
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int item = threadIdx.x + it * kAttThreads;
+      const int r = item >> 3, c = item & 7;                   // row of the tile, chunk of 8 head-dim values
+      const int t = qt * kAttMQ + r;
+      u[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      v[it] = u[it];
+      if (t < T) {
+        const float* src = qkv + ((int64_t)bb * T + t) * row_floats + (0 * H + hh) * kAttHd + c * 8;
+        u[it] = ldg_stream4(src);
+        v[it] = ldg_stream4(src + 4);
+      }
     }
-  }
-  ptx::mbar_wait(bar_qk, 0);
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int item = threadIdx.x + it * kAttThreads;
+      const int r = item >> 3, c = item & 7;
+      uint4 c1, c2, c3;
+      split3_chunk(u[it], v[it], c1, c2, c3);
+      const int off = r * 128 + ((c ^ (r & 7)) << 4);
+      *reinterpret_cast<uint4*>(g_q + off) = c1;
+      *reinterpret_cast<uint4*>(g_q + kQPlane + off) = c2;
+      *reinterpret_cast<uint4*>(g_q + 2 * kQPlane + off) = c3;
+    }
+  };
+  if (threadIdx.x == 0 && (int)blockIdx.x < total_work) issue_k(blockIdx.x);
+  uint32_t par = 0;                                            // every mbarrier completes exactly once per work item
+#pragma unroll 1
+  for (int work = blockIdx.x; work < total_work; work += gridDim.x, par ^= 1u) {
+  const int q_tile = work % q_tiles, h = (work / q_tiles) % H, b = work / (q_tiles * H);
+  const int q0 = q_tile * kAttMQ;
+  long long ts[8];
+  const bool prof = dbg && blockIdx.x == 0 && threadIdx.x == 64 && work == (int)(blockIdx.x + gridDim.x);   // 2nd item of CTA 0
+  if (prof) ts[0] = clock64();
 
-  // ---- phase 2: hi / lo planes
-  split_plane(g_q_hi, g_q_lo, 2 * kQSub);
-  split_plane(g_kv_hi, g_kv_lo, 2 * kKSub);
+  // ---- phase 1: (raw K is in flight) the Q planes of this item were written during the previous item's PV product
+  if (work == (int)blockIdx.x) convert_q(work);
+  // ---- phase 2: raw K (two 128B-swizzled sub-tiles of 32 floats) -> three bf16 planes
+  if (prof) ts[1] = clock64();
+  ptx::mbar_wait(bar_k, par);
+  for (int item = threadIdx.x; item < kAttNK * 8; item += kAttThreads) {
+    const int r = item >> 3, c = item & 7;
+    const uint8_t* src = g_raw + (c >> 2) * kRawSub + r * 128;
+    const int cc = (c & 3) * 2;
+    const float4 u = *reinterpret_cast<const float4*>(src + (((cc) ^ (r & 7)) << 4));
+    const float4 v = *reinterpret_cast<const float4*>(src + (((cc + 1) ^ (r & 7)) << 4));
+    uint4 c1, c2, c3;
+    split3_chunk(u, v, c1, c2, c3);
+    const int off = r * 128 + ((c ^ (r & 7)) << 4);
+    *reinterpret_cast<uint4*>(g_kv + off) = c1;
+    *reinterpret_cast<uint4*>(g_kv + kKVPlane + off) = c2;
+    *reinterpret_cast<uint4*>(g_kv + 2 * kKVPlane + off) = c3;
+  }
   ptx::fence_proxy_async_smem();
   __syncthreads();
+  if (prof) ts[2] = clock64();
 
-  // ---- phase 3: S = Q K^T  (3 x TF32)
+  // ---- phase 3: S = Q K^T  (6 bf16 terms)
   if (threadIdx.x == 32) {
     ptx::tc_fence_after();
-    constexpr uint32_t idesc = make_idesc_tf32(kAttMQ, kAttNK, false);
+    constexpr uint32_t idesc = make_idesc_bf16(kAttMQ, kAttNK);
     uint32_t acc = 0;
 #pragma unroll 1
-    for (int term = 0; term < 3; ++term) {
-      const uint32_t a_base = (term == 1) ? q_lo : q_hi;       // hi*hi, lo*hi, hi*lo
-      const uint32_t b_base = (term == 2) ? kv_lo : kv_hi;
+    for (int term = 0; term < 6; ++term) {
+      const uint32_t a_base = q_pl + kTermA[term] * kQPlane;
+      const uint32_t b_base = kv_pl + kTermB[term] * kKVPlane;
 #pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {                         // 8 floats (32 B) of the head dim per MMA
-        const uint32_t sub = ks >> 2, kk = ks & 3;
-        const uint64_t a_desc = ptx::make_kmajor_sw128_desc(a_base + sub * kQSub + kk * 32);
-        const uint64_t b_desc = ptx::make_kmajor_sw128_desc(b_base + sub * kKSub + kk * 32);
-        mma_tf32_ss(t_s, a_desc, b_desc, idesc, acc);
+      for (int ks = 0; ks < kAttHd / 16; ++ks) {               // 16 head-dim values (32 B) per MMA
+        mma_bf16_ss(t_s, ptx::make_kmajor_sw128_desc(a_base + ks * 32), ptx::make_kmajor_sw128_desc(b_base + ks * 32), idesc, acc);
         acc = 1;
       }
     }
     ptx::mma_commit(bar_s);
   }
-  // the raw V tile may overwrite the Q planes as soon as the S MMAs have retired
+  // the raw V tile may overwrite the raw K tile right away (phase 2 is behind the barrier above)
   if (threadIdx.x == 0) {
-    ptx::mbar_wait(bar_s, 0);
-    ptx::mbar_expect_tx(bar_v, 2 * kKSub);
-    for (int s = 0; s < 2; ++s) tma_load_3d(q_hi + s * kKSub, &tmap_kv, bar_v, (2 * H + h) * kAttHd + s * 32, 0, b);
+    ptx::mbar_expect_tx(bar_v, 2 * kRawSub);
+    for (int s = 0; s < 2; ++s) tma_load_3d(raw + s * kRawSub, &tmap_kv, bar_v, (2 * H + h) * kAttHd + s * 32, 0, b);
   }
-  ptx::mbar_wait(bar_s, 0);
+  ptx::mbar_wait(bar_s, par);
   ptx::tc_fence_after();
+  if (prof) ts[3] = clock64();
 
   // ---- phase 4: softmax.  thread = row (lane quarter = warp & 3), column half = warp >> 2 (104 columns each)
   const int row = (warp & 3) * 32 + lane;
   const int half = warp >> 2;
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
   const int col0 = half * (kAttNK / 2);
-  float mx = -INFINITY;
-#pragma unroll 1
-  for (int c = 0; c < 3; ++c) {                                // 3 chunks of 32 columns ...
+  float p[kAttNK / 2];                                         // this thread's 104 scores, then probabilities
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
     uint32_t r[32];
     ptx::tmem_ld_32x32(t_s + lane_addr + (uint32_t)(col0 + c * 32), r);
     ptx::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      if (col0 + c * 32 + j < T) mx = fmaxf(mx, __uint_as_float(r[j]));
-    if (dbg) {
-      float* d = dbg + ((((int64_t)b * H + h) * 256 + q0 + ((warp & 3) * 32 + lane)) * 512) + col0 + c * 32;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) d[j] = __uint_as_float(r[j]);
-    }
+    for (int j = 0; j < 32; ++j) p[c * 32 + j] = __uint_as_float(r[j]);
   }
-  {                                                            // ... and a tail of 8 (104 = 3 * 32 + 8)
+  {
     uint32_t r[8];
     tmem_ld_32x8(t_s + lane_addr + (uint32_t)(col0 + 96), r);
     ptx::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (col0 + 96 + j < T) mx = fmaxf(mx, __uint_as_float(r[j]));
-    if (dbg) {
-      float* d = dbg + ((((int64_t)b * H + h) * 256 + q0 + ((warp & 3) * 32 + lane)) * 512) + col0 + 96;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) d[j] = __uint_as_float(r[j]);
-    }
+    for (int j = 0; j < 8; ++j) p[96 + j] = __uint_as_float(r[j]);
   }
+  if (dump) {
+    float* d = dbg + ((((int64_t)b * H + h) * 256 + q0 + row) * 512) + col0;
+#pragma unroll
+    for (int j = 0; j < kAttNK / 2; ++j) d[j] = p[j];
+  }
+  float mx = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < kAttNK / 2; ++j)
+    if (col0 + j < T) mx = fmaxf(mx, p[j]);
   red_max[half * kAttMQ + row] = mx;
-  __syncthreads();
+  ptx::tc_fence_before();
+  __syncthreads();                                             // also: every thread has finished READING S from TMEM
+  ptx::tc_fence_after();
   mx = fmaxf(red_max[row], red_max[kAttMQ + row]);
   const float mbias = mx * scale_log2e;
   float sum = 0.f;
-#pragma unroll 1
-  for (int c = 0; c < 3; ++c) {
-    const int cbase = col0 + c * 32;
-    uint32_t r[32], lo[32];
-    ptx::tmem_ld_32x32(t_s + lane_addr + (uint32_t)cbase, r);
-    ptx::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j) {
-      float p = exp2f(fmaf(__uint_as_float(r[j]), scale_log2e, -mbias));
-      if (cbase + j >= T) p = 0.f;
-      sum += p;
-      tf32_split(p, r[j], lo[j]);
-      if (dbg) dbg[((((int64_t)b * H + h) * 256 + q0 + row) * 512) + 208 + cbase + j] = p;
-    }
-    tmem_st_32x32(t_s + lane_addr + (uint32_t)cbase, r);
-    tmem_st_32x32(t_plo + lane_addr + (uint32_t)cbase, lo);
+  for (int j = 0; j < kAttNK / 2; ++j) {
+    float e = ex2_approx(fmaf(p[j], scale_log2e, -mbias));     // <= 2 ulp, argument <= 0
+    if (col0 + j >= T) e = 0.f;
+    sum += e;
+    p[j] = e;
   }
-  {
-    const int cbase = col0 + 96;
-    uint32_t r[8], lo[8];
-    tmem_ld_32x8(t_s + lane_addr + (uint32_t)cbase, r);
-    ptx::tmem_ld_wait();
+  if (dump) {
+    float* d = dbg + ((((int64_t)b * H + h) * 256 + q0 + row) * 512) + 208 + col0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      float p = exp2f(fmaf(__uint_as_float(r[j]), scale_log2e, -mbias));
-      if (cbase + j >= T) p = 0.f;
-      sum += p;
-      tf32_split(p, r[j], lo[j]);
-      if (dbg) dbg[((((int64_t)b * H + h) * 256 + q0 + row) * 512) + 208 + cbase + j] = p;
-    }
-    tmem_st_32x8(t_s + lane_addr + (uint32_t)cbase, r);
-    tmem_st_32x8(t_plo + lane_addr + (uint32_t)cbase, lo);
+    for (int j = 0; j < kAttNK / 2; ++j) d[j] = p[j];
   }
-  tmem_st_wait();
   red_sum[half * kAttMQ + row] = sum;
+  {
+    // three packed-bf16 planes: plane q occupies TMEM columns [q*104, q*104 + 104); this thread owns 52 of them
+    uint32_t w1[52], w2[52], w3[52];
+#pragma unroll
+    for (int j = 0; j < 52; ++j) split3_pair(p[2 * j], p[2 * j + 1], w1[j], w2[j], w3[j]);
+    const uint32_t cbase = t_s + lane_addr + (uint32_t)(half * 52);
+    tmem_st_n<32>(cbase, w1);          tmem_st_n<16>(cbase + 32, w1 + 32);          tmem_st_n<4>(cbase + 48, w1 + 48);
+    tmem_st_n<32>(cbase + kPCols, w2); tmem_st_n<16>(cbase + kPCols + 32, w2 + 32); tmem_st_n<4>(cbase + kPCols + 48, w2 + 48);
+    tmem_st_n<32>(cbase + 2 * kPCols, w3);
+    tmem_st_n<16>(cbase + 2 * kPCols + 32, w3 + 32);
+    tmem_st_n<4>(cbase + 2 * kPCols + 48, w3 + 48);
+    tmem_st_wait();
+  }
 
-  // ---- phase 5: V planes, then O = P V
-  ptx::mbar_wait(bar_v, 0);
-  transpose_split_v(g_q_hi, g_kv_hi, g_kv_lo);
+  // ---- phase 5: raw V [key rows x 64 floats] -> three transposed bf16 planes V^T [64 x keys] (sub-tiles of 64 keys)
+  if (prof) ts[4] = clock64();
+  ptx::mbar_wait(bar_v, par);
+  for (int item = warp; item < 2 * (kAttNK / 8); item += kAttThreads / 32) {
+    const int hsub = item / (kAttNK / 8), kg = item - hsub * (kAttNK / 8);   // 32 head-dim rows x 8 consecutive keys
+    const int hd = hsub * 32 + lane;
+    float x[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int key = 8 * kg + i;
+      x[i] = *reinterpret_cast<const float*>(g_raw + hsub * kRawSub + key * 128 + (((lane >> 2) ^ (key & 7)) << 4) +
+                                             ((lane & 3) << 2));
+    }
+    uint4 c1, c2, c3;
+    split3_chunk(make_float4(x[0], x[1], x[2], x[3]), make_float4(x[4], x[5], x[6], x[7]), c1, c2, c3);
+    // layout [64-key sub-tile][plane][64 head-dim rows x 128 B]: the three planes of a sub-tile are contiguous, so one
+    // MMA with N = 192 / 128 / 64 multiplies a P plane with V1|V2|V3, V1|V2 or V1 at once
+    const int off = (kg >> 3) * (3 * kVtSub) + hd * 128 + (((kg & 7) ^ (hd & 7)) << 4);
+    *reinterpret_cast<uint4*>(g_kv + off) = c1;
+    *reinterpret_cast<uint4*>(g_kv + kVtSub + off) = c2;
+    *reinterpret_cast<uint4*>(g_kv + 2 * kVtSub + off) = c3;
+  }
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
-  if (threadIdx.x == 32 && diag == 1) {
-    // diagnostic: O_diag[m][n] = sum_{k<64} P_hi[m][k] * Q_hi[n][k]  (TS mode against a K-major operand known to work)
+  if (prof) ts[5] = clock64();
+  if (threadIdx.x == 0 && work + (int)gridDim.x < total_work) issue_k(work + gridDim.x);   // raw tile is free again
+  if (threadIdx.x == 32) {
+    // O partials: acc[0:64) += P1 V1 + P2 V1 + P3 V1, acc[64:128) += P1 V2 + P2 V2, acc[128:192) += P1 V3  (6 terms, 3 MMAs per k-step)
     ptx::tc_fence_after();
-    constexpr uint32_t idesc = make_idesc_tf32(kAttMQ, kAttHd, false);
     uint32_t acc = 0;
-    for (int ks = 0; ks < 8; ++ks) {
-      const uint32_t sub = ks >> 2, kk = ks & 3;
-      const uint64_t b_desc = ptx::make_kmajor_sw128_desc(q_hi + sub * kQSub + kk * 32);
-      mma_tf32_ts(t_o, t_s + (uint32_t)(ks * 8), b_desc, idesc, acc);
+#pragma unroll 1
+    for (int ks = 0; ks < kAttNK / 16; ++ks) {                 // 16 keys per MMA: 8 TMEM columns of A, 32 B of each V^T row
+      const uint64_t b_desc = ptx::make_kmajor_sw128_desc(kv_pl + (ks >> 2) * (3 * kVtSub) + (ks & 3) * 32);
+      mma_bf16_ts(t_o, t_s + (uint32_t)(ks * 8), b_desc, make_idesc_bf16(kAttMQ, 192), acc);
+      mma_bf16_ts(t_o, t_s + (uint32_t)(kPCols + ks * 8), b_desc, make_idesc_bf16(kAttMQ, 128), 1u);
+      mma_bf16_ts(t_o, t_s + (uint32_t)(2 * kPCols + ks * 8), b_desc, make_idesc_bf16(kAttMQ, 64), 1u);
       acc = 1;
     }
     ptx::mma_commit(bar_o);
-  } else if (threadIdx.x == 32) {
-    ptx::tc_fence_after();
-    constexpr uint32_t idesc = make_idesc_tf32(kAttMQ, kAttHd, false);
-    uint32_t acc = 0;
-#pragma unroll 1
-    for (int term = 0; term < 3; ++term) {
-      const uint32_t a_t = (term == 1) ? t_plo : t_s;          // P_hi*V_hi, P_lo*V_hi, P_hi*V_lo
-      const uint32_t b_base = (term == 2) ? kv_lo : kv_hi;
-#pragma unroll 2
-      for (int ks = 0; ks < kAttNK / 8; ++ks) {                // 8 keys (32 B of a V^T row) per MMA
-        const uint64_t b_desc = ptx::make_kmajor_sw128_desc(b_base + (ks >> 2) * kVtSub + (ks & 3) * 32);
-        mma_tf32_ts(t_o, a_t + (uint32_t)(ks * 8), b_desc, idesc, acc);
-        acc = 1;
-      }
-    }
-    ptx::mma_commit(bar_o);
   }
-  ptx::mbar_wait(bar_o, 0);
+  // meanwhile: the Q planes are dead since the S product -> fetch and convert the NEXT work item's Q tile
+  if (work + (int)gridDim.x < total_work) convert_q(work + gridDim.x);
+  ptx::mbar_wait(bar_o, par);
   ptx::tc_fence_after();
+  if (prof) ts[6] = clock64();
 
   // ---- phase 6: normalise and store.  warps 0-3: head-dim 0..31, warps 4-7: 32..63
   {
     const float inv = __fdiv_rn(1.0f, red_sum[row] + red_sum[kAttMQ + row]);
-    uint32_t r[32];
+    uint32_t r[32], r2[32], r3[32];
     ptx::tmem_ld_32x32(t_o + lane_addr + (uint32_t)(half * 32), r);
+    ptx::tmem_ld_32x32(t_o + lane_addr + (uint32_t)(64 + half * 32), r2);
+    ptx::tmem_ld_32x32(t_o + lane_addr + (uint32_t)(128 + half * 32), r3);
     ptx::tmem_ld_wait();
-    if (dbg) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j)
+      r[j] = __float_as_uint((__uint_as_float(r3[j]) + __uint_as_float(r2[j])) + __uint_as_float(r[j]));   // small terms first
+    if (dump) {
       float* d = dbg + ((((int64_t)b * H + h) * 256 + q0 + row) * 512) + 416;
 #pragma unroll
       for (int j = 0; j < 32; ++j) d[half * 32 + j] = __uint_as_float(r[j]);
@@ -371,6 +403,16 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_co
                    __float_as_uint(__uint_as_float(r[4 * j + 2]) * inv), __float_as_uint(__uint_as_float(r[4 * j + 3]) * inv));
     }
   }
+  // the next work item overwrites the Q planes (generic proxy) and TMEM: everyone must be done with this one
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (prof) {
+    ts[7] = clock64();
+    for (int i = 0; i < 7; ++i) dbg[255 * 512 + 500 + i] = (float)(ts[i + 1] - ts[0]);
+  }
+  }  // persistent loop
+
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -421,15 +463,12 @@ static int attention_launch(const float* qkv, int B, int T, int H, int head_dim,
     return QVIT_ERR_UNSUPPORTED;
   }
   const uint64_t row_floats = 3ull * H * kAttHd;
-  CUtensorMap tq, tkv;
+  CUtensorMap tkv;
   cuuint64_t dims[3] = {row_floats, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t strides[2] = {row_floats * 4, row_floats * 4 * (cuuint64_t)T};
   cuuint32_t estr[3] = {1, 1, 1};
-  cuuint32_t box_q[3] = {32, (cuuint32_t)kAttMQ, 1};
   cuuint32_t box_kv[3] = {32, (cuuint32_t)kAttNK, 1};
-  CUresult r1 = enc(&tq, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(qkv), dims, strides, box_q, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r1 = CUDA_SUCCESS;
   CUresult r2 = enc(&tkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(qkv), dims, strides, box_kv, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -446,9 +485,11 @@ static int attention_launch(const float* qkv, int B, int T, int H, int head_dim,
     }
     attr_set[dev] = true;
   }
-  dim3 grid((unsigned)((T + kAttMQ - 1) / kAttMQ), (unsigned)H, (unsigned)B);
-  attention_f32_kernel<<<grid, kAttThreads, kAttSmem, (cudaStream_t)stream>>>(tq, tkv, out, T, H,
-                                                                             scale * 1.4426950408889634f, dbg, diag);
+  const int64_t total_work = (int64_t)((T + kAttMQ - 1) / kAttMQ) * H * B;
+  QVIT_REQUIRE(total_work < (1ll << 30), "qvit_attention_f32: problem too large");
+  const int grid = (int)(total_work < sm_count() ? total_work : sm_count());
+  attention_f32_kernel<<<grid, kAttThreads, kAttSmem, (cudaStream_t)stream>>>(tkv, qkv, out, T, H, (int)total_work,
+                                                                             scale * 1.4426950408889634f, dbg, (dbg != nullptr && diag == 0) ? 1 : 0);
   return check_launch("qvit_attention_f32");
 }
 

@@ -125,9 +125,10 @@ class ViTInferenceEngine:
         c1, _ = ops.layernorm_quantize(h2, sd[f"{pre}.norm1.weight"], sd[f"{pre}.norm1.bias"], self.eps, qkv_l.d_act,
                                        qkv_l.qm_act, qkv_l.t_act, flags=self.flags)
         qkv = self._gemm(c1, qkv_l, out_kind=ops.QVIT_OUT_BF16 if bf16 else ops.QVIT_OUT_F32)
-        # "auto" keeps the library fp32 kernel until the tensor-core kernel reaches plain-fp32 accuracy (3xTF32 measures
-        # 3e-6 vs 1e-6 on a sharp softmax, which triples the tie flips of the proj-input quantizer)
-        use_tc3x = self.attention == "tc3x"
+        # own tensor-core kernel (exact 3-way bf16 split, fp32 accumulation in TMEM): 2.2x faster than the library fp32
+        # kernel at 3e-6 vs 1e-6 max-norm error (tensor-core accumulation rounding), i.e. 0-5 proj-input code flips per
+        # 302 592 elements and Block against the CPU reference (tests/test_gpu_models.py); attention="sdpa" selects the library
+        use_tc3x = self.attention == "tc3x" or (self.attention == "auto" and not bf16 and ops.attention_f32_supported(NT, hd))
         if use_tc3x:
             # own kernel: 3xTF32 on tcgen05, fp32-equivalent accuracy, reads the qkv matrix in place (vit_model.py:133-149)
             o = ops.attention_f32(qkv.view(B, NT, 3 * D), H).view(B * NT, D)
