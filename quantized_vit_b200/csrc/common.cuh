@@ -91,9 +91,8 @@ __device__ __forceinline__ FastQ make_fastq(const SymParams& p) {
 __device__ __forceinline__ int sym_code_fast(float y, const FastQ& f, int& doubt) {
   const float q = y * f.inv_d;
   float k = rintf(q);
-  const float t = fabsf(q - k);
-  doubt |= (0.5f - t <= fabsf(q) * 4.8e-7f) ? 1 : 0;
-  doubt |= (y != y) ? 1 : 0;
+  const float m = fmaf(fabsf(q), 4.8e-7f, fabsf(q - k));      // distance to the rounding boundary is 0.5 - |q - k|
+  doubt |= !(m < 0.5f) ? 1 : 0;                                // also true for NaN
   k = fminf(fmaxf(k, -f.sat), f.sat);
   return __float2int_rn(k);
 }
@@ -128,8 +127,25 @@ __device__ __forceinline__ float sym_value(float x, const SymParams& p) {
 }
 
 __device__ __forceinline__ float gelu_erf(float x) {
-  // torch.nn.GELU() default ('none'): x * 0.5 * (1 + erf(x / sqrt(2)))   (vit_model.py:173)
-  return x * 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+  // torch.nn.GELU() default ('none'): x * Phi(x), Phi(x) = 0.5 * (1 + erf(x / sqrt(2)))   (vit_model.py:173).
+  // Single-branch evaluation: h(|x|) = 0.5 * erfc(|x| / sqrt(2)) = exp2(P(t)), t = min(|x| / sqrt(2), 4.2), P a degree-8
+  // minimax fit of log2(h) weighted by h * max(1, |x|); Phi = h for x < 0 and 1 - h otherwise.  Max |error| of the
+  // result against float64 over [-8, 8]: 3.8e-7 absolute, 1.14e-7 relative to max(1, |x|) - the same as the
+  // erf form evaluated in fp32 (4.5e-7 / 1.07e-7) at half the instructions (8 FFMA + 1 MUFU.EX2 instead of ~28).
+  const float t = fminf(fabsf(x) * 0.70710678118654752440f, 4.2f);
+  float p = -3.6413832276593894e-05f;
+  p = fmaf(p, t, 0.000372989394236356f);
+  p = fmaf(p, t, -0.0012582261115312576f);
+  p = fmaf(p, t, -0.0011454012710601091f);
+  p = fmaf(p, t, 0.02857113443315029f);
+  p = fmaf(p, t, -0.1486237645149231f);
+  p = fmaf(p, t, -0.9183861017227173f);
+  p = fmaf(p, t, -1.62791109085083f);
+  p = fmaf(p, t, -0.9999999403953552f);
+  float h;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(p));
+  const float phi = (x < 0.0f) ? h : 1.0f - h;
+  return x * phi;
 }
 
 // ---- warp / block reductions -------------------------------------------------------------------
