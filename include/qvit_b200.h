@@ -173,6 +173,10 @@ typedef struct qvit_epilogue {
 } qvit_epilogue_t;
 /* y = act( float(acc) * (|scale_a|*|scale_w|*scale_const) * col_scale[n] + bias[n] ) + residual[m,n]  */
 
+/* tile mode of the tensor-core backend: 0 = automatic (CTA pairs, tcgen05 cta_group::2, once the problem has a full
+ * wave of [256 x 256] tiles), 1 = single-CTA [128 x BN] tiles, 2 = CTA pairs whenever BN = 256.  Process-wide; tests / benches. */
+int qvit_gemm_set_cta_group(int cta_group);
+
 int qvit_gemm_i8(const void* a, int64_t lda, int a_unsigned,
                  const int8_t* w, int64_t ldw,
                  int M, int N, int K,

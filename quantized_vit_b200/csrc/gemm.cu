@@ -10,6 +10,8 @@ bool gemm_tc_supported(const void* a, int64_t lda, const void* w, int64_t ldw, i
 int gemm_tc_launch(const void* a, int64_t lda, int a_unsigned, const int8_t* w, int64_t ldw, const EpiParams& ep, int K,
                    cudaStream_t s);
 
+void gemm_tc_force_cta_group(int cg);
+
 constexpr int kST = 64;        // SIMT tile (rows and cols)
 constexpr int kSK = 64;        // bytes of K per step
 
@@ -103,6 +105,13 @@ __global__ void gemm_k0_kernel(const EpiParams ep) {
 }  // namespace qvit
 
 using namespace qvit;
+
+extern "C" int qvit_gemm_set_cta_group(int cta_group) {
+  QVIT_REQUIRE((cta_group >= 0 && cta_group <= 2) || cta_group == 11 || cta_group == 12,
+               "qvit_gemm_set_cta_group: 0 (auto), 1 or 2 (11 / 12: same with operand loads skipped in QVIT_OUT_NONE runs)");
+  gemm_tc_force_cta_group(cta_group);
+  return QVIT_OK;
+}
 
 extern "C" int qvit_gemm_i8(const void* a, int64_t lda, int a_unsigned, const int8_t* w, int64_t ldw, int M, int N, int K,
                             void* out, int64_t ldo, const qvit_epilogue_t* epi, int backend, qvit_stream_t stream) {

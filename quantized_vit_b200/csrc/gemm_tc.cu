@@ -30,11 +30,14 @@ constexpr int kEpiWarps = 16;     // four warps per TMEM lane quarter ("quads"),
 constexpr int kGemmThreads = 64 + 32 * kEpiWarps;   // warp 0 TMA, warp 1 MMA, warps 2..17 epilogue
 constexpr int kBoxBytes = kBM * 128;                // staging buffer of one quad: 128 rows x (<=128) B, swizzled
 
-template <int BN>
+// CG = 1: one CTA computes a [128 x BN] tile.  CG = 2: a CTA pair (tcgen05 cta_group::2) computes a [256 x BN] tile;
+// each CTA stages its own 128 rows of A and HALF of the W rows, the tensor core reads both halves - 1.5x less
+// L2->SM operand traffic per MAC and 32 KiB stages (5 deep) instead of 48 KiB (3 deep).
+template <int BN, int CG = 1>
 struct GemmSmem {
-  static constexpr int kStages = (BN == 256) ? 3 : 5;
+  static constexpr int kStages = (BN == 256 && CG == 1) ? 3 : 5;
   static constexpr int kABytes = kBM * kBK;
-  static constexpr int kBBytes = BN * kBK;
+  static constexpr int kBBytes = (BN / CG) * kBK;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutBytes = 4 * kBoxBytes;     // one buffer per quad
   static constexpr int kBarBytes = 256;
@@ -103,14 +106,17 @@ __device__ __forceinline__ void epi_compute32(EpiParams e, const uint32_t (&acc)
   }
 }
 
-template <int BN, int OUT>
+template <int BN, int OUT, int CG>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
-                  const EpiParams ep, const int K, const uint32_t idesc, const int tma_store, const int res_tma) {
-  using S = GemmSmem<BN>;
+                  const EpiParams ep, const int K, const uint32_t idesc, const int tma_store, const int res_tma,
+                  const int mma_only) {
+  using S = GemmSmem<BN, CG>;
   constexpr int kStages = S::kStages;
   constexpr int kTmemCols = 2 * BN;   // 256 or 512: a power of two >= 32
+  constexpr int kTileM = kBM * CG;    // rows of the (pair) tile
+  const uint32_t rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
@@ -129,10 +135,11 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  const int m_tiles = (ep.M + kBM - 1) / kBM;
+  const int m_tiles = (ep.M + kTileM - 1) / kTileM;
   const int n_tiles = (ep.N + BN - 1) / BN;
   const int total_tiles = m_tiles * n_tiles;
   const int k_blocks = (K + kBK - 1) / kBK;
+  const int tile_first = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmap_a);
@@ -148,17 +155,18 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       }
       for (int a = 0; a < 2; ++a) {
         ptx::mbar_init(tfull_bar(a), 1);
-        ptx::mbar_init(tempty_bar(a), kEpiWarps);      // one arrive per epilogue warp
+        ptx::mbar_init(tempty_bar(a), kEpiWarps * CG); // one arrive per epilogue warp (of both CTAs of a pair)
       }
       for (int q = 0; q < 4; ++q) ptx::mbar_init(res_bar(q), 1);
       ptx::fence_mbar_init();
     }
     __syncwarp();
-    ptx::tmem_alloc<1>(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
-    ptx::tmem_relinquish<1>();
+    ptx::tmem_alloc<CG>(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), kTmemCols);
+    ptx::tmem_relinquish<CG>();
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG == 2) ptx::cluster_sync();   // the peer's barriers are initialised before any remote arrive / TMA signal
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -167,27 +175,43 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+        const int a_row = m_blk * kTileM + (int)rank * kBM;          // this CTA's 128 rows of A
+        const int w_row = n_blk * BN + (int)rank * (BN / CG);        // this CTA's share of the W rows
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * S::kStageBytes;
           const uint32_t b_dst = a_dst + S::kABytes;
-          ptx::mbar_expect_tx(full_bar(stage), S::kStageBytes);
-          ptx::tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * kBK, m_blk * kBM);
-          ptx::tma_load_2d(b_dst, &tmap_w, full_bar(stage), kb * kBK, n_blk * BN);
+          if (mma_only && (tile != tile_first || kb >= kStages)) {
+            // benchmark mode (QVIT_OUT_NONE only): operands stay whatever the first kStages loads brought in -
+            // measures the tensor-core issue rate with no L2 / HBM traffic at all
+            if (rank == 0) ptx::mbar_arrive(full_bar(stage));
+          } else if (CG == 1) {
+            ptx::mbar_expect_tx(full_bar(stage), S::kStageBytes);
+            ptx::tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * kBK, a_row);
+            ptx::tma_load_2d(b_dst, &tmap_w, full_bar(stage), kb * kBK, w_row);
+          } else {
+            // both CTAs signal the LEADER's barrier (peer bit of the shared::cluster address cleared); the leader arms it
+            // for the bytes of both.  A peer completion that overtakes the leader's expect_tx only makes the pending
+            // tx-count transiently negative: the phase cannot complete before the leader's (single) arrival.
+            const uint32_t lead_bar = full_bar(stage) & 0xFEFFFFFFu;
+            if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * S::kStageBytes);
+            ptx::tma_load_2d_cg2(a_dst, &tmap_a, lead_bar, kb * kBK, a_row);
+            ptx::tma_load_2d_cg2(b_dst, &tmap_w, lead_bar, kb * kBK, w_row);
+          }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA of a pair only)
+    if (lane == 0 && rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);     // epilogue has drained this accumulator
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -200,13 +224,14 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             // advance both descriptors by k*32 bytes inside the swizzle atom (address field is >>4)
-            ptx::mma_i8<1>(d_tmem, a_desc + (uint64_t)(k * (kUmmaK >> 4)), b_desc + (uint64_t)(k * (kUmmaK >> 4)), idesc,
-                           (uint32_t)((kb | k) != 0));
+            ptx::mma_i8<CG>(d_tmem, a_desc + (uint64_t)(k * (kUmmaK >> 4)), b_desc + (uint64_t)(k * (kUmmaK >> 4)), idesc,
+                            (uint32_t)((kb | k) != 0));
           }
-          ptx::mma_commit(empty_bar(stage));                 // smem slot free once these MMAs retire
+          // smem slot free once these MMAs retire (in both CTAs of a pair)
+          if (CG == 1) ptx::mma_commit(empty_bar(stage)); else ptx::mma_commit_cg2(empty_bar(stage), 0x3);
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        ptx::mma_commit(tfull_bar(acc));                     // accumulator complete
+        if (CG == 1) ptx::mma_commit(tfull_bar(acc)); else ptx::mma_commit_cg2(tfull_bar(acc), 0x3);   // accumulator complete
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
@@ -238,11 +263,12 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t buf = out_base + (uint32_t)(quad * kBoxBytes);
     const uint32_t row_off = (uint32_t)(row * kBoxW);
     const uint32_t sw = (row_off >> 7) & kSwzMask;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
-      const int64_t m = (int64_t)m_blk * kBM + row;
+      const int row0 = m_blk * kTileM + (int)rank * kBM;      // first output row of this CTA's half of the tile
+      const int64_t m = (int64_t)row0 + row;
       const bool row_ok = m < ep.M;
       const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN);
 #pragma unroll
@@ -253,7 +279,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           // buffer free again -> fetch the [128 x 32] fp32 residual tile (coalesced, async) while the math runs
           ptx::tma_store_wait_read<0>();
           ptx::mbar_expect_tx(res_bar(quad), (uint32_t)(kBM * 128));
-          ptx::tma_load_2d(buf, &tmap_res, res_bar(quad), n0, m_blk * kBM);
+          ptx::tma_load_2d(buf, &tmap_res, res_bar(quad), n0, row0);
         }
         uint32_t r[32];
         ptx::tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
@@ -261,7 +287,10 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         if (cq == kChunksPerQuad - 1) {                      // all TMEM reads of this warp for this tile are done
           ptx::tc_fence_before();
           __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(tempty_bar(acc));
+          if (lane == 0) {
+            if (CG == 1) ptx::mbar_arrive(tempty_bar(acc));
+            else ptx::mbar_arrive_cluster(tempty_bar(acc), 0);   // the leader's MMA warp waits for both CTAs
+          }
         }
         if (OUT == QVIT_OUT_NONE) continue;                  // main-loop benchmark mode
         if (!tma_store) {
@@ -328,7 +357,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           named_bar_sync(1 + quad, 128);
           if (leader) {
             const int box_n0 = n_blk * BN + (c - in_box) * 32;
-            ptx::tma_store_2d(&tmap_out, buf, box_n0, m_blk * kBM);
+            ptx::tma_store_2d(&tmap_out, buf, box_n0, row0);
             ptx::tma_store_commit();
           }
         }
@@ -343,9 +372,10 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   ptx::tc_fence_before();
   __syncthreads();
+  if (CG == 2) ptx::cluster_sync();   // the peer may still be reading this CTA's operands / signalling its barriers
   if (warp == 1) {
     ptx::tc_fence_after();
-    ptx::tmem_dealloc<1>(tmem_base, kTmemCols);
+    ptx::tmem_dealloc<CG>(tmem_base, kTmemCols);
   }
 }
 
@@ -432,44 +462,69 @@ bool gemm_tc_supported(const void* a, int64_t lda, const void* w, int64_t ldw, i
   return maj == 10 && get_encode_fn() != nullptr;
 }
 
+static int g_force_cg = 0;   // 0 = automatic, 1 / 2 = force single-CTA / CTA-pair tiles (tests, benchmarks)
+static int g_mma_only = 0;   // benchmark: skip operand loads after the first pipeline fill (QVIT_OUT_NONE only)
+void gemm_tc_force_cta_group(int cg) {
+  g_mma_only = (cg >= 10) ? 1 : 0;
+  g_force_cg = cg % 10;
+}
+
 struct TcMaps {
   CUtensorMap a, w, out, res;
   int tma_store, res_tma;
 };
 
-template <int BN, int OUT>
+template <int BN, int OUT, int CG>
 static int launch_tc(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsigned, int max_ctas, cudaStream_t s) {
-  using S = GemmSmem<BN>;
+  using S = GemmSmem<BN, CG>;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel<BN, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel<BN, OUT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(smem=%d): %s", S::kTotal, cudaGetErrorString(e));
       return QVIT_ERR_CUDA;
     }
     attr_set[dev] = true;
   }
-  const int m_tiles = (ep.M + kBM - 1) / kBM, n_tiles = (ep.N + BN - 1) / BN;
-  int grid = m_tiles * n_tiles;
+  const int m_tiles = (ep.M + kBM * CG - 1) / (kBM * CG), n_tiles = (ep.N + BN - 1) / BN;
+  int grid = m_tiles * n_tiles * CG;
   if (grid > max_ctas) grid = max_ctas;
-  const uint32_t idesc = ptx::make_idesc_i8(kBM, BN, !a_unsigned, true);
-  gemm_i8_tc_kernel<BN, OUT><<<grid, kGemmThreads, S::kTotal, s>>>(tm.a, tm.w, tm.out, tm.res, ep, K, idesc, tm.tma_store,
-                                                                   tm.res_tma);
+  if (CG == 2) grid &= ~1;
+  const uint32_t idesc = ptx::make_idesc_i8(kBM * CG, BN, !a_unsigned, true);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(kGemmThreads);
+  cfg.dynamicSmemBytes = S::kTotal;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_i8_tc_kernel<BN, OUT, CG>, tm.a, tm.w, tm.out, tm.res, ep, K, idesc,
+                                     tm.tma_store, tm.res_tma, (OUT == QVIT_OUT_NONE) ? g_mma_only : 0);
+  if (e != cudaSuccess) {
+    set_error("gemm_i8_tc_kernel launch: %s", cudaGetErrorString(e));
+    return QVIT_ERR_CUDA;
+  }
   return check_launch("gemm_i8_tc_kernel");
 }
 
-template <int BN>
+template <int BN, int CG>
 static int launch_tc_kind(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsigned, int max_ctas, cudaStream_t s) {
   switch (ep.out_kind) {
-    case QVIT_OUT_I32: return launch_tc<BN, QVIT_OUT_I32>(tm, ep, K, a_unsigned, max_ctas, s);
-    case QVIT_OUT_F32: return launch_tc<BN, QVIT_OUT_F32>(tm, ep, K, a_unsigned, max_ctas, s);
-    case QVIT_OUT_BF16: return launch_tc<BN, QVIT_OUT_BF16>(tm, ep, K, a_unsigned, max_ctas, s);
-    case QVIT_OUT_I8: return launch_tc<BN, QVIT_OUT_I8>(tm, ep, K, a_unsigned, max_ctas, s);
-    default: return launch_tc<BN, QVIT_OUT_NONE>(tm, ep, K, a_unsigned, max_ctas, s);
+    case QVIT_OUT_I32: return launch_tc<BN, QVIT_OUT_I32, CG>(tm, ep, K, a_unsigned, max_ctas, s);
+    case QVIT_OUT_F32: return launch_tc<BN, QVIT_OUT_F32, CG>(tm, ep, K, a_unsigned, max_ctas, s);
+    case QVIT_OUT_BF16: return launch_tc<BN, QVIT_OUT_BF16, CG>(tm, ep, K, a_unsigned, max_ctas, s);
+    case QVIT_OUT_I8: return launch_tc<BN, QVIT_OUT_I8, CG>(tm, ep, K, a_unsigned, max_ctas, s);
+    default: return launch_tc<BN, QVIT_OUT_NONE, CG>(tm, ep, K, a_unsigned, max_ctas, s);
   }
 }
+
 
 int gemm_tc_launch(const void* a, int64_t lda, int a_unsigned, const int8_t* w, int64_t ldw, const EpiParams& ep, int K,
                    cudaStream_t s) {
@@ -482,10 +537,20 @@ int gemm_tc_launch(const void* a, int64_t lda, int a_unsigned, const int8_t* w, 
     const int64_t t256 = (int64_t)((M + kBM - 1) / kBM) * ((N + 255) / 256);
     if (t256 < sms) bn = 128;
   }
+  // CTA pairs once there is at least one full wave of [256 x 256] pair tiles
+  // Measured (tools/epi_bench.py, M = 50 432): pairs win when the epilogue is light (main loop only 129 -> 114 us, bf16
+  // out 181 -> 167 us) and lose a little when it is the bottleneck (fp32 + residual 282 -> 310 us, int8 + GELU 310 -> 320 us),
+  // so automatic mode uses them for the raw / bf16 kinds only.
+  int cg = 1;
+  if (bn == 256 && (int64_t)((M + 2 * kBM - 1) / (2 * kBM)) * ((N + 255) / 256) * 2 >= sms &&
+      (ep.out_kind == QVIT_OUT_BF16 || ep.out_kind == QVIT_OUT_I32 || ep.out_kind == QVIT_OUT_NONE) && !ep.residual)
+    cg = 2;
+  if (g_force_cg == 1) cg = 1;
+  if (g_force_cg == 2 && bn == 256) cg = 2;
   TcMaps tm;
   int rc = make_tmap_bytes(&tm.a, a, M, K, lda, kBM);
   if (rc) return rc;
-  rc = make_tmap_bytes(&tm.w, w, N, K, ldw, bn);
+  rc = make_tmap_bytes(&tm.w, w, N, K, ldw, bn / cg);
   if (rc) return rc;
   // Coalesced output through shared memory + TMA store when the output matrix is TMA-addressable;
   // predicated per-thread vector stores otherwise.
@@ -505,8 +570,9 @@ int gemm_tc_launch(const void* a, int64_t lda, int a_unsigned, const int8_t* w, 
     rc = make_tmap_out(&tm.res, const_cast<float*>(ep.residual), M, N, ep.ld_res, QVIT_OUT_F32, 128);
     if (rc) return rc;
   }
-  if (bn == 256) return launch_tc_kind<256>(tm, ep, K, a_unsigned != 0, sms, s);
-  return launch_tc_kind<128>(tm, ep, K, a_unsigned != 0, sms, s);
+  if (cg == 2) return launch_tc_kind<256, 2>(tm, ep, K, a_unsigned != 0, sms, s);
+  if (bn == 256) return launch_tc_kind<256, 1>(tm, ep, K, a_unsigned != 0, sms, s);
+  return launch_tc_kind<128, 1>(tm, ep, K, a_unsigned != 0, sms, s);
 }
 
 }  // namespace qvit

@@ -128,3 +128,35 @@ def test_unaligned_pitch_falls_back_to_simt_and_tc_refuses(ops):
     assert torch.equal(got.cpu().to(torch.int64), want)
     with pytest.raises(RuntimeError, match="tcgen05"):
         ops.gemm_i8(a.cuda(), w.cuda(), K, N, out_kind=ops.QVIT_OUT_I32, backend=ops.QVIT_GEMM_TCGEN05)
+
+
+@pytest.mark.parametrize("cta_group", [1, 2])
+@pytest.mark.parametrize("M,N,K", [(5120, 1024, 896), (5001, 1000, 776), (50432, 768, 768), (4990, 2304, 768)])
+def test_cta_pair_mode_bit_exact(ops, cta_group, M, N, K):
+    """tcgen05 cta_group::2 (CTA pairs, [256 x 256] tiles) against single-CTA tiles and the exact int64 contraction,
+    including ragged M / N / K and every epilogue kind."""
+    from quantized_vit_b200 import _lib
+    a = _codes(M, K, -127, 127, 21)
+    w = _codes(N, K, -7, 7, 22)
+    want = (a[:, :K].to(torch.float32).cuda() @ w[:, :K].to(torch.float32).cuda().t()).to(torch.int64).cpu() if K * 127 * 7 < 2 ** 24 \
+        else a[:, :K].to(torch.int64) @ w[:, :K].to(torch.int64).t()
+    L = _lib.lib()
+    assert L.qvit_gemm_set_cta_group(cta_group) == 0
+    try:
+        ag, wg = a.cuda(), w.cuda()
+        got = ops.gemm_i8(ag, wg, K, N, out_kind=ops.QVIT_OUT_I32, backend=ops.QVIT_GEMM_TCGEN05)
+        assert torch.equal(got.cpu().to(torch.int64), want)
+        bias = torch.randn(N).cuda()
+        res = torch.randn(M, N).cuda()
+        y = ops.gemm_i8(ag, wg, K, N, out_kind=ops.QVIT_OUT_F32, bias=bias, residual=res, scale_a=0.01, scale_w=0.02,
+                        backend=ops.QVIT_GEMM_TCGEN05)
+        ref = want.to(torch.float32).cuda() * (0.01 * 0.02) + bias + res
+        assert torch.allclose(y, ref, rtol=1e-5, atol=1e-4)
+        c8 = ops.gemm_i8(ag, wg, K, N, out_kind=ops.QVIT_OUT_I8, bias=bias, act=ops.QVIT_ACT_GELU, scale_a=0.01, scale_w=0.02,
+                         next_q=(0.3, 2.1, None), backend=ops.QVIT_GEMM_TCGEN05)
+        L.qvit_gemm_set_cta_group(1)
+        c8_ref = ops.gemm_i8(ag, wg, K, N, out_kind=ops.QVIT_OUT_I8, bias=bias, act=ops.QVIT_ACT_GELU, scale_a=0.01, scale_w=0.02,
+                             next_q=(0.3, 2.1, None), backend=ops.QVIT_GEMM_SIMT)
+        assert torch.equal(c8, c8_ref)
+    finally:
+        L.qvit_gemm_set_cta_group(0)

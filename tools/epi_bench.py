@@ -20,9 +20,14 @@ cases = [("none", dict(out_kind=ops.QVIT_OUT_NONE, backend=ops.QVIT_GEMM_TCGEN05
          ("i8+relu", dict(out_kind=ops.QVIT_OUT_I8, bias=bias, act=ops.QVIT_ACT_RELU, next_q=(0.3, 2.1, None))),
          ("i8+gelu", dict(out_kind=ops.QVIT_OUT_I8, bias=bias, act=ops.QVIT_ACT_GELU, next_q=(0.3, 2.1, None))),
          ("i8+gelu nonlinear-q", dict(out_kind=ops.QVIT_OUT_I8, bias=bias, act=ops.QVIT_ACT_GELU, next_q=(0.3, 2.1, 1.0)))]
-for name, kw in cases:
+from quantized_vit_b200 import _lib
+for cg in (1, 2):
+  _lib.lib().qvit_gemm_set_cta_group(cg)
+  print(f"--- cta_group {cg}")
+  for name, kw in cases:
     kw = dict(kw, scale_a=0.1, scale_w=0.01)
     if kw["out_kind"] != ops.QVIT_OUT_NONE:
         kw["out"] = ops.gemm_i8(a, w, K, N, **kw)
     med, best = timeit(lambda: ops.gemm_i8(a, w, K, N, **kw), iters=10)
     print(f"{name:22s} {med*1e3:8.1f} us  {2.0*M*K*N/(med*1e-3)/1e12:7.1f} TOPS", flush=True)
+_lib.lib().qvit_gemm_set_cta_group(0)
