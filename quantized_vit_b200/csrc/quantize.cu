@@ -180,6 +180,35 @@ im2col_quantize_kernel(const float* __restrict__ x, ConvGeom g, const float* __r
   if (fl && flags && (threadIdx.x & 31) == 0) atomicOr(flags, fl);
 }
 
+// Non-overlapping patches (kernel == stride, no padding, no dilation, kw % 4 == 0, W % 4 == 0): ViT PatchEmbed
+// (vit_model.py:94-100).  One thread = 4 consecutive pixels of one patch row = 4 consecutive K entries: a 128-bit
+// coalesced load along W and one coalesced 32-bit store along K.
+__global__ void __launch_bounds__(kThreads)
+patchify_quantize_kernel(const float* __restrict__ x, ConvGeom g, const float* __restrict__ d, const float* __restrict__ qm,
+                         const float* __restrict__ t, int8_t* __restrict__ cols, int64_t ld_cols, int32_t* __restrict__ flags) {
+  const SymParams p = load_sym_params(d, qm, t);
+  const FastQ fq = make_fastq(p);
+  int fl = 0;
+  const int w4 = g.W / 4;                                  // float4 groups per image row
+  const int64_t total = (int64_t)g.B * g.C * g.H * w4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int xg = (int)(i % w4);
+    const int ih = (int)((i / w4) % g.H);
+    const int c = (int)((i / ((int64_t)w4 * g.H)) % g.C);
+    const int b = (int)(i / ((int64_t)w4 * g.H * g.C));
+    const int iw = xg * 4;
+    const int oh = ih / g.kh, ki = ih - oh * g.kh;
+    const int ow = iw / g.kw, kj = iw - ow * g.kw;
+    if (oh >= g.OH || ow >= g.OW) continue;                // pixels beyond the last full patch are not used
+    const float4 v = ldg_stream4(x + i * 4);
+    const int64_t row = ((int64_t)b * g.OH + oh) * g.OW + ow;
+    const int k = (c * g.kh + ki) * g.kw + kj;
+    *reinterpret_cast<uint32_t*>(cols + row * ld_cols + k) = sym_codes4(v.x, v.y, v.z, v.w, p, fq, fl);
+  }
+  fl = warp_or(fl);
+  if (fl && flags && (threadIdx.x & 31) == 0) atomicOr(flags, fl);
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm + quantize: one warp per row, the row lives in registers (cols = 128 * V, V <= 16)
 // ------------------------------------------------------------------------------------------------
@@ -364,6 +393,15 @@ int qvit_im2col_quantize_sym(const float* x, int B, int C, int H, int W, int kh,
   QVIT_REQUIRE(g.OH > 0 && g.OW > 0, "qvit_im2col_quantize_sym: empty output");
   QVIT_REQUIRE(ld_cols >= g.K && ld_cols % 4 == 0 && (reinterpret_cast<uintptr_t>(cols) & 3) == 0,
                "qvit_im2col_quantize_sym: ld_cols must be >= C*kh*kw and a multiple of 4");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (kh == sh && kw == sw && ph == 0 && pw == 0 && dh == 1 && dw == 1 && (kw % 4) == 0 && (W % 4) == 0 &&
+      (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+    if (ld_cols > g.K)      // K padding columns (none for ViT: K = 768)
+      cudaMemsetAsync(cols, 0, (size_t)B * g.OH * g.OW * ld_cols, s);
+    const int64_t groups = (int64_t)B * C * H * (W / 4);
+    patchify_quantize_kernel<<<stream_grid(groups, kThreads * 4), kThreads, 0, s>>>(x, g, d, q_m, t, cols, ld_cols, flags);
+    return check_launch("qvit_im2col_quantize_sym(patchify)");
+  }
   const int64_t words = (int64_t)B * g.OH * g.OW * (ld_cols / 4);
   im2col_quantize_kernel<<<stream_grid(words, kThreads * 2), kThreads, 0, (cudaStream_t)stream>>>(x, g, d, q_m, t, cols,
                                                                                                   ld_cols, flags);

@@ -156,9 +156,11 @@ bn_act_pool_nchw_kernel(const float* __restrict__ x, int B, int C, int H, int W,
 // CTA = 256 threads = (pixels in a TH x 16 tile) x (channel groups of 16 output channels).
 // Shared memory: input halo tile [(TH+kh-1) x (16+kw-1)] pixels x Cw words (+1 word pad per pixel: no bank
 // conflicts for the per-thread pixel stride), weights [O][kh*kw*Cw] words, output code tile for pooling.
-constexpr int kOPT = 16;       // output channels per thread
 constexpr int kTW = 16;        // tile width in pixels
 
+// kOPT = output channels per thread: 16 for large maps, 4 for the small late layers (4x more threads per pixel, so a
+// 10 x 20 map still spreads over >= 13 CTAs instead of 4)
+template <int kOPT>
 __global__ void __launch_bounds__(kUT)
 ultra_conv_bn_act_kernel(const uint8_t* __restrict__ in, int B, int H, int W, int C, const int8_t* __restrict__ wc, int O,
                          int kh, int kw, int pad, float acc_scale, const float* __restrict__ bn_scale,
@@ -170,8 +172,8 @@ ultra_conv_bn_act_kernel(const uint8_t* __restrict__ in, int B, int H, int W, in
   const int in_w = kTW + kw - 1, in_h = TH + kh - 1;
   const int KW = kh * kw * Cw;                    // words per output channel
   const int groups = (O + kOPT - 1) / kOPT;
-  uint32_t* s_in = smem;                                    // in_h*in_w*pix_stride
-  uint32_t* s_w = s_in + in_h * in_w * pix_stride;          // O*KW
+  uint32_t* s_in = smem;                                    // in_h*in_w*pix_stride (rounded up to 16 bytes)
+  uint32_t* s_w = s_in + ((in_h * in_w * pix_stride + 3) & ~3);   // O*KW
   uint8_t* s_out = reinterpret_cast<uint8_t*>(s_w + O * KW);   // TH*kTW*O  (pool only)
 
   const int tile = blockIdx.x;
@@ -180,6 +182,12 @@ ultra_conv_bn_act_kernel(const uint8_t* __restrict__ in, int B, int H, int W, in
   const int tx0 = (tile % tiles_x) * kTW;
 
   // ---- stage weights: global [O][kh][kw][C] int8 -> smem words (zero padded to 4 channels)
+  if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(wc) & 15) == 0 && ((O * KW) & 3) == 0) {
+    // channels already fill whole words: the global layout IS the shared layout -> straight 128-bit copies
+    const uint4* src = reinterpret_cast<const uint4*>(wc);
+    uint4* dst = reinterpret_cast<uint4*>(s_w);
+    for (int i = threadIdx.x; i < (O * KW) / 4; i += blockDim.x) dst[i] = __ldg(src + i);
+  } else
   for (int i = threadIdx.x; i < O * KW; i += blockDim.x) {
     const int o = i / KW, r = i - o * KW;
     const int tap = r / Cw, cw = r - tap * Cw;
@@ -274,8 +282,10 @@ ultra_conv_bn_act_kernel(const uint8_t* __restrict__ in, int B, int H, int W, in
   if (!pool) {
     if (in_img) {
       uint8_t* dst = out_codes + (((int64_t)b * OHf + oy) * OWf + ox) * O + grp * kOPT;
-      if ((O % kOPT) == 0) {
-        *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+      if ((O % kOPT) == 0 && kOPT == 16) {
+        *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[kOPT / 4 - 1]);
+      } else if ((O % kOPT) == 0 && kOPT == 4) {
+        *reinterpret_cast<uint32_t*>(dst) = packed[0];
       } else {
 #pragma unroll
         for (int j = 0; j < kOPT; ++j)
@@ -413,26 +423,41 @@ int qvit_ultra_conv_bn_act(const uint8_t* in_codes, int B, int H, int W, int C, 
   QVIT_REQUIRE(OH > 0 && OW > 0, "qvit_ultra_conv_bn_act: empty output");
   QVIT_REQUIRE(!pool || (out_codes && !out_f32), "qvit_ultra_conv_bn_act: pooling applies to the code output only");
   QVIT_REQUIRE(out_f32 || (out_levels >= 1 && out_levels <= 255), "qvit_ultra_conv_bn_act: out_levels in [1,255]");
-  const int groups = (O + kOPT - 1) / kOPT;
+  // channels per thread: 16 when that already gives >= 2 CTAs per SM, else 4 (small late layers, batch-1 latency)
+  int opt = 16;
+  {
+    const int g16 = (O + 15) / 16;
+    int th16 = kUT / (g16 * kTW);
+    if (th16 < 1) th16 = 1;
+    const int64_t ctas16 = (int64_t)B * ((OW + kTW - 1) / kTW) * ((OH + th16 - 1) / th16);
+    if (ctas16 < 2 * sm_count() && O <= 64 && !(pool && kUT / (((O + 3) / 4) * kTW) < 2)) opt = 4;
+  }
+  const int groups = (O + opt - 1) / opt;
   QVIT_REQUIRE(groups <= 16, "qvit_ultra_conv_bn_act: O too large");
   int TH = kUT / (groups * kTW);                  // 16, 8, 4, 2 or 1 rows of 16 pixels
   if (TH < 1) TH = 1;
   if (pool) QVIT_REQUIRE(TH >= 2 && (TH % 2) == 0, "qvit_ultra_conv_bn_act: pooling needs O <= 128");
   const int Cw = (C + 3) / 4;
-  const size_t smem = sizeof(uint32_t) * ((size_t)(TH + kh - 1) * (kTW + kw - 1) * (Cw + 1) + (size_t)O * kh * kw * Cw) +
-                      (pool ? (size_t)TH * kTW * groups * kOPT : 0);
+  const size_t in_words = ((size_t)(TH + kh - 1) * (kTW + kw - 1) * (Cw + 1) + 3) & ~(size_t)3;
+  const size_t smem = sizeof(uint32_t) * (in_words + (size_t)O * kh * kw * Cw) + (pool ? (size_t)TH * kTW * groups * opt : 0);
   QVIT_REQUIRE(smem <= 200 * 1024, "qvit_ultra_conv_bn_act: layer too large for the fused kernel (%zu B smem)", smem);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(ultra_conv_bn_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(ultra_conv_bn_act_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaFuncSetAttribute(ultra_conv_bn_act_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     attr_set = true;
   }
   const int tiles_x = (OW + kTW - 1) / kTW, tiles_y = (OH + TH - 1) / TH;
   const int64_t grid = (int64_t)B * tiles_x * tiles_y;
   QVIT_REQUIRE(grid < (1ll << 31), "qvit_ultra_conv_bn_act: grid too large");
-  ultra_conv_bn_act_kernel<<<(unsigned)grid, kUT, smem, (cudaStream_t)stream>>>(
-      in_codes, B, H, W, C, w_codes, O, kh, kw, pad, acc_scale, bn_scale, bn_bias, out_levels, pool, out_codes, out_f32,
-      tiles_x, tiles_y, TH);
+  if (opt == 16)
+    ultra_conv_bn_act_kernel<16><<<(unsigned)grid, kUT, smem, (cudaStream_t)stream>>>(
+        in_codes, B, H, W, C, w_codes, O, kh, kw, pad, acc_scale, bn_scale, bn_bias, out_levels, pool, out_codes, out_f32,
+        tiles_x, tiles_y, TH);
+  else
+    ultra_conv_bn_act_kernel<4><<<(unsigned)grid, kUT, smem, (cudaStream_t)stream>>>(
+        in_codes, B, H, W, C, w_codes, O, kh, kw, pad, acc_scale, bn_scale, bn_bias, out_levels, pool, out_codes, out_f32,
+        tiles_x, tiles_y, TH);
   return check_launch("qvit_ultra_conv_bn_act");
 }
 
