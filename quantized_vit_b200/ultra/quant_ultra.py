@@ -139,6 +139,60 @@ def conv2d_Q_fn(w_bit):
     return Conv2d_Q
 
 
+def _folded_bn(mod):
+    """(w, b) of QU:106-111 / QU:190-195: w = gamma / (sqrt(var) + eps), b = beta - mean / (sqrt(var) + eps) * gamma
+    (eps OUTSIDE the sqrt), computed by the K5 fold kernel."""
+    return ops.bn_fold(mod.weight.detach(), mod.bias.detach(), mod.running_mean, mod.running_var, mod.eps, mode=1)
+
+
+def batchNorm2d_Q_fn(w_bit):
+    """QU:94-132.  The fold is clamped to [-1, 1], mapped to [0, 1], quantised on the 2^w_bit-1 grid and mapped back; the
+    layer then applies y = x * w_q + b_q (upstream calls F.batch_norm with zero mean, unit variance and eps = 0, which
+    torch >= 2 rejects with a ValueError - that forward cannot run there, so this class is 'parity unpinned':
+    checked against the oracle restatement only).  Unused by mymodel.py (it uses nn.BatchNorm2d, MM:74)."""
+
+    class BatchNorm2d_Q(nn.BatchNorm2d):
+        def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
+            super(BatchNorm2d_Q, self).__init__(num_features, eps, momentum, affine, track_running_stats)
+            self.w_bit = w_bit
+            self.quantize_fn = uniform_quantize(k=w_bit)
+
+        def folded_quantized(self):
+            w, b = _folded_bn(self)
+            w_q = 2 * self.quantize_fn(torch.clamp(w, -1, 1) / 2 + 0.5) - 1
+            b_q = 2 * self.quantize_fn(torch.clamp(b, -1, 1) / 2 + 0.5) - 1
+            return w_q, b_q
+
+        def forward(self, input):
+            ops._lib.require_cuda(input, self.weight)
+            w_q, b_q = self.folded_quantized()
+            shape = (1, -1) + (1,) * (input.dim() - 2)
+            return input * w_q.view(shape) + b_q.view(shape)
+
+    return BatchNorm2d_Q
+
+
+def batchNorm1d_Q_fn(w_bit):
+    """QU:135-207: the folded scale is quantised directly (no range mapping), the folded bias is NOT quantised
+    (QU:190-206).  Same eps = 0 caveat as BatchNorm2d_Q."""
+
+    class BatchNorm1d_Q(nn.BatchNorm1d):
+        def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):
+            super(BatchNorm1d_Q, self).__init__(num_features, eps, momentum, affine, track_running_stats)
+            self.w_bit = w_bit
+            self.quantize_fn = uniform_quantize(k=w_bit)
+
+        def forward(self, input):
+            self._check_input_dim(input)
+            ops._lib.require_cuda(input, self.weight)
+            w, b = _folded_bn(self)
+            _ = self.quantize_fn(w)           # upstream computes w_q and then applies the UN-quantised w (QU:196, 203)
+            shape = (1, -1) + (1,) * (input.dim() - 2)
+            return input * w.view(shape) + b.view(shape)
+
+    return BatchNorm1d_Q
+
+
 def linear_Q_fn(w_bit):
     """QU:210-222."""
 
