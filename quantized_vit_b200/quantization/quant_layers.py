@@ -75,6 +75,9 @@ def check_nan_flags(raise_error: bool = True) -> int:
         w.zero_()
     if raise_error and bits & ops._lib.QVIT_FLAG_NAN_GRAD:
         raise NanInGradientError("Error: NaN appears in gradient! (reported by the fused quantizer backward)")
+    if raise_error and bits & ops._lib.QVIT_FLAG_OVERFLOW:
+        raise RuntimeError("a quantizer produced codes beyond +-127 on the int8 path (d_quant shrank below q_m/127): "
+                           "call module.invalidate_quant_cache() / re-create the modules so the wide path is selected")
     return bits
 
 
@@ -155,6 +158,53 @@ class DGEQuantizer(torch.autograd.Function):
         if EAGER_NAN_CHECK and torch.isnan(gx).any():
             raise NanInGradientError("NaN in gradient computation")
         return gx, gd, gq, None, None, None
+
+
+class QuantLinearFunction(torch.autograd.Function):
+    """Fused QAT step of QuantizeLinear (QL:495-499 forward; QL:163-205 / 71-125 backward for both quantizers).
+
+    forward : activation and weight codes (K2/K1) -> exact int8 tensor-core GEMM -> fp32 dequant + bias (K3).  This equals
+              F.linear(x_q, w_q, bias) of the reference up to fp32 rounding, without materialising x_q / w_q.
+    backward: grad_x_q = g @ w_q and grad_w_q = g^T @ x_q (the gradient operand is never quantized upstream, so these two
+              stay fp32 library GEMMs for now), then ONE fused kernel per quantizer for the STE mask and the step-size /
+              range / exponent gradient reductions (K6).  Saved for backward: x, W and the int8 codes (1 B/element)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, d_a, qm_a, t_a, d_w, qm_w, t_w, clip_a, clip_w):
+        K, N = weight.shape[1], weight.shape[0]
+        x2 = x.reshape(-1, K).contiguous()
+        flags = _flags_for(x.device)
+        a_codes = ops.quantize_sym(x2, d_a, qm_a, t_a, ld_codes=ops.pad16(K), flags=flags)
+        w_codes = ops.quantize_sym(weight.detach(), d_w, qm_w, t_w, ld_codes=ops.pad16(K), flags=flags)
+        y = ops.gemm_i8(a_codes, w_codes, K, N, out_kind=ops.QVIT_OUT_F32, scale_a=d_a, scale_w=d_w,
+                        bias=None if bias is None else bias.detach(), flags=flags)
+        ctx.clip_a, ctx.clip_w, ctx.has_bias, ctx.nl = clip_a, clip_w, bias is not None, t_a is not None
+        ctx.x_shape = x.shape
+        saved = [x2, weight, d_a, qm_a, d_w, qm_w, a_codes, w_codes] + ([t_a, t_w] if t_a is not None else [])
+        ctx.save_for_backward(*saved)
+        return y.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.nl:
+            x2, weight, d_a, qm_a, d_w, qm_w, a_codes, w_codes, t_a, t_w = ctx.saved_tensors
+        else:
+            (x2, weight, d_a, qm_a, d_w, qm_w, a_codes, w_codes), t_a, t_w = ctx.saved_tensors, None, None
+        K, N = weight.shape[1], weight.shape[0]
+        g2 = g.reshape(-1, N).contiguous()
+        flags = _flags_for(g.device)
+        # fake-quant values from the saved codes: value = code * |d| (exactly what the reference forward produced)
+        x_q = a_codes[:, :K].to(torch.float32) * d_a.detach().abs()
+        w_q = w_codes[:, :K].to(torch.float32) * d_w.detach().abs()
+        grad_xq = g2 @ w_q
+        grad_wq = g2.t() @ x_q
+        grad_x, s_a = ops.sym_backward(x2, grad_xq, d_a, qm_a, t_a, ctx.clip_a, want_grad_x=ctx.needs_input_grad[0], flags=flags)
+        grad_w, s_w = ops.sym_backward(weight.detach(), grad_wq, d_w, qm_w, t_w, ctx.clip_w, flags=flags)
+        grad_b = g2.sum(0) if ctx.has_bias else None
+        if EAGER_NAN_CHECK:
+            check_nan_flags()
+        return (None if grad_x is None else grad_x.view(ctx.x_shape), grad_w, grad_b, s_a[0:1], s_a[1:2],
+                s_a[2:3] if ctx.nl else None, s_w[0:1], s_w[1:2], s_w[2:3] if ctx.nl else None, None, None)
 
 
 def _get_quantizer(qtype: QuantizationType):
@@ -261,6 +311,7 @@ class QuantizeMixin:
     # ---- integer-path plumbing -----------------------------------------------------------------
     def invalidate_quant_cache(self) -> None:
         self.__dict__["_qcache"] = _QuantCache()
+        self.__dict__["_train_int8"] = None
 
     def _wt_qparams(self):
         return self.d_quant_wt, self.q_m_wt, getattr(self, "t_quant_wt", None)
@@ -303,6 +354,20 @@ class QuantizeMixin:
         return (self.quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION and self.quant_type != QuantizationType.DGE
                 and c.w_sat <= 127 and c.a_sat is not None and c.a_sat <= 127)
 
+    def _int8_train_ok(self) -> bool:
+        """Training dispatch: is the exact int8 forward applicable?  Evaluated once per parameter identity (one host
+        read) - the optimizer changes d / q_m every step, so re-evaluating per version would synchronise every layer
+        every step.  Safety net: the quantize kernels clamp to +-127 and raise QVIT_FLAG_OVERFLOW, which
+        check_nan_flags() turns into an error."""
+        if self.quant_mode != QuantizationMode.WEIGHT_AND_ACTIVATION or self.quant_type == QuantizationType.DGE:
+            return False
+        key = tuple(p.data_ptr() for p in (*self._wt_qparams(), *self._act_qparams()) if p is not None)
+        st = self.__dict__.get("_train_int8")
+        if st is None or st[0] != key:
+            ok = self._sat_level(*self._wt_qparams()) <= 127 and self._sat_level(*self._act_qparams()) <= 127
+            st = self.__dict__["_train_int8"] = (key, ok)
+        return st[1]
+
     def _weight_codes(self, c: _QuantCache) -> torch.Tensor:
         """[out, pad16(K)] int8 codes, K = in_features or C*kh*kw ordered (c, kh, kw) = weight.reshape(O, -1)."""
         if c.w_codes is None:
@@ -332,6 +397,7 @@ class QuantizeMixin:
 
     def __getstate__(self):
         st = self.__dict__.copy()
+        st["_train_int8"] = None
         st["_qcache"] = None          # whole-model pickles (pruning_compression.py:34) never carry device caches
         return st
 
@@ -390,6 +456,11 @@ class QuantizeLinear(QuantizeMixin, nn.Linear):
         """QL:495-499."""
         ops._lib.require_cuda(input_, self.weight)
         if self._needs_autograd(input_):
+            if self._int8_train_ok() and input_.dtype == torch.float32:
+                d_a, q_a, t_a = self._act_qparams()
+                d_w, q_w, t_w = self._wt_qparams()
+                return QuantLinearFunction.apply(input_, self.weight, self.bias, d_a, q_a, t_a, d_w, q_w, t_w,
+                                                 _clip_pair(self.act_clip_val), _clip_pair(self.weight_clip_val))
             weight = self.quantize_weight(self.weight)
             if self.quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION:
                 input_ = self.quantize_act(input_)
