@@ -27,12 +27,13 @@ namespace qvit {
 constexpr int kAttHd = 64;            // head dim
 constexpr int kAttMQ = 128;           // queries per CTA
 constexpr int kAttNK = 208;           // keys per CTA (13 x 16): UMMA N of the S tile, K extent of the PV product
-constexpr int kAttThreads = 256;
+constexpr int kAttThreads = 512;      // 16 warps: four per TMEM lane quarter, each owning a quarter (52) of the key columns
+constexpr int kColQ = kAttNK / 4;     // 52 key columns per thread in the softmax
 constexpr int kQPlane = kAttMQ * 128;             // bf16 Q plane   [128 rows x 64 bf16]            16 KiB
 constexpr int kKVPlane = 4 * kAttHd * 128;        // bf16 K plane [208 x 64] (26 KiB) or V^T plane: 4 sub-tiles [64 x 64 keys] 32 KiB
 constexpr int kVtSub = kAttHd * 128;               // one V^T sub-tile of one plane: [64 head-dim rows x 64 keys] 8 KiB
 constexpr int kRawSub = kAttNK * 128;             // raw fp32 sub-tile [208 rows x 32 floats]        26 KiB
-constexpr int kAttSmem = 3 * kQPlane + 3 * kKVPlane + 2 * kRawSub + 4096 + 1024;
+constexpr int kAttSmem = 3 * kQPlane + 3 * kKVPlane + 2 * kRawSub + 8192 + 1024;
 constexpr int kPCols = kAttNK / 2;                // TMEM columns of one packed-bf16 P plane (104)
 constexpr int kOCol = 320;                        // TMEM columns [320, 512): three partial O accumulators of 64 columns
 
@@ -80,6 +81,30 @@ __device__ __forceinline__ void tmem_st_n<4>(uint32_t taddr, const uint32_t* r) 
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};"
                ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
                : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t* r) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_32x4(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(taddr)
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_st_n<8>(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+template <>
+__device__ __forceinline__ void tmem_st_n<2>(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_32x8(uint32_t taddr, uint32_t (&r)[8]) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -147,8 +172,8 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
   uint8_t* misc = g_raw + 2 * kRawSub;
   const uint32_t bar_k = misc_a, bar_v = misc_a + 8, bar_s = misc_a + 16, bar_o = misc_a + 24;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc + 32);
-  float* red_max = reinterpret_cast<float*>(misc + 64);          // [2][128]
-  float* red_sum = red_max + 2 * kAttMQ;                         // [2][128]
+  float* red_max = reinterpret_cast<float*>(misc + 64);          // [4][128]
+  float* red_sum = red_max + 4 * kAttMQ;                         // [4][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row_floats = 3ll * H * kAttHd;
@@ -182,9 +207,10 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
   // issued before the first use: one memory round trip.
   auto convert_q = [&](int w) {
     const int qt = w % q_tiles, hh = (w / q_tiles) % H, bb = w / (q_tiles * H);
-    float4 u[4], v[4];
+    constexpr int kIt = kAttMQ * 8 / kAttThreads;
+    float4 u[kIt], v[kIt];
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < kIt; ++it) {
       const int item = threadIdx.x + it * kAttThreads;
       const int r = item >> 3, c = item & 7;                   // row of the tile, chunk of 8 head-dim values
       const int t = qt * kAttMQ + r;
@@ -197,7 +223,7 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
       }
     }
 #pragma unroll
-    for (int it = 0; it < 4; ++it) {
+    for (int it = 0; it < kIt; ++it) {
       const int item = threadIdx.x + it * kAttThreads;
       const int r = item >> 3, c = item & 7;
       uint4 c1, c2, c3;
@@ -266,67 +292,57 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
   ptx::tc_fence_after();
   if (prof) ts[3] = clock64();
 
-  // ---- phase 4: softmax.  thread = row (lane quarter = warp & 3), column half = warp >> 2 (104 columns each)
+  // ---- phase 4: softmax.  thread = row (lane quarter = warp & 3), column quarter = warp >> 2 (52 key columns each)
   const int row = (warp & 3) * 32 + lane;
-  const int half = warp >> 2;
+  const int cq = warp >> 2;
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
-  const int col0 = half * (kAttNK / 2);
-  float p[kAttNK / 2];                                         // this thread's 104 scores, then probabilities
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    uint32_t r[32];
-    ptx::tmem_ld_32x32(t_s + lane_addr + (uint32_t)(col0 + c * 32), r);
-    ptx::tmem_ld_wait();
-#pragma unroll
-    for (int j = 0; j < 32; ++j) p[c * 32 + j] = __uint_as_float(r[j]);
-  }
+  const int col0 = cq * kColQ;
+  float p[kColQ];                                              // this thread's 52 scores, then probabilities
   {
-    uint32_t r[8];
-    tmem_ld_32x8(t_s + lane_addr + (uint32_t)(col0 + 96), r);
+    uint32_t r[kColQ];
+    ptx::tmem_ld_32x32(t_s + lane_addr + (uint32_t)col0, reinterpret_cast<uint32_t(&)[32]>(r[0]));
+    tmem_ld_32x16(t_s + lane_addr + (uint32_t)(col0 + 32), r + 32);
+    tmem_ld_32x4(t_s + lane_addr + (uint32_t)(col0 + 48), r + 48);
     ptx::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 8; ++j) p[96 + j] = __uint_as_float(r[j]);
+    for (int j = 0; j < kColQ; ++j) p[j] = (col0 + j < T) ? __uint_as_float(r[j]) : -INFINITY;   // masked keys: exp2(-inf) = 0
   }
   if (dump) {
     float* d = dbg + ((((int64_t)b * H + h) * 256 + q0 + row) * 512) + col0;
 #pragma unroll
-    for (int j = 0; j < kAttNK / 2; ++j) d[j] = p[j];
+    for (int j = 0; j < kColQ; ++j) d[j] = p[j];
   }
   float mx = -INFINITY;
 #pragma unroll
-  for (int j = 0; j < kAttNK / 2; ++j)
-    if (col0 + j < T) mx = fmaxf(mx, p[j]);
-  red_max[half * kAttMQ + row] = mx;
+  for (int j = 0; j < kColQ; ++j) mx = fmaxf(mx, p[j]);
+  red_max[cq * kAttMQ + row] = mx;
   ptx::tc_fence_before();
   __syncthreads();                                             // also: every thread has finished READING S from TMEM
   ptx::tc_fence_after();
-  mx = fmaxf(red_max[row], red_max[kAttMQ + row]);
+  mx = fmaxf(fmaxf(red_max[row], red_max[kAttMQ + row]), fmaxf(red_max[2 * kAttMQ + row], red_max[3 * kAttMQ + row]));
   const float mbias = mx * scale_log2e;
   float sum = 0.f;
 #pragma unroll
-  for (int j = 0; j < kAttNK / 2; ++j) {
-    float e = ex2_approx(fmaf(p[j], scale_log2e, -mbias));     // <= 2 ulp, argument <= 0
-    if (col0 + j >= T) e = 0.f;
+  for (int j = 0; j < kColQ; ++j) {
+    const float e = ex2_approx(fmaf(p[j], scale_log2e, -mbias));     // <= 2 ulp, argument <= 0
     sum += e;
     p[j] = e;
   }
   if (dump) {
     float* d = dbg + ((((int64_t)b * H + h) * 256 + q0 + row) * 512) + 208 + col0;
 #pragma unroll
-    for (int j = 0; j < kAttNK / 2; ++j) d[j] = p[j];
+    for (int j = 0; j < kColQ; ++j) d[j] = p[j];
   }
-  red_sum[half * kAttMQ + row] = sum;
+  red_sum[cq * kAttMQ + row] = sum;
   {
-    // three packed-bf16 planes: plane q occupies TMEM columns [q*104, q*104 + 104); this thread owns 52 of them
-    uint32_t w1[52], w2[52], w3[52];
+    // three packed-bf16 planes: plane q occupies TMEM columns [q*104, q*104 + 104); this thread owns 26 of them
+    uint32_t w1[26], w2[26], w3[26];
 #pragma unroll
-    for (int j = 0; j < 52; ++j) split3_pair(p[2 * j], p[2 * j + 1], w1[j], w2[j], w3[j]);
-    const uint32_t cbase = t_s + lane_addr + (uint32_t)(half * 52);
-    tmem_st_n<32>(cbase, w1);          tmem_st_n<16>(cbase + 32, w1 + 32);          tmem_st_n<4>(cbase + 48, w1 + 48);
-    tmem_st_n<32>(cbase + kPCols, w2); tmem_st_n<16>(cbase + kPCols + 32, w2 + 32); tmem_st_n<4>(cbase + kPCols + 48, w2 + 48);
-    tmem_st_n<32>(cbase + 2 * kPCols, w3);
-    tmem_st_n<16>(cbase + 2 * kPCols + 32, w3 + 32);
-    tmem_st_n<4>(cbase + 2 * kPCols + 48, w3 + 48);
+    for (int j = 0; j < 26; ++j) split3_pair(p[2 * j], p[2 * j + 1], w1[j], w2[j], w3[j]);
+    const uint32_t cbase = t_s + lane_addr + (uint32_t)(cq * 26);
+    tmem_st_n<16>(cbase, w1);              tmem_st_n<8>(cbase + 16, w1 + 16);              tmem_st_n<2>(cbase + 24, w1 + 24);
+    tmem_st_n<16>(cbase + kPCols, w2);     tmem_st_n<8>(cbase + kPCols + 16, w2 + 16);     tmem_st_n<2>(cbase + kPCols + 24, w2 + 24);
+    tmem_st_n<16>(cbase + 2 * kPCols, w3); tmem_st_n<8>(cbase + 2 * kPCols + 16, w3 + 16); tmem_st_n<2>(cbase + 2 * kPCols + 24, w3 + 24);
     tmem_st_wait();
   }
 
@@ -377,28 +393,28 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
   ptx::tc_fence_after();
   if (prof) ts[6] = clock64();
 
-  // ---- phase 6: normalise and store.  warps 0-3: head-dim 0..31, warps 4-7: 32..63
+  // ---- phase 6: normalise and store.  Column quarter cq of each lane quarter takes head-dim [16*cq, 16*cq + 16)
   {
-    const float inv = __fdiv_rn(1.0f, red_sum[row] + red_sum[kAttMQ + row]);
-    uint32_t r[32], r2[32], r3[32];
-    ptx::tmem_ld_32x32(t_o + lane_addr + (uint32_t)(half * 32), r);
-    ptx::tmem_ld_32x32(t_o + lane_addr + (uint32_t)(64 + half * 32), r2);
-    ptx::tmem_ld_32x32(t_o + lane_addr + (uint32_t)(128 + half * 32), r3);
+    const float inv = __fdiv_rn(1.0f, (red_sum[row] + red_sum[kAttMQ + row]) + (red_sum[2 * kAttMQ + row] + red_sum[3 * kAttMQ + row]));
+    uint32_t r[16], r2[16], r3[16];
+    tmem_ld_32x16(t_o + lane_addr + (uint32_t)(cq * 16), r);
+    tmem_ld_32x16(t_o + lane_addr + (uint32_t)(64 + cq * 16), r2);
+    tmem_ld_32x16(t_o + lane_addr + (uint32_t)(128 + cq * 16), r3);
     ptx::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
+    for (int j = 0; j < 16; ++j)
       r[j] = __float_as_uint((__uint_as_float(r3[j]) + __uint_as_float(r2[j])) + __uint_as_float(r[j]));   // small terms first
     if (dump) {
       float* d = dbg + ((((int64_t)b * H + h) * 256 + q0 + row) * 512) + 416;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) d[half * 32 + j] = __uint_as_float(r[j]);
-      if (half == 0) { d[64] = red_sum[row]; d[65] = red_sum[kAttMQ + row]; d[66] = inv; }
+      for (int j = 0; j < 16; ++j) d[cq * 16 + j] = __uint_as_float(r[j]);
+      if (cq == 0) { d[64] = red_sum[row] + red_sum[kAttMQ + row]; d[65] = red_sum[2 * kAttMQ + row] + red_sum[3 * kAttMQ + row]; d[66] = inv; }
     }
     const int t = q0 + row;
     if (t < T) {
-      float* dst = out + ((int64_t)b * T + t) * ((int64_t)H * kAttHd) + h * kAttHd + half * 32;
+      float* dst = out + ((int64_t)b * T + t) * ((int64_t)H * kAttHd) + h * kAttHd + cq * 16;
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
+      for (int j = 0; j < 4; ++j)
         stg_v4_b32(dst + 4 * j, __float_as_uint(__uint_as_float(r[4 * j]) * inv), __float_as_uint(__uint_as_float(r[4 * j + 1]) * inv),
                    __float_as_uint(__uint_as_float(r[4 * j + 2]) * inv), __float_as_uint(__uint_as_float(r[4 * j + 3]) * inv));
     }
