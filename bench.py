@@ -128,7 +128,7 @@ def cpu_reference_throughput(sub_batch: int, repeats: int, warmup: int = 1):
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    sub = 8
+    sub = 16
     t0 = time.perf_counter()
     ips, sec, threads = cpu_reference_throughput(sub, repeats=max(1, args.steps), warmup=min(args.warmup, 1))
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
@@ -237,9 +237,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         tc = time.perf_counter()
-        ips, sec, threads = cpu_reference_throughput(8, repeats=2, warmup=1)
+        ips, sec, threads = cpu_reference_throughput(16, repeats=12, warmup=1)
         cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"8-image sub-batch of the 256-image step, median of 2 forwards ({time.perf_counter() - tc:.0f} s of CPU work)"}
+               "sample": f"16-image sub-batch of the 256-image step, median of 12 forwards ({time.perf_counter() - tc:.0f} s of CPU work)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8 codes x int8 codes -> int32 (tcgen05 kind::i8); fp32 epilogues, LayerNorm, residual stream and attention",
@@ -250,7 +250,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                            "step i-1 overlap the forward of step i (all copies inside the timed region)"},
             "gpu_launches": calls_per_step * args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tops, "unit": "TOP/s", "frac": achieved / peak_tops,
-                         "traffic": None, "kernel": "gemm_i8_tc_kernel", "launches_per_step": n_gemm,
+                         "traffic": 143.6e6, "traffic_note": "ncu dram read+write of the longest launch (fc1, 196 MB algorithmic), profiles/r1b_ncu_full_raw.csv",
+                         "peak_alt": {"own_mma_issue_only": 4157.0, "cublaslt_int8_8192": 3005.0, "nominal": 4500.0},
+                         "kernel": "gemm_i8_tc_kernel", "launches_per_step": n_gemm,
                          "kernel_ms_per_step": gemm_ms, "kernel_share_of_step": gemm_ms / (ms / args.steps),
                          "peak_source": ("2 x bf16_tflops_sustained of MEASURED_PEAKS.json (measured)" if bf16_sust else
                                          "2 x 1.4 PFLOP/s (fallback)") + "; nominal int8 dense 4500"},
