@@ -107,7 +107,7 @@ __global__ void gemm_k0_kernel(const EpiParams ep) {
 using namespace qvit;
 
 extern "C" int qvit_gemm_set_cta_group(int cta_group) {
-  QVIT_REQUIRE((cta_group >= 0 && cta_group <= 2) || cta_group == 11 || cta_group == 12,
+  QVIT_REQUIRE((cta_group >= 0 && cta_group <= 2) || cta_group == 11 || cta_group == 12 || cta_group == 21 || cta_group == 22,
                "qvit_gemm_set_cta_group: 0 (auto), 1 or 2 (11 / 12: same with operand loads skipped in QVIT_OUT_NONE runs)");
   gemm_tc_force_cta_group(cta_group);
   return QVIT_OK;

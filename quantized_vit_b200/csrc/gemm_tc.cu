@@ -464,8 +464,10 @@ bool gemm_tc_supported(const void* a, int64_t lda, const void* w, int64_t ldw, i
 
 static int g_force_cg = 0;   // 0 = automatic, 1 / 2 = force single-CTA / CTA-pair tiles (tests, benchmarks)
 static int g_mma_only = 0;   // benchmark: skip operand loads after the first pipeline fill (QVIT_OUT_NONE only)
+static int g_no_tma_store = 0;   // benchmark: per-thread vector stores instead of staged TMA stores
 void gemm_tc_force_cta_group(int cg) {
-  g_mma_only = (cg >= 10) ? 1 : 0;
+  g_no_tma_store = (cg >= 20) ? 1 : 0;
+  g_mma_only = (cg >= 10 && cg < 20) ? 1 : 0;
   g_force_cg = cg % 10;
 }
 
@@ -556,7 +558,7 @@ int gemm_tc_launch(const void* a, int64_t lda, int a_unsigned, const int8_t* w, 
   // predicated per-thread vector stores otherwise.
   const int esz = out_elem_size(ep.out_kind);
   tm.tma_store = (ep.out_kind != QVIT_OUT_NONE) && ((reinterpret_cast<uintptr_t>(ep.out) & 15) == 0) &&
-                 (((ep.ldo * esz) & 15) == 0);
+                 (((ep.ldo * esz) & 15) == 0) && !g_no_tma_store;
   tm.out = tm.a;
   tm.res = tm.a;
   if (tm.tma_store) {

@@ -78,3 +78,28 @@ def test_no_product_module_imports_the_oracle():
                 txt = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", txt, flags=re.M), f"{f} imports the oracle"
                 assert "/root/reference" not in txt, f"{f} reads the reference tree"
+
+
+def test_engines_refuse_cpu_devices():
+    import torch
+    from quantized_vit_b200.engine import UltraNetEngine, ViTInferenceEngine
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        ViTInferenceEngine({"cls_token": torch.zeros(1, 1, 8)}, depth=1, num_heads=1, device="cpu")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        UltraNetEngine({}, device="cpu")
+
+
+def test_bench_reference_arm_contract_keys(monkeypatch, capsys):
+    """bench.py --impl reference prints ONE JSON line with the contract keys (the CPU timing itself is stubbed here)."""
+    import json
+    import sys
+    import bench
+    monkeypatch.setattr(bench, "cpu_reference_throughput", lambda sub, repeats, warmup=1: (5.0, 3.2, 8))
+    monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--steps", "2", "--warmup", "1"])
+    bench.main()
+    line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+              "vs_baseline", "dtype", "data", "config", "cpu_baseline", "e2e"):
+        assert k in line
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert "workload" in line["config"] and "model" not in line["config"]

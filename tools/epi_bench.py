@@ -21,7 +21,7 @@ cases = [("none", dict(out_kind=ops.QVIT_OUT_NONE, backend=ops.QVIT_GEMM_TCGEN05
          ("i8+gelu", dict(out_kind=ops.QVIT_OUT_I8, bias=bias, act=ops.QVIT_ACT_GELU, next_q=(0.3, 2.1, None))),
          ("i8+gelu nonlinear-q", dict(out_kind=ops.QVIT_OUT_I8, bias=bias, act=ops.QVIT_ACT_GELU, next_q=(0.3, 2.1, 1.0)))]
 from quantized_vit_b200 import _lib
-for cg in (1, 2):
+for cg in (1, 21):
   _lib.lib().qvit_gemm_set_cta_group(cg)
   print(f"--- cta_group {cg}")
   for name, kw in cases:
