@@ -183,6 +183,26 @@ int qvit_gemm_i8(const void* a, int64_t lda, int a_unsigned,
                  void* out, int64_t ldo,
                  const qvit_epilogue_t* epi, int backend, qvit_stream_t stream);
 
+/* ------------------------------------------------------------------ QAT gradient GEMMs
+ * Backward of F.linear(x_q, w_q) in QuantizeLinear.forward (QL:499): grad_x_q = g @ w_q, grad_w_q = g^T @ x_q.  The
+ * reference never quantizes g, so the int8 pipe does not apply; g is split EXACTLY into three bf16 planes and the
+ * integer codes become one bf16 plane (|code| <= 127 is exact), and (g1 + g2 + g3) * codes runs on tcgen05 kind::f16
+ * with fp32 accumulation in TMEM.
+ *
+ * qvit_split3_bf16: x [rows, cols] fp32 -> out bf16, three planes side by side.
+ *   transpose = 0: out [rows, 3 * plane_cols], plane p in columns [p*plane_cols, ...), plane_cols >= cols, zero padded;
+ *   transpose = 1: out [cols, 3 * plane_cols], element (c, r) = plane_p(x[r][c]), plane_cols >= rows, zero padded.
+ * qvit_codes_to_bf16_t: codes [rows, cols] int8 -> out [cols, out_cols] bf16 (transposed), out_cols >= rows, zero padded.
+ * plane_cols / out_cols must be multiples of 64.
+ * qvit_gemm_bf16_split: out[M, N] (fp32) = epilogue( sum_p A_p[M, K] * B[N, K]^T ); A = [M, lda >= planes*Kp] bf16,
+ *   B = [N, ldb >= Kp] bf16, Kp = K rounded up to 64; epilogue as qvit_gemm_i8 with QVIT_OUT_F32 / QVIT_ACT_NONE. */
+int qvit_split3_bf16(const float* x, int64_t rows, int64_t cols, int64_t ld_x, int transpose, void* out, int64_t plane_cols,
+                     qvit_stream_t stream);
+int qvit_codes_to_bf16_t(const int8_t* codes, int64_t rows, int64_t cols, int64_t ld, void* out, int64_t out_cols,
+                         qvit_stream_t stream);
+int qvit_gemm_bf16_split(const void* a_planes, int64_t lda, int planes, const void* b, int64_t ldb, int M, int N, int K,
+                         float* out, int64_t ldo, const qvit_epilogue_t* epi, qvit_stream_t stream);
+
 /* ------------------------------------------------------------------ glue fused with the quantizer
  * ("next" rows of SURVEY.md section 8f, built on the same quantizer device function)
  * LayerNorm (vit_model.py:206-207, eps inside sqrt, biased variance) followed by the consumer layer's

@@ -55,6 +55,9 @@ PROTOTYPES = {
     "qvit_unpack_int4": (_i, [_p, _i64, _i, _p, _p]),
     "qvit_gemm_set_cta_group": (_i, [_i]),
     "qvit_gemm_i8": (_i, [_p, _i64, _i, _p, _i64, _i, _i, _i, _p, _i64, C.POINTER(Epilogue), _i, _p]),
+    "qvit_split3_bf16": (_i, [_p, _i64, _i64, _i64, _i, _p, _i64, _p]),
+    "qvit_codes_to_bf16_t": (_i, [_p, _i64, _i64, _i64, _p, _i64, _p]),
+    "qvit_gemm_bf16_split": (_i, [_p, _i64, _i, _p, _i64, _i, _i, _i, _p, _i64, C.POINTER(Epilogue), _p]),
     "qvit_layernorm_quantize": (_i, [_p, _i64, _i, _p, _p, _f, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "qvit_attention_f32": (_i, [_p, _i, _i, _i, _i, _f, _p, _p]),
     "qvit_attention_f32_debug": (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _i, _p]),

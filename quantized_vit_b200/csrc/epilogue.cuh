@@ -35,14 +35,18 @@ __device__ __forceinline__ float epi_scale(const EpiParams& e) {
   return s;
 }
 
-__device__ __forceinline__ float epi_value(const EpiParams& e, int acc, float scale, int64_t m, int n) {
-  float y = (float)acc * scale;
+__device__ __forceinline__ float epi_value_f(const EpiParams& e, float acc, float scale, int64_t m, int n) {
+  float y = acc * scale;
   if (e.col_scale) y *= __ldg(e.col_scale + n);
   if (e.bias) y += __ldg(e.bias + n);
   if (e.act == QVIT_ACT_GELU) y = gelu_erf(y);
   else if (e.act == QVIT_ACT_RELU) y = fmaxf(y, 0.0f);
   if (e.residual) y += e.residual[m * e.ld_res + n];
   return y;
+}
+
+__device__ __forceinline__ float epi_value(const EpiParams& e, int acc, float scale, int64_t m, int n) {
+  return epi_value_f(e, (float)acc, scale, m, n);
 }
 
 // scalar store of one element (any kind)

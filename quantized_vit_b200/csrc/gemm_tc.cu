@@ -60,6 +60,7 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, ui
 }
 
 // y[32] for columns [n0, n0+32) of row m (dequant, col-scale, bias, activation, residual); guarded when ragged.
+template <bool FACC>   // FACC: the accumulators are fp32 (bf16 GEMM) instead of int32
 __device__ __forceinline__ void epi_compute32(EpiParams e, const uint32_t (&acc)[32], float scale, int64_t m, int n0,
                                               bool row_ok, float (&y)[32], bool skip_residual) {
   if (skip_residual) e.residual = nullptr;                  // the caller adds it from the TMA-staged tile
@@ -69,7 +70,7 @@ __device__ __forceinline__ void epi_compute32(EpiParams e, const uint32_t (&acc)
                       (!e.residual || ((reinterpret_cast<uintptr_t>(e.residual + m * e.ld_res + n0) & 15) == 0));
   if (vec_in) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) y[j] = (float)(int32_t)acc[j] * scale;
+    for (int j = 0; j < 32; ++j) y[j] = (FACC ? __uint_as_float(acc[j]) : (float)(int32_t)acc[j]) * scale;
     if (e.col_scale) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -102,16 +103,19 @@ __device__ __forceinline__ void epi_compute32(EpiParams e, const uint32_t (&acc)
   } else {
 #pragma unroll
     for (int j = 0; j < 32; ++j)
-      y[j] = (row_ok && n0 + j < e.N) ? epi_value(e, (int32_t)acc[j], scale, m, n0 + j) : 0.0f;
+      y[j] = (row_ok && n0 + j < e.N) ? epi_value_f(e, FACC ? __uint_as_float(acc[j]) : (float)(int32_t)acc[j], scale, m, n0 + j) : 0.0f;
   }
 }
 
-template <int BN, int OUT, int CG>
+// KIND 0: int8 x int8 -> int32 (tcgen05 kind::i8).  KIND 1: bf16 x bf16 -> fp32 (kind::f16) for the QAT gradient GEMMs:
+// the fp32 gradient operand arrives as three exact bf16 planes concatenated along K, the integer codes as one bf16
+// plane that is re-read for every A plane (`b_wrap` k-blocks), i.e. D = (A1 + A2 + A3) * B^T with fp32 accumulation.
+template <int BN, int OUT, int CG, int KIND>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                   const EpiParams ep, const int K, const uint32_t idesc, const int tma_store, const int res_tma,
-                  const int mma_only) {
+                  const int mma_only, const int b_wrap) {
   using S = GemmSmem<BN, CG>;
   constexpr int kStages = S::kStages;
   constexpr int kTmemCols = 2 * BN;   // 256 or 512: a power of two >= 32
@@ -190,7 +194,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           } else if (CG == 1) {
             ptx::mbar_expect_tx(full_bar(stage), S::kStageBytes);
             ptx::tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * kBK, a_row);
-            ptx::tma_load_2d(b_dst, &tmap_w, full_bar(stage), kb * kBK, w_row);
+            ptx::tma_load_2d(b_dst, &tmap_w, full_bar(stage), (kb % b_wrap) * kBK, w_row);
           } else {
             // both CTAs signal the LEADER's barrier (peer bit of the shared::cluster address cleared); the leader arms it
             // for the bytes of both.  A peer completion that overtakes the leader's expect_tx only makes the pending
@@ -198,7 +202,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             const uint32_t lead_bar = full_bar(stage) & 0xFEFFFFFFu;
             if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * S::kStageBytes);
             ptx::tma_load_2d_cg2(a_dst, &tmap_a, lead_bar, kb * kBK, a_row);
-            ptx::tma_load_2d_cg2(b_dst, &tmap_w, lead_bar, kb * kBK, w_row);
+            ptx::tma_load_2d_cg2(b_dst, &tmap_w, lead_bar, (kb % b_wrap) * kBK, w_row);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
@@ -224,8 +228,12 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 #pragma unroll
           for (int k = 0; k < kBK / kUmmaK; ++k) {
             // advance both descriptors by k*32 bytes inside the swizzle atom (address field is >>4)
-            ptx::mma_i8<CG>(d_tmem, a_desc + (uint64_t)(k * (kUmmaK >> 4)), b_desc + (uint64_t)(k * (kUmmaK >> 4)), idesc,
-                            (uint32_t)((kb | k) != 0));
+            if (KIND == 0)
+              ptx::mma_i8<CG>(d_tmem, a_desc + (uint64_t)(k * (kUmmaK >> 4)), b_desc + (uint64_t)(k * (kUmmaK >> 4)), idesc,
+                              (uint32_t)((kb | k) != 0));
+            else
+              ptx::mma_bf16<CG>(d_tmem, a_desc + (uint64_t)(k * (kUmmaK >> 4)), b_desc + (uint64_t)(k * (kUmmaK >> 4)), idesc,
+                                (uint32_t)((kb | k) != 0));
           }
           // smem slot free once these MMAs retire (in both CTAs of a pair)
           if (CG == 1) ptx::mma_commit(empty_bar(stage)); else ptx::mma_commit_cg2(empty_bar(stage), 0x3);
@@ -294,7 +302,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         }
         if (OUT == QVIT_OUT_NONE) continue;                  // main-loop benchmark mode
         if (!tma_store) {
-          if (row_ok) epi_store_chunk32(ep, &nq, r, scale, m, n0, fl);
+          if (row_ok && KIND == 0) epi_store_chunk32(ep, &nq, r, scale, m, n0, fl);   // (KIND 1 always uses the TMA path)
           continue;
         }
         // ---- math first (registers only), so that the previous TMA store of this quad drains meanwhile
@@ -304,7 +312,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           for (int j = 0; j < 32; ++j) w[j % (kChunkBytes / 4)] = r[j];      // kChunkBytes/4 == 32 here
         } else {
           float y[32];
-          epi_compute32(ep, r, scale, m, n0, row_ok, y, use_res_tma);
+          epi_compute32<KIND == 1>(ep, r, scale, m, n0, row_ok, y, use_res_tma);
           if (use_res_tma) {
             ptx::mbar_wait(res_bar(quad), res_phase);
             res_phase ^= 1u;
@@ -476,14 +484,15 @@ struct TcMaps {
   int tma_store, res_tma;
 };
 
-template <int BN, int OUT, int CG>
-static int launch_tc(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsigned, int max_ctas, cudaStream_t s) {
+template <int BN, int OUT, int CG, int KIND = 0>
+static int launch_tc(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsigned, int max_ctas, cudaStream_t s,
+                     int b_wrap = 1 << 30) {
   using S = GemmSmem<BN, CG>;
   static bool attr_set[64] = {false};
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel<BN, OUT, CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel<BN, OUT, CG, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(smem=%d): %s", S::kTotal, cudaGetErrorString(e));
       return QVIT_ERR_CUDA;
@@ -494,7 +503,7 @@ static int launch_tc(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsign
   int grid = m_tiles * n_tiles * CG;
   if (grid > max_ctas) grid = max_ctas;
   if (CG == 2) grid &= ~1;
-  const uint32_t idesc = ptx::make_idesc_i8(kBM * CG, BN, !a_unsigned, true);
+  const uint32_t idesc = KIND == 0 ? ptx::make_idesc_i8(kBM * CG, BN, !a_unsigned, true) : ptx::make_idesc_bf16_f32(kBM * CG, BN);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kGemmThreads);
@@ -507,8 +516,8 @@ static int launch_tc(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsign
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_i8_tc_kernel<BN, OUT, CG>, tm.a, tm.w, tm.out, tm.res, ep, K, idesc,
-                                     tm.tma_store, tm.res_tma, (OUT == QVIT_OUT_NONE) ? g_mma_only : 0);
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_i8_tc_kernel<BN, OUT, CG, KIND>, tm.a, tm.w, tm.out, tm.res, ep, K, idesc,
+                                     tm.tma_store, tm.res_tma, (OUT == QVIT_OUT_NONE) ? g_mma_only : 0, b_wrap);
   if (e != cudaSuccess) {
     set_error("gemm_i8_tc_kernel launch: %s", cudaGetErrorString(e));
     return QVIT_ERR_CUDA;
@@ -575,6 +584,40 @@ int gemm_tc_launch(const void* a, int64_t lda, int a_unsigned, const int8_t* w, 
   if (cg == 2) return launch_tc_kind<256, 2>(tm, ep, K, a_unsigned != 0, sms, s);
   if (bn == 256) return launch_tc_kind<256, 1>(tm, ep, K, a_unsigned != 0, sms, s);
   return launch_tc_kind<128, 1>(tm, ep, K, a_unsigned != 0, sms, s);
+}
+
+// D[M, N] (fp32) = scale * sum_p A_p[M, K] * B[N, K]^T : A holds `planes` bf16 planes side by side ([M, planes * Kp]),
+// B one bf16 plane [N, >= Kp]; Kp = K rounded up to 64 elements (one 128-byte k-block).
+int gemm_tc_launch_bf16_split(const void* a, int64_t lda, int planes, const void* b, int64_t ldb, const EpiParams& ep, int K,
+                              cudaStream_t s) {
+  const int M = ep.M, N = ep.N;
+  const int Kp = (K + 63) / 64 * 64;
+  const int sms = sm_count();
+  int bn = 256;
+  if (N <= 128 || (int64_t)((M + kBM - 1) / kBM) * ((N + 255) / 256) < sms) bn = 128;
+  TcMaps tm;
+  // byte views: the A row holds planes * Kp bf16 = 2 * planes * Kp bytes; OOB rows / k are zero filled
+  int rc = make_tmap_bytes(&tm.a, a, M, (int64_t)2 * planes * Kp, lda * 2, kBM);
+  if (rc) return rc;
+  rc = make_tmap_bytes(&tm.w, b, N, (int64_t)2 * Kp, ldb * 2, bn);
+  if (rc) return rc;
+  if ((reinterpret_cast<uintptr_t>(ep.out) & 15) || ((ep.ldo * 4) & 15)) {
+    set_error("qvit_gemm_bf16_split: output must be 16-byte aligned with a pitch that is a multiple of 4 floats");
+    return QVIT_ERR_UNSUPPORTED;
+  }
+  tm.tma_store = 1;
+  tm.res = tm.a;
+  rc = make_tmap_out(&tm.out, ep.out, M, N, ep.ldo, QVIT_OUT_F32, out_box_bytes(bn, QVIT_OUT_F32));
+  if (rc) return rc;
+  tm.res_tma = ep.residual != nullptr && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0) && (((ep.ld_res * 4) & 15) == 0);
+  if (tm.res_tma) {
+    rc = make_tmap_out(&tm.res, const_cast<float*>(ep.residual), M, N, ep.ld_res, QVIT_OUT_F32, 128);
+    if (rc) return rc;
+  }
+  const int k_bytes = 2 * planes * Kp;          // contraction length of the kernel's byte-wise K loop
+  const int b_wrap = (2 * Kp) / kBK;            // k-blocks per plane: the B coordinate wraps, A runs through all planes
+  if (bn == 256) return launch_tc<256, QVIT_OUT_F32, 1, 1>(tm, ep, k_bytes, false, sms, s, b_wrap);
+  return launch_tc<128, QVIT_OUT_F32, 1, 1>(tm, ep, k_bytes, false, sms, s, b_wrap);
 }
 
 }  // namespace qvit

@@ -1,0 +1,185 @@
+// Operand preparation for the QAT gradient GEMMs (grad_x_q = g @ w_q, grad_w_q = g^T @ x_q; the backward of the
+// F.linear in QuantizeLinear.forward, quant_layers.py:499).  The reference never quantizes the gradient g, so the int8
+// pipe cannot be used; instead g is split EXACTLY into three bf16 planes (8 + 8 + 8 mantissa bits) and the integer
+// codes (|code| <= 127, exact in bf16) become one bf16 plane, so that  (g1 + g2 + g3) * codes  on the bf16 tensor cores
+// with fp32 accumulation reproduces the fp32 product.  HBM-bound elementwise / transpose kernels.
+#include "common.cuh"
+
+namespace qvit {
+
+__device__ __forceinline__ void split3_pair_bf16(float x, float y, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(x, y);
+  const float2 af = __bfloat1622float2(a);
+  const float rx = x - af.x, ry = y - af.y;                    // exact
+  const __nv_bfloat162 b = __floats2bfloat162_rn(rx, ry);
+  const float2 bf = __bfloat1622float2(b);
+  const __nv_bfloat162 c = __floats2bfloat162_rn(rx - bf.x, ry - bf.y);
+  p1 = *reinterpret_cast<const uint32_t*>(&a);
+  p2 = *reinterpret_cast<const uint32_t*>(&b);
+  p3 = *reinterpret_cast<const uint32_t*>(&c);
+}
+
+// x [R, C] fp32 (pitch ld_x) -> out [R, 3 * Cp] bf16, plane p in columns [p * Cp, p * Cp + Cp); columns >= C are zero
+__global__ void __launch_bounds__(256)
+split3_rows_kernel(const float* __restrict__ x, int64_t R, int C, int64_t ld_x, int Cp, __nv_bfloat16* __restrict__ out) {
+  const int chunks = Cp / 8;
+  const int64_t total = R * chunks;
+  const bool vec = ((ld_x & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / chunks;
+    const int c0 = (int)(i - r * chunks) * 8;
+    float v[8];
+    const float* src = x + r * ld_x + c0;
+    if (vec && c0 + 8 <= C) {
+      const float4 a = ldg_stream4(src), b = ldg_stream4(src + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c0 + j < C) ? src[j] : 0.0f;
+    }
+    uint4 p1, p2, p3;
+    split3_pair_bf16(v[0], v[1], p1.x, p2.x, p3.x);
+    split3_pair_bf16(v[2], v[3], p1.y, p2.y, p3.y);
+    split3_pair_bf16(v[4], v[5], p1.z, p2.z, p3.z);
+    split3_pair_bf16(v[6], v[7], p1.w, p2.w, p3.w);
+    __nv_bfloat16* dst = out + r * (3ll * Cp) + c0;
+    *reinterpret_cast<uint4*>(dst) = p1;
+    *reinterpret_cast<uint4*>(dst + Cp) = p2;
+    *reinterpret_cast<uint4*>(dst + 2 * Cp) = p3;
+  }
+}
+
+// x [R, C] fp32 -> out [C, 3 * Rp] bf16 (transposed), plane p in columns [p * Rp, p * Rp + Rp); columns >= R are zero.
+// Tile = 64 rows (r) x 32 columns (c) through shared memory: coalesced 128-byte reads and 128-byte writes.
+__global__ void __launch_bounds__(256)
+split3_transpose_kernel(const float* __restrict__ x, int64_t R, int C, int64_t ld_x, int64_t Rp, __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[64][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 64;
+  const int c0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;      // 8 warps
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t r = r0 + wy * 8 + i;
+    const int c = c0 + lane;
+    tile[wy * 8 + i][lane] = (r < R && c < C) ? x[r * ld_x + c] : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cl = wy * 4 + i;                                   // output row inside the tile
+    const int c = c0 + cl;
+    if (c >= C) continue;
+    uint32_t p1, p2, p3;
+    split3_pair_bf16(tile[2 * lane][cl], tile[2 * lane + 1][cl], p1, p2, p3);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out + (int64_t)c * (3 * Rp) + r0) + lane;   // r0 is a multiple of 64
+    dst[0] = p1;
+    dst[Rp / 2] = p2;
+    dst[Rp] = p3;
+  }
+}
+
+// codes [R, C] int8 (pitch ld) -> out [C, Rp] bf16 (transposed); columns >= R are zero
+__global__ void __launch_bounds__(256)
+codes_transpose_bf16_kernel(const int8_t* __restrict__ codes, int64_t R, int C, int64_t ld, int64_t Rp,
+                            __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[64][33];
+  const int64_t r0 = (int64_t)blockIdx.y * 64;
+  const int c0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int64_t r = r0 + wy * 8 + i;
+    const int c = c0 + lane;
+    tile[wy * 8 + i][lane] = (r < R && c < C) ? (float)codes[r * ld + c] : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int cl = wy * 4 + i;
+    const int c = c0 + cl;
+    if (c >= C) continue;
+    const __nv_bfloat162 v = __floats2bfloat162_rn(tile[2 * lane][cl], tile[2 * lane + 1][cl]);
+    reinterpret_cast<uint32_t*>(out + (int64_t)c * Rp + r0)[lane] = *reinterpret_cast<const uint32_t*>(&v);
+  }
+}
+
+int gemm_tc_launch_bf16_split(const void* a, int64_t lda, int planes, const void* b, int64_t ldb, const struct EpiParams& ep, int K,
+                              cudaStream_t s);
+
+}  // namespace qvit
+
+#include "epilogue.cuh"
+using namespace qvit;
+
+extern "C" {
+
+int qvit_split3_bf16(const float* x, int64_t rows, int64_t cols, int64_t ld_x, int transpose, void* out, int64_t plane_cols,
+                     qvit_stream_t stream) {
+  QVIT_REQUIRE(x && out && rows > 0 && cols > 0 && ld_x >= cols, "qvit_split3_bf16: bad argument");
+  QVIT_REQUIRE(plane_cols % 64 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0, "qvit_split3_bf16: plane_cols must be a multiple of 64");
+  QVIT_REQUIRE(cols < (1ll << 31) && rows < (1ll << 40), "qvit_split3_bf16: too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!transpose) {
+    QVIT_REQUIRE(plane_cols >= cols, "qvit_split3_bf16: plane_cols < cols");
+    const int64_t total = rows * (plane_cols / 8);
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 8;
+    if (blocks > cap) blocks = cap;
+    split3_rows_kernel<<<(int)blocks, 256, 0, s>>>(x, rows, (int)cols, ld_x, (int)plane_cols, reinterpret_cast<__nv_bfloat16*>(out));
+  } else {
+    QVIT_REQUIRE(plane_cols >= rows, "qvit_split3_bf16: plane_cols < rows (transposed)");
+    dim3 grid((unsigned)((cols + 31) / 32), (unsigned)(plane_cols / 64));
+    QVIT_REQUIRE(grid.y <= 65535u, "qvit_split3_bf16: too many rows for the transposed form");
+    split3_transpose_kernel<<<grid, 256, 0, s>>>(x, rows, (int)cols, ld_x, plane_cols, reinterpret_cast<__nv_bfloat16*>(out));
+  }
+  return check_launch("qvit_split3_bf16");
+}
+
+int qvit_codes_to_bf16_t(const int8_t* codes, int64_t rows, int64_t cols, int64_t ld, void* out, int64_t out_cols,
+                         qvit_stream_t stream) {
+  QVIT_REQUIRE(codes && out && rows > 0 && cols > 0 && ld >= cols, "qvit_codes_to_bf16_t: bad argument");
+  QVIT_REQUIRE(out_cols % 64 == 0 && out_cols >= rows && (reinterpret_cast<uintptr_t>(out) & 3) == 0,
+               "qvit_codes_to_bf16_t: out_cols must be a multiple of 64 and >= rows");
+  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)(out_cols / 64));
+  QVIT_REQUIRE(grid.y <= 65535u, "qvit_codes_to_bf16_t: too many rows");
+  codes_transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(codes, rows, (int)cols, ld, out_cols,
+                                                                     reinterpret_cast<__nv_bfloat16*>(out));
+  return check_launch("qvit_codes_to_bf16_t");
+}
+
+int qvit_gemm_bf16_split(const void* a_planes, int64_t lda, int planes, const void* b, int64_t ldb, int M, int N, int K,
+                         float* out, int64_t ldo, const qvit_epilogue_t* epi, qvit_stream_t stream) {
+  QVIT_REQUIRE(a_planes && b && out && epi, "qvit_gemm_bf16_split: null pointer");
+  QVIT_REQUIRE(M > 0 && N > 0 && K > 0 && planes >= 1 && planes <= 3 && ldo >= N, "qvit_gemm_bf16_split: bad shape");
+  const int Kp = (K + 63) / 64 * 64;
+  QVIT_REQUIRE(lda >= (int64_t)planes * Kp && ldb >= Kp && (lda % 8) == 0 && (ldb % 8) == 0,
+               "qvit_gemm_bf16_split: lda >= planes*Kp, ldb >= Kp (Kp = K rounded up to 64) and both multiples of 8 elements");
+  QVIT_REQUIRE(((reinterpret_cast<uintptr_t>(a_planes) | reinterpret_cast<uintptr_t>(b)) & 15) == 0, "qvit_gemm_bf16_split: alignment");
+  QVIT_REQUIRE(epi->out_kind == QVIT_OUT_F32 && epi->act == QVIT_ACT_NONE, "qvit_gemm_bf16_split: fp32 output without activation only");
+  int dev = 0, maj = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev);
+  if (maj != 10) {
+    set_error("qvit_gemm_bf16_split: needs sm_100");
+    return QVIT_ERR_UNSUPPORTED;
+  }
+  EpiParams ep;
+  ep.out_kind = QVIT_OUT_F32;
+  ep.act = QVIT_ACT_NONE;
+  ep.scale_const = epi->scale_const;
+  ep.scale_a = epi->scale_a;
+  ep.scale_w = epi->scale_w;
+  ep.col_scale = epi->col_scale;
+  ep.bias = epi->bias;
+  ep.residual = epi->residual;
+  ep.ld_res = epi->ld_res;
+  ep.next_d = ep.next_qm = ep.next_t = nullptr;
+  ep.flags = epi->flags;
+  ep.out = out;
+  ep.ldo = ldo;
+  ep.M = M;
+  ep.N = N;
+  return gemm_tc_launch_bf16_split(a_planes, lda, planes, b, ldb, ep, K, (cudaStream_t)stream);
+}
+
+}  // extern "C"

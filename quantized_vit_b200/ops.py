@@ -17,7 +17,7 @@ from ._lib import (QVIT_ACT_GELU, QVIT_ACT_NONE, QVIT_ACT_RELU, QVIT_GEMM_AUTO, 
                    QVIT_OUT_BF16, QVIT_OUT_F32, QVIT_OUT_I8, QVIT_OUT_I32, QVIT_OUT_NONE)
 
 __all__ = ["pad16", "quantize_sym", "fake_quantize_sym", "sym_backward", "absmax", "im2col_quantize_sym", "gemm_i8",
-           "layernorm_quantize", "attention_f32", "attention_f32_supported", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "bn_fold",
+           "layernorm_quantize", "attention_f32", "attention_f32_supported", "split3_bf16", "codes_to_bf16_t", "gemm_bf16_split", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "bn_fold",
            "bn_act_quantize_int", "pack_int4", "unpack_int4", "new_flags", "QVIT_OUT_I32", "QVIT_OUT_F32",
            "QVIT_OUT_BF16", "QVIT_OUT_I8", "QVIT_OUT_NONE", "QVIT_ACT_NONE", "QVIT_ACT_GELU", "QVIT_ACT_RELU", "QVIT_GEMM_AUTO",
            "QVIT_GEMM_TCGEN05", "QVIT_GEMM_SIMT"]
@@ -250,6 +250,49 @@ def gemm_i8(a: torch.Tensor, w: torch.Tensor, K: int, N: Optional[int] = None, *
     epi.flags = _lib.ptr(flags)
     _lib.check(_lib.lib().qvit_gemm_i8(_lib.ptr(a), lda, 1 if a.dtype == torch.uint8 else 0, _lib.ptr(w), ldw, M, N, int(K),
                                        _lib.ptr(out), ldo, C.byref(epi), backend, _lib.stream()), "qvit_gemm_i8")
+    return out
+
+
+def _pad64(n: int) -> int:
+    return (int(n) + 63) // 64 * 64
+
+
+def split3_bf16(x: torch.Tensor, transpose: bool = False) -> torch.Tensor:
+    """Exact 3-way bf16 split of a 2-D fp32 matrix, planes side by side: [R, 3*pad64(C)] or (transposed) [C, 3*pad64(R)]."""
+    x = _f32c(x, "split3_bf16")
+    R, Cc = x.shape
+    pc = _pad64(R if transpose else Cc)
+    out = torch.empty((Cc if transpose else R, 3 * pc), dtype=torch.bfloat16, device=x.device)
+    _lib.check(_lib.lib().qvit_split3_bf16(_lib.ptr(x), R, Cc, x.stride(0), 1 if transpose else 0, _lib.ptr(out), pc, _lib.stream()),
+               "qvit_split3_bf16")
+    return out
+
+
+def codes_to_bf16_t(codes: torch.Tensor, cols: int) -> torch.Tensor:
+    """int8 codes [R, >=cols] -> bf16 [cols, pad64(R)] (transposed, zero padded)."""
+    _lib.require_cuda(codes)
+    R = codes.shape[0]
+    out = torch.empty((cols, _pad64(R)), dtype=torch.bfloat16, device=codes.device)
+    _lib.check(_lib.lib().qvit_codes_to_bf16_t(_lib.ptr(codes), R, int(cols), codes.stride(0), _lib.ptr(out), out.shape[1], _lib.stream()),
+               "qvit_codes_to_bf16_t")
+    return out
+
+
+def gemm_bf16_split(a_planes: torch.Tensor, b: torch.Tensor, K: int, planes: int = 3, scale=None,
+                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M, N] fp32 = |scale| * sum_p A_p[M, :K] @ B[N, :K]^T on tcgen05 kind::f16 (fp32 accumulation in TMEM)."""
+    _lib.require_cuda(a_planes, b)
+    M, N = a_planes.shape[0], b.shape[0]
+    if out is None:
+        out = torch.empty((M, N), dtype=torch.float32, device=a_planes.device)
+    epi = _lib.Epilogue()
+    epi.out_kind, epi.act, epi.scale_const = QVIT_OUT_F32, QVIT_ACT_NONE, 1.0
+    keep = None
+    if scale is not None:
+        keep = _scalar_param(scale, a_planes.device, "scale")
+        epi.scale_a = keep.data_ptr()
+    _lib.check(_lib.lib().qvit_gemm_bf16_split(_lib.ptr(a_planes), a_planes.stride(0), planes, _lib.ptr(b), b.stride(0), M, N, int(K),
+                                               _lib.ptr(out), out.stride(0), C.byref(epi), _lib.stream()), "qvit_gemm_bf16_split")
     return out
 
 

@@ -55,6 +55,7 @@ class QuantizationMode(Enum):          # QL:27-29
 # ---------------------------------------------------------------------------------------------------
 _flag_words = {}
 EAGER_NAN_CHECK = False
+TENSOR_CORE_BACKWARD = True     # QAT gradient GEMMs on tcgen05 (exact bf16 split); False = library fp32 GEMMs
 
 
 def _flags_for(device: torch.device) -> torch.Tensor:
@@ -165,8 +166,9 @@ class QuantLinearFunction(torch.autograd.Function):
 
     forward : activation and weight codes (K2/K1) -> exact int8 tensor-core GEMM -> fp32 dequant + bias (K3).  This equals
               F.linear(x_q, w_q, bias) of the reference up to fp32 rounding, without materialising x_q / w_q.
-    backward: grad_x_q = g @ w_q and grad_w_q = g^T @ x_q (the gradient operand is never quantized upstream, so these two
-              stay fp32 library GEMMs for now), then ONE fused kernel per quantizer for the STE mask and the step-size /
+    backward: grad_x_q = g @ w_q and grad_w_q = g^T @ x_q: the gradient operand is never quantized upstream, so it is split
+              exactly into three bf16 planes and multiplied with the integer codes on tcgen05 kind::f16 (fp32 accumulation,
+              qvit_gemm_bf16_split); then ONE fused kernel per quantizer for the STE mask and the step-size /
               range / exponent gradient reductions (K6).  Saved for backward: x, W and the int8 codes (1 B/element)."""
 
     @staticmethod
@@ -193,12 +195,23 @@ class QuantLinearFunction(torch.autograd.Function):
         K, N = weight.shape[1], weight.shape[0]
         g2 = g.reshape(-1, N).contiguous()
         flags = _flags_for(g.device)
-        # fake-quant values from the saved codes: value = code * |d| (exactly what the reference forward produced)
-        x_q = a_codes[:, :K].to(torch.float32) * d_a.detach().abs()
-        w_q = w_codes[:, :K].to(torch.float32) * d_w.detach().abs()
-        grad_xq = g2 @ w_q
-        grad_wq = g2.t() @ x_q
-        grad_x, s_a = ops.sym_backward(x2, grad_xq, d_a, qm_a, t_a, ctx.clip_a, want_grad_x=ctx.needs_input_grad[0], flags=flags)
+        M = g2.shape[0]
+        if TENSOR_CORE_BACKWARD and K % 4 == 0:
+            # grad_x_q = g @ w_q = |d_w| * (g1 + g2 + g3) @ codes_w   and   grad_w_q = g^T @ x_q = |d_a| * (g^T planes) @ codes_a:
+            # exact 3-way bf16 split of g, integer codes as bf16, tcgen05 kind::f16 with fp32 accumulation
+            grad_xq = ops.gemm_bf16_split(ops.split3_bf16(g2), ops.codes_to_bf16_t(w_codes, K), N, scale=d_w) \
+                if ctx.needs_input_grad[0] else None
+            grad_wq = ops.gemm_bf16_split(ops.split3_bf16(g2, transpose=True), ops.codes_to_bf16_t(a_codes, K), M, scale=d_a)
+        else:
+            # fake-quant values from the saved codes: value = code * |d| (exactly what the reference forward produced)
+            x_q = a_codes[:, :K].to(torch.float32) * d_a.detach().abs()
+            w_q = w_codes[:, :K].to(torch.float32) * d_w.detach().abs()
+            grad_xq = g2 @ w_q
+            grad_wq = g2.t() @ x_q
+        if grad_xq is None:
+            grad_x, s_a = None, torch.zeros(3, dtype=torch.float32, device=g.device)
+        else:
+            grad_x, s_a = ops.sym_backward(x2, grad_xq, d_a, qm_a, t_a, ctx.clip_a, want_grad_x=True, flags=flags)
         grad_w, s_w = ops.sym_backward(weight.detach(), grad_wq, d_w, qm_w, t_w, ctx.clip_w, flags=flags)
         grad_b = g2.sum(0) if ctx.has_bias else None
         if EAGER_NAN_CHECK:

@@ -160,3 +160,32 @@ def test_cta_pair_mode_bit_exact(ops, cta_group, M, N, K):
         assert torch.equal(c8, c8_ref)
     finally:
         L.qvit_gemm_set_cta_group(0)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 96, 200), (2000, 768, 3072), (768, 768, 25216), (130, 260, 64)])
+def test_bf16_split_gemm_matches_fp64(ops, M, N, K):
+    """QAT gradient GEMM: fp32 operand as three exact bf16 planes x integer codes as bf16, fp32 accumulation in TMEM.
+    The split is exact; what remains is the tensor core's fp32 accumulation (truncating adds), which grows with the
+    contraction length: measured 1e-6 (K=200) .. 4e-5 (K=25216) of max|ref|, against the 1e-3 the gradients are held to
+     - a plain fp32 GEMM scores ~1e-6, single-pass TF32 ~5e-4, bf16 ~4e-3.  Bar: 1e-4."""
+    g = torch.Generator().manual_seed(M + N + K)
+    x = torch.randn(M, K, generator=g).cuda() * 0.37
+    codes = torch.randint(-127, 128, (N, K + 16), generator=g, dtype=torch.int64).to(torch.int8).cuda()
+    ref = (x.double() @ codes[:, :K].double().t()) * 0.0123
+    # forward-like: contraction along the columns of both operands
+    a = ops.split3_bf16(x)                                   # [M, 3 * pad64(K)]
+    assert a.shape == (M, 3 * ((K + 63) // 64 * 64))
+    parts = a.float().view(M, 3, -1)[:, :, :K].sum(1)
+    assert torch.equal(parts, x), "the three bf16 planes must add up to the fp32 value exactly"
+    b = codes[:, :K].to(torch.bfloat16)
+    bp = torch.zeros((N, (K + 63) // 64 * 64), dtype=torch.bfloat16, device="cuda")
+    bp[:, :K] = b
+    out = ops.gemm_bf16_split(a, bp, K, scale=torch.tensor([0.0123]))
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    print(f"bf16-split GEMM M={M} N={N} K={K}: max-norm error {err:.2e}")
+    assert err <= 1e-4, err
+    # transposed forms used by the backward: x^T planes and codes^T
+    at = ops.split3_bf16(x, transpose=True)                  # [K, 3 * pad64(M)]
+    assert torch.equal(at.float().view(K, 3, -1)[:, :, :M].sum(1), x.t())
+    ct = ops.codes_to_bf16_t(codes, K)                       # [K, pad64(N)]
+    assert torch.equal(ct[:, :N].float(), codes[:, :K].float().t()) and float(ct[:, N:].abs().sum()) == 0.0
