@@ -162,6 +162,8 @@ typedef struct qvit_epilogue {
   const float* scale_a;    /* (1,) device: |.| is taken  (d_quant_act)  or NULL = 1                    */
   const float* scale_w;    /* (1,) device: |.| is taken  (d_quant_wt)   or NULL = 1                    */
   float scale_const;       /* host multiplier (1.0; 1/(7*15) for UltraNet codes)                      */
+  int32_t acc_abs_max;     /* caller's promise |accumulator| <= acc_abs_max (sat_a * sat_w * K), 0 = unknown.
+                              Below 2^22 the epilogue converts int32 -> fp32 without the conversion unit.  */
   const float* col_scale;  /* [N] per-output-channel multiplier (folded BN) or NULL                    */
   const float* bias;       /* [N] or NULL                                                              */
   const float* residual;   /* [M, ld_res] fp32 added after act, or NULL                                */
@@ -176,6 +178,9 @@ typedef struct qvit_epilogue {
 /* tile mode of the tensor-core backend: 0 = automatic (CTA pairs, tcgen05 cta_group::2, once the problem has a full
  * wave of [256 x 256] tiles), 1 = single-CTA [128 x BN] tiles, 2 = CTA pairs whenever BN = 256.  Process-wide; tests / benches. */
 int qvit_gemm_set_cta_group(int cta_group);
+/* developer hook: with mode + 50 the tensor-core kernel stamps clock64 timelines of CTA 0 (8 slots per tile, see
+ * gemm_tc.cu); copies up to n stamps to host memory (synchronises the device), returns the count or -1. */
+int qvit_gemm_read_profile(long long* host, int n);
 
 int qvit_gemm_i8(const void* a, int64_t lda, int a_unsigned,
                  const int8_t* w, int64_t ldw,

@@ -28,7 +28,7 @@ _f = C.c_float
 class Epilogue(C.Structure):
     """struct qvit_epilogue (include/qvit_b200.h)."""
     _fields_ = [("out_kind", C.c_int32), ("act", C.c_int32), ("scale_a", _p), ("scale_w", _p),
-                ("scale_const", C.c_float), ("col_scale", _p), ("bias", _p), ("residual", _p),
+                ("scale_const", C.c_float), ("acc_abs_max", C.c_int32), ("col_scale", _p), ("bias", _p), ("residual", _p),
                 ("ld_res", C.c_int64), ("next_d", _p), ("next_qm", _p), ("next_t", _p), ("flags", _p)]
 
 
@@ -54,6 +54,7 @@ PROTOTYPES = {
     "qvit_pack_int4": (_i, [_p, _i64, _p, _p]),
     "qvit_unpack_int4": (_i, [_p, _i64, _i, _p, _p]),
     "qvit_gemm_set_cta_group": (_i, [_i]),
+    "qvit_gemm_read_profile": (_i, [_p, _i]),
     "qvit_gemm_i8": (_i, [_p, _i64, _i, _p, _i64, _i, _i, _i, _p, _i64, C.POINTER(Epilogue), _i, _p]),
     "qvit_split3_bf16": (_i, [_p, _i64, _i64, _i64, _i, _p, _i64, _p]),
     "qvit_codes_to_bf16_t": (_i, [_p, _i64, _i64, _i64, _p, _i64, _p]),

@@ -71,10 +71,19 @@ __device__ __forceinline__ int sym_code(float x, const SymParams& p, int& flags)
   return x < 0.0f ? -c : (x > 0.0f ? c : 0);
 }
 
-// Same code, ~4x fewer instructions for the hot epilogue: k = rint(y * (1/d)) agrees with rint(RN(y/d)) unless the
-// quotient lies within 2^-21 relative of a rounding boundary, in which case the exact IEEE division decides.
-// (|RN(y * RN(1/d)) - RN(y/d)| <= 1.5 * 2^-23 |q|, so the 2^-21 guard band is conservative.)  Saturation:
-// for q_m > 0, "|y| >= q_m -> sat" equals clamping to +-sat because RN division and rint are monotone.
+// Same code, ~4x fewer instructions and NO conversion-unit (XU) instruction for the hot epilogue:
+//   q  = y * RN(1/d)                        differs from the reference's RN(y/d) by at most 3 * 2^-24 |q|
+//   qc = clamp(q, -sat, +sat)               for q_m > 0, "|y| >= q_m -> sat" equals clamping: RN division and rint are monotone,
+//                                           and rint(clamp(q)) == clamp(rint(q)) because sat is an integer
+//   t  = qc + 1.5 * 2^23                    the fp32 add rounds qc to the nearest integer, ties to even, exactly like rintf
+//                                           for |qc| <= 127; the low BYTE of t's bit pattern is the two's-complement int8 code
+//   k  = t - 1.5 * 2^23                     the rounded value back as a float (exact)
+//   m  = |q| * 3e-7 + |qc - k|              >= 0.5 (or NaN) <=> q lies within the 3 * 2^-24 |q| error band (+ the fma's own
+//                                           2^-25 rounding) of a rounding boundary: the exact IEEE division has to decide.
+// Callers fold as_uint(m) into a running unsigned max (NaN = 0x7fffffff sorts above every finite value) and redo only
+// the doubtful elements with sym_code().
+constexpr float kRoundMagic = 12582912.0f;      // 1.5 * 2^23
+constexpr uint32_t kDoubtBits = 0x3F000000u;    // bit pattern of 0.5f
 struct FastQ {
   float inv_d, d, sat;
   int generic;     // non-linear quantizer, q_m <= 0 or codes beyond int8: use the general path
@@ -87,35 +96,37 @@ __device__ __forceinline__ FastQ make_fastq(const SymParams& p) {
   f.generic = (p.nonlinear || !(p.qm > 0.0f) || !(p.sat <= 127.0f) || !(p.d > 0.0f)) ? 1 : 0;
   return f;
 }
-// branch-free fast code; `doubt` is OR-ed with 1 when the exact division has to decide (caller redoes the element)
-__device__ __forceinline__ int sym_code_fast(float y, const FastQ& f, int& doubt) {
+// returns t (code in the low byte); m_bits = as_uint(m)
+__device__ __forceinline__ float sym_code_fast(float y, const FastQ& f, uint32_t& m_bits) {
   const float q = y * f.inv_d;
-  float k = rintf(q);
-  const float m = fmaf(fabsf(q), 4.8e-7f, fabsf(q - k));      // distance to the rounding boundary is 0.5 - |q - k|
-  doubt |= !(m < 0.5f) ? 1 : 0;                                // also true for NaN
-  k = fminf(fmaxf(k, -f.sat), f.sat);
-  return __float2int_rn(k);
+  const float qc = fminf(fmaxf(q, -f.sat), f.sat);
+  const float t = qc + kRoundMagic;
+  const float k = t - kRoundMagic;
+  m_bits = __float_as_uint(fmaf(fabsf(q), 3.0e-7f, fabsf(qc - k)));
+  return t;
 }
-
-// four codes packed little-endian into one word: fast path + exact redo when any of the four is in doubt
+// low bytes of four 32-bit words -> one little-endian word (3 PRMT)
+__device__ __forceinline__ uint32_t pack4_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
 __device__ __forceinline__ uint32_t pack4_i8_fwd(int a, int b, int c, int d);
+
+// four codes packed little-endian into one word: fast path + exact redo of the elements in doubt
 __device__ __forceinline__ uint32_t sym_codes4(float x0, float x1, float x2, float x3, const SymParams& p, const FastQ& f,
                                                int& flags) {
-  int doubt = f.generic;
-  int c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-  if (!f.generic) {
-    c0 = sym_code_fast(x0, f, doubt);
-    c1 = sym_code_fast(x1, f, doubt);
-    c2 = sym_code_fast(x2, f, doubt);
-    c3 = sym_code_fast(x3, f, doubt);
+  if (f.generic) return pack4_i8_fwd(sym_code(x0, p, flags), sym_code(x1, p, flags), sym_code(x2, p, flags), sym_code(x3, p, flags));
+  uint32_t m0, m1, m2, m3;
+  uint32_t t0 = __float_as_uint(sym_code_fast(x0, f, m0));
+  uint32_t t1 = __float_as_uint(sym_code_fast(x1, f, m1));
+  uint32_t t2 = __float_as_uint(sym_code_fast(x2, f, m2));
+  uint32_t t3 = __float_as_uint(sym_code_fast(x3, f, m3));
+  if (max(max(m0, m1), max(m2, m3)) >= kDoubtBits) {
+    if (m0 >= kDoubtBits) t0 = (uint32_t)sym_code(x0, p, flags);
+    if (m1 >= kDoubtBits) t1 = (uint32_t)sym_code(x1, p, flags);
+    if (m2 >= kDoubtBits) t2 = (uint32_t)sym_code(x2, p, flags);
+    if (m3 >= kDoubtBits) t3 = (uint32_t)sym_code(x3, p, flags);
   }
-  if (doubt) {
-    c0 = sym_code(x0, p, flags);
-    c1 = sym_code(x1, p, flags);
-    c2 = sym_code(x2, p, flags);
-    c3 = sym_code(x3, p, flags);
-  }
-  return pack4_i8_fwd(c0, c1, c2, c3);
+  return pack4_low_bytes(t0, t1, t2, t3);
 }
 
 // fake-quantized value exactly as the reference returns it: sign(x) * (d * round(p/d))
@@ -128,24 +139,128 @@ __device__ __forceinline__ float sym_value(float x, const SymParams& p) {
 
 __device__ __forceinline__ float gelu_erf(float x) {
   // torch.nn.GELU() default ('none'): x * Phi(x), Phi(x) = 0.5 * (1 + erf(x / sqrt(2)))   (vit_model.py:173).
-  // Single-branch evaluation: h(|x|) = 0.5 * erfc(|x| / sqrt(2)) = exp2(P(t)), t = min(|x| / sqrt(2), 4.2), P a degree-8
-  // minimax fit of log2(h) weighted by h * max(1, |x|); Phi = h for x < 0 and 1 - h otherwise.  Max |error| of the
-  // result against float64 over [-8, 8]: 3.8e-7 absolute, 1.14e-7 relative to max(1, |x|) - the same as the
-  // erf form evaluated in fp32 (4.5e-7 / 1.07e-7) at half the instructions (8 FFMA + 1 MUFU.EX2 instead of ~28).
-  const float t = fminf(fabsf(x) * 0.70710678118654752440f, 4.2f);
-  float p = -3.6413832276593894e-05f;
-  p = fmaf(p, t, 0.000372989394236356f);
-  p = fmaf(p, t, -0.0012582261115312576f);
-  p = fmaf(p, t, -0.0011454012710601091f);
-  p = fmaf(p, t, 0.02857113443315029f);
-  p = fmaf(p, t, -0.1486237645149231f);
-  p = fmaf(p, t, -0.9183861017227173f);
-  p = fmaf(p, t, -1.62791109085083f);
+  // Single-branch evaluation: h(|x|) = 0.5 * erfc(|x| / sqrt(2)) = exp2(P(t)), t = min(|x|, 4.2 * sqrt(2)), P a degree-8
+  // minimax fit of log2(h) weighted by h * max(1, |x|) (coefficients pre-scaled by powers of 1/sqrt(2)); then
+  // x * Phi(x) = max(x, 0) - |x| * h for either sign.  Max |error| against float64 over [-8, 8] (tools/gelu_fit_check.py):
+  // 2.5e-7 absolute, 8.4e-8 relative to max(1, |x|) - better than the erf form evaluated in fp32 (4.5e-7 / 1.06e-7) at
+  // 11 instructions (FMNMX, 8 FFMA, MUFU.EX2, FMNMX, FFMA) instead of ~28.
+  const float t = fminf(fabsf(x), 5.939696788787842f);
+  float p = -2.2758645172871184e-06f;
+  p = fmaf(p, t, 3.296791692264378e-05f);
+  p = fmaf(p, t, -0.0001572782639414072f);
+  p = fmaf(p, t, -0.00020248025248292834f);
+  p = fmaf(p, t, 0.007142783608287573f);
+  p = fmaf(p, t, -0.052546434104442596f);
+  p = fmaf(p, t, -0.45919305086135864f);
+  p = fmaf(p, t, -1.1511069536209106f);
   p = fmaf(p, t, -0.9999999403953552f);
   float h;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(p));
-  const float phi = (x < 0.0f) ? h : 1.0f - h;
-  return x * phi;
+  float r;                                    // max(x, 0) that keeps NaN (fmaxf would drop it) and +inf
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(0.0f));
+  return fmaf(-t, h, r);                      // t == |x| wherever h is not negligible (|x| <= 5.94)
+}
+
+// ---- packed fp32 pairs: FFMA2 / FADD2 / FMUL2 of sm_100 process two elements per issue slot ------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float a, float b) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 pk1(float a) { return pk2(a, a); }
+__device__ __forceinline__ void unpk2(f32x2 p, float& a, float& b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(p)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// gelu_erf() on a pair, bit-identical to the scalar form: the polynomial runs in t' = -min(|x|, 5.94) with the odd
+// coefficients negated (every Horner step is the exact mirror image), so that the last step is fma(t', h, max(x, 0)).
+__device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
+  float x0, x1;
+  unpk2(x, x0, x1);
+  const f32x2 t = pk2(fmaxf(-fabsf(x0), -5.939696788787842f), fmaxf(-fabsf(x1), -5.939696788787842f));
+  f32x2 p = pk1(-2.2758645172871184e-06f);
+  p = fma2(p, t, pk1(-3.296791692264378e-05f));
+  p = fma2(p, t, pk1(-0.0001572782639414072f));
+  p = fma2(p, t, pk1(0.00020248025248292834f));
+  p = fma2(p, t, pk1(0.007142783608287573f));
+  p = fma2(p, t, pk1(0.052546434104442596f));
+  p = fma2(p, t, pk1(-0.45919305086135864f));
+  p = fma2(p, t, pk1(1.1511069536209106f));
+  p = fma2(p, t, pk1(-0.9999999403953552f));
+  float p0, p1, h0, h1, r0, r1;
+  unpk2(p, p0, p1);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h0) : "f"(p0));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(p1));
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r0) : "f"(x0), "f"(0.0f));
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r1) : "f"(x1), "f"(0.0f));
+  return fma2(t, pk2(h0, h1), pk2(r0, r1));
+}
+
+// Pair form of the fast quantizer for the GEMM epilogue (no conversion-unit instruction, 2 FFMA2-slots per element):
+//   ta = fma(y, inv_hi, 1.5 * 2^23), tb = fma(y, inv_lo, 1.5 * 2^23),  inv_hi/lo = RN(1/d) * (1 +- 3e-7)
+// each fma rounds the exact product to the nearest integer (ties to even).  The reference's quotient RN(y / d) lies
+// strictly between y * inv_lo and y * inv_hi (both margins exceed 2^-24 after the roundings of the constants), so
+// ta == tb means rint(RN(y / d)) is that integer; ta != tb (or NaN / inf, caught because (ta - tb)^2 is then NaN) sends
+// the whole 32-column chunk of the warp to the exact path.  Codes = low byte of clamp(ta) (saturation == clamp, q_m > 0).
+struct FastQ2 {
+  f32x2 inv_hi, inv_lo;
+  float t_lo, t_hi;        // 1.5 * 2^23 -+ sat
+  float inv_d, d;
+  int generic;
+};
+__device__ __forceinline__ FastQ2 make_fastq2(const SymParams& p) {
+  FastQ2 f;
+  const float inv_d = __fdiv_rn(1.0f, p.d);
+  f.inv_hi = pk1(fmaf(inv_d, 3.0e-7f, inv_d));
+  f.inv_lo = pk1(fmaf(inv_d, -3.0e-7f, inv_d));
+  f.t_lo = kRoundMagic - p.sat;
+  f.t_hi = kRoundMagic + p.sat;
+  f.inv_d = inv_d;
+  f.d = p.d;
+  f.generic = (p.nonlinear || !(p.qm > 0.0f) || !(p.sat <= 127.0f) || !(p.d > 1.0e-10f) || !(p.d < 1.0e10f)) ? 1 : 0;
+  return f;
+}
+// Exact code of one element without the division unit, for the elements the interval test could not decide:
+// Markstein's correction (q' = q + (y - q d) * RN(1/d), residual exact in an fma) applied twice turns q0 = RN(y * RN(1/d))
+// into the correctly rounded quotient RN(y / d) - the first step makes q faithful, the second is then exact by
+// Markstein's theorem (no overflow / underflow: callers guarantee 1e-10 < d < 1e10 and |y| < 1e30) - and the add of
+// 1.5 * 2^23 rounds it to the nearest integer, ties to even, like torch.round.  Returns the clamped t (code in the low byte).
+__device__ __forceinline__ float sym_t_exact(float y, const FastQ2& f) {
+  const float q0 = y * f.inv_d;
+  const float q1 = fmaf(fmaf(-q0, f.d, y), f.inv_d, q0);
+  const float q2 = fmaf(fmaf(-q1, f.d, y), f.inv_d, q1);
+  return fminf(fmaxf(q2 + kRoundMagic, f.t_lo), f.t_hi);
+}
+// four elements (two pairs) -> one word of four int8 codes; dacc accumulates (ta - tb)^2
+__device__ __forceinline__ uint32_t sym_codes4_fast2(f32x2 y01, f32x2 y23, const FastQ2& f, f32x2& dacc) {
+  const f32x2 magic = pk1(kRoundMagic), mone = pk1(-1.0f);
+  const f32x2 ta01 = fma2(y01, f.inv_hi, magic), tb01 = fma2(y01, f.inv_lo, magic);
+  const f32x2 ta23 = fma2(y23, f.inv_hi, magic), tb23 = fma2(y23, f.inv_lo, magic);
+  const f32x2 d01 = fma2(tb01, mone, ta01), d23 = fma2(tb23, mone, ta23);
+  dacc = fma2(d01, d01, dacc);
+  dacc = fma2(d23, d23, dacc);
+  float a0, a1, a2, a3;
+  unpk2(ta01, a0, a1);
+  unpk2(ta23, a2, a3);
+  a0 = fminf(fmaxf(a0, f.t_lo), f.t_hi);
+  a1 = fminf(fmaxf(a1, f.t_lo), f.t_hi);
+  a2 = fminf(fmaxf(a2, f.t_lo), f.t_hi);
+  a3 = fminf(fmaxf(a3, f.t_lo), f.t_hi);
+  return pack4_low_bytes(__float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(a3));
 }
 
 // ---- warp / block reductions -------------------------------------------------------------------

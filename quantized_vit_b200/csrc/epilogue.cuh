@@ -1,5 +1,5 @@
 // Fused GEMM/conv epilogue shared by every integer-contraction kernel (tcgen05, SIMT, direct conv):
-//   y = act( float(acc) * (|d_a| * |d_w| * scale_const) * col_scale[n] + bias[n] ) + residual[m, n]
+//   y = act( fma(float(acc), (|d_a| * |d_w| * scale_const) * col_scale[n], bias[n]) ) + residual[m, n]
 // followed by the store in the requested kind (raw int32 / fp32 / bf16 / int8 re-quantised with the
 // consumer layer's quantizer).  Replaces the fp32 tail of QuantizeLinear.forward (quant_layers.py:499:
 // F.linear adds the bias), nn.GELU of Mlp.forward (vit_model.py:173), the residual adds of Block.forward
@@ -13,6 +13,7 @@ struct EpiParams {
   int out_kind;
   int act;
   float scale_const;
+  int acc_abs_max;
   const float* scale_a;
   const float* scale_w;
   const float* col_scale;
@@ -36,9 +37,10 @@ __device__ __forceinline__ float epi_scale(const EpiParams& e) {
 }
 
 __device__ __forceinline__ float epi_value_f(const EpiParams& e, float acc, float scale, int64_t m, int n) {
-  float y = acc * scale;
-  if (e.col_scale) y *= __ldg(e.col_scale + n);
-  if (e.bias) y += __ldg(e.bias + n);
+  // one canonical rounding sequence for every backend: s = scale * col_scale[n], y = fma(acc, s, bias[n])
+  float s = scale;
+  if (e.col_scale) s *= __ldg(e.col_scale + n);
+  float y = e.bias ? fmaf(acc, s, __ldg(e.bias + n)) : acc * s;
   if (e.act == QVIT_ACT_GELU) y = gelu_erf(y);
   else if (e.act == QVIT_ACT_RELU) y = fmaxf(y, 0.0f);
   if (e.residual) y += e.residual[m * e.ld_res + n];
@@ -87,21 +89,28 @@ __device__ __forceinline__ void epi_store_chunk32(const EpiParams& e, const SymP
                       (!e.col_scale || ((reinterpret_cast<uintptr_t>(e.col_scale + n0) & 15) == 0)) &&
                       (!e.residual || ((reinterpret_cast<uintptr_t>(e.residual + m * e.ld_res + n0) & 15) == 0));
   if (vec_in) {
+    float sc[32];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) y[j] = (float)(int32_t)acc[j] * scale;
+    for (int j = 0; j < 32; ++j) sc[j] = scale;
     if (e.col_scale) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 c = __ldg(reinterpret_cast<const float4*>(e.col_scale + n0) + j);
-        y[4 * j] *= c.x; y[4 * j + 1] *= c.y; y[4 * j + 2] *= c.z; y[4 * j + 3] *= c.w;
+        sc[4 * j] *= c.x; sc[4 * j + 1] *= c.y; sc[4 * j + 2] *= c.z; sc[4 * j + 3] *= c.w;
       }
     }
     if (e.bias) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const float4 c = __ldg(reinterpret_cast<const float4*>(e.bias + n0) + j);
-        y[4 * j] += c.x; y[4 * j + 1] += c.y; y[4 * j + 2] += c.z; y[4 * j + 3] += c.w;
+        y[4 * j] = fmaf((float)(int32_t)acc[4 * j], sc[4 * j], c.x);
+        y[4 * j + 1] = fmaf((float)(int32_t)acc[4 * j + 1], sc[4 * j + 1], c.y);
+        y[4 * j + 2] = fmaf((float)(int32_t)acc[4 * j + 2], sc[4 * j + 2], c.z);
+        y[4 * j + 3] = fmaf((float)(int32_t)acc[4 * j + 3], sc[4 * j + 3], c.w);
       }
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) y[j] = (float)(int32_t)acc[j] * sc[j];
     }
     if (e.act == QVIT_ACT_GELU) {
 #pragma unroll

@@ -11,6 +11,7 @@ int gemm_tc_launch(const void* a, int64_t lda, int a_unsigned, const int8_t* w, 
                    cudaStream_t s);
 
 void gemm_tc_force_cta_group(int cg);
+int gemm_tc_read_profile(long long* host, int n);
 
 constexpr int kST = 64;        // SIMT tile (rows and cols)
 constexpr int kSK = 64;        // bytes of K per step
@@ -106,9 +107,11 @@ __global__ void gemm_k0_kernel(const EpiParams ep) {
 
 using namespace qvit;
 
+extern "C" int qvit_gemm_read_profile(long long* host, int n) { return gemm_tc_read_profile(host, n); }
+
 extern "C" int qvit_gemm_set_cta_group(int cta_group) {
-  QVIT_REQUIRE((cta_group >= 0 && cta_group <= 2) || cta_group == 11 || cta_group == 12 || cta_group == 21 || cta_group == 22,
-               "qvit_gemm_set_cta_group: 0 (auto), 1 or 2 (11 / 12: same with operand loads skipped in QVIT_OUT_NONE runs)");
+  QVIT_REQUIRE(cta_group >= 0 && cta_group % 10 <= 2 && (cta_group / 10) % 10 <= 9 && cta_group < 300,
+               "qvit_gemm_set_cta_group: 0 (auto), 1 or 2; +10 / +20 / +30 / +40 select benchmark modes (see gemm_tc.cu)");
   gemm_tc_force_cta_group(cta_group);
   return QVIT_OK;
 }
@@ -129,6 +132,7 @@ extern "C" int qvit_gemm_i8(const void* a, int64_t lda, int a_unsigned, const in
   ep.out_kind = epi->out_kind;
   ep.act = epi->act;
   ep.scale_const = epi->scale_const;
+  ep.acc_abs_max = epi->acc_abs_max;
   ep.scale_a = epi->scale_a;
   ep.scale_w = epi->scale_w;
   ep.col_scale = epi->col_scale;

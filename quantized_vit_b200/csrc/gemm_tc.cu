@@ -32,16 +32,17 @@ constexpr int kBoxBytes = kBM * 128;                // staging buffer of one qua
 
 // CG = 1: one CTA computes a [128 x BN] tile.  CG = 2: a CTA pair (tcgen05 cta_group::2) computes a [256 x BN] tile;
 // each CTA stages its own 128 rows of A and HALF of the W rows, the tensor core reads both halves - 1.5x less
-// L2->SM operand traffic per MAC and 32 KiB stages (5 deep) instead of 48 KiB (3 deep).
+// L2->SM operand traffic per MAC and 32 KiB stages (4 deep) instead of 48 KiB (3 deep).
 template <int BN, int CG = 1>
 struct GemmSmem {
-  static constexpr int kStages = (BN == 256 && CG == 1) ? 3 : 5;
+  static constexpr int kStages = (BN == 256 && CG == 1) ? 3 : 4;   // 48 KiB or 32 KiB per stage
   static constexpr int kABytes = kBM * kBK;
   static constexpr int kBBytes = (BN / CG) * kBK;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutBytes = 4 * kBoxBytes;     // one buffer per quad
-  static constexpr int kBarBytes = 256;
-  static constexpr int kTotal = kStages * kStageBytes + kOutBytes + kBarBytes + 1024;   // +1024 for manual alignment
+  static constexpr int kBarBytes = 512;
+  static constexpr int kBiasBytes = kEpiWarps * 256;   // per epilogue warp: the 64 bias values of its columns of the current tile
+  static constexpr int kTotal = kStages * kStageBytes + kOutBytes + kBarBytes + kBiasBytes + 1024;   // +1024 for manual alignment
 };
 
 __host__ __device__ constexpr int out_elem_size(int out_kind) {
@@ -59,53 +60,140 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, ui
   asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
-// y[32] for columns [n0, n0+32) of row m (dequant, col-scale, bias, activation, residual); guarded when ragged.
-template <bool FACC>   // FACC: the accumulators are fp32 (bf16 GEMM) instead of int32
-__device__ __forceinline__ void epi_compute32(EpiParams e, const uint32_t (&acc)[32], float scale, int64_t m, int n0,
-                                              bool row_ok, float (&y)[32], bool skip_residual) {
-  if (skip_residual) e.residual = nullptr;                  // the caller adds it from the TMA-staged tile
-  const bool full = (n0 + 32 <= e.N);
-  const bool vec_in = full && row_ok && (!e.bias || ((reinterpret_cast<uintptr_t>(e.bias + n0) & 15) == 0)) &&
-                      (!e.col_scale || ((reinterpret_cast<uintptr_t>(e.col_scale + n0) & 15) == 0)) &&
-                      (!e.residual || ((reinterpret_cast<uintptr_t>(e.residual + m * e.ld_res + n0) & 15) == 0));
-  if (vec_in) {
+// ---- epilogue, hot path: y for 32 consecutive columns of one row as 16 fp32 pairs (FFMA2 / FADD2 / FMUL2).
+// Preconditions (checked by the caller, warp-uniform): the chunk lies inside N and bias / col_scale are 16-byte aligned.
+// `bias_sm`: shared-memory address of the chunk's 32 bias values (prefetched one tile ahead by the warp: a global load here
+// would queue behind the warp's own output stores and expose ~1000 cycles per chunk).
+__device__ __forceinline__ void lds_pair2(uint32_t addr, f32x2& a, f32x2& b) {
+  asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
+}
+template <bool FACC>
+__device__ __forceinline__ void epi_math32(const EpiParams& e, const uint32_t (&acc)[32], float scale, int n0, uint32_t bias_sm,
+                                           f32x2 (&y)[16]) {
+  // accumulator -> fp32
+  if (FACC) {
 #pragma unroll
-    for (int j = 0; j < 32; ++j) y[j] = (FACC ? __uint_as_float(acc[j]) : (float)(int32_t)acc[j]) * scale;
-    if (e.col_scale) {
+    for (int j = 0; j < 16; ++j) y[j] = pk2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
+  } else if (e.acc_abs_max > 0 && e.acc_abs_max < (1 << 22)) {
+    // |acc| < 2^22: as_float(0x4B400000 + acc) = 1.5 * 2^23 + acc exactly, so one integer add and one fp32 subtract give
+    // float(acc) without the quarter-rate conversion unit
+    const f32x2 mm = pk1(-kRoundMagic);
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 c = __ldg(reinterpret_cast<const float4*>(e.col_scale + n0) + j);
-        y[4 * j] *= c.x; y[4 * j + 1] *= c.y; y[4 * j + 2] *= c.z; y[4 * j + 3] *= c.w;
-      }
+    for (int j = 0; j < 16; ++j)
+      y[j] = add2(pk2(__uint_as_float(acc[2 * j] + 0x4B400000u), __uint_as_float(acc[2 * j + 1] + 0x4B400000u)), mm);
+  } else {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = pk2((float)(int32_t)acc[2 * j], (float)(int32_t)acc[2 * j + 1]);
+  }
+  // y = fma(acc, scale * col_scale[n], bias[n])  (the canonical sequence of epilogue.cuh)
+  const f32x2 s2 = pk1(scale);
+  if (e.col_scale) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 c = __ldg(reinterpret_cast<const float4*>(e.col_scale + n0) + j);
+      y[2 * j] = mul2(y[2 * j], mul2(s2, pk2(c.x, c.y)));          // (acc * (scale * cs)): same product as fma(acc, s, 0)
+      y[2 * j + 1] = mul2(y[2 * j + 1], mul2(s2, pk2(c.z, c.w)));
     }
     if (e.bias) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        const float4 c = __ldg(reinterpret_cast<const float4*>(e.bias + n0) + j);
-        y[4 * j] += c.x; y[4 * j + 1] += c.y; y[4 * j + 2] += c.z; y[4 * j + 3] += c.w;
+        f32x2 b0, b1;
+        lds_pair2(bias_sm + 16u * j, b0, b1);
+        y[2 * j] = add2(y[2 * j], b0);
+        y[2 * j + 1] = add2(y[2 * j + 1], b1);
       }
     }
-    if (e.act == QVIT_ACT_GELU) {
+  } else if (e.bias) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j) y[j] = gelu_erf(y[j]);
-    } else if (e.act == QVIT_ACT_RELU) {
-#pragma unroll
-      for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.0f);
-    }
-    if (e.residual) {
-      const float* r = e.residual + m * e.ld_res + n0;
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float4 c = *reinterpret_cast<const float4*>(r + 4 * j);   // plain load: `out` may alias `residual`
-        y[4 * j] += c.x; y[4 * j + 1] += c.y; y[4 * j + 2] += c.z; y[4 * j + 3] += c.w;
-      }
+    for (int j = 0; j < 8; ++j) {
+      f32x2 b0, b1;
+      lds_pair2(bias_sm + 16u * j, b0, b1);
+      y[2 * j] = fma2(y[2 * j], s2, b0);
+      y[2 * j + 1] = fma2(y[2 * j + 1], s2, b1);
     }
   } else {
 #pragma unroll
-    for (int j = 0; j < 32; ++j)
-      y[j] = (row_ok && n0 + j < e.N) ? epi_value_f(e, FACC ? __uint_as_float(acc[j]) : (float)(int32_t)acc[j], scale, m, n0 + j) : 0.0f;
+    for (int j = 0; j < 16; ++j) y[j] = mul2(y[j], s2);
+  }
+  if (e.act == QVIT_ACT_GELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = gelu_erf2(y[j]);
+  } else if (e.act == QVIT_ACT_RELU) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      float a, b;
+      unpk2(y[j], a, b);
+      y[j] = pk2(fmaxf(a, 0.0f), fmaxf(b, 0.0f));
+    }
   }
 }
+
+// ---- epilogue, rare path (ragged N, unaligned operands or output, generic quantizer, NaN / inf): re-reads the chunk from
+// TMEM eight columns at a time and evaluates every element with the scalar reference sequence (epilogue.cuh / common.cuh:
+// IEEE division).  Writes into the warp's staging slab when `stage` != 0 (address of this row inside the slab, `byte0` =
+// first byte of the chunk inside the row, `swz` = XOR of the 16-byte piece index), else straight to global memory.
+// Warp-collective (tcgen05.ld): call in uniform control flow.
+template <int OUT, bool FACC>
+__device__ __noinline__ void epi_chunk_generic(const EpiParams& e_in, const SymParams& nq_in, uint32_t taddr, float scale, int64_t m,
+                                               int n0, bool row_ok, uint32_t stage, uint32_t swz, uint32_t byte0, int* flags) {
+  constexpr int kEsz = out_elem_size(OUT);
+  const EpiParams e = e_in;        // private copies: the volatile shared-memory stores below must not force re-loads
+  const SymParams nq = nq_in;
+  int fl = 0;
+#pragma unroll 1
+  for (int g = 0; g < 4; ++g) {
+    uint32_t r[8];
+    ptx::tmem_ld_32x32_x8(taddr + (uint32_t)(8 * g), r);
+    ptx::tmem_ld_wait();
+    uint32_t bits[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + 8 * g + j;
+      const bool ok = row_ok && n < e.N;
+      bits[j] = r[j];                                        // QVIT_OUT_I32: the raw accumulator
+      if (OUT != QVIT_OUT_I32) {
+        const float v = ok ? epi_value_f(e, FACC ? __uint_as_float(r[j]) : (float)(int32_t)r[j], scale, m, n) : 0.0f;
+        if (OUT == QVIT_OUT_F32) bits[j] = __float_as_uint(v);
+        else if (OUT == QVIT_OUT_BF16) bits[j] = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn(v));
+        else bits[j] = (uint32_t)sym_code(v, nq, fl) & 0xffu;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int n = n0 + 8 * g + j;
+      if (stage) {
+        const uint32_t off = byte0 + (uint32_t)((8 * g + j) * kEsz);
+        const uint32_t addr = stage + (((off >> 4) ^ swz) << 4) + (off & 15u);
+        if (kEsz == 4) asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(bits[j]));
+        else if (kEsz == 2) asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"((uint16_t)bits[j]));
+        else asm volatile("st.shared.b8 [%0], %1;" ::"r"(addr), "r"(bits[j]));
+      } else if (row_ok && n < e.N) {
+        if (kEsz == 4) reinterpret_cast<uint32_t*>(e.out)[m * e.ldo + n] = bits[j];
+        else if (kEsz == 2) reinterpret_cast<uint16_t*>(e.out)[m * e.ldo + n] = (uint16_t)bits[j];
+        else reinterpret_cast<uint8_t*>(e.out)[m * e.ldo + n] = (uint8_t)bits[j];
+      }
+    }
+  }
+  asm volatile("" ::: "memory");   // the staged bytes are consumed by the TMA engine after the caller's fence.proxy.async
+  *flags |= fl;
+}
+
+// Developer timeline (qvit_gemm_set_cta_group tens digit >= 5): clock64 stamps of CTA 0's MMA thread and first epilogue warp,
+// 8 slots per tile: [0] MMA: accumulator free  [1] MMA: last k-block issued  [2] EPI: accumulator full  [3] chunk 0 loaded
+// [4] chunk 0 math done  [5] chunk 0 staged  [6] last chunk loaded  [7] tile done.  Read back with qvit_gemm_read_profile.
+constexpr int kProfTiles = 64;
+constexpr int kProfCtas = 160;
+// + {clock64, globaltimer ns} at the start and end of CTA 0, then {start ns, end ns, smid} of every CTA
+__device__ long long g_gemm_prof[kProfTiles * 8 + 4 + 3 * kProfCtas];
+__device__ __forceinline__ long long global_ns() {
+  long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+#define QVIT_PROF(slot)                                                                        \
+  do {                                                                                         \
+    if (prof && prof_tile < kProfTiles) g_gemm_prof[prof_tile * 8 + (slot)] = clock64();       \
+  } while (0)
 
 // KIND 0: int8 x int8 -> int32 (tcgen05 kind::i8).  KIND 1: bf16 x bf16 -> fp32 (kind::f16) for the QAT gradient GEMMs:
 // the fp32 gradient operand arrives as three exact bf16 planes concatenated along K, the integer codes as one bf16
@@ -115,7 +203,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                   const EpiParams ep, const int K, const uint32_t idesc, const int tma_store, const int res_tma,
-                  const int mma_only, const int b_wrap) {
+                  const int mma_only_flags, const int b_wrap) {
   using S = GemmSmem<BN, CG>;
   constexpr int kStages = S::kStages;
   constexpr int kTmemCols = 2 * BN;   // 256 or 512: a power of two >= 32
@@ -132,12 +220,25 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   auto empty_bar = [&](int s) { return bar_base + 8u * (kStages + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * kStages + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * kStages + 2 + a); };
-  auto res_bar = [&](int q) { return bar_base + 8u * (2 * kStages + 4 + q); };
+  auto res_bar = [&](int w) { return bar_base + 8u * (2 * kStages + 4 + w); };     // one per epilogue warp
   volatile uint32_t* tmem_slot =
-      reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * S::kStageBytes + S::kOutBytes + 8 * (2 * kStages + 8));
+      reinterpret_cast<volatile uint32_t*>(smem_gen + kStages * S::kStageBytes + S::kOutBytes + 8 * (2 * kStages + 4 + kEpiWarps));
 
-  const int warp = threadIdx.x >> 5;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform for the compiler as well
   const int lane = threadIdx.x & 31;
+  const bool prof = (mma_only_flags & 2) && blockIdx.x == 0 && lane == 0 && (warp == 1 || warp == 2);
+  const int mma_only = mma_only_flags & 1;
+  int prof_tile = 0;
+  if ((mma_only_flags & 2) && blockIdx.x == 0 && threadIdx.x == 0) {
+    g_gemm_prof[kProfTiles * 8] = clock64();
+    g_gemm_prof[kProfTiles * 8 + 1] = global_ns();
+  }
+  if ((mma_only_flags & 2) && blockIdx.x < kProfCtas && threadIdx.x == 0) {
+    uint32_t smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    g_gemm_prof[kProfTiles * 8 + 4 + 3 * blockIdx.x] = global_ns();
+    g_gemm_prof[kProfTiles * 8 + 4 + 3 * blockIdx.x + 2] = smid;
+  }
 
   const int m_tiles = (ep.M + kTileM - 1) / kTileM;
   const int n_tiles = (ep.N + BN - 1) / BN;
@@ -161,7 +262,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         ptx::mbar_init(tfull_bar(a), 1);
         ptx::mbar_init(tempty_bar(a), kEpiWarps * CG); // one arrive per epilogue warp (of both CTAs of a pair)
       }
-      for (int q = 0; q < 4; ++q) ptx::mbar_init(res_bar(q), 1);
+      for (int q = 0; q < kEpiWarps; ++q) ptx::mbar_init(res_bar(q), 1);
       ptx::fence_mbar_init();
     }
     __syncwarp();
@@ -176,7 +277,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
-    if (lane == 0) {
+    // The whole warp runs the loop in uniform control flow (addresses and coordinates stay in uniform registers); one
+    // elected lane issues the copies.
+    {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
@@ -187,30 +290,36 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * S::kStageBytes;
           const uint32_t b_dst = a_dst + S::kABytes;
-          if (mma_only && (tile != tile_first || kb >= kStages)) {
-            // benchmark mode (QVIT_OUT_NONE only): operands stay whatever the first kStages loads brought in -
-            // measures the tensor-core issue rate with no L2 / HBM traffic at all
-            if (rank == 0) ptx::mbar_arrive(full_bar(stage));
-          } else if (CG == 1) {
-            ptx::mbar_expect_tx(full_bar(stage), S::kStageBytes);
-            ptx::tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * kBK, a_row);
-            ptx::tma_load_2d(b_dst, &tmap_w, full_bar(stage), (kb % b_wrap) * kBK, w_row);
-          } else {
-            // both CTAs signal the LEADER's barrier (peer bit of the shared::cluster address cleared); the leader arms it
-            // for the bytes of both.  A peer completion that overtakes the leader's expect_tx only makes the pending
-            // tx-count transiently negative: the phase cannot complete before the leader's (single) arrival.
-            const uint32_t lead_bar = full_bar(stage) & 0xFEFFFFFFu;
-            if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * S::kStageBytes);
-            ptx::tma_load_2d_cg2(a_dst, &tmap_a, lead_bar, kb * kBK, a_row);
-            ptx::tma_load_2d_cg2(b_dst, &tmap_w, lead_bar, (kb % b_wrap) * kBK, w_row);
+          if (ptx::elect_one()) {
+            if (mma_only && (tile != tile_first || kb >= kStages)) {
+              // benchmark mode: operands stay whatever the first kStages loads brought in - measures the tensor-core
+              // issue rate with no L2 / HBM traffic at all
+              if (rank == 0) ptx::mbar_arrive(full_bar(stage));
+            } else if (CG == 1) {
+              ptx::mbar_expect_tx(full_bar(stage), S::kStageBytes);
+              ptx::tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * kBK, a_row);
+              ptx::tma_load_2d(b_dst, &tmap_w, full_bar(stage), (kb % b_wrap) * kBK, w_row);
+            } else {
+              // both CTAs signal the LEADER's barrier (peer bit of the shared::cluster address cleared); the leader arms
+              // it for the bytes of both.  A peer completion that overtakes the leader's expect_tx only makes the pending
+              // tx-count transiently negative: the phase cannot complete before the leader's (single) arrival.
+              const uint32_t lead_bar = full_bar(stage) & 0xFEFFFFFFu;
+              if (rank == 0) ptx::mbar_expect_tx(full_bar(stage), 2 * S::kStageBytes);
+              ptx::tma_load_2d_cg2(a_dst, &tmap_a, lead_bar, kb * kBK, a_row);
+              ptx::tma_load_2d_cg2(b_dst, &tmap_w, lead_bar, (kb % b_wrap) * kBK, w_row);
+            }
           }
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA of a pair only)
-    if (lane == 0 && rank == 0) {
+    // Warp-uniform loop, one elected lane issues: the descriptors live in uniform registers, so each tcgen05.mma is a
+    // single UTCIMMA (a lane-0-only branch makes the compiler wrap every MMA in an ELECT / R2UR.BROADCAST loop, ~15
+    // instructions each, and this latency-critical thread then starves behind the 16 epilogue warps).
+    if (rank == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
@@ -218,6 +327,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
         ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);     // epilogue has drained this accumulator
         ptx::tc_fence_after();
+        QVIT_PROF(0);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < k_blocks; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);
@@ -225,74 +335,212 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           const uint32_t a_src = smem_base + stage * S::kStageBytes;
           const uint64_t a_desc = ptx::make_kmajor_sw128_desc(a_src);
           const uint64_t b_desc = ptx::make_kmajor_sw128_desc(a_src + S::kABytes);
+          if (ptx::elect_one()) {
 #pragma unroll
-          for (int k = 0; k < kBK / kUmmaK; ++k) {
-            // advance both descriptors by k*32 bytes inside the swizzle atom (address field is >>4)
-            if (KIND == 0)
-              ptx::mma_i8<CG>(d_tmem, a_desc + (uint64_t)(k * (kUmmaK >> 4)), b_desc + (uint64_t)(k * (kUmmaK >> 4)), idesc,
-                              (uint32_t)((kb | k) != 0));
-            else
-              ptx::mma_bf16<CG>(d_tmem, a_desc + (uint64_t)(k * (kUmmaK >> 4)), b_desc + (uint64_t)(k * (kUmmaK >> 4)), idesc,
+            for (int k = 0; k < kBK / kUmmaK; ++k) {
+              // advance both descriptors by k*32 bytes inside the swizzle atom (address field is >>4)
+              if (KIND == 0)
+                ptx::mma_i8<CG>(d_tmem, a_desc + (uint64_t)(k * (kUmmaK >> 4)), b_desc + (uint64_t)(k * (kUmmaK >> 4)), idesc,
                                 (uint32_t)((kb | k) != 0));
+              else
+                ptx::mma_bf16<CG>(d_tmem, a_desc + (uint64_t)(k * (kUmmaK >> 4)), b_desc + (uint64_t)(k * (kUmmaK >> 4)), idesc,
+                                  (uint32_t)((kb | k) != 0));
+            }
+            // smem slot free once these MMAs retire (in both CTAs of a pair)
+            if (CG == 1) ptx::mma_commit(empty_bar(stage)); else ptx::mma_commit_cg2(empty_bar(stage), 0x3);
+            // accumulator complete after the last k-block
+            if (kb == k_blocks - 1) {
+              if (CG == 1) ptx::mma_commit(tfull_bar(acc)); else ptx::mma_commit_cg2(tfull_bar(acc), 0x3);
+            }
           }
-          // smem slot free once these MMAs retire (in both CTAs of a pair)
-          if (CG == 1) ptx::mma_commit(empty_bar(stage)); else ptx::mma_commit_cg2(empty_bar(stage), 0x3);
+          __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        if (CG == 1) ptx::mma_commit(tfull_bar(acc)); else ptx::mma_commit_cg2(tfull_bar(acc), 0x3);   // accumulator complete
+        if (k_blocks == 0 && ptx::elect_one()) {             // (K = 0 never reaches this kernel; keep the protocol total)
+          if (CG == 1) ptx::mma_commit(tfull_bar(acc)); else ptx::mma_commit_cg2(tfull_bar(acc), 0x3);
+        }
+        QVIT_PROF(1);
+        ++prof_tile;
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1u;
       }
     }
   } else {
     // ------------------------------------------------------------------ epilogue (warps 2..17)
+    // Warp w owns TMEM lanes [32 * (w & 3), +32) (32 rows of the tile) and, with the three other warps of its "quad", a
+    // quarter of the tile's columns, in chunks of 32 columns.  Per chunk: tcgen05.ld -> packed fp32 math in registers ->
+    // the row goes to the warp's PRIVATE staging slab (XOR-swizzled, conflict free) -> one lane issues a TMA store of
+    // the [32 rows x <= 128 B] box.  Nothing wider than the warp synchronises; the slab drains asynchronously while the
+    // warp loads and converts its next chunk.
     const int lane_grp = warp & 3;                           // TMEM lanes [32*lane_grp, +32) are this warp's
-    const int quad = (warp - 2) >> 2;                        // 0..3: which quarter of the tile's columns
-    const int row = lane_grp * 32 + lane;                    // row inside the tile
-    const bool leader = (lane_grp == 2 && lane == 0);        // first warp of each quad (warps 2, 6, 10, 14)
+    const int ew = warp - 2;                                 // 0..15
+    const int quad = ew >> 2;                                // 0..3: which quarter of the tile's columns
     constexpr int kChunksPerQuad = BN / 128;                 // 32-column chunks per quad and tile (2 or 1)
     constexpr int kEsz = out_elem_size(OUT);
     constexpr int kBoxW = out_box_bytes(BN, OUT);            // 128, 64 or 32 bytes per staged row
     constexpr int kChunkBytes = 32 * kEsz;
     constexpr int kChunksPerBox = kBoxW / kChunkBytes;       // 1 or 2
-    constexpr uint32_t kSwzMask = kBoxW / 16 - 1;            // TMA swizzle: 16B-chunk index ^= (byte offset >> 7) & mask
+    constexpr uint32_t kSwzMask = kBoxW / 16 - 1;            // TMA swizzle: 16B-piece index ^= (byte offset >> 7) & mask
     const float scale = epi_scale(ep);
     SymParams nq;
-    FastQ fq;
+    FastQ2 fq;
+    fq.generic = 0;
     if (OUT == QVIT_OUT_I8) {
       nq = load_sym_params(ep.next_d, ep.next_qm, ep.next_t);
-      fq = make_fastq(nq);
+      fq = make_fastq2(nq);
     }
     int fl = 0;
     int acc = 0;
     uint32_t acc_phase = 0;
     uint32_t res_phase = 0;
-    const bool use_res_tma = (OUT == QVIT_OUT_F32) && res_tma;   // residual tile staged by TMA into the output buffer
-    const uint32_t buf = out_base + (uint32_t)(quad * kBoxBytes);
-    const uint32_t row_off = (uint32_t)(row * kBoxW);
+    const bool use_res_tma = (OUT == QVIT_OUT_F32) && res_tma;   // residual rows staged by TMA into the slab
+    const uint32_t slab = out_base + (uint32_t)(ew * 4096);
+    const uint32_t row_off = (uint32_t)(lane * kBoxW);
     const uint32_t sw = (row_off >> 7) & kSwzMask;
+    const uint32_t bias_sm = bar_base + (uint32_t)S::kBarBytes + (uint32_t)(ew * 256);   // this warp's 64 bias values of the tile
+    // hot path = packed-pair math on whole, aligned chunks; anything else (warp-uniform conditions only) takes
+    // epi_chunk_generic.  tma_store: the output is TMA-addressable (16-byte pointer and pitch); 2 = benchmark, store nothing.
+    const bool hot_ok = tma_store && !fq.generic && (!ep.col_scale || ((reinterpret_cast<uintptr_t>(ep.col_scale) & 15) == 0)) &&
+                        (!ep.residual || use_res_tma) && !(mma_only_flags & 8);
+    // bias of the warp's columns: loaded one tile ahead into registers, parked in shared memory for the tile
+    float nb[kChunksPerQuad];
+    auto bias_fetch = [&](int t) {
+      const int nblk = t % n_tiles;
+#pragma unroll
+      for (int cq = 0; cq < kChunksPerQuad; ++cq) {
+        const int col = nblk * BN + (quad * kChunksPerQuad + cq) * 32 + lane;
+        nb[cq] = (ep.bias && t < total_tiles && col < ep.N) ? __ldg(ep.bias + col) : 0.0f;
+      }
+    };
+    bias_fetch(tile_first);
     for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
       const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+#pragma unroll
+      for (int cq = 0; cq < kChunksPerQuad; ++cq)
+        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_sm + (uint32_t)(cq * 128 + lane * 4)), "f"(nb[cq]) : "memory");
+      bias_fetch(tile + tile_step);                          // lands while this tile is processed
+      __syncwarp();
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
-      const int row0 = m_blk * kTileM + (int)rank * kBM;      // first output row of this CTA's half of the tile
-      const int64_t m = (int64_t)row0 + row;
+      QVIT_PROF(2);
+      const int row0 = m_blk * kTileM + (int)rank * kBM + lane_grp * 32;   // first output row of this warp
+      const int64_t m = (int64_t)row0 + lane;
       const bool row_ok = m < ep.M;
       const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(acc * BN);
-#pragma unroll
+#pragma unroll 1
       for (int cq = 0; cq < kChunksPerQuad; ++cq) {
         const int c = quad * kChunksPerQuad + cq;            // chunk index inside the tile
         const int n0 = n_blk * BN + c * 32;
-        if (use_res_tma && leader) {
-          // buffer free again -> fetch the [128 x 32] fp32 residual tile (coalesced, async) while the math runs
-          ptx::tma_store_wait_read<0>();
-          ptx::mbar_expect_tx(res_bar(quad), (uint32_t)(kBM * 128));
-          ptx::tma_load_2d(buf, &tmap_res, res_bar(quad), n0, row0);
+        const int in_box = cq % kChunksPerBox;
+        const uint32_t byte0 = (uint32_t)(in_box * kChunkBytes);
+        const bool last = (cq == kChunksPerQuad - 1);
+        if (OUT == QVIT_OUT_NONE) {                          // main-loop benchmark mode: drain and release
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
+          ptx::tmem_ld_wait();
+        } else if (n0 < ep.N) {
+          const bool hot = hot_ok && (n0 + 32 <= ep.N);
+          if (tma_store && in_box == 0) {
+            if (lane == 0) {
+              if (tma_store == 1) ptx::tma_store_wait_read<0>();   // the warp's previous box has left the slab
+              if (use_res_tma) {
+                // fetch this warp's [32 x 32] fp32 residual rows while the accumulator is loaded and converted
+                // (rows beyond M are zero filled)
+                ptx::mbar_expect_tx(res_bar(ew), 4096u);
+                ptx::tma_load_2d(slab, &tmap_res, res_bar(ew), n0, row0);
+              }
+            }
+            __syncwarp();
+          }
+          bool redo = !hot;
+          if (hot) {
+            uint32_t w[kChunkBytes / 4];
+            uint32_t r[32];
+            ptx::tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
+            ptx::tmem_ld_wait();
+            QVIT_PROF(cq == 0 ? 3 : 6);
+            if (OUT == QVIT_OUT_I32) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) w[j % (kChunkBytes / 4)] = r[j];      // kChunkBytes/4 == 32 here
+            } else {
+              f32x2 y[16];
+              epi_math32<KIND == 1>(ep, r, scale, n0, bias_sm + (uint32_t)(cq * 128), y);
+              if (use_res_tma) {
+                ptx::mbar_wait(res_bar(ew), res_phase);
+                res_phase ^= 1u;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  f32x2 ra, rb;
+                  lds_pair2(slab + row_off + ((((uint32_t)j) ^ sw) << 4), ra, rb);
+                  y[2 * j] = add2(y[2 * j], ra);
+                  y[2 * j + 1] = add2(y[2 * j + 1], rb);
+                }
+              }
+              if (OUT == QVIT_OUT_F32) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  float a, b;
+                  unpk2(y[j], a, b);
+                  w[(2 * j) % (kChunkBytes / 4)] = __float_as_uint(a);
+                  w[(2 * j + 1) % (kChunkBytes / 4)] = __float_as_uint(b);
+                }
+              } else if (OUT == QVIT_OUT_BF16) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  float a, b;
+                  unpk2(y[j], a, b);
+                  const __nv_bfloat162 p2 = __floats2bfloat162_rn(a, b);
+                  w[j % (kChunkBytes / 4)] = *reinterpret_cast<const uint32_t*>(&p2);
+                }
+              } else {
+                f32x2 dacc = pk1(0.0f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) w[j % (kChunkBytes / 4)] = sym_codes4_fast2(y[2 * j], y[2 * j + 1], fq, dacc);
+                float d0, d1;
+                unpk2(dacc, d0, d1);
+                bool bad = false;
+                if (!(d0 + d1 == 0.0f) || (mma_only_flags & 4)) {
+                  // some element of this row sits on a rounding boundary (or is NaN / inf): exact codes for the row
+                  // (lane-local branch; (mma_only_flags & 4) forces it for the tests)
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) {
+                    float a0, a1, a2, a3;
+                    unpk2(y[2 * j], a0, a1);
+                    unpk2(y[2 * j + 1], a2, a3);
+                    bad = bad || !(fabsf(a0) < 1.0e30f) || !(fabsf(a1) < 1.0e30f) || !(fabsf(a2) < 1.0e30f) || !(fabsf(a3) < 1.0e30f);
+                    w[j % (kChunkBytes / 4)] = pack4_low_bytes(__float_as_uint(sym_t_exact(a0, fq)), __float_as_uint(sym_t_exact(a1, fq)),
+                                                               __float_as_uint(sym_t_exact(a2, fq)), __float_as_uint(sym_t_exact(a3, fq)));
+                  }
+                }
+                // NaN / inf / absurd magnitudes: the scalar reference sequence decides (and raises the flag bits)
+                redo = __any_sync(0xffffffffu, bad);
+                if ((mma_only_flags & 2) && lane == 0 && !(d0 + d1 == 0.0f))
+                  atomicAdd(reinterpret_cast<unsigned long long*>(&g_gemm_prof[kProfTiles * 8 + 4 + 3 * 159]), 1ull);
+              }
+            }
+            if (cq == 0) QVIT_PROF(4);
+            if (tma_store == 2) {                            // benchmark: math only (keep it alive, store nothing)
+              uint32_t x = redo ? 1u : 0u;
+#pragma unroll
+              for (int j = 0; j < kChunkBytes / 4; ++j) x ^= w[j];
+              if (x == 0x9e3779b9u && ep.flags) atomicOr(ep.flags, 8);
+            } else if (!redo) {
+#pragma unroll
+              for (int j = 0; j < kChunkBytes / 16; ++j) {
+                const uint32_t piece = (uint32_t)(in_box * (kChunkBytes / 16) + j);
+                sts_v4(slab + row_off + ((piece ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
+              }
+            }
+          } else if (use_res_tma) {                          // keep the residual barrier protocol; the rare path reads global
+            ptx::mbar_wait(res_bar(ew), res_phase);
+            res_phase ^= 1u;
+          }
+          if (redo && tma_store != 2)
+            epi_chunk_generic<OUT, KIND == 1>(ep, nq, t_row + (uint32_t)(c * 32), scale, m, n0, row_ok,
+                                              tma_store ? slab + row_off : 0u, sw, byte0, &fl);
         }
-        uint32_t r[32];
-        ptx::tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
-        ptx::tmem_ld_wait();
-        if (cq == kChunksPerQuad - 1) {                      // all TMEM reads of this warp for this tile are done
+        if (last) {                                          // all TMEM reads of this warp for this tile are done
+          QVIT_PROF(6);
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -300,86 +548,38 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             else ptx::mbar_arrive_cluster(tempty_bar(acc), 0);   // the leader's MMA warp waits for both CTAs
           }
         }
-        if (OUT == QVIT_OUT_NONE) continue;                  // main-loop benchmark mode
-        if (!tma_store) {
-          if (row_ok && KIND == 0) epi_store_chunk32(ep, &nq, r, scale, m, n0, fl);   // (KIND 1 always uses the TMA path)
-          continue;
-        }
-        // ---- math first (registers only), so that the previous TMA store of this quad drains meanwhile
-        uint32_t w[kChunkBytes / 4];
-        if (OUT == QVIT_OUT_I32) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) w[j % (kChunkBytes / 4)] = r[j];      // kChunkBytes/4 == 32 here
-        } else {
-          float y[32];
-          epi_compute32<KIND == 1>(ep, r, scale, m, n0, row_ok, y, use_res_tma);
-          if (use_res_tma) {
-            ptx::mbar_wait(res_bar(quad), res_phase);
-            res_phase ^= 1u;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float4 rv;
-              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
-                           : "=f"(rv.x), "=f"(rv.y), "=f"(rv.z), "=f"(rv.w)
-                           : "r"(buf + row_off + ((((uint32_t)j) ^ sw) << 4)));
-              y[4 * j] += rv.x; y[4 * j + 1] += rv.y; y[4 * j + 2] += rv.z; y[4 * j + 3] += rv.w;
-            }
-          }
-          if (OUT == QVIT_OUT_F32) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) w[j % (kChunkBytes / 4)] = __float_as_uint(y[j]);
-          } else if (OUT == QVIT_OUT_BF16) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const __nv_bfloat162 p2 = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
-              w[j % (kChunkBytes / 4)] = *reinterpret_cast<const uint32_t*>(&p2);
-            }
-          } else {
-            int doubt = fq.generic;
-            if (!fq.generic) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                w[j % (kChunkBytes / 4)] = pack4_i8(sym_code_fast(y[4 * j], fq, doubt), sym_code_fast(y[4 * j + 1], fq, doubt),
-                                                    sym_code_fast(y[4 * j + 2], fq, doubt), sym_code_fast(y[4 * j + 3], fq, doubt));
-            }
-            if (doubt) {                                     // rare: an element sits on a rounding boundary (or generic quantizer)
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                w[j % (kChunkBytes / 4)] = pack4_i8(sym_code(y[4 * j], nq, fl), sym_code(y[4 * j + 1], nq, fl),
-                                                    sym_code(y[4 * j + 2], nq, fl), sym_code(y[4 * j + 3], nq, fl));
+        if (OUT != QVIT_OUT_NONE && tma_store == 1 && (in_box == kChunksPerBox - 1 || last)) {
+          // (a box whose later chunks lie beyond N is stored as soon as its last in-range chunk is staged: TMA clips it)
+          const int box_n0 = n_blk * BN + (c - in_box) * 32;
+          if (box_n0 < ep.N) {
+            ptx::fence_proxy_async_smem();                   // generic-proxy writes -> visible to the TMA engine
+            __syncwarp();
+            if (lane == 0) {
+              ptx::tma_store_2d(&tmap_out, slab, box_n0, row0);
+              ptx::tma_store_commit();
             }
           }
         }
-        const int in_box = cq % kChunksPerBox;
-        if (in_box == 0 && !use_res_tma) {
-          if (leader) ptx::tma_store_wait_read<0>();         // the quad's previous box has left shared memory
-          named_bar_sync(1 + quad, 128);
-        }
-#pragma unroll
-        for (int j = 0; j < kChunkBytes / 16; ++j) {
-          const uint32_t chunk16 = (uint32_t)(in_box * (kChunkBytes / 16) + j);
-          sts_v4(buf + row_off + ((chunk16 ^ sw) << 4), w[4 * j], w[4 * j + 1], w[4 * j + 2], w[4 * j + 3]);
-        }
-        if (in_box == kChunksPerBox - 1) {
-          ptx::fence_proxy_async_smem();                     // generic-proxy writes -> visible to the TMA engine
-          named_bar_sync(1 + quad, 128);
-          if (leader) {
-            const int box_n0 = n_blk * BN + (c - in_box) * 32;
-            ptx::tma_store_2d(&tmap_out, buf, box_n0, row0);
-            ptx::tma_store_commit();
-          }
-        }
+        if (cq == 0) QVIT_PROF(5);
       }
+      QVIT_PROF(7);
+      ++prof_tile;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
-    if (tma_store && leader) ptx::tma_store_wait<0>();
+    if (tma_store == 1 && lane == 0) ptx::tma_store_wait<0>();
     fl = warp_or(fl);
     if (fl && ep.flags && lane == 0) atomicOr(ep.flags, fl);
   }
 
   ptx::tc_fence_before();
   __syncthreads();
+  if ((mma_only_flags & 2) && blockIdx.x == 0 && threadIdx.x == 0) {
+    g_gemm_prof[kProfTiles * 8 + 2] = clock64();
+    g_gemm_prof[kProfTiles * 8 + 3] = global_ns();
+  }
+  if ((mma_only_flags & 2) && blockIdx.x < kProfCtas && threadIdx.x == 0)
+    g_gemm_prof[kProfTiles * 8 + 4 + 3 * blockIdx.x + 1] = global_ns();
   if (CG == 2) ptx::cluster_sync();   // the peer may still be reading this CTA's operands / signalling its barriers
   if (warp == 1) {
     ptx::tc_fence_after();
@@ -432,8 +632,8 @@ static int make_tmap_bytes(CUtensorMap* map, const void* base, int64_t rows, int
   return QVIT_OK;
 }
 
-// output matrix [M, N] with row pitch ldo (elements): box = 128 rows x box_bytes, swizzle mode = box width
-static int make_tmap_out(CUtensorMap* map, void* base, int64_t M, int64_t N, int64_t ldo, int out_kind, int box_bytes) {
+// fp32 / int matrix [M, N] with row pitch ldo (elements): box = box_rows x box_bytes, swizzle mode = box width
+static int make_tmap_out(CUtensorMap* map, void* base, int64_t M, int64_t N, int64_t ldo, int out_kind, int box_bytes, int box_rows) {
   EncodeTiledFn enc = get_encode_fn();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled not available from the driver");
@@ -448,7 +648,7 @@ static int make_tmap_out(CUtensorMap* map, void* base, int64_t M, int64_t N, int
                                                   : (box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   cuuint64_t dims[2] = {(cuuint64_t)N, (cuuint64_t)M};
   cuuint64_t strides[1] = {(cuuint64_t)(ldo * esz)};
-  cuuint32_t box[2] = {(cuuint32_t)(box_bytes / esz), (cuuint32_t)kBM};
+  cuuint32_t box[2] = {(cuuint32_t)(box_bytes / esz), (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, dt, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -471,11 +671,25 @@ bool gemm_tc_supported(const void* a, int64_t lda, const void* w, int64_t ldw, i
 }
 
 static int g_force_cg = 0;   // 0 = automatic, 1 / 2 = force single-CTA / CTA-pair tiles (tests, benchmarks)
-static int g_mma_only = 0;   // benchmark: skip operand loads after the first pipeline fill (QVIT_OUT_NONE only)
+static int g_mma_only = 0;   // benchmark: skip operand loads after the first pipeline fill (results are garbage)
 static int g_no_tma_store = 0;   // benchmark: per-thread vector stores instead of staged TMA stores
+static int g_skip_store = 0;     // benchmark: epilogue math only, nothing staged or stored
+static int g_profile = 0;        // developer timeline into g_gemm_prof
+static int g_force_path = 0;     // tests: 1 = exact redo of every int8-output chunk, 2 = scalar reference path for every chunk
+int gemm_tc_read_profile(long long* host, int n) {
+  if (n > kProfTiles * 8 + 4 + 3 * kProfCtas) n = kProfTiles * 8 + 4 + 3 * kProfCtas;
+  return cudaMemcpyFromSymbol(host, g_gemm_prof, sizeof(long long) * n) == cudaSuccess ? n : -1;
+}
 void gemm_tc_force_cta_group(int cg) {
-  g_no_tma_store = (cg >= 20) ? 1 : 0;
-  g_mma_only = (cg >= 10 && cg < 20) ? 1 : 0;
+  // tens digit: 1 = mma only, 2 = no TMA store, 3 = skip the store, 4 = mma only + skip the store
+  g_force_path = (cg / 100) % 10;   // hundreds digit
+  cg %= 100;
+  int t = cg / 10;
+  g_profile = (t >= 5) ? 1 : 0;      // +50: same modes with the timeline switched on
+  if (t >= 5) t -= 5;
+  g_no_tma_store = (t == 2) ? 1 : 0;
+  g_mma_only = (t == 1 || t == 4) ? 1 : 0;
+  g_skip_store = (t == 3 || t == 4) ? 1 : 0;
   g_force_cg = cg % 10;
 }
 
@@ -517,7 +731,7 @@ static int launch_tc(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsign
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_i8_tc_kernel<BN, OUT, CG, KIND>, tm.a, tm.w, tm.out, tm.res, ep, K, idesc,
-                                     tm.tma_store, tm.res_tma, (OUT == QVIT_OUT_NONE) ? g_mma_only : 0, b_wrap);
+                                     (tm.tma_store && g_skip_store) ? 2 : tm.tma_store, tm.res_tma, g_mma_only | (g_profile << 1) | (g_force_path == 1 ? 4 : 0) | (g_force_path == 2 ? 8 : 0), b_wrap);
   if (e != cudaSuccess) {
     set_error("gemm_i8_tc_kernel launch: %s", cudaGetErrorString(e));
     return QVIT_ERR_CUDA;
@@ -563,22 +777,22 @@ int gemm_tc_launch(const void* a, int64_t lda, int a_unsigned, const int8_t* w, 
   if (rc) return rc;
   rc = make_tmap_bytes(&tm.w, w, N, K, ldw, bn / cg);
   if (rc) return rc;
-  // Coalesced output through shared memory + TMA store when the output matrix is TMA-addressable;
-  // predicated per-thread vector stores otherwise.
+  // Coalesced 16-byte stores through the per-warp staging slabs when the output matrix is 16-byte addressable (pointer and
+  // pitch); the scalar path otherwise.
   const int esz = out_elem_size(ep.out_kind);
   tm.tma_store = (ep.out_kind != QVIT_OUT_NONE) && ((reinterpret_cast<uintptr_t>(ep.out) & 15) == 0) &&
                  (((ep.ldo * esz) & 15) == 0) && !g_no_tma_store;
   tm.out = tm.a;
   tm.res = tm.a;
   if (tm.tma_store) {
-    rc = make_tmap_out(&tm.out, ep.out, M, N, ep.ldo, ep.out_kind, out_box_bytes(bn, ep.out_kind));
+    rc = make_tmap_out(&tm.out, ep.out, M, N, ep.ldo, ep.out_kind, out_box_bytes(bn, ep.out_kind), 32);
     if (rc) return rc;
   }
   // fp32 residual (Block.forward's "x + ...", vit_model.py:206-207) staged tile-wise by TMA instead of per-thread row reads
   tm.res_tma = tm.tma_store && ep.out_kind == QVIT_OUT_F32 && ep.residual != nullptr &&
                ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0) && (((ep.ld_res * 4) & 15) == 0);
   if (tm.res_tma) {
-    rc = make_tmap_out(&tm.res, const_cast<float*>(ep.residual), M, N, ep.ld_res, QVIT_OUT_F32, 128);
+    rc = make_tmap_out(&tm.res, const_cast<float*>(ep.residual), M, N, ep.ld_res, QVIT_OUT_F32, 128, 32);
     if (rc) return rc;
   }
   if (cg == 2) return launch_tc_kind<256, 2>(tm, ep, K, a_unsigned != 0, sms, s);
@@ -607,11 +821,11 @@ int gemm_tc_launch_bf16_split(const void* a, int64_t lda, int planes, const void
   }
   tm.tma_store = 1;
   tm.res = tm.a;
-  rc = make_tmap_out(&tm.out, ep.out, M, N, ep.ldo, QVIT_OUT_F32, out_box_bytes(bn, QVIT_OUT_F32));
+  rc = make_tmap_out(&tm.out, ep.out, M, N, ep.ldo, QVIT_OUT_F32, out_box_bytes(bn, QVIT_OUT_F32), 32);
   if (rc) return rc;
   tm.res_tma = ep.residual != nullptr && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0) && (((ep.ld_res * 4) & 15) == 0);
   if (tm.res_tma) {
-    rc = make_tmap_out(&tm.res, const_cast<float*>(ep.residual), M, N, ep.ld_res, QVIT_OUT_F32, 128);
+    rc = make_tmap_out(&tm.res, const_cast<float*>(ep.residual), M, N, ep.ld_res, QVIT_OUT_F32, 128, 32);
     if (rc) return rc;
   }
   const int k_bytes = 2 * planes * Kp;          // contraction length of the kernel's byte-wise K loop

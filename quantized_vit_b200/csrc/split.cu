@@ -167,6 +167,7 @@ int qvit_gemm_bf16_split(const void* a_planes, int64_t lda, int planes, const vo
   ep.out_kind = QVIT_OUT_F32;
   ep.act = QVIT_ACT_NONE;
   ep.scale_const = epi->scale_const;
+  ep.acc_abs_max = 0;
   ep.scale_a = epi->scale_a;
   ep.scale_w = epi->scale_w;
   ep.col_scale = epi->col_scale;

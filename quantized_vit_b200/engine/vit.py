@@ -35,7 +35,7 @@ VIT_CONFIGS = {
 
 
 class _QLayer:
-    __slots__ = ("w_codes", "bias", "d_wt", "d_act", "qm_act", "t_act", "K", "N")
+    __slots__ = ("w_codes", "bias", "d_wt", "d_act", "qm_act", "t_act", "K", "N", "acc_abs_max")
 
 
 class ViTInferenceEngine:
@@ -80,6 +80,7 @@ class ViTInferenceEngine:
         w2 = w.reshape(w.shape[0], -1).contiguous()
         L.N, L.K = w2.shape
         d, q, t = sd[f"{name}.d_quant_wt"].float(), sd[f"{name}.q_m_wt"].float(), sd.get(f"{name}.t_quant_wt")
+        sats = []
         for (dd, qq, tt, what) in ((d, q, t, "weight"), (sd[f"{name}.d_quant_act"], sd[f"{name}.q_m_act"],
                                                         sd.get(f"{name}.t_quant_act"), "activation")):
             r = qq.float().abs()
@@ -88,6 +89,8 @@ class ViTInferenceEngine:
             sat = torch.abs(torch.round(r / dd.float().abs())).item()
             if not (sat <= 127):
                 raise ValueError(f"{name}: {what} codes reach {sat} > 127 - not representable on the int8 pipe")
+            sats.append(int(sat))
+        L.acc_abs_max = sats[0] * sats[1] * L.K      # |int32 accumulator| can never exceed this (epilogue hint)
         flags = ops.new_flags(self.device)
         L.w_codes = ops.quantize_sym(w2, d, q, t, ld_codes=ops.pad16(L.K), flags=flags)
         L.bias = sd[f"{name}.bias"].float().contiguous() if f"{name}.bias" in sd else None
@@ -104,10 +107,12 @@ class ViTInferenceEngine:
     # ------------------------------------------------------------------ forward
     def _gemm(self, a_codes, L: _QLayer, **kw):
         if self.gemm_events is None:
-            return ops.gemm_i8(a_codes, L.w_codes, L.K, L.N, scale_a=L.d_act, scale_w=L.d_wt, bias=L.bias, flags=self.flags, **kw)
+            return ops.gemm_i8(a_codes, L.w_codes, L.K, L.N, scale_a=L.d_act, scale_w=L.d_wt, bias=L.bias, flags=self.flags,
+                               acc_abs_max=L.acc_abs_max, **kw)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        y = ops.gemm_i8(a_codes, L.w_codes, L.K, L.N, scale_a=L.d_act, scale_w=L.d_wt, bias=L.bias, flags=self.flags, **kw)
+        y = ops.gemm_i8(a_codes, L.w_codes, L.K, L.N, scale_a=L.d_act, scale_w=L.d_wt, bias=L.bias, flags=self.flags,
+                               acc_abs_max=L.acc_abs_max, **kw)
         e1.record()
         self.gemm_events.append((L, 2.0 * a_codes.shape[0] * L.K * L.N, e0, e1))
         return y

@@ -189,8 +189,11 @@ def gemm_i8(a: torch.Tensor, w: torch.Tensor, K: int, N: Optional[int] = None, *
             act: int = QVIT_ACT_NONE, scale_a=None, scale_w=None, scale_const: float = 1.0,
             col_scale: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
             residual: Optional[torch.Tensor] = None, next_q=None, flags: Optional[torch.Tensor] = None,
-            backend: int = QVIT_GEMM_AUTO, out: Optional[torch.Tensor] = None, ldo: Optional[int] = None) -> torch.Tensor:
+            backend: int = QVIT_GEMM_AUTO, out: Optional[torch.Tensor] = None, ldo: Optional[int] = None,
+            acc_abs_max: int = 0) -> torch.Tensor:
     """acc = A[M, :K] @ W[N, :K]^T (int8/uint8 x int8 -> int32) + fused epilogue (include/qvit_b200.h).
+
+    acc_abs_max: optional promise |acc| <= sat_a * sat_w * K (0 = unknown) - lets the epilogue skip the conversion unit.
 
     a: [M, lda] int8 or uint8 codes, w: [N, ldw] int8 codes; both row-major with the pitch as second dim.
     next_q = (d, q_m, t|None) of the consumer layer for QVIT_OUT_I8."""
@@ -218,6 +221,7 @@ def gemm_i8(a: torch.Tensor, w: torch.Tensor, K: int, N: Optional[int] = None, *
         ldo = out.stride(0) if M > 1 else out.shape[1]
     epi = _lib.Epilogue()
     epi.out_kind, epi.act, epi.scale_const = out_kind, act, float(scale_const)
+    epi.acc_abs_max = int(min(max(int(acc_abs_max), 0), 2**31 - 1))
     keep = []
 
     def sp(v, what):

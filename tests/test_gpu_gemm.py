@@ -162,6 +162,51 @@ def test_cta_pair_mode_bit_exact(ops, cta_group, M, N, K):
         L.qvit_gemm_set_cta_group(0)
 
 
+@pytest.mark.parametrize("d_next", [0.3, 2.1 / 127.0])
+def test_requantize_paths_agree(ops, d_next):
+    """The int8-output epilogue has three levels: packed interval test (hot), exact two-step Markstein division for rows
+    the interval test cannot decide, and the scalar IEEE-division sequence (ragged / NaN / generic quantizers; also what
+    the SIMT backend runs).  Forcing each level on the same data must give identical codes - for 4-bit steps (few doubts)
+    and 8-bit steps (|q| up to 127: many doubts) - and identical fp32 / bf16 outputs for the scalar path."""
+    from quantized_vit_b200 import _lib
+    M, N, K = 3000, 512, 768
+    a = _codes(M, K, -7, 7, 31).cuda()
+    w = _codes(N, K, -7, 7, 32).cuda()
+    bias = torch.randn(N).cuda()
+    # plant exact rounding ties: acc * s + bias = (k + 0.5) * d for some columns is not controllable, but a zero scale
+    # makes every output equal to its bias -> choose biases that ARE ties / boundaries of the next quantizer
+    bias[:64] = torch.arange(64, dtype=torch.float32).cuda().sub(32).add(0.5) * d_next
+    L = _lib.lib()
+    outs = {}
+    try:
+        for mode in (1, 101, 201):
+            assert L.qvit_gemm_set_cta_group(mode) == 0
+            for act in (ops.QVIT_ACT_NONE, ops.QVIT_ACT_GELU):
+                for sa in (0.01, 0.0):
+                    outs[(mode, act, sa)] = ops.gemm_i8(a, w, K, N, out_kind=ops.QVIT_OUT_I8, bias=bias, act=act, scale_a=sa, scale_w=0.02,
+                                                        next_q=(d_next, 2.1, None), backend=ops.QVIT_GEMM_TCGEN05, acc_abs_max=49 * K)
+            outs[(mode, "f32")] = ops.gemm_i8(a, w, K, N, out_kind=ops.QVIT_OUT_F32, bias=bias, act=ops.QVIT_ACT_GELU, scale_a=0.01,
+                                              scale_w=0.02, backend=ops.QVIT_GEMM_TCGEN05, acc_abs_max=49 * K)
+            outs[(mode, "bf16")] = ops.gemm_i8(a, w, K, N, out_kind=ops.QVIT_OUT_BF16, bias=bias, scale_a=0.01, scale_w=0.02,
+                                               backend=ops.QVIT_GEMM_TCGEN05)
+    finally:
+        L.qvit_gemm_set_cta_group(0)
+    for key, ref in outs.items():
+        if key[0] != 1:
+            continue
+        for mode in (101, 201):
+            got = outs[(mode,) + key[1:]]
+            assert torch.equal(got, ref), (key, mode, int((got != ref).sum()))
+    simt = ops.gemm_i8(a, w, K, N, out_kind=ops.QVIT_OUT_I8, bias=bias, act=ops.QVIT_ACT_GELU, scale_a=0.01, scale_w=0.02,
+                       next_q=(d_next, 2.1, None), backend=ops.QVIT_GEMM_SIMT)
+    assert torch.equal(simt, outs[(1, ops.QVIT_ACT_GELU, 0.01)])
+    # ties themselves: scale 0 -> y = bias exactly -> round-half-even of (k + 0.5), saturated at |q_m| / d
+    sat = round(2.1 / d_next)
+    d32 = torch.tensor([d_next], dtype=torch.float32)        # tensor / tensor: true fp32 division, as the reference does
+    want = torch.round(bias.cpu() / d32).clamp(-sat, sat).to(torch.int8)
+    assert torch.equal(outs[(1, ops.QVIT_ACT_NONE, 0.0)][0].cpu(), want)
+
+
 @pytest.mark.parametrize("M,N,K", [(300, 96, 200), (2000, 768, 3072), (768, 768, 25216), (130, 260, 64)])
 def test_bf16_split_gemm_matches_fp64(ops, M, N, K):
     """QAT gradient GEMM: fp32 operand as three exact bf16 planes x integer codes as bf16, fp32 accumulation in TMEM.
