@@ -229,6 +229,12 @@ int qvit_attention_f32(const float* qkv, int B, int T, int H, int head_dim, floa
                        qvit_stream_t stream);
 /* test hook: same, and dumps raw scores (cols 0..207) and un-normalised probabilities (cols 208..415) of every query
  * row into dbg [B, H, 256, 512] fp32 (caller-zeroed; cols 416..479 raw O, 480..482 row sums and 1/sum).                                                            */
+/* Same product with the consumer layer's quantize_act (QL:356-381; `proj` in ViTAttention.forward, VIT:151) fused into
+ * the epilogue: codes [B*T, ld_codes] int8, column h * head_dim + i, ld_codes >= H * head_dim and a multiple of 16 (padding
+ * columns are not written).  out (fp32 context) is optional.  d / q_m / t as qvit_quantize_sym. */
+int qvit_attention_quantize_sym(const float* qkv, int B, int T, int H, int head_dim, float scale, const float* d,
+                                const float* q_m, const float* t, int8_t* codes, int64_t ld_codes, float* out,
+                                int32_t* flags, qvit_stream_t stream);
 int qvit_attention_f32_debug(const float* qkv, int B, int T, int H, int head_dim, float scale, float* out,
                              float* dbg, int diag, qvit_stream_t stream);
 

@@ -61,6 +61,7 @@ PROTOTYPES = {
     "qvit_gemm_bf16_split": (_i, [_p, _i64, _i, _p, _i64, _i, _i, _i, _p, _i64, C.POINTER(Epilogue), _p]),
     "qvit_layernorm_quantize": (_i, [_p, _i64, _i, _p, _p, _f, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "qvit_attention_f32": (_i, [_p, _i, _i, _i, _i, _f, _p, _p]),
+    "qvit_attention_quantize_sym": (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "qvit_attention_f32_debug": (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _i, _p]),
     "qvit_quantize_sym_bf16": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _p, _p]),
 }

@@ -134,16 +134,22 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 // exact three-way split of two fp32 values into packed bf16 pairs (low half = first value)
+__device__ __forceinline__ uint32_t bf16x2_rn(float lo, float hi) {
+  const __nv_bfloat162 a = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&a);
+}
 __device__ __forceinline__ void split3_pair(float x, float y, uint32_t& p1, uint32_t& p2, uint32_t& p3) {
-  const __nv_bfloat162 a = __floats2bfloat162_rn(x, y);
-  const float2 af = __bfloat1622float2(a);
-  const float rx = x - af.x, ry = y - af.y;                    // exact
-  const __nv_bfloat162 b = __floats2bfloat162_rn(rx, ry);
-  const float2 bf = __bfloat1622float2(b);
-  const __nv_bfloat162 c = __floats2bfloat162_rn(rx - bf.x, ry - bf.y);   // exact remainder, <= 8 significant bits
-  p1 = *reinterpret_cast<const uint32_t*>(&a);
-  p2 = *reinterpret_cast<const uint32_t*>(&b);
-  p3 = *reinterpret_cast<const uint32_t*>(&c);
+  // per level: one F2FP (round both to bf16), two ALU ops to widen them again, one packed subtract (FFMA2, exact)
+  const f32x2 mone = pk1(-1.0f);
+  p1 = bf16x2_rn(x, y);
+  const f32x2 r1 = fma2(pk2(__uint_as_float(p1 << 16), __uint_as_float(p1 & 0xffff0000u)), mone, pk2(x, y));
+  float r1x, r1y;
+  unpk2(r1, r1x, r1y);
+  p2 = bf16x2_rn(r1x, r1y);
+  const f32x2 r2 = fma2(pk2(__uint_as_float(p2 << 16), __uint_as_float(p2 & 0xffff0000u)), mone, r1);
+  float r2x, r2y;
+  unpk2(r2, r2x, r2y);
+  p3 = bf16x2_rn(r2x, r2y);                                     // exact remainder, <= 8 significant bits
 }
 
 // 8 consecutive fp32 -> one 16-byte chunk (8 bf16) per plane
@@ -160,7 +166,9 @@ __device__ __constant__ const int kTermB[6] = {0, 1, 0, 1, 2, 0};
 
 __global__ void __launch_bounds__(kAttThreads, 1)
 attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* __restrict__ qkv, float* __restrict__ out,
-                     int T, int H, int total_work, float scale_log2e, float* __restrict__ dbg, int dump) {
+                     int T, int H, int total_work, float scale_log2e, float* __restrict__ dbg, int dump,
+                     int8_t* __restrict__ codes, int64_t ld_codes, const float* __restrict__ q_d, const float* __restrict__ q_qm,
+                     const float* __restrict__ q_t, int32_t* __restrict__ q_flags) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
@@ -177,6 +185,14 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row_floats = 3ll * H * kAttHd;
+  // optional fused activation quantizer of the consumer layer (`proj`): codes instead of / beside the fp32 context
+  SymParams qp;
+  FastQ qf;
+  int qfl = 0;
+  if (codes) {
+    qp = load_sym_params(q_d, q_qm, q_t);
+    qf = make_fastq(qp);
+  }
   const int q_tiles = (T + kAttMQ - 1) / kAttMQ;
 
   if (threadIdx.x == 0) {
@@ -305,7 +321,12 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
     tmem_ld_32x4(t_s + lane_addr + (uint32_t)(col0 + 48), r + 48);
     ptx::tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < kColQ; ++j) p[j] = (col0 + j < T) ? __uint_as_float(r[j]) : -INFINITY;   // masked keys: exp2(-inf) = 0
+    for (int j = 0; j < kColQ; ++j) p[j] = __uint_as_float(r[j]);
+    if (col0 + kColQ > T) {                                    // only the last column quarter holds padding keys
+#pragma unroll
+      for (int j = 0; j < kColQ; ++j)
+        if (col0 + j >= T) p[j] = -INFINITY;                   // masked keys: exp2(-inf) = 0
+    }
   }
   if (dump) {
     float* d = dbg + ((((int64_t)b * H + h) * 256 + q0 + row) * 512) + col0;
@@ -317,17 +338,25 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
   for (int j = 0; j < kColQ; ++j) mx = fmaxf(mx, p[j]);
   red_max[cq * kAttMQ + row] = mx;
   ptx::tc_fence_before();
-  __syncthreads();                                             // also: every thread has finished READING S from TMEM
+  // the four warps of a lane quarter share their rows' statistics and TMEM lanes: a 128-thread named barrier is enough
+  // (it also orders "all of them have READ S" before the P planes overwrite those columns)
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + (warp & 3)) : "memory");
   ptx::tc_fence_after();
   mx = fmaxf(fmaxf(red_max[row], red_max[kAttMQ + row]), fmaxf(red_max[2 * kAttMQ + row], red_max[3 * kAttMQ + row]));
-  const float mbias = mx * scale_log2e;
-  float sum = 0.f;
+  const f32x2 sc2 = pk1(scale_log2e), nb2 = pk1(-(mx * scale_log2e));
+  f32x2 sum2 = pk1(0.0f);
 #pragma unroll
-  for (int j = 0; j < kColQ; ++j) {
-    const float e = ex2_approx(fmaf(p[j], scale_log2e, -mbias));     // <= 2 ulp, argument <= 0
-    sum += e;
-    p[j] = e;
+  for (int j = 0; j < kColQ / 2; ++j) {
+    float a0, a1;
+    unpk2(fma2(pk2(p[2 * j], p[2 * j + 1]), sc2, nb2), a0, a1);
+    const float e0 = ex2_approx(a0), e1 = ex2_approx(a1);         // <= 2 ulp, argument <= 0
+    sum2 = add2(sum2, pk2(e0, e1));
+    p[2 * j] = e0;
+    p[2 * j + 1] = e1;
   }
+  float sum, sum_hi;
+  unpk2(sum2, sum, sum_hi);
+  sum += sum_hi;
   if (dump) {
     float* d = dbg + ((((int64_t)b * H + h) * 256 + q0 + row) * 512) + 208 + col0;
 #pragma unroll
@@ -412,11 +441,21 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
     }
     const int t = q0 + row;
     if (t < T) {
-      float* dst = out + ((int64_t)b * T + t) * ((int64_t)H * kAttHd) + h * kAttHd + cq * 16;
+      float v[16];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        stg_v4_b32(dst + 4 * j, __float_as_uint(__uint_as_float(r[4 * j]) * inv), __float_as_uint(__uint_as_float(r[4 * j + 1]) * inv),
-                   __float_as_uint(__uint_as_float(r[4 * j + 2]) * inv), __float_as_uint(__uint_as_float(r[4 * j + 3]) * inv));
+      for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(r[j]) * inv;
+      if (out) {
+        float* dst = out + ((int64_t)b * T + t) * ((int64_t)H * kAttHd) + h * kAttHd + cq * 16;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          stg_v4_b32(dst + 4 * j, __float_as_uint(v[4 * j]), __float_as_uint(v[4 * j + 1]), __float_as_uint(v[4 * j + 2]),
+                     __float_as_uint(v[4 * j + 3]));
+      }
+      if (codes) {                                             // quantize_act of the consumer layer (quant_layers.py:356-381)
+        int8_t* dst = codes + ((int64_t)b * T + t) * ld_codes + h * kAttHd + cq * 16;
+        stg_v4_b32(dst, sym_codes4(v[0], v[1], v[2], v[3], qp, qf, qfl), sym_codes4(v[4], v[5], v[6], v[7], qp, qf, qfl),
+                   sym_codes4(v[8], v[9], v[10], v[11], qp, qf, qfl), sym_codes4(v[12], v[13], v[14], v[15], qp, qf, qfl));
+      }
     }
   }
   // the next work item overwrites the Q planes (generic proxy) and TMEM: everyone must be done with this one
@@ -429,6 +468,10 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
   }
   }  // persistent loop
 
+  if (codes) {
+    qfl = warp_or(qfl);
+    if (qfl && q_flags && lane == 0) atomicOr(q_flags, qfl);
+  }
   ptx::tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -462,8 +505,13 @@ static EncodeTiledFn att_encode_fn() {
 using namespace qvit;
 
 static int attention_launch(const float* qkv, int B, int T, int H, int head_dim, float scale, float* out, float* dbg,
-                            int diag, qvit_stream_t stream) {
-  QVIT_REQUIRE(qkv && out && B > 0 && T > 0 && H > 0, "qvit_attention_f32: bad argument");
+                            int diag, qvit_stream_t stream, int8_t* codes = nullptr, int64_t ld_codes = 0,
+                            const float* q_d = nullptr, const float* q_qm = nullptr, const float* q_t = nullptr,
+                            int32_t* q_flags = nullptr) {
+  QVIT_REQUIRE(qkv && (out || codes) && B > 0 && T > 0 && H > 0, "qvit_attention_f32: bad argument");
+  QVIT_REQUIRE(!codes || (q_d && q_qm && ld_codes >= (int64_t)H * head_dim && (ld_codes & 15) == 0 &&
+                          (reinterpret_cast<uintptr_t>(codes) & 15) == 0),
+               "qvit_attention_quantize_sym: codes need 16-byte alignment, a pitch >= H * head_dim that is a multiple of 16, and d / q_m");
   if (head_dim != kAttHd || T > kAttNK) {
     set_error("qvit_attention_f32: supports head_dim == 64 and T <= 208 (got head_dim=%d, T=%d)", head_dim, T);
     return QVIT_ERR_UNSUPPORTED;
@@ -505,13 +553,23 @@ static int attention_launch(const float* qkv, int B, int T, int H, int head_dim,
   QVIT_REQUIRE(total_work < (1ll << 30), "qvit_attention_f32: problem too large");
   const int grid = (int)(total_work < sm_count() ? total_work : sm_count());
   attention_f32_kernel<<<grid, kAttThreads, kAttSmem, (cudaStream_t)stream>>>(tkv, qkv, out, T, H, (int)total_work,
-                                                                             scale * 1.4426950408889634f, dbg, (dbg != nullptr && diag == 0) ? 1 : 0);
+                                                                             scale * 1.4426950408889634f, dbg, (dbg != nullptr && diag == 0) ? 1 : 0,
+                                                                             codes, ld_codes, q_d, q_qm, q_t, q_flags);
   return check_launch("qvit_attention_f32");
 }
 
 extern "C" int qvit_attention_f32(const float* qkv, int B, int T, int H, int head_dim, float scale, float* out,
                                   qvit_stream_t stream) {
   return attention_launch(qkv, B, T, H, head_dim, scale, out, nullptr, 0, stream);
+}
+
+// Attention core with the consumer layer's activation quantizer fused into the epilogue: int8 codes [B*T, ld_codes]
+// (columns h * 64 + i) of softmax(QK^T scale) V, optionally the fp32 context as well (out may be NULL).
+extern "C" int qvit_attention_quantize_sym(const float* qkv, int B, int T, int H, int head_dim, float scale, const float* d,
+                                           const float* q_m, const float* t, int8_t* codes, int64_t ld_codes, float* out,
+                                           int32_t* flags, qvit_stream_t stream) {
+  QVIT_REQUIRE(codes != nullptr, "qvit_attention_quantize_sym: codes is NULL");
+  return attention_launch(qkv, B, T, H, head_dim, scale, out, nullptr, 0, stream, codes, ld_codes, d, q_m, t, flags);
 }
 
 // test hook: additionally dumps raw scores S (cols 0..207) and un-normalised probabilities P (cols 208..415) per query row

@@ -199,6 +199,7 @@ __device__ __forceinline__ long long global_ns() {
 // the fp32 gradient operand arrives as three exact bf16 planes concatenated along K, the integer codes as one bf16
 // plane that is re-read for every A plane (`b_wrap` k-blocks), i.e. D = (A1 + A2 + A3) * B^T with fp32 accumulation.
 template <int BN, int OUT, int CG, int KIND>
+// (96 registers is the ceiling for 18 warps: the register file is allocated per warp in units that put 104..112 out of reach)
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,

@@ -134,9 +134,13 @@ class ViTInferenceEngine:
         # kernel at 3e-6 vs 1e-6 max-norm error (tensor-core accumulation rounding), i.e. 0-5 proj-input code flips per
         # 302 592 elements and Block against the CPU reference (tests/test_gpu_models.py); attention="sdpa" selects the library
         use_tc3x = self.attention == "tc3x" or (self.attention == "auto" and not bf16 and ops.attention_f32_supported(NT, hd))
+        cp = None
         if use_tc3x:
-            # own kernel: 3xTF32 on tcgen05, fp32-equivalent accuracy, reads the qkv matrix in place (vit_model.py:133-149)
-            o = ops.attention_f32(qkv.view(B, NT, 3 * D), H).view(B * NT, D)
+            # own kernel, reads the qkv matrix in place (vit_model.py:133-149); proj's quantize_act (QL:356-381) is fused
+            # into its epilogue, so the fp32 context never touches HBM unless a tap asks for it
+            cp, o = ops.attention_quantize_sym(qkv.view(B, NT, 3 * D), H, proj_l.d_act, proj_l.qm_act, proj_l.t_act,
+                                               want_context=taps is not None, flags=self.flags)
+            o = None if o is None else o.view(B * NT, D)
         else:
             qkv = qkv.view(B, NT, 3, H, hd)
             q, k, v = (qkv[:, :, j].transpose(1, 2) for j in range(3))        # [B, H, NT, hd] views
@@ -147,7 +151,8 @@ class ViTInferenceEngine:
             o = o.transpose(1, 2).reshape(B * NT, D)
         if taps is not None:
             taps[f"{pre}.attn.proj.in"] = o.float().view(B, NT, D).clone()
-        cp = ops.quantize_sym(o, proj_l.d_act, proj_l.qm_act, proj_l.t_act, ld_codes=ops.pad16(D), flags=self.flags)
+        if cp is None:
+            cp = ops.quantize_sym(o, proj_l.d_act, proj_l.qm_act, proj_l.t_act, ld_codes=ops.pad16(D), flags=self.flags)
         self._gemm(cp, proj_l, out_kind=ops.QVIT_OUT_F32, residual=h2, out=h2)  # h += proj(o)   (vit_model.py:206)
         c2, _ = ops.layernorm_quantize(h2, sd[f"{pre}.norm2.weight"], sd[f"{pre}.norm2.bias"], self.eps, fc1_l.d_act,
                                        fc1_l.qm_act, fc1_l.t_act, flags=self.flags)

@@ -180,6 +180,31 @@ def attention_f32(qkv: torch.Tensor, num_heads: int, scale: Optional[float] = No
     return out
 
 
+def attention_quantize_sym(qkv: torch.Tensor, num_heads: int, d, q_m, t=None, *, scale: Optional[float] = None,
+                           want_context: bool = False, flags: Optional[torch.Tensor] = None):
+    """attention_f32 with the consumer layer's quantize_act fused into the epilogue (ViTAttention.forward, vit_model.py:141-151:
+    the context only feeds `proj`).  Returns (codes [B*T, pad16(H*64)] int8, context [B, T, H*64] fp32 | None)."""
+    qkv = _f32c(qkv, "attention_quantize_sym")
+    B, T, C3 = qkv.shape
+    hd = C3 // (3 * num_heads)
+    if hd * 3 * num_heads != C3:
+        raise ValueError("attention_quantize_sym: last dim must be 3 * num_heads * head_dim")
+    dev = qkv.device
+    C = num_heads * hd
+    ld = pad16(C)
+    codes = torch.empty((B * T, ld), dtype=torch.int8, device=dev)
+    if ld > C:
+        codes[:, C:].zero_()
+    ctx = torch.empty((B, T, C), dtype=torch.float32, device=dev) if want_context else None
+    d_, q_ = _scalar_param(d, dev, "d_quant"), _scalar_param(q_m, dev, "q_m")
+    t_ = None if t is None else _scalar_param(t, dev, "t_quant")
+    sc = float(hd) ** -0.5 if scale is None else float(scale)
+    _lib.check(_lib.lib().qvit_attention_quantize_sym(_lib.ptr(qkv), B, T, num_heads, hd, sc, _lib.ptr(d_), _lib.ptr(q_), _lib.ptr(t_),
+                                                      _lib.ptr(codes), ld, _lib.ptr(ctx), _lib.ptr(flags), _lib.stream()),
+               "qvit_attention_quantize_sym")
+    return codes, ctx
+
+
 def attention_f32_supported(T: int, head_dim: int) -> bool:
     return head_dim == 64 and T <= 208
 

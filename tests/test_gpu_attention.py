@@ -38,3 +38,21 @@ def test_attention_rejects_unsupported_shapes():
         ops.attention_f32(torch.randn(1, 10, 3 * 2 * 32).cuda(), 2)
     with pytest.raises(RuntimeError, match="T <= 208"):
         ops.attention_f32(torch.randn(1, 300, 3 * 64).cuda(), 1)
+
+
+@pytest.mark.parametrize("B,T,H", [(2, 197, 12), (3, 129, 2), (1, 5, 1)])
+@pytest.mark.parametrize("nonlinear", [False, True])
+def test_fused_quantizer_equals_separate_quantize(B, T, H, nonlinear):
+    """qvit_attention_quantize_sym = qvit_attention_f32 followed by qvit_quantize_sym (the consumer's quantize_act,
+    quant_layers.py:356-381), bit for bit, and the optional fp32 context equals the unfused one."""
+    from quantized_vit_b200 import ops
+    g = torch.Generator().manual_seed(B * 77 + T)
+    qkv = torch.randn(B, T, 3 * H * 64, generator=g).cuda()
+    d, qm, t = 0.031, 0.217, (0.9 if nonlinear else None)
+    ctx = ops.attention_f32(qkv, H)
+    want = ops.quantize_sym(ctx.view(B * T, H * 64), d, qm, t, ld_codes=ops.pad16(H * 64))
+    codes, ctx2 = ops.attention_quantize_sym(qkv, H, d, qm, t, want_context=True)
+    assert torch.equal(ctx2, ctx)
+    assert torch.equal(codes, want)
+    codes_only, none = ops.attention_quantize_sym(qkv, H, d, qm, t)
+    assert none is None and torch.equal(codes_only, want)
