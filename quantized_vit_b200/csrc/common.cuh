@@ -210,6 +210,35 @@ __device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
   return fma2(t, pk2(h0, h1), pk2(r0, r1));
 }
 
+// Four pairs at once, coefficient-major (four independent Horner chains per thread for the scheduler to interleave).
+__device__ __forceinline__ void gelu_erf2x4(f32x2 (&x)[4]) {
+  f32x2 t[4], p[4];
+  float x0[4], x1[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    unpk2(x[i], x0[i], x1[i]);
+    t[i] = pk2(fmaxf(-fabsf(x0[i]), -5.939696788787842f), fmaxf(-fabsf(x1[i]), -5.939696788787842f));
+    p[i] = fma2(pk1(-2.2758645172871184e-06f), t[i], pk1(-3.296791692264378e-05f));
+  }
+  constexpr float c[7] = {-0.0001572782639414072f, 0.00020248025248292834f, 0.007142783608287573f, 0.052546434104442596f,
+                          -0.45919305086135864f, 1.1511069536209106f, -0.9999999403953552f};
+#pragma unroll
+  for (int k = 0; k < 7; ++k) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = fma2(p[i], t[i], pk1(c[k]));
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float p0, p1, h0, h1, r0, r1;
+    unpk2(p[i], p0, p1);
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h0) : "f"(p0));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(p1));
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r0) : "f"(x0[i]), "f"(0.0f));
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r1) : "f"(x1[i]), "f"(0.0f));
+    x[i] = fma2(t[i], pk2(h0, h1), pk2(r0, r1));
+  }
+}
+
 // Pair form of the fast quantizer for the GEMM epilogue (no conversion-unit instruction, 2 FFMA2-slots per element):
 //   ta = fma(y, inv_hi, 1.5 * 2^23), tb = fma(y, inv_lo, 1.5 * 2^23),  inv_hi/lo = RN(1/d) * (1 +- 3e-7)
 // each fma rounds the exact product to the nearest integer (ties to even).  The reference's quotient RN(y / d) lies

@@ -117,7 +117,7 @@ __device__ __forceinline__ void epi_math32(const EpiParams& e, const uint32_t (&
   }
   if (e.act == QVIT_ACT_GELU) {
 #pragma unroll
-    for (int j = 0; j < 16; ++j) y[j] = gelu_erf2(y[j]);
+    for (int g = 0; g < 4; ++g) gelu_erf2x4(reinterpret_cast<f32x2(&)[4]>(y[4 * g]));
   } else if (e.act == QVIT_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {

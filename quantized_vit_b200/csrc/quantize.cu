@@ -228,14 +228,24 @@ layernorm_quantize_kernel(const float* __restrict__ x, int64_t rows, const float
   const int64_t warp_stride = (int64_t)gridDim.x * (kThreads / 32);
   const float4* g4 = reinterpret_cast<const float4*>(gamma);
   const float4* b4 = reinterpret_cast<const float4*>(beta);
+  // software pipeline: the loads of the warp's NEXT row are in flight while the current row is reduced, normalised and
+  // stored (two dependent warp reductions per row would otherwise leave the memory system idle in between)
+  float4 nxt[V];
+  if (warp_global < rows) {
+#pragma unroll
+    for (int j = 0; j < V; ++j) nxt[j] = ldg_stream4(x + warp_global * cols + j * 128 + lane * 4);
+  }
   for (int64_t r = warp_global; r < rows; r += warp_stride) {
-    const float* src = x + r * cols;
     float4 v[V];
     float s = 0.f;
 #pragma unroll
     for (int j = 0; j < V; ++j) {
-      v[j] = ldg_stream4(src + j * 128 + lane * 4);
+      v[j] = nxt[j];
       s += (v[j].x + v[j].y) + (v[j].z + v[j].w);
+    }
+    if (r + warp_stride < rows) {
+#pragma unroll
+      for (int j = 0; j < V; ++j) nxt[j] = ldg_stream4(x + (r + warp_stride) * cols + j * 128 + lane * 4);
     }
     const float mean = warp_sum(s) * (1.0f / cols);
     float q = 0.f;
@@ -420,11 +430,19 @@ int qvit_layernorm_quantize(const float* x, int64_t rows, int cols, const float*
                     ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && ((reinterpret_cast<uintptr_t>(codes) & 3) == 0) &&
                     ((reinterpret_cast<uintptr_t>(gamma) & 15) == 0) && ((reinterpret_cast<uintptr_t>(beta) & 15) == 0) &&
                     (!ln_out || (reinterpret_cast<uintptr_t>(ln_out) & 15) == 0);
+  // persistent sizing: as many CTAs as are resident at once (the row loop is software pipelined, a second wave would
+  // only pay the pipeline prologue again)
 #define QVIT_LN_CASE(V)                                                                                            \
-  case V:                                                                                                          \
-    layernorm_quantize_kernel<V><<<grid, kThreads, 0, s>>>(x, rows, gamma, beta, eps, d, q_m, t, codes, ld_codes,  \
-                                                           ln_out, flags);                                         \
-    break;
+  case V: {                                                                                                        \
+    static int per_sm = 0;                                                                                         \
+    if (per_sm == 0 &&                                                                                             \
+        (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, layernorm_quantize_kernel<V>, kThreads, 0) !=      \
+             cudaSuccess || per_sm < 1))                                                                           \
+      per_sm = 1;                                                                                                  \
+    const int g = stream_grid(rows, kThreads / 32, per_sm);                                                        \
+    layernorm_quantize_kernel<V><<<g, kThreads, 0, s>>>(x, rows, gamma, beta, eps, d, q_m, t, codes, ld_codes,     \
+                                                        ln_out, flags);                                            \
+  } break;
   if (fast) {
     switch (cols / 128) {
       QVIT_LN_CASE(1) QVIT_LN_CASE(2) QVIT_LN_CASE(3) QVIT_LN_CASE(4) QVIT_LN_CASE(5) QVIT_LN_CASE(6) QVIT_LN_CASE(7)
