@@ -418,13 +418,14 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
   }
   // meanwhile: the Q planes are dead since the S product -> fetch and convert the NEXT work item's Q tile
   if (work + (int)gridDim.x < total_work) convert_q(work + gridDim.x);
+  // (the row sums are complete since the barrier after phase 5)
+  const float inv = __fdiv_rn(1.0f, (red_sum[row] + red_sum[kAttMQ + row]) + (red_sum[2 * kAttMQ + row] + red_sum[3 * kAttMQ + row]));
   ptx::mbar_wait(bar_o, par);
   ptx::tc_fence_after();
   if (prof) ts[6] = clock64();
 
   // ---- phase 6: normalise and store.  Column quarter cq of each lane quarter takes head-dim [16*cq, 16*cq + 16)
   {
-    const float inv = __fdiv_rn(1.0f, (red_sum[row] + red_sum[kAttMQ + row]) + (red_sum[2 * kAttMQ + row] + red_sum[3 * kAttMQ + row]));
     uint32_t r[16], r2[16], r3[16];
     tmem_ld_32x16(t_o + lane_addr + (uint32_t)(cq * 16), r);
     tmem_ld_32x16(t_o + lane_addr + (uint32_t)(64 + cq * 16), r2);

@@ -763,13 +763,13 @@ int gemm_tc_launch(const void* a, int64_t lda, int a_unsigned, const int8_t* w, 
     const int64_t t256 = (int64_t)((M + kBM - 1) / kBM) * ((N + 255) / 256);
     if (t256 < sms) bn = 128;
   }
-  // CTA pairs once there is at least one full wave of [256 x 256] pair tiles
-  // Measured (tools/epi_bench.py, M = 50 432): pairs win when the epilogue is light (main loop only 129 -> 114 us, bf16
-  // out 181 -> 167 us) and lose a little when it is the bottleneck (fp32 + residual 282 -> 310 us, int8 + GELU 310 -> 320 us),
-  // so automatic mode uses them for the raw / bf16 kinds only.
+  // CTA pairs once there is at least one full wave of [256 x 256] pair tiles.  Measured (tools/epi_bench.py, M = 50 432,
+  // graph-timed): pairs win when the main loop dominates - raw / bf16 output (768 -> 3072: 124 -> 120 us) and long
+  // contractions (3072 -> 768 fp32 + residual: 122 -> 113 us) - and lose where the epilogue or HBM is the limit
+  // (768 -> 2304 fp32: 120 -> 123 us, 768 -> 768 fp32 + residual: 63 -> 71 us, int8 + GELU: 174 -> 181 us).
   int cg = 1;
   if (bn == 256 && (int64_t)((M + 2 * kBM - 1) / (2 * kBM)) * ((N + 255) / 256) * 2 >= sms &&
-      (ep.out_kind == QVIT_OUT_BF16 || ep.out_kind == QVIT_OUT_I32 || ep.out_kind == QVIT_OUT_NONE) && !ep.residual)
+      (K >= 2048 || ((ep.out_kind == QVIT_OUT_BF16 || ep.out_kind == QVIT_OUT_I32 || ep.out_kind == QVIT_OUT_NONE) && !ep.residual)))
     cg = 2;
   if (g_force_cg == 1) cg = 1;
   if (g_force_cg == 2 && bn == 256) cg = 2;

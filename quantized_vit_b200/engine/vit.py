@@ -237,7 +237,8 @@ class ViTInferenceEngine:
     def infer_many(self, host_batches) -> list:
         """Pipelined end-to-end inference over a sequence of pinned HOST batches of one shape: the host->device copy
         of batch i+1 (copy stream, double-buffered staging) and the device->host copy of the logits of batch i-1 run
-        while the captured forward of batch i executes.  Returns one host logits tensor per batch."""
+        while the captured forward of batch i executes.  Returns one host logits tensor per batch; they live in the
+        engine's pinned result pool and stay valid until the next infer_many call (clone to keep them longer)."""
         batches = list(host_batches)
         if not batches:
             return []
@@ -249,7 +250,10 @@ class ViTInferenceEngine:
             st = self._pinned[key] = {
                 "stage": [torch.empty_like(xs) for _ in range(2)], "h2d": torch.cuda.Stream(device=self.device),
                 "d2h": torch.cuda.Stream(device=self.device), "ydev": [torch.empty_like(ys) for _ in range(2)]}
-        outs = [torch.empty(ys.shape, dtype=ys.dtype, pin_memory=True) for _ in batches]
+        pool = st.setdefault("outs", [])                      # page-locked allocations cost milliseconds: made once, reused
+        while len(pool) < len(batches):
+            pool.append(torch.empty(ys.shape, dtype=ys.dtype, pin_memory=True))
+        outs = pool[:len(batches)]
         main = torch.cuda.current_stream()
         copied = [torch.cuda.Event() for _ in range(2)]      # staging[j] filled
         consumed = [torch.cuda.Event() for _ in range(2)]    # staging[j] read by the compute stream

@@ -237,6 +237,22 @@ def test_vit_engine_cuda_graph_replay_is_identical(golden):
     assert torch.equal(ys, eager)
 
 
+def test_vit_engine_pipelined_host_api(golden):
+    """infer_many (pinned host batches in, host logits out, copies overlapped with the captured forward) returns exactly
+    what the device-resident forward returns, batch by batch, also when the result pool is reused by a second call."""
+    from quantized_vit_b200.engine import ViTInferenceEngine
+    g, sd, x, cfg = _vit_case(golden, "vit_tiny_w4a4_calib")
+    eng = ViTInferenceEngine(sd, **cfg)
+    gen = torch.Generator().manual_seed(5)
+    batches = [torch.randn(x.shape, generator=gen).pin_memory() for _ in range(5)]
+    want = [eng(b.cuda()).cpu() for b in batches]
+    got = [o.clone() for o in eng.infer_many(batches)]
+    assert all(torch.equal(a, b) for a, b in zip(got, want))
+    again = eng.infer_many(batches[::-1])
+    assert all(torch.equal(a, b) for a, b in zip(again, want[::-1]))
+    assert torch.equal(eng.infer(batches[2]), want[2])
+
+
 def test_vit_dropin_modules_equal_engine(golden):
     """The same network assembled from the drop-in QuantizeLinear/QuantizeConv2d modules (module-by-module path, fp32 in
     and out of every layer) agrees with the reference logits as well."""

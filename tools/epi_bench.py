@@ -3,7 +3,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from quantized_vit_b200 import ops
 from tools.quick_bench import timeit
-M, K, N = 50432, 768, 3072
+M, K, N = 50432, int(os.environ.get("K", 768)), int(os.environ.get("N", 3072))
 a = torch.randint(-7, 8, (M, K), dtype=torch.int8, device="cuda")
 w = torch.randint(-7, 8, (N, K), dtype=torch.int8, device="cuda")
 bias = torch.randn(N, device="cuda")
