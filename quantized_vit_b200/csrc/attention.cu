@@ -7,16 +7,17 @@
 // and each product is evaluated as b1*b1' + b1*b2' + b2*b1' + b2*b2' + b1*b3' + b3*b1' with fp32 accumulation in
 // TMEM (dropped terms <= 2^-24 relative): fp32-level accuracy at tensor-core speed, same MMA count as 3xTF32.
 //
-// One CTA = one (batch, head) and one tile of 128 queries; keys/values of the whole sequence (T <= 208) are resident.
-//   phase 1  TMA loads the raw fp32 K tile [208 x 64]; meanwhile all threads read the Q tile from global memory and
-//            write its three bf16 planes (K-major, 128B swizzle: one 128-byte row = the 64 head-dim values)
-//   phase 2  raw K -> three bf16 planes
-//   phase 3  S = Q K^T: 4 k-steps x 6 terms of tcgen05.mma kind::f16 (M=128, N=208, K=16), accumulator in TMEM
-//   phase 4  softmax over the row held by each thread (thread = query row; two warps share a row's columns);
-//            P = exp2((S - max) * scale * log2e) goes back to TMEM as three packed-bf16 planes (A operand of phase 5);
-//            meanwhile TMA loads the raw V tile
-//   phase 5  raw V -> three TRANSPOSED bf16 planes V^T [64 x keys] (K-major); O = P V: 13 k-steps x 6 terms, A from TMEM
-//   phase 6  O / rowsum -> global [B, T, H*64]
+// One work unit = one (batch, head): its K planes [208 x 64] and V^T planes [64 x 208] stay resident in shared memory
+// for both tiles of 128 queries (T <= 208).  All conversions read the fp32 qkv matrix in place (global loads issued ahead
+// of a running MMA batch) and write K-major, 128-byte-swizzled bf16 planes.  Per query tile:
+//   phase A  S = Q K^T: 4 k-steps x 6 terms of tcgen05.mma kind::f16 (M=128, N=208, K=16), accumulator in TMEM
+//            || V -> three TRANSPOSED bf16 planes V^T (first tile of the pair)
+//   phase B  softmax over the row held by each thread (thread = query row; four warps share a row's columns);
+//            P = exp2((S - max) * scale * log2e) goes back to TMEM as three packed-bf16 planes (A operand of phase C)
+//   phase C  O = P V: 13 k-steps x 6 terms, A from TMEM, B = V^T planes stacked to N = 192 / 128 / 64
+//            || Q planes of the next tile (and K planes of the next pair)
+//   phase D  O / rowsum -> (quantize ->) global [B, T, H*64]
+// TMEM: S 208 columns, overwritten by P (3 x 104), O partials 192 columns.  Shared memory: 222 KiB of planes.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -30,10 +31,10 @@ constexpr int kAttNK = 208;           // keys per CTA (13 x 16): UMMA N of the S
 constexpr int kAttThreads = 512;      // 16 warps: four per TMEM lane quarter, each owning a quarter (52) of the key columns
 constexpr int kColQ = kAttNK / 4;     // 52 key columns per thread in the softmax
 constexpr int kQPlane = kAttMQ * 128;             // bf16 Q plane   [128 rows x 64 bf16]            16 KiB
-constexpr int kKVPlane = 4 * kAttHd * 128;        // bf16 K plane [208 x 64] (26 KiB) or V^T plane: 4 sub-tiles [64 x 64 keys] 32 KiB
+constexpr int kKVPlane = 4 * kAttHd * 128;        // bf16 V^T plane: 4 sub-tiles [64 head-dim rows x 64 keys]        32 KiB
 constexpr int kVtSub = kAttHd * 128;               // one V^T sub-tile of one plane: [64 head-dim rows x 64 keys] 8 KiB
-constexpr int kRawSub = kAttNK * 128;             // raw fp32 sub-tile [208 rows x 32 floats]        26 KiB
-constexpr int kAttSmem = 3 * kQPlane + 3 * kKVPlane + 2 * kRawSub + 8192 + 1024;
+constexpr int kKPlane = kAttNK * 128;             // bf16 K plane [208 key rows x 64 bf16]             26 KiB
+constexpr int kAttSmem = 3 * kQPlane + 3 * kKPlane + 3 * kKVPlane + 128 + 1024;   // 222 KiB of planes + barriers + alignment slack
 constexpr int kPCols = kAttNK / 2;                // TMEM columns of one packed-bf16 P plane (104)
 constexpr int kOCol = 320;                        // TMEM columns [320, 512): three partial O accumulators of 64 columns
 
@@ -165,26 +166,28 @@ __device__ __constant__ const int kTermA[6] = {0, 0, 1, 1, 0, 2};
 __device__ __constant__ const int kTermB[6] = {0, 1, 0, 1, 2, 0};
 
 __global__ void __launch_bounds__(kAttThreads, 1)
-attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* __restrict__ qkv, float* __restrict__ out,
-                     int T, int H, int total_work, float scale_log2e, float* __restrict__ dbg, int dump,
-                     int8_t* __restrict__ codes, int64_t ld_codes, const float* __restrict__ q_d, const float* __restrict__ q_qm,
-                     const float* __restrict__ q_t, int32_t* __restrict__ q_flags) {
+attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int T, int H, int total_pairs, float scale_log2e,
+                     float* __restrict__ dbg, int dump, int8_t* __restrict__ codes, int64_t ld_codes,
+                     const float* __restrict__ q_d, const float* __restrict__ q_qm, const float* __restrict__ q_t,
+                     int32_t* __restrict__ q_flags) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
-  // layout: Q planes (3 x 16 KiB) | K / V^T planes (3 x 32 KiB) | raw fp32 K or V tile (2 x 26 KiB) | misc
-  const uint32_t q_pl = base, kv_pl = base + 3 * kQPlane, raw = kv_pl + 3 * kKVPlane, misc_a = raw + 2 * kRawSub;
+  // layout: Q planes (3 x 16 KiB) | K planes (3 x 26 KiB) | V^T planes (3 x 32 KiB) | barriers.  The softmax row statistics
+  // (4 KiB) alias the Q planes, which are dead between the S product and the conversion of the next Q tile.
+  const uint32_t q_pl = base, k_pl = base + 3 * kQPlane, v_pl = k_pl + 3 * kKPlane, misc_a = v_pl + 3 * kKVPlane;
   uint8_t* g_q = gen;
-  uint8_t* g_kv = gen + 3 * kQPlane;
-  uint8_t* g_raw = g_kv + 3 * kKVPlane;
-  uint8_t* misc = g_raw + 2 * kRawSub;
-  const uint32_t bar_k = misc_a, bar_v = misc_a + 8, bar_s = misc_a + 16, bar_o = misc_a + 24;
-  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc + 32);
-  float* red_max = reinterpret_cast<float*>(misc + 64);          // [4][128]
+  uint8_t* g_k = gen + 3 * kQPlane;
+  uint8_t* g_v = g_k + 3 * kKPlane;
+  uint8_t* misc = g_v + 3 * kKVPlane;
+  const uint32_t bar_s = misc_a, bar_o = misc_a + 8;
+  volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(misc + 16);
+  float* red_max = reinterpret_cast<float*>(g_q);                 // [4][128]
   float* red_sum = red_max + 4 * kAttMQ;                         // [4][128]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t row_floats = 3ll * H * kAttHd;
+  const int q_tiles = (T + kAttMQ - 1) / kAttMQ;
   // optional fused activation quantizer of the consumer layer (`proj`): codes instead of / beside the fp32 context
   SymParams qp;
   FastQ qf;
@@ -193,12 +196,8 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
     qp = load_sym_params(q_d, q_qm, q_t);
     qf = make_fastq(qp);
   }
-  const int q_tiles = (T + kAttMQ - 1) / kAttMQ;
 
   if (threadIdx.x == 0) {
-    ptx::prefetch_tmap(&tmap_kv);
-    ptx::mbar_init(bar_k, 1);
-    ptx::mbar_init(bar_v, 1);
     ptx::mbar_init(bar_s, 1);
     ptx::mbar_init(bar_o, 1);
     ptx::fence_mbar_init();
@@ -213,16 +212,11 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
   const uint32_t tmem = *tmem_slot;
   const uint32_t t_s = tmem, t_o = tmem + kOCol;
 
-  // persistent over (batch, head, query tile); the raw K tile of the NEXT work item is prefetched during phase 5/6
-  auto issue_k = [&](int w) {
-    const int hh = (w / q_tiles) % H, bb = w / (q_tiles * H);
-    ptx::mbar_expect_tx(bar_k, 2 * kRawSub);
-    for (int s = 0; s < 2; ++s) tma_load_3d(raw + s * kRawSub, &tmap_kv, bar_k, (1 * H + hh) * kAttHd + s * 32, 0, bb);
-  };
-  // Q tile of work item w: global fp32 -> three bf16 planes (K-major, 128B swizzle).  All eight 16-byte loads are
-  // issued before the first use: one memory round trip.
-  auto convert_q = [&](int w) {
-    const int qt = w % q_tiles, hh = (w / q_tiles) % H, bb = w / (q_tiles * H);
+  // ---- operand conversions, straight from global memory (the qkv matrix is read in place): fp32 -> three exact bf16 planes,
+  // K-major with the 128-byte swizzle.  All loads of a pass are issued before the first use: one memory round trip, which
+  // the caller hides behind a running MMA batch.
+  // Q tile (128 queries x 64) of (bb, hh, qt)
+  auto convert_q = [&](int bb, int hh, int qt) {
     constexpr int kIt = kAttMQ * 8 / kAttThreads;
     float4 u[kIt], v[kIt];
 #pragma unroll
@@ -250,39 +244,106 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
       *reinterpret_cast<uint4*>(g_q + 2 * kQPlane + off) = c3;
     }
   };
-  if (threadIdx.x == 0 && (int)blockIdx.x < total_work) issue_k(blockIdx.x);
-  uint32_t par = 0;                                            // every mbarrier completes exactly once per work item
-#pragma unroll 1
-  for (int work = blockIdx.x; work < total_work; work += gridDim.x, par ^= 1u) {
-  const int q_tile = work % q_tiles, h = (work / q_tiles) % H, b = work / (q_tiles * H);
-  const int q0 = q_tile * kAttMQ;
-  long long ts[8];
-  const bool prof = dbg && blockIdx.x == 0 && threadIdx.x == 64 && work == (int)(blockIdx.x + gridDim.x);   // 2nd item of CTA 0
-  if (prof) ts[0] = clock64();
+  // K (208 key rows x 64; rows >= T are zero) of (bb, hh): two passes of two pieces per thread
+  auto convert_k = [&](int bb, int hh) {
+    constexpr int kIt = (kAttNK * 8 + kAttThreads - 1) / kAttThreads;   // 4 (the last one covers 128 threads)
+    float4 u[kIt], v[kIt];
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      const int item = threadIdx.x + it * kAttThreads;
+      const int r = item >> 3, c = item & 7;
+      u[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      v[it] = u[it];
+      if (item < kAttNK * 8 && r < T) {
+        const float* src = qkv + ((int64_t)bb * T + r) * row_floats + (1 * H + hh) * kAttHd + c * 8;
+        u[it] = ldg_stream4(src);
+        v[it] = ldg_stream4(src + 4);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      const int item = threadIdx.x + it * kAttThreads;
+      if (item < kAttNK * 8) {
+        const int r = item >> 3, c = item & 7;
+        uint4 c1, c2, c3;
+        split3_chunk(u[it], v[it], c1, c2, c3);
+        const int off = r * 128 + ((c ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(g_k + off) = c1;
+        *reinterpret_cast<uint4*>(g_k + kKPlane + off) = c2;
+        *reinterpret_cast<uint4*>(g_k + 2 * kKPlane + off) = c3;
+      }
+    }
+  };
+  // V (keys x 64) of (bb, hh) -> three TRANSPOSED planes V^T [64 head-dim rows x keys]; one warp item = 32 head-dim rows x
+  // 8 consecutive keys (lane = head-dim index: every load instruction reads 128 contiguous bytes of one key row).
+  // Layout [64-key sub-tile][plane][64 rows x 128 B]: the three planes of a sub-tile are contiguous, so one MMA with
+  // N = 192 / 128 / 64 multiplies a P plane with V1|V2|V3, V1|V2 or V1 at once.
+  auto convert_vt = [&](int bb, int hh) {
+    constexpr int kItems = 2 * (kAttNK / 8), kWarps = kAttThreads / 32, kIt = (kItems + kWarps - 1) / kWarps;   // 52 items, 4 per warp
+    float x[kIt][8];
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      const int item = warp + it * kWarps;
+      const int hsub = item / (kAttNK / 8), kg = item - hsub * (kAttNK / 8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int key = 8 * kg + i;
+        x[it][i] = (item < kItems && key < T)
+                       ? __ldg(qkv + ((int64_t)bb * T + key) * row_floats + (2 * H + hh) * kAttHd + hsub * 32 + lane)
+                       : 0.0f;
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kIt; ++it) {
+      const int item = warp + it * kWarps;
+      if (item < kItems) {
+        const int hsub = item / (kAttNK / 8), kg = item - hsub * (kAttNK / 8);
+        const int hd = hsub * 32 + lane;
+        uint4 c1, c2, c3;
+        split3_chunk(make_float4(x[it][0], x[it][1], x[it][2], x[it][3]), make_float4(x[it][4], x[it][5], x[it][6], x[it][7]), c1, c2, c3);
+        const int off = (kg >> 3) * (3 * kVtSub) + hd * 128 + (((kg & 7) ^ (hd & 7)) << 4);
+        *reinterpret_cast<uint4*>(g_v + off) = c1;
+        *reinterpret_cast<uint4*>(g_v + kVtSub + off) = c2;
+        *reinterpret_cast<uint4*>(g_v + 2 * kVtSub + off) = c3;
+      }
+    }
+  };
+  // L2 prefetch of the 128-byte lines a later conversion reads (one line per thread): the conversion's loads then see an
+  // L2 hit instead of an HBM round trip.  part: 0 = Q tile qt, 1 = K, 2 = V of (bb, hh).
+  auto prefetch_rows = [&](int part, int bb, int hh, int qt) {
+    const int rows = part == 0 ? kAttMQ : kAttNK;
+    const int r = threadIdx.x >> 1, half = threadIdx.x & 1;
+    const int t = (part == 0 ? qt * kAttMQ : 0) + r;
+    if (r < rows && t < T) {
+      const float* src = qkv + ((int64_t)bb * T + t) * row_floats + (part * H + hh) * kAttHd + half * 32;
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
+    }
+  };
 
-  // ---- phase 1: (raw K is in flight) the Q planes of this item were written during the previous item's PV product
-  if (work == (int)blockIdx.x) convert_q(work);
-  // ---- phase 2: raw K (two 128B-swizzled sub-tiles of 32 floats) -> three bf16 planes
-  if (prof) ts[1] = clock64();
-  ptx::mbar_wait(bar_k, par);
-  for (int item = threadIdx.x; item < kAttNK * 8; item += kAttThreads) {
-    const int r = item >> 3, c = item & 7;
-    const uint8_t* src = g_raw + (c >> 2) * kRawSub + r * 128;
-    const int cc = (c & 3) * 2;
-    const float4 u = *reinterpret_cast<const float4*>(src + (((cc) ^ (r & 7)) << 4));
-    const float4 v = *reinterpret_cast<const float4*>(src + (((cc + 1) ^ (r & 7)) << 4));
-    uint4 c1, c2, c3;
-    split3_chunk(u, v, c1, c2, c3);
-    const int off = r * 128 + ((c ^ (r & 7)) << 4);
-    *reinterpret_cast<uint4*>(g_kv + off) = c1;
-    *reinterpret_cast<uint4*>(g_kv + kKVPlane + off) = c2;
-    *reinterpret_cast<uint4*>(g_kv + 2 * kKVPlane + off) = c3;
+  // Persistent over (batch, head); both query tiles of a pair run back to back on the same K / V^T planes.
+  // Per tile:  A  S = Q K^T on the tensor core        || V^T conversion (first tile of the pair)
+  //            B  softmax, P planes -> TMEM
+  //            C  O = P V on the tensor core           || Q (and K) conversion of the NEXT tile / pair
+  //            D  normalise, (quantize,) store
+  if ((int)blockIdx.x < total_pairs) {
+    convert_q(blockIdx.x / H, blockIdx.x % H, 0);
+    convert_k(blockIdx.x / H, blockIdx.x % H);
   }
   ptx::fence_proxy_async_smem();
   __syncthreads();
-  if (prof) ts[2] = clock64();
+  uint32_t par = 0;                                            // every mbarrier completes exactly once per tile
+  int tile_no = 0;
+#pragma unroll 1
+  for (int pair = blockIdx.x; pair < total_pairs; pair += gridDim.x) {
+  const int h = pair % H, b = pair / H;
+#pragma unroll 1
+  for (int q_tile = 0; q_tile < q_tiles; ++q_tile, par ^= 1u, ++tile_no) {
+  const int q0 = q_tile * kAttMQ;
+  long long ts[8];
+  const bool prof = dbg && blockIdx.x == 0 && threadIdx.x == 64 && (tile_no == 2 || tile_no == 3);   // both tiles of the CTA's second pair
+  if (prof) ts[0] = clock64();
 
-  // ---- phase 3: S = Q K^T  (6 bf16 terms)
+  // ---- phase A: S = Q K^T  (6 bf16 terms), V^T conversion underneath
   if (threadIdx.x == 32) {
     ptx::tc_fence_after();
     constexpr uint32_t idesc = make_idesc_bf16(kAttMQ, kAttNK);
@@ -290,7 +351,7 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
 #pragma unroll 1
     for (int term = 0; term < 6; ++term) {
       const uint32_t a_base = q_pl + kTermA[term] * kQPlane;
-      const uint32_t b_base = kv_pl + kTermB[term] * kKVPlane;
+      const uint32_t b_base = k_pl + kTermB[term] * kKPlane;
 #pragma unroll
       for (int ks = 0; ks < kAttHd / 16; ++ks) {               // 16 head-dim values (32 B) per MMA
         mma_bf16_ss(t_s, ptx::make_kmajor_sw128_desc(a_base + ks * 32), ptx::make_kmajor_sw128_desc(b_base + ks * 32), idesc, acc);
@@ -299,16 +360,22 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
     }
     ptx::mma_commit(bar_s);
   }
-  // the raw V tile may overwrite the raw K tile right away (phase 2 is behind the barrier above)
-  if (threadIdx.x == 0) {
-    ptx::mbar_expect_tx(bar_v, 2 * kRawSub);
-    for (int s = 0; s < 2; ++s) tma_load_3d(raw + s * kRawSub, &tmap_kv, bar_v, (2 * H + h) * kAttHd + s * 32, 0, b);
-  }
+  if (q_tile == 0) convert_vt(b, h);                           // (the previous tile's P V product is complete: phase C waited)
+  if (prof) ts[1] = clock64();
   ptx::mbar_wait(bar_s, par);
   ptx::tc_fence_after();
-  if (prof) ts[3] = clock64();
+  if (prof) ts[2] = clock64();
 
-  // ---- phase 4: softmax.  thread = row (lane quarter = warp & 3), column quarter = warp >> 2 (52 key columns each)
+  // ---- phase B: softmax.  thread = row (lane quarter = warp & 3), column quarter = warp >> 2 (52 key columns each)
+  // (first: pull what phase C will convert into L2)
+  if (q_tile + 1 < q_tiles) {
+    prefetch_rows(0, b, h, q_tile + 1);
+  } else if (pair + (int)gridDim.x < total_pairs) {
+    const int np = pair + gridDim.x;
+    prefetch_rows(0, np / H, np % H, 0);
+    prefetch_rows(1, np / H, np % H, 0);
+    prefetch_rows(2, np / H, np % H, 0);
+  }
   const int row = (warp & 3) * 32 + lane;
   const int cq = warp >> 2;
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
@@ -374,41 +441,24 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
     tmem_st_n<16>(cbase + 2 * kPCols, w3); tmem_st_n<8>(cbase + 2 * kPCols + 16, w3 + 16); tmem_st_n<2>(cbase + 2 * kPCols + 24, w3 + 24);
     tmem_st_wait();
   }
-
-  // ---- phase 5: raw V [key rows x 64 floats] -> three transposed bf16 planes V^T [64 x keys] (sub-tiles of 64 keys)
-  if (prof) ts[4] = clock64();
-  ptx::mbar_wait(bar_v, par);
-  for (int item = warp; item < 2 * (kAttNK / 8); item += kAttThreads / 32) {
-    const int hsub = item / (kAttNK / 8), kg = item - hsub * (kAttNK / 8);   // 32 head-dim rows x 8 consecutive keys
-    const int hd = hsub * 32 + lane;
-    float x[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const int key = 8 * kg + i;
-      x[i] = *reinterpret_cast<const float*>(g_raw + hsub * kRawSub + key * 128 + (((lane >> 2) ^ (key & 7)) << 4) +
-                                             ((lane & 3) << 2));
-    }
-    uint4 c1, c2, c3;
-    split3_chunk(make_float4(x[0], x[1], x[2], x[3]), make_float4(x[4], x[5], x[6], x[7]), c1, c2, c3);
-    // layout [64-key sub-tile][plane][64 head-dim rows x 128 B]: the three planes of a sub-tile are contiguous, so one
-    // MMA with N = 192 / 128 / 64 multiplies a P plane with V1|V2|V3, V1|V2 or V1 at once
-    const int off = (kg >> 3) * (3 * kVtSub) + hd * 128 + (((kg & 7) ^ (hd & 7)) << 4);
-    *reinterpret_cast<uint4*>(g_kv + off) = c1;
-    *reinterpret_cast<uint4*>(g_kv + kVtSub + off) = c2;
-    *reinterpret_cast<uint4*>(g_kv + 2 * kVtSub + off) = c3;
-  }
-  ptx::fence_proxy_async_smem();
+  // row sums of the lane quarter are complete after its second barrier; 1 / sum stays in a register (the statistics
+  // buffer aliases the Q planes, which phase C overwrites)
+  asm volatile("bar.sync %0, 128;" ::"r"(1 + (warp & 3)) : "memory");
+  const float rs0 = red_sum[row], rs1 = red_sum[kAttMQ + row], rs2 = red_sum[2 * kAttMQ + row], rs3 = red_sum[3 * kAttMQ + row];
+  const float inv = __fdiv_rn(1.0f, (rs0 + rs1) + (rs2 + rs3));
+  ptx::fence_proxy_async_smem();                               // V^T planes (generic-proxy stores of phase A) -> tensor core
   ptx::tc_fence_before();
   __syncthreads();
-  if (prof) ts[5] = clock64();
-  if (threadIdx.x == 0 && work + (int)gridDim.x < total_work) issue_k(work + gridDim.x);   // raw tile is free again
+  if (prof) ts[3] = clock64();
+
+  // ---- phase C: O = P V, conversions of the next tile underneath
   if (threadIdx.x == 32) {
     // O partials: acc[0:64) += P1 V1 + P2 V1 + P3 V1, acc[64:128) += P1 V2 + P2 V2, acc[128:192) += P1 V3  (6 terms, 3 MMAs per k-step)
     ptx::tc_fence_after();
     uint32_t acc = 0;
 #pragma unroll 1
     for (int ks = 0; ks < kAttNK / 16; ++ks) {                 // 16 keys per MMA: 8 TMEM columns of A, 32 B of each V^T row
-      const uint64_t b_desc = ptx::make_kmajor_sw128_desc(kv_pl + (ks >> 2) * (3 * kVtSub) + (ks & 3) * 32);
+      const uint64_t b_desc = ptx::make_kmajor_sw128_desc(v_pl + (ks >> 2) * (3 * kVtSub) + (ks & 3) * 32);
       mma_bf16_ts(t_o, t_s + (uint32_t)(ks * 8), b_desc, make_idesc_bf16(kAttMQ, 192), acc);
       mma_bf16_ts(t_o, t_s + (uint32_t)(kPCols + ks * 8), b_desc, make_idesc_bf16(kAttMQ, 128), 1u);
       mma_bf16_ts(t_o, t_s + (uint32_t)(2 * kPCols + ks * 8), b_desc, make_idesc_bf16(kAttMQ, 64), 1u);
@@ -416,15 +466,22 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
     }
     ptx::mma_commit(bar_o);
   }
-  // meanwhile: the Q planes are dead since the S product -> fetch and convert the NEXT work item's Q tile
-  if (work + (int)gridDim.x < total_work) convert_q(work + gridDim.x);
-  // (the row sums are complete since the barrier after phase 5)
-  const float inv = __fdiv_rn(1.0f, (red_sum[row] + red_sum[kAttMQ + row]) + (red_sum[2 * kAttMQ + row] + red_sum[3 * kAttMQ + row]));
+  {
+    // the Q planes (and, at the end of a pair, the K planes) are dead since the S product
+    if (q_tile + 1 < q_tiles) {
+      convert_q(b, h, q_tile + 1);
+    } else if (pair + (int)gridDim.x < total_pairs) {
+      const int np = pair + gridDim.x;
+      convert_q(np / H, np % H, 0);
+      convert_k(np / H, np % H);
+    }
+  }
+  if (prof) ts[4] = clock64();
   ptx::mbar_wait(bar_o, par);
   ptx::tc_fence_after();
-  if (prof) ts[6] = clock64();
+  if (prof) ts[5] = clock64();
 
-  // ---- phase 6: normalise and store.  Column quarter cq of each lane quarter takes head-dim [16*cq, 16*cq + 16)
+  // ---- phase D: normalise and store.  Column quarter cq of each lane quarter takes head-dim [16*cq, 16*cq + 16)
   {
     uint32_t r[16], r2[16], r3[16];
     tmem_ld_32x16(t_o + lane_addr + (uint32_t)(cq * 16), r);
@@ -438,7 +495,7 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
       float* d = dbg + ((((int64_t)b * H + h) * 256 + q0 + row) * 512) + 416;
 #pragma unroll
       for (int j = 0; j < 16; ++j) d[cq * 16 + j] = __uint_as_float(r[j]);
-      if (cq == 0) { d[64] = red_sum[row] + red_sum[kAttMQ + row]; d[65] = red_sum[2 * kAttMQ + row] + red_sum[3 * kAttMQ + row]; d[66] = inv; }
+      if (cq == 0) { d[64] = rs0 + rs1; d[65] = rs2 + rs3; d[66] = inv; }
     }
     const int t = q0 + row;
     if (t < T) {
@@ -459,15 +516,17 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
       }
     }
   }
-  // the next work item overwrites the Q planes (generic proxy) and TMEM: everyone must be done with this one
+  // the next tile reads the Q / K planes written in phase C (generic proxy -> tensor core) and overwrites TMEM
+  ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   if (prof) {
-    ts[7] = clock64();
-    for (int i = 0; i < 7; ++i) dbg[255 * 512 + 500 + i] = (float)(ts[i + 1] - ts[0]);
+    ts[6] = clock64();
+    for (int i = 0; i < 6; ++i) dbg[255 * 512 + 500 + (tile_no - 2) * 8 + i] = (float)(ts[i + 1] - ts[0]);
   }
-  }  // persistent loop
+  }  // query tiles of the pair
+  }  // persistent loop over (batch, head)
 
   if (codes) {
     qfl = warp_or(qfl);
@@ -479,26 +538,6 @@ attention_f32_kernel(const __grid_constant__ CUtensorMap tmap_kv, const float* _
     ptx::tc_fence_after();
     ptx::tmem_dealloc<1>(tmem, 512);
   }
-}
-
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn att_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult q;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-        q == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-    else
-      cudaGetLastError();
-  }
-  return fn;
 }
 
 }  // namespace qvit
@@ -522,24 +561,9 @@ static int attention_launch(const float* qkv, int B, int T, int H, int head_dim,
   int dev = 0, maj = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev);
-  EncodeTiledFn enc = att_encode_fn();
-  if (maj != 10 || !enc) {
-    set_error("qvit_attention_f32: needs sm_100 and cuTensorMapEncodeTiled");
+  if (maj != 10) {
+    set_error("qvit_attention_f32: needs sm_100 (tcgen05)");
     return QVIT_ERR_UNSUPPORTED;
-  }
-  const uint64_t row_floats = 3ull * H * kAttHd;
-  CUtensorMap tkv;
-  cuuint64_t dims[3] = {row_floats, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[2] = {row_floats * 4, row_floats * 4 * (cuuint64_t)T};
-  cuuint32_t estr[3] = {1, 1, 1};
-  cuuint32_t box_kv[3] = {32, (cuuint32_t)kAttNK, 1};
-  CUresult r1 = CUDA_SUCCESS;
-  CUresult r2 = enc(&tkv, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(qkv), dims, strides, box_kv, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
-    set_error("qvit_attention_f32: cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
-    return QVIT_ERR_CUDA;
   }
   static bool attr_set[64] = {false};
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
@@ -550,10 +574,10 @@ static int attention_launch(const float* qkv, int B, int T, int H, int head_dim,
     }
     attr_set[dev] = true;
   }
-  const int64_t total_work = (int64_t)((T + kAttMQ - 1) / kAttMQ) * H * B;
-  QVIT_REQUIRE(total_work < (1ll << 30), "qvit_attention_f32: problem too large");
-  const int grid = (int)(total_work < sm_count() ? total_work : sm_count());
-  attention_f32_kernel<<<grid, kAttThreads, kAttSmem, (cudaStream_t)stream>>>(tkv, qkv, out, T, H, (int)total_work,
+  const int64_t total_pairs = (int64_t)H * B;                  // work unit: one (batch, head), all of its query tiles
+  QVIT_REQUIRE(total_pairs < (1ll << 30), "qvit_attention_f32: problem too large");
+  const int grid = (int)(total_pairs < sm_count() ? total_pairs : sm_count());
+  attention_f32_kernel<<<grid, kAttThreads, kAttSmem, (cudaStream_t)stream>>>(qkv, out, T, H, (int)total_pairs,
                                                                              scale * 1.4426950408889634f, dbg, (dbg != nullptr && diag == 0) ? 1 : 0,
                                                                              codes, ld_codes, q_d, q_qm, q_t, q_flags);
   return check_launch("qvit_attention_f32");
