@@ -51,7 +51,7 @@ class ViTInferenceEngine:
             raise RuntimeError("ViTInferenceEngine runs on CUDA (sm_100a) only - there is no CPU fallback")
         self.depth, self.num_heads, self.patch, self.eps, self.precision = depth, num_heads, patch_size, ln_eps, precision
         if attention not in ("auto", "tc3x", "sdpa", "math"):
-            raise ValueError("attention must be 'auto', 'tc3x' (own 3xTF32 tcgen05 kernel), 'sdpa' (library fused kernel) "
+            raise ValueError("attention must be 'auto', 'tc3x' (own tcgen05 kernel, exact 3 x bf16 split), 'sdpa' (library fused kernel) "
                              "or 'math' (explicit fp32 matmul/softmax)")
         self.attention = attention
         sd = {k: v.detach().to(self.device) for k, v in state_dict.items()}

@@ -167,7 +167,7 @@ def layernorm_quantize(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
 
 def attention_f32(qkv: torch.Tensor, num_heads: int, scale: Optional[float] = None) -> torch.Tensor:
     """softmax(q k^T * scale) v for qkv [B, T, 3*H*64] fp32 (ViTAttention.forward, vit_model.py:133-149) -> [B, T, H*64] fp32.
-    3xTF32 on tcgen05: fp32-equivalent accuracy.  Requires head_dim == 64 and T <= 208."""
+    Exact 3-way bf16 split on tcgen05 kind::f16: fp32-equivalent accuracy.  Requires head_dim == 64 and T <= 208."""
     qkv = _f32c(qkv, "attention_f32")
     B, T, C3 = qkv.shape
     hd = C3 // (3 * num_heads)
