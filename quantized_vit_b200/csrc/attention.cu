@@ -320,17 +320,38 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
     }
   };
 
+  // S = Q K^T  (6 bf16 terms) of the tile whose Q / K planes are in shared memory; completion on bar_s
+  auto issue_s = [&]() {
+    if (threadIdx.x == 32) {
+      ptx::tc_fence_after();
+      constexpr uint32_t idesc = make_idesc_bf16(kAttMQ, kAttNK);
+      uint32_t acc = 0;
+#pragma unroll 1
+      for (int term = 0; term < 6; ++term) {
+        const uint32_t a_base = q_pl + kTermA[term] * kQPlane;
+        const uint32_t b_base = k_pl + kTermB[term] * kKPlane;
+#pragma unroll
+        for (int ks = 0; ks < kAttHd / 16; ++ks) {             // 16 head-dim values (32 B) per MMA
+          mma_bf16_ss(t_s, ptx::make_kmajor_sw128_desc(a_base + ks * 32), ptx::make_kmajor_sw128_desc(b_base + ks * 32), idesc, acc);
+          acc = 1;
+        }
+      }
+      ptx::mma_commit(bar_s);
+    }
+  };
+
   // Persistent over (batch, head); both query tiles of a pair run back to back on the same K / V^T planes.
-  // Per tile:  A  S = Q K^T on the tensor core        || V^T conversion (first tile of the pair)
+  // Per tile:  A  S = Q K^T on the tensor core        || epilogue D of the PREVIOUS tile, V^T conversion (first tile of a pair)
   //            B  softmax, P planes -> TMEM
   //            C  O = P V on the tensor core           || Q (and K) conversion of the NEXT tile / pair
-  //            D  normalise, (quantize,) store
+  //            D  normalise, (quantize,) store         (runs under the next tile's S product)
   if ((int)blockIdx.x < total_pairs) {
     convert_q(blockIdx.x / H, blockIdx.x % H, 0);
     convert_k(blockIdx.x / H, blockIdx.x % H);
   }
   ptx::fence_proxy_async_smem();
   __syncthreads();
+  if ((int)blockIdx.x < total_pairs) issue_s();
   uint32_t par = 0;                                            // every mbarrier completes exactly once per tile
   int tile_no = 0;
 #pragma unroll 1
@@ -343,23 +364,7 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
   const bool prof = dbg && blockIdx.x == 0 && threadIdx.x == 64 && (tile_no == 2 || tile_no == 3);   // both tiles of the CTA's second pair
   if (prof) ts[0] = clock64();
 
-  // ---- phase A: S = Q K^T  (6 bf16 terms), V^T conversion underneath
-  if (threadIdx.x == 32) {
-    ptx::tc_fence_after();
-    constexpr uint32_t idesc = make_idesc_bf16(kAttMQ, kAttNK);
-    uint32_t acc = 0;
-#pragma unroll 1
-    for (int term = 0; term < 6; ++term) {
-      const uint32_t a_base = q_pl + kTermA[term] * kQPlane;
-      const uint32_t b_base = k_pl + kTermB[term] * kKPlane;
-#pragma unroll
-      for (int ks = 0; ks < kAttHd / 16; ++ks) {               // 16 head-dim values (32 B) per MMA
-        mma_bf16_ss(t_s, ptx::make_kmajor_sw128_desc(a_base + ks * 32), ptx::make_kmajor_sw128_desc(b_base + ks * 32), idesc, acc);
-        acc = 1;
-      }
-    }
-    ptx::mma_commit(bar_s);
-  }
+  // ---- phase A: S = Q K^T was issued before the previous tile's epilogue (or in the prologue); V^T conversion underneath
   if (q_tile == 0) convert_vt(b, h);                           // (the previous tile's P V product is complete: phase C waited)
   if (prof) ts[1] = clock64();
   ptx::mbar_wait(bar_s, par);
@@ -478,7 +483,13 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
   }
   if (prof) ts[4] = clock64();
   ptx::mbar_wait(bar_o, par);
+  // the next tile's S product reads the Q / K planes written above (generic proxy -> tensor core) and overwrites the
+  // P columns of TMEM; it leaves the O columns alone, so it is issued BEFORE this tile's epilogue
+  ptx::fence_proxy_async_smem();
+  ptx::tc_fence_before();
+  __syncthreads();
   ptx::tc_fence_after();
+  if (q_tile + 1 < q_tiles || pair + (int)gridDim.x < total_pairs) issue_s();
   if (prof) ts[5] = clock64();
 
   // ---- phase D: normalise and store.  Column quarter cq of each lane quarter takes head-dim [16*cq, 16*cq + 16)
@@ -516,11 +527,6 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
       }
     }
   }
-  // the next tile reads the Q / K planes written in phase C (generic proxy -> tensor core) and overwrites TMEM
-  ptx::fence_proxy_async_smem();
-  ptx::tc_fence_before();
-  __syncthreads();
-  ptx::tc_fence_after();
   if (prof) {
     ts[6] = clock64();
     for (int i = 0; i < 6; ++i) dbg[255 * 512 + 500 + (tile_no - 2) * 8 + i] = (float)(ts[i + 1] - ts[0]);
