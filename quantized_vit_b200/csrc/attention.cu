@@ -274,37 +274,96 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
       }
     }
   };
-  // V (keys x 64) of (bb, hh) -> three TRANSPOSED planes V^T [64 head-dim rows x keys]; one warp item = 32 head-dim rows x
-  // 8 consecutive keys (lane = head-dim index: every load instruction reads 128 contiguous bytes of one key row).
+  // Q tile 0 and K of a NEW pair in one go: the loads of both are in flight together (one round trip instead of two)
+  auto convert_qk = [&](int bb, int hh) {
+    constexpr int kItQ = kAttMQ * 8 / kAttThreads, kItK = (kAttNK * 8 + kAttThreads - 1) / kAttThreads;
+    float4 uq[kItQ], vq[kItQ], uk[kItK], vk[kItK];
+#pragma unroll
+    for (int it = 0; it < kItK; ++it) {
+      const int item = threadIdx.x + it * kAttThreads;
+      const int r = item >> 3, c = item & 7;
+      uk[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      vk[it] = uk[it];
+      if (item < kAttNK * 8 && r < T) {
+        const float* src = qkv + ((int64_t)bb * T + r) * row_floats + (1 * H + hh) * kAttHd + c * 8;
+        uk[it] = ldg_stream4(src);
+        vk[it] = ldg_stream4(src + 4);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kItQ; ++it) {
+      const int item = threadIdx.x + it * kAttThreads;
+      const int r = item >> 3, c = item & 7;
+      uq[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      vq[it] = uq[it];
+      if (r < T) {
+        const float* src = qkv + ((int64_t)bb * T + r) * row_floats + (0 * H + hh) * kAttHd + c * 8;
+        uq[it] = ldg_stream4(src);
+        vq[it] = ldg_stream4(src + 4);
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kItK; ++it) {
+      const int item = threadIdx.x + it * kAttThreads;
+      if (item < kAttNK * 8) {
+        const int r = item >> 3, c = item & 7;
+        uint4 c1, c2, c3;
+        split3_chunk(uk[it], vk[it], c1, c2, c3);
+        const int off = r * 128 + ((c ^ (r & 7)) << 4);
+        *reinterpret_cast<uint4*>(g_k + off) = c1;
+        *reinterpret_cast<uint4*>(g_k + kKPlane + off) = c2;
+        *reinterpret_cast<uint4*>(g_k + 2 * kKPlane + off) = c3;
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < kItQ; ++it) {
+      const int item = threadIdx.x + it * kAttThreads;
+      const int r = item >> 3, c = item & 7;
+      uint4 c1, c2, c3;
+      split3_chunk(uq[it], vq[it], c1, c2, c3);
+      const int off = r * 128 + ((c ^ (r & 7)) << 4);
+      *reinterpret_cast<uint4*>(g_q + off) = c1;
+      *reinterpret_cast<uint4*>(g_q + kQPlane + off) = c2;
+      *reinterpret_cast<uint4*>(g_q + 2 * kQPlane + off) = c3;
+    }
+  };
+  // V (keys x 64) of (bb, hh) -> three TRANSPOSED planes V^T [64 head-dim rows x keys].
   // Layout [64-key sub-tile][plane][64 rows x 128 B]: the three planes of a sub-tile are contiguous, so one MMA with
   // N = 192 / 128 / 64 multiplies a P plane with V1|V2|V3, V1|V2 or V1 at once.
   auto convert_vt = [&](int bb, int hh) {
-    constexpr int kItems = 2 * (kAttNK / 8), kWarps = kAttThreads / 32, kIt = (kItems + kWarps - 1) / kWarps;   // 52 items, 4 per warp
-    float x[kIt][8];
+    // one warp item = all 64 head-dim rows x 8 consecutive keys; lane = head-dim pair (2l, 2l+1): every load instruction
+    // reads the 256 contiguous bytes of one key row, 16 loads per lane in all (26 items over 16 warps)
+    constexpr int kItems = kAttNK / 8, kWarps = kAttThreads / 32, kIt = (kItems + kWarps - 1) / kWarps;
+    float2 x[kIt][8];
 #pragma unroll
     for (int it = 0; it < kIt; ++it) {
-      const int item = warp + it * kWarps;
-      const int hsub = item / (kAttNK / 8), kg = item - hsub * (kAttNK / 8);
+      const int kg = warp + it * kWarps;
+      const float* src = qkv + ((int64_t)bb * T + 8 * kg) * row_floats + (2 * H + hh) * kAttHd + 2 * lane;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int key = 8 * kg + i;
-        x[it][i] = (item < kItems && key < T)
-                       ? __ldg(qkv + ((int64_t)bb * T + key) * row_floats + (2 * H + hh) * kAttHd + hsub * 32 + lane)
-                       : 0.0f;
+        x[it][i] = make_float2(0.f, 0.f);
+        if (kg < kItems && 8 * kg + i < T) x[it][i] = __ldg(reinterpret_cast<const float2*>(src + i * row_floats));
       }
     }
 #pragma unroll
     for (int it = 0; it < kIt; ++it) {
-      const int item = warp + it * kWarps;
-      if (item < kItems) {
-        const int hsub = item / (kAttNK / 8), kg = item - hsub * (kAttNK / 8);
-        const int hd = hsub * 32 + lane;
-        uint4 c1, c2, c3;
-        split3_chunk(make_float4(x[it][0], x[it][1], x[it][2], x[it][3]), make_float4(x[it][4], x[it][5], x[it][6], x[it][7]), c1, c2, c3);
-        const int off = (kg >> 3) * (3 * kVtSub) + hd * 128 + (((kg & 7) ^ (hd & 7)) << 4);
-        *reinterpret_cast<uint4*>(g_v + off) = c1;
-        *reinterpret_cast<uint4*>(g_v + kVtSub + off) = c2;
-        *reinterpret_cast<uint4*>(g_v + 2 * kVtSub + off) = c3;
+      const int kg = warp + it * kWarps;
+      if (kg < kItems) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          const int hd = 2 * lane + half;
+          uint4 c1, c2, c3;
+          if (half == 0)
+            split3_chunk(make_float4(x[it][0].x, x[it][1].x, x[it][2].x, x[it][3].x),
+                         make_float4(x[it][4].x, x[it][5].x, x[it][6].x, x[it][7].x), c1, c2, c3);
+          else
+            split3_chunk(make_float4(x[it][0].y, x[it][1].y, x[it][2].y, x[it][3].y),
+                         make_float4(x[it][4].y, x[it][5].y, x[it][6].y, x[it][7].y), c1, c2, c3);
+          const int off = (kg >> 3) * (3 * kVtSub) + hd * 128 + (((kg & 7) ^ (hd & 7)) << 4);
+          *reinterpret_cast<uint4*>(g_v + off) = c1;
+          *reinterpret_cast<uint4*>(g_v + kVtSub + off) = c2;
+          *reinterpret_cast<uint4*>(g_v + 2 * kVtSub + off) = c3;
+        }
       }
     }
   };
@@ -385,6 +444,11 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
   const int cq = warp >> 2;
   const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
   const int col0 = cq * kColQ;
+  // a lane quarter whose 32 query rows all lie beyond T (the tail of the last tile) has nothing to do in phases B and D:
+  // its TMEM rows keep stale P values, which only ever reach output rows that are never stored (MMA rows are independent)
+  const bool rows_live = q0 + (warp & 3) * 32 < T;
+  float inv = 0.0f, rs0 = 0.0f, rs1 = 0.0f, rs2 = 0.0f, rs3 = 0.0f;
+  if (rows_live) {
   float p[kColQ];                                              // this thread's 52 scores, then probabilities
   {
     uint32_t r[kColQ];
@@ -449,8 +513,9 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
   // row sums of the lane quarter are complete after its second barrier; 1 / sum stays in a register (the statistics
   // buffer aliases the Q planes, which phase C overwrites)
   asm volatile("bar.sync %0, 128;" ::"r"(1 + (warp & 3)) : "memory");
-  const float rs0 = red_sum[row], rs1 = red_sum[kAttMQ + row], rs2 = red_sum[2 * kAttMQ + row], rs3 = red_sum[3 * kAttMQ + row];
-  const float inv = __fdiv_rn(1.0f, (rs0 + rs1) + (rs2 + rs3));
+  rs0 = red_sum[row], rs1 = red_sum[kAttMQ + row], rs2 = red_sum[2 * kAttMQ + row], rs3 = red_sum[3 * kAttMQ + row];
+  inv = __fdiv_rn(1.0f, (rs0 + rs1) + (rs2 + rs3));
+  }  // rows_live
   ptx::fence_proxy_async_smem();                               // V^T planes (generic-proxy stores of phase A) -> tensor core
   ptx::tc_fence_before();
   __syncthreads();
@@ -477,8 +542,7 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
       convert_q(b, h, q_tile + 1);
     } else if (pair + (int)gridDim.x < total_pairs) {
       const int np = pair + gridDim.x;
-      convert_q(np / H, np % H, 0);
-      convert_k(np / H, np % H);
+      convert_qk(np / H, np % H);
     }
   }
   if (prof) ts[4] = clock64();
@@ -493,7 +557,7 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
   if (prof) ts[5] = clock64();
 
   // ---- phase D: normalise and store.  Column quarter cq of each lane quarter takes head-dim [16*cq, 16*cq + 16)
-  {
+  if (rows_live) {
     uint32_t r[16], r2[16], r3[16];
     tmem_ld_32x16(t_o + lane_addr + (uint32_t)(cq * 16), r);
     tmem_ld_32x16(t_o + lane_addr + (uint32_t)(64 + cq * 16), r2);

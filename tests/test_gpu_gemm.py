@@ -98,6 +98,31 @@ def test_fused_epilogues(ops, backend):
     assert int(yc[:, N:].abs().sum()) == 0
 
 
+def test_requantize_nan_inf_and_accumulator_hint(ops):
+    """Non-finite epilogue values in the int8-output path: the packed fast path cannot represent them, the row falls
+    through to the scalar reference sequence - NaN -> code 0 + QVIT_FLAG_NAN (the reference would propagate NaN),
+    +-inf -> +-saturation (|x| >= q_m, QL:159).  And the `acc_abs_max` promise (magic-number int -> float conversion)
+    changes nothing but speed."""
+    M, N, K = 700, 256, 512
+    a = _codes(M, K, -7, 7, 41).cuda()
+    w = _codes(N, K, -7, 7, 42).cuda()
+    bias = torch.randn(N)
+    bias[5], bias[70], bias[200] = float("nan"), float("inf"), float("-inf")
+    bias = bias.cuda()
+    flags = ops.new_flags("cuda")
+    for be in (ops.QVIT_GEMM_TCGEN05, ops.QVIT_GEMM_SIMT):
+        flags.zero_()
+        c = ops.gemm_i8(a, w, K, N, out_kind=ops.QVIT_OUT_I8, bias=bias, scale_a=0.01, scale_w=0.02, next_q=(0.3, 2.1, None),
+                        flags=flags, backend=be, acc_abs_max=49 * K)
+        assert int(flags.item()) & 1, "NaN must raise the NaN flag"
+        assert int(c[:, 5].abs().max()) == 0 and bool((c[:, 70] == 7).all()) and bool((c[:, 200] == -7).all())
+    kw = dict(bias=torch.randn(N).cuda(), scale_a=0.01, scale_w=0.02, act=ops.QVIT_ACT_GELU, backend=ops.QVIT_GEMM_TCGEN05)
+    for kind, extra in ((ops.QVIT_OUT_F32, {}), (ops.QVIT_OUT_BF16, {}), (ops.QVIT_OUT_I8, dict(next_q=(0.3, 2.1, None)))):
+        with_hint = ops.gemm_i8(a, w, K, N, out_kind=kind, acc_abs_max=49 * K, **kw, **extra)
+        without = ops.gemm_i8(a, w, K, N, out_kind=kind, acc_abs_max=0, **kw, **extra)
+        assert torch.equal(with_hint, without)
+
+
 def test_backends_agree_on_random_epilogue(ops):
     M, N, K = 517, 392, 1000 // 16 * 16
     a = _codes(M, K, -127, 127, 11)
