@@ -190,11 +190,11 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
   const int q_tiles = (T + kAttMQ - 1) / kAttMQ;
   // optional fused activation quantizer of the consumer layer (`proj`): codes instead of / beside the fp32 context
   SymParams qp;
-  FastQ qf;
+  FastQ2 qf;
   int qfl = 0;
   if (codes) {
     qp = load_sym_params(q_d, q_qm, q_t);
-    qf = make_fastq(qp);
+    qf = make_fastq2(qp);
   }
 
   if (threadIdx.x == 0) {
@@ -586,8 +586,8 @@ attention_f32_kernel(const float* __restrict__ qkv, float* __restrict__ out, int
       }
       if (codes) {                                             // quantize_act of the consumer layer (quant_layers.py:356-381)
         int8_t* dst = codes + ((int64_t)b * T + t) * ld_codes + h * kAttHd + cq * 16;
-        stg_v4_b32(dst, sym_codes4(v[0], v[1], v[2], v[3], qp, qf, qfl), sym_codes4(v[4], v[5], v[6], v[7], qp, qf, qfl),
-                   sym_codes4(v[8], v[9], v[10], v[11], qp, qf, qfl), sym_codes4(v[12], v[13], v[14], v[15], qp, qf, qfl));
+        const uint4 w = sym_codes16(v, qp, qf, qfl);
+        stg_v4_b32(dst, w.x, w.y, w.z, w.w);
       }
     }
   }

@@ -292,6 +292,46 @@ __device__ __forceinline__ uint32_t sym_codes4_fast2(f32x2 y01, f32x2 y23, const
   return pack4_low_bytes(__float_as_uint(a0), __float_as_uint(a1), __float_as_uint(a2), __float_as_uint(a3));
 }
 
+// 16 consecutive values of one row -> 16 int8 codes (four words), for kernel epilogues that quantize what they just
+// computed (attention context -> `proj` codes).  Hot path: packed interval test; rows in doubt: exact Markstein division;
+// NaN / inf / generic quantizers: the scalar reference sequence, out of line so that the hot code stays small.
+static __device__ __noinline__ uint4 sym_codes16_slow(float a0, float a1, float a2, float a3, float a4, float a5, float a6, float a7,
+                                               float a8, float a9, float a10, float a11, float a12, float a13, float a14,
+                                               float a15, SymParams p, int* flags) {
+  int fl = 0;
+  uint4 w;
+  w.x = pack4_i8_fwd(sym_code(a0, p, fl), sym_code(a1, p, fl), sym_code(a2, p, fl), sym_code(a3, p, fl));
+  w.y = pack4_i8_fwd(sym_code(a4, p, fl), sym_code(a5, p, fl), sym_code(a6, p, fl), sym_code(a7, p, fl));
+  w.z = pack4_i8_fwd(sym_code(a8, p, fl), sym_code(a9, p, fl), sym_code(a10, p, fl), sym_code(a11, p, fl));
+  w.w = pack4_i8_fwd(sym_code(a12, p, fl), sym_code(a13, p, fl), sym_code(a14, p, fl), sym_code(a15, p, fl));
+  *flags |= fl;
+  return w;
+}
+__device__ __forceinline__ uint4 sym_codes16(const float (&v)[16], const SymParams& p, const FastQ2& f, int& flags) {
+  uint32_t w[4];
+  bool slow = f.generic != 0;
+  if (!slow) {
+    f32x2 dacc = pk1(0.0f);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) w[j] = sym_codes4_fast2(pk2(v[4 * j], v[4 * j + 1]), pk2(v[4 * j + 2], v[4 * j + 3]), f, dacc);
+    float d0, d1;
+    unpk2(dacc, d0, d1);
+    if (!(d0 + d1 == 0.0f)) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        slow = slow || !(fabsf(v[4 * j]) < 1.0e30f) || !(fabsf(v[4 * j + 1]) < 1.0e30f) || !(fabsf(v[4 * j + 2]) < 1.0e30f) ||
+               !(fabsf(v[4 * j + 3]) < 1.0e30f);
+        w[j] = pack4_low_bytes(__float_as_uint(sym_t_exact(v[4 * j], f)), __float_as_uint(sym_t_exact(v[4 * j + 1], f)),
+                               __float_as_uint(sym_t_exact(v[4 * j + 2], f)), __float_as_uint(sym_t_exact(v[4 * j + 3], f)));
+      }
+    }
+  }
+  if (slow)
+    return sym_codes16_slow(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7], v[8], v[9], v[10], v[11], v[12], v[13], v[14], v[15], p,
+                            &flags);
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // ---- warp / block reductions -------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
