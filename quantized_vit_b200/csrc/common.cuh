@@ -332,6 +332,32 @@ __device__ __forceinline__ uint4 sym_codes16(const float (&v)[16], const SymPara
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// four values -> one word of codes with the same three levels (elementwise kernels: LayerNorm + quantize)
+static __device__ __noinline__ uint32_t sym_codes4_slow(float a0, float a1, float a2, float a3, SymParams p, int* flags) {
+  int fl = 0;
+  const uint32_t w = pack4_i8_fwd(sym_code(a0, p, fl), sym_code(a1, p, fl), sym_code(a2, p, fl), sym_code(a3, p, fl));
+  *flags |= fl;
+  return w;
+}
+__device__ __forceinline__ uint32_t sym_codes4_v2(float a0, float a1, float a2, float a3, const SymParams& p, const FastQ2& f,
+                                                  int& flags) {
+  bool slow = f.generic != 0;
+  uint32_t w = 0;
+  if (!slow) {
+    f32x2 dacc = pk1(0.0f);
+    w = sym_codes4_fast2(pk2(a0, a1), pk2(a2, a3), f, dacc);
+    float d0, d1;
+    unpk2(dacc, d0, d1);
+    if (!(d0 + d1 == 0.0f)) {
+      slow = !(fabsf(a0) < 1.0e30f) || !(fabsf(a1) < 1.0e30f) || !(fabsf(a2) < 1.0e30f) || !(fabsf(a3) < 1.0e30f);
+      w = pack4_low_bytes(__float_as_uint(sym_t_exact(a0, f)), __float_as_uint(sym_t_exact(a1, f)),
+                          __float_as_uint(sym_t_exact(a2, f)), __float_as_uint(sym_t_exact(a3, f)));
+    }
+  }
+  if (slow) return sym_codes4_slow(a0, a1, a2, a3, p, &flags);
+  return w;
+}
+
 // ---- warp / block reductions -------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

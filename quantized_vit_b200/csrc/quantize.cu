@@ -221,7 +221,7 @@ layernorm_quantize_kernel(const float* __restrict__ x, int64_t rows, const float
                           int32_t* __restrict__ flags) {
   constexpr int cols = V * 128;
   const SymParams p = load_sym_params(d, qm, t);
-  const FastQ fq = make_fastq(p);
+  const FastQ2 fq = make_fastq2(p);
   int fl = 0;
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -265,7 +265,7 @@ layernorm_quantize_kernel(const float* __restrict__ x, int64_t rows, const float
       y.z = (v[j].z - mean) * rstd * gm.z + bt.z;
       y.w = (v[j].w - mean) * rstd * gm.w + bt.w;
       if (ln_out) reinterpret_cast<float4*>(ln_out + r * cols)[j * 32 + lane] = y;
-      dst[j * 32 + lane] = sym_codes4(y.x, y.y, y.z, y.w, p, fq, fl);
+      dst[j * 32 + lane] = sym_codes4_v2(y.x, y.y, y.z, y.w, p, fq, fl);
     }
     // zero the K padding, if any
     for (int64_t c = cols + lane; c < ld_codes; c += 32) codes[r * ld_codes + c] = 0;
