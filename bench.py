@@ -251,7 +251,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                            "step i-1 overlap the forward of step i (all copies inside the timed region)"},
             "gpu_launches": calls_per_step * args.steps,
             "roofline": {"bound": "tensor", "achieved": achieved, "peak": peak_tops, "unit": "TOP/s", "frac": achieved / peak_tops,
-                         "traffic": 156.5e6, "traffic_note": "ncu dram read+write of the longest launch (fc1, 196 MB algorithmic), profiles/r1c_ncu_full_raw.csv",
+                         "traffic": 157.0e6, "traffic_note": "ncu dram read+write of the longest launch (fc1, 196 MB algorithmic), profiles/r1c_ncu_full_raw.csv",
                          "peak_alt": {"own_main_loop_768x3072": 3740.0, "own_mma_issue_only": 4280.0, "cublaslt_int8_8192": 3086.0, "nominal": 4500.0},
                          "kernel": "gemm_i8_tc_kernel", "launches_per_step": n_gemm,
                          "kernel_ms_per_step": gemm_ms, "kernel_share_of_step": gemm_ms / (ms / args.steps),
