@@ -56,6 +56,8 @@ class QuantizationMode(Enum):          # QL:27-29
 _flag_words = {}
 EAGER_NAN_CHECK = False
 TENSOR_CORE_BACKWARD = True     # QAT gradient GEMMs on tcgen05 (exact bf16 split); False = library fp32 GEMMs
+GRADIENT_PLANES = 3             # bf16 planes of the gradient operand: 3 = exact fp32 (default), 2 = 16 significant bits
+                                # (relative error <= 2^-17 per element, ~1e-5 on the result, a third less tensor-core work)
 
 
 def _flags_for(device: torch.device) -> torch.Tensor:
@@ -199,9 +201,10 @@ class QuantLinearFunction(torch.autograd.Function):
         if TENSOR_CORE_BACKWARD and K % 4 == 0:
             # grad_x_q = g @ w_q = |d_w| * (g1 + g2 + g3) @ codes_w   and   grad_w_q = g^T @ x_q = |d_a| * (g^T planes) @ codes_a:
             # exact 3-way bf16 split of g, integer codes as bf16, tcgen05 kind::f16 with fp32 accumulation
-            grad_xq = ops.gemm_bf16_split(ops.split3_bf16(g2), ops.codes_to_bf16_t(w_codes, K), N, scale=d_w) \
+            grad_xq = ops.gemm_bf16_split(ops.split3_bf16(g2), ops.codes_to_bf16_t(w_codes, K), N, planes=GRADIENT_PLANES, scale=d_w) \
                 if ctx.needs_input_grad[0] else None
-            grad_wq = ops.gemm_bf16_split(ops.split3_bf16(g2, transpose=True), ops.codes_to_bf16_t(a_codes, K), M, scale=d_a)
+            grad_wq = ops.gemm_bf16_split(ops.split3_bf16(g2, transpose=True), ops.codes_to_bf16_t(a_codes, K), M,
+                                          planes=GRADIENT_PLANES, scale=d_a)
         else:
             # fake-quant values from the saved codes: value = code * |d| (exactly what the reference forward produced)
             x_q = a_codes[:, :K].to(torch.float32) * d_a.detach().abs()

@@ -254,6 +254,11 @@ def test_bf16_split_gemm_matches_fp64(ops, M, N, K):
     err = float((out.double() - ref).abs().max() / ref.abs().max())
     print(f"bf16-split GEMM M={M} N={N} K={K}: max-norm error {err:.2e}")
     assert err <= 1e-4, err
+    # two planes only (quant_layers.GRADIENT_PLANES = 2): 16 significant bits of the gradient operand
+    out2 = ops.gemm_bf16_split(a, bp, K, planes=2, scale=torch.tensor([0.0123]))
+    err2 = float((out2.double() - ref).abs().max() / ref.abs().max())
+    print(f"  two planes: max-norm error {err2:.2e}")
+    assert err2 <= 2e-4, err2
     # transposed forms used by the backward: x^T planes and codes^T
     at = ops.split3_bf16(x, transpose=True)                  # [K, 3 * pad64(M)]
     assert torch.equal(at.float().view(K, 3, -1)[:, :, :M].sum(1), x.t())

@@ -16,6 +16,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     qtype = sys.argv[1] if len(sys.argv) > 1 else "symmetric+linear"
     global_batch, steps = 128, int(sys.argv[2]) if len(sys.argv) > 2 else 5
+    if len(sys.argv) > 3:                    # optional: bf16 planes of the gradient operand (3 = exact, 2 = 16 significant bits)
+        from quantized_vit_b200.quantization import quant_layers
+        quant_layers.GRADIENT_PLANES = int(sys.argv[3])
     torch.manual_seed(0)
     model = VisionTransformer(num_classes=1000)
     model = model_to_quantize_model(model, num_bits=4, quant_type=qtype, quant_mode="weight_and_activation").cuda().train()
@@ -59,7 +62,8 @@ def main():
         print(json.dumps({"config": "ViT-B/16 4-bit QAT fwd+bwd+allreduce+clip", "quant_type": qtype, "n_gpus": world,
                           "global_batch": global_batch, "ms_per_step": float(ms), "img_per_s": global_batch / float(ms) * 1e3,
                           "loss": float(loss), "grad_norm_after_clip": float(gn), "grad_d_quant_act_block0_qkv": dq,
-                          "nan_flags": flags}), flush=True)
+                          "nan_flags": flags,
+                          "gradient_planes": __import__("quantized_vit_b200.quantization.quant_layers", fromlist=["x"]).GRADIENT_PLANES}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
