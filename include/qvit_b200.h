@@ -140,6 +140,12 @@ int qvit_bn_act_quantize_int(const void* gamma, const void* beta, const void* me
  * n must be even; packed has n/2 bytes.                                                               */
 int qvit_pack_int4(const int8_t* codes, int64_t n, uint8_t* packed, qvit_stream_t stream);
 int qvit_unpack_int4(const uint8_t* packed, int64_t n, int is_signed, int8_t* codes, qvit_stream_t stream);
+/* FPGA (HLS) weight layout, QNNLayerMemProcess.conv / w_to_hls_array (MEM:84-130, 152-157): codes [O, I, kh, kw] ->
+ * rows reordered to (kh, kw, I), cut into runs of `simd` codes (ragged last run allowed), each run packed as above into one
+ * word of simd * w_bit <= 64 bits; word (oc, j) is stored at words[(oc % pe) * tiles + (oc / pe) * runs + j],
+ * runs = ceil(kh*kw*I / simd), tiles = runs * O / pe.  O must be a multiple of pe.                       */
+int qvit_pack_hls_weights(const int8_t* codes, int O, int I, int kh, int kw, int w_bit, int simd, int pe,
+                          unsigned long long* words, qvit_stream_t stream);
 
 /* ------------------------------------------------------------------ QuantLinear GEMM
  * Replaces nn.functional.linear(x_q, w_q, bias) on fake-quant values (QL:499, QU:220) by the exact integer

@@ -226,6 +226,37 @@ def golden_ultra():
     np.savez_compressed(os.path.join(OUT, "ultra.npz"), **out)
 
 
+HLS_CASES = [  # (name, out_ch, in_ch, kernel, simd, pe): the shapes of ultranet_param_gen.py:14-24 plus a ragged one
+    ("conv0", 16, 3, 3, 3, 16), ("conv1", 32, 16, 3, 16, 8), ("conv3", 64, 64, 3, 16, 4), ("conv4", 64, 64, 3, 8, 2),
+    ("conv8", 36, 64, 1, 8, 2), ("ragged", 4, 5, 3, 8, 2)]
+
+
+def golden_ultra_hls():
+    """FPGA parameter layout of the reference (qnn_mem_process.py:84-170): int4 weight codes -> [pe][tiles] words of
+    simd * w_bit bits, BN thresholds -> [pe][a_tiles].  The methods are called on a QNNLayerMemProcess object created
+    without its file-reading constructor (only pe / simd / w_bit are used by them)."""
+    mp = R.qnn_mem_process()
+    out = {}
+    rng = np.random.RandomState(11)
+    for name, o, i, k, simd, pe in HLS_CASES:
+        w = rng.randint(-7, 8, size=(o, i, k, k)).astype(np.int32)
+        proc = object.__new__(mp.QNNLayerMemProcess)
+        proc.pe, proc.simd, proc.w_bit = pe, simd, 4
+        con_w = w.transpose(0, 2, 3, 1).reshape(o, -1)                    # qnn_mem_process.py:152-154
+        import contextlib, io
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = proc.w_to_hls_array(con_w)
+        out[f"{name}.codes"] = w.astype(np.int8)
+        out[f"{name}.cfg"] = np.array([o, i, k, simd, pe], dtype=np.int64)
+        out[f"{name}.words"] = np.array(res, dtype=np.uint64)            # simd * 4 <= 64 bits in every case
+        out[f"{name}.w_tiles"] = np.int64(proc.w_tiles)
+        inc = rng.randint(-2000, 2000, size=o).astype(np.int32)
+        bias = rng.randint(-(1 << 20), 1 << 20, size=o).astype(np.int32)
+        hi, hb = proc.inc_bias_to_hls_array(inc, bias)
+        out[f"{name}.inc"], out[f"{name}.bias"], out[f"{name}.hls_inc"], out[f"{name}.hls_bias"] = inc, bias, hi, hb
+    np.savez_compressed(os.path.join(OUT, "ultra_hls.npz"), **out)
+
+
 def golden_ultranet():
     mm = R.mymodel()
     torch.manual_seed(0)

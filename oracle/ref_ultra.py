@@ -182,3 +182,29 @@ def unpack_int4_bytes(packed: np.ndarray, signed: bool = True) -> np.ndarray:
     if signed:
         out = np.where(out >= 8, out - 16, out)
     return out.astype(np.int8)
+
+
+# ---------------------------------------------------------------- FPGA (HLS) parameter layout
+
+def hls_weight_words(codes: np.ndarray, w_bit: int, simd: int, pe: int) -> np.ndarray:
+    """QNNLayerMemProcess.conv + w_to_hls_array (qnn_mem_process.py:84-130, 152-157): integer weight codes
+    [O, I, kh, kw] -> reordered to (O, kh, kw, I), flattened per output channel, cut into runs of `simd` codes (the last
+    run may be shorter), each run packed by pack_words; word (out_ch, j) lands at res[out_ch % pe][(out_ch // pe) * runs + j].
+    Returns uint64 [pe, tiles] (simd * w_bit <= 64)."""
+    codes = np.asarray(codes)
+    o = codes.shape[0]
+    assert o % pe == 0 and simd * w_bit <= 64
+    flat = codes.transpose(0, 2, 3, 1).reshape(o, -1)
+    h = flat.shape[1]
+    runs = (h + simd - 1) // simd
+    res = np.zeros((pe, runs * (o // pe)), dtype=np.uint64)
+    for oc in range(o):
+        for j in range(runs):
+            res[oc % pe, (oc // pe) * runs + j] = np.uint64(pack_words(flat[oc, j * simd:(j + 1) * simd].tolist(), w_bit))
+    return res
+
+
+def hls_inc_bias(inc: np.ndarray, bias: np.ndarray, pe: int) -> Tuple[np.ndarray, np.ndarray]:
+    """inc_bias_to_hls_array (qnn_mem_process.py:133-143): per-channel vectors -> [pe, channels // pe] (channel c at
+    [c % pe, c // pe])."""
+    return np.asarray(inc).reshape(-1, pe).T, np.asarray(bias).reshape(-1, pe).T

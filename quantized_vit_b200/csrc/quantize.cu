@@ -337,6 +337,29 @@ pack_int4_kernel(const int8_t* __restrict__ codes, int64_t nbytes, uint8_t* __re
   }
 }
 
+// FPGA weight layout of the reference (qnn_mem_process.py:84-130, 152-157): one thread per output word.
+// codes [O, I, kh, kw] int8 -> word (oc, j) = runs of `simd` codes of the (kh, kw, I)-ordered row, element e in bits
+// [w_bit * e, +w_bit) two's complement; stored at out[(oc % pe) * tiles + (oc / pe) * runs + j].
+__global__ void __launch_bounds__(kThreads)
+pack_hls_weights_kernel(const int8_t* __restrict__ codes, int O, int I, int kh, int kw, int w_bit, int simd, int pe, int runs,
+                        unsigned long long* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)O * runs) return;
+  const int oc = (int)(idx / runs), j = (int)(idx - (int64_t)oc * runs);
+  const int h = kh * kw * I;
+  const unsigned long long mask = (1ull << w_bit) - 1ull;
+  unsigned long long word = 0;
+  for (int e = 0; e < simd; ++e) {
+    const int pos = j * simd + e;                              // position in the (kh, kw, I) order
+    if (pos >= h) break;                                       // ragged last run
+    const int ic = pos % I, rc = pos / I, r = rc / kw, c = rc - r * kw;
+    const int v = codes[(((int64_t)oc * I + ic) * kh + r) * kw + c];
+    word |= ((unsigned long long)(long long)v & mask) << (w_bit * e);
+  }
+  const int64_t tiles = (int64_t)runs * (O / pe);
+  out[(int64_t)(oc % pe) * tiles + (int64_t)(oc / pe) * runs + j] = word;
+}
+
 __global__ void __launch_bounds__(kThreads)
 unpack_int4_kernel(const uint8_t* __restrict__ packed, int64_t nbytes, int is_signed, int8_t* __restrict__ codes) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nbytes; i += (int64_t)gridDim.x * blockDim.x) {
@@ -470,6 +493,18 @@ int qvit_pack_int4(const int8_t* codes, int64_t n, uint8_t* packed, qvit_stream_
   if (n == 0) return QVIT_OK;
   pack_int4_kernel<<<stream_grid(n / 2, kThreads * 4), kThreads, 0, (cudaStream_t)stream>>>(codes, n / 2, packed);
   return check_launch("qvit_pack_int4");
+}
+
+int qvit_pack_hls_weights(const int8_t* codes, int O, int I, int kh, int kw, int w_bit, int simd, int pe,
+                          unsigned long long* words, qvit_stream_t stream) {
+  QVIT_REQUIRE(codes && words && O > 0 && I > 0 && kh > 0 && kw > 0, "qvit_pack_hls_weights: bad argument");
+  QVIT_REQUIRE(w_bit >= 1 && simd >= 1 && simd * w_bit <= 64, "qvit_pack_hls_weights: simd * w_bit must fit 64 bits");
+  QVIT_REQUIRE(pe >= 1 && O % pe == 0, "qvit_pack_hls_weights: out_ch mod pe must be 0 (qnn_mem_process.py:86)");
+  const int runs = (kh * kw * I + simd - 1) / simd;
+  const int64_t n = (int64_t)O * runs;
+  pack_hls_weights_kernel<<<(unsigned)((n + kThreads - 1) / kThreads), kThreads, 0, (cudaStream_t)stream>>>(
+      codes, O, I, kh, kw, w_bit, simd, pe, runs, words);
+  return check_launch("qvit_pack_hls_weights");
 }
 
 int qvit_unpack_int4(const uint8_t* packed, int64_t n, int is_signed, int8_t* codes, qvit_stream_t stream) {

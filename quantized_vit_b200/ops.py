@@ -468,3 +468,23 @@ def unpack_int4(packed: torch.Tensor, signed: bool = True) -> torch.Tensor:
     _lib.check(_lib.lib().qvit_unpack_int4(_lib.ptr(packed), out.numel(), 1 if signed else 0, _lib.ptr(out), _lib.stream()),
                "qvit_unpack_int4")
     return out
+
+
+def pack_hls_weights(codes: torch.Tensor, w_bit: int, simd: int, pe: int) -> torch.Tensor:
+    """FPGA (HLS) weight layout of the reference exporter (qnn_mem_process.py:84-130, 152-157).
+
+    codes: [O, I, kh, kw] integer weight codes (weight_quantize_int, QZ:24-31).  Returns int64 [pe, tiles] whose bit
+    patterns are the reference's words (runs of `simd` codes in (kh, kw, I) order, element e in bits [w_bit*e, +w_bit),
+    two's complement; word (oc, j) at [oc % pe, (oc // pe) * runs + j]); `& (2**64 - 1)` gives the unsigned value."""
+    _lib.require_cuda(codes)
+    if codes.dim() != 4:
+        raise ValueError("pack_hls_weights: codes must be [O, I, kh, kw]")
+    c8 = codes.to(torch.int8).contiguous()
+    O, I, kh, kw = c8.shape
+    if O % pe != 0:
+        raise AssertionError("out_ch mod pe must 0")             # the reference's own assert (qnn_mem_process.py:86)
+    runs = (kh * kw * I + simd - 1) // simd
+    out = torch.empty((pe, runs * (O // pe)), dtype=torch.int64, device=c8.device)
+    _lib.check(_lib.lib().qvit_pack_hls_weights(_lib.ptr(c8), O, I, kh, kw, int(w_bit), int(simd), int(pe), _lib.ptr(out),
+                                                _lib.stream()), "qvit_pack_hls_weights")
+    return out

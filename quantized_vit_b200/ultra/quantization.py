@@ -30,3 +30,15 @@ def bn_act_w_bias_float(gamma, beta, mean, var, eps):
 def bn_act_quantize_int(gamma, beta, mean, var, eps, w_bit=2, in_bit=4, out_bit=4, l_shift=4):
     """QZ:68-89 -> (inc, bias) int32."""
     return ops.bn_act_quantize_int(gamma, beta, mean, var, eps, w_bit, in_bit, out_bit, l_shift)
+
+
+def w_to_hls_array(weight_codes: torch.Tensor, w_bit: int, simd: int, pe: int) -> torch.Tensor:
+    """QNNLayerMemProcess.conv + w_to_hls_array (qnn_mem_process.py:84-130, 152-157): integer weight codes [O, I, kh, kw]
+    -> int64 [pe, tiles] whose bit patterns are the reference's words of ``simd * w_bit`` bits (``& (2**64 - 1)`` gives the
+    unsigned value the reference prints into param.h)."""
+    return ops.pack_hls_weights(weight_codes, w_bit, simd, pe)
+
+
+def inc_bias_to_hls_array(inc: torch.Tensor, bias: torch.Tensor, pe: int):
+    """qnn_mem_process.py:133-143: per-channel thresholds -> [pe, channels // pe] (channel c at [c % pe, c // pe])."""
+    return inc.reshape(-1, pe).t().contiguous(), bias.reshape(-1, pe).t().contiguous()

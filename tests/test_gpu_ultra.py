@@ -145,3 +145,18 @@ def test_batchnorm_q_modules_match_oracle_restatement(golden):
     with torch.no_grad():
         got1 = bn1.cuda()(x1.cuda()).cpu()
     assert torch.allclose(got1, want1, rtol=1e-5, atol=1e-6)
+
+
+def test_hls_parameter_layout_matches_reference(golden):
+    """qvit_pack_hls_weights (w_to_hls_array) and inc_bias_to_hls_array: the FPGA parameter words of the reference exporter
+    (qnn_mem_process.py:84-170), bit for bit, for every UltraNet layer shape of ultranet_param_gen.py and a ragged one."""
+    from quantized_vit_b200.ultra import quantization as qz
+    g = golden("ultra_hls")
+    for n in sorted({k.split(".")[0] for k in g.files}):
+        o, i, k, simd, pe = (int(v) for v in g[f"{n}.cfg"])
+        words = qz.w_to_hls_array(torch.from_numpy(g[f"{n}.codes"]).cuda(), 4, simd, pe).cpu().numpy()
+        assert np.array_equal(words.view(np.uint64), g[f"{n}.words"]), n
+        hi, hb = qz.inc_bias_to_hls_array(torch.from_numpy(g[f"{n}.inc"]).cuda(), torch.from_numpy(g[f"{n}.bias"]).cuda(), pe)
+        assert np.array_equal(hi.cpu().numpy(), g[f"{n}.hls_inc"]) and np.array_equal(hb.cpu().numpy(), g[f"{n}.hls_bias"])
+    with pytest.raises(AssertionError, match="out_ch mod pe"):
+        qz.w_to_hls_array(torch.zeros(6, 3, 3, 3, dtype=torch.int8).cuda(), 4, 3, 4)

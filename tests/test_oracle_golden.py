@@ -149,6 +149,21 @@ def test_bn_fold_and_pack_kats(golden):
         assert np.array_equal(ref_ultra.unpack_int4_bytes(by), row)
 
 
+def test_hls_parameter_layout(golden):
+    """oracle.hls_weight_words / hls_inc_bias against QNNLayerMemProcess.w_to_hls_array / inc_bias_to_hls_array run on
+    the reference itself (tests/golden/ultra_hls.npz, oracle/make_golden.py::golden_ultra_hls)."""
+    g = golden("ultra_hls")
+    names = sorted({k.split(".")[0] for k in g.files})
+    assert "ragged" in names and len(names) == 6
+    for n in names:
+        o, i, k, simd, pe = (int(v) for v in g[f"{n}.cfg"])
+        words = ref_ultra.hls_weight_words(g[f"{n}.codes"], 4, simd, pe)
+        assert words.shape == g[f"{n}.words"].shape and words.shape[1] == int(g[f"{n}.w_tiles"])
+        assert np.array_equal(words, g[f"{n}.words"]), n
+        hi, hb = ref_ultra.hls_inc_bias(g[f"{n}.inc"], g[f"{n}.bias"], pe)
+        assert np.array_equal(hi, g[f"{n}.hls_inc"]) and np.array_equal(hb, g[f"{n}.hls_bias"])
+
+
 def test_ultranet_whole_model(golden):
     g = golden("ultranet")
     from tests.fixtures import ultranet_state_dict, ultranet_input
