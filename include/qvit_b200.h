@@ -147,6 +147,24 @@ int qvit_unpack_int4(const uint8_t* packed, int64_t n, int is_signed, int8_t* co
 int qvit_pack_hls_weights(const int8_t* codes, int O, int I, int kh, int kw, int w_bit, int simd, int pe,
                           unsigned long long* words, qvit_stream_t stream);
 
+/* ------------------------------------------------------------------ GETA quant-parameter step
+ * The quantizer-scalar half of GETA.step() (optimizer/geta.py:571-772, 787-804; base_optimizer.py:17-86) in ONE launch:
+ * optional gradient clamp (geta.py:160-165), SGD / momentum / Adam / AdamW direction with the reference's moment
+ * initialisation (first buffer = grad) and bias corrections bc = 1 - beta^t, decoupled weight decay, step with lr_quant,
+ * and the projection of every d_quant onto [d(max_bit), d(min_bit)] (mode 1) or onto d(fixed bit) (mode 2),
+ * d(b) = exp(t * log(max(|q_m|, 1e-10))) / (2^(b-1) - 1).  mode 0 = plain descent (stage 1).
+ * params / grads: device arrays of `layers * 6` device pointers to the (1,) fp32 scalars, slot order d_quant_wt, q_m_wt,
+ * t_quant_wt, d_quant_act, q_m_act, t_quant_act; NULL = absent (or no gradient this step).  m1 / m2 / inited: persistent
+ * state, `layers * 6` elements, zero-initialised by the caller.  variant: 0 sgd, 1 adam, 2 adamw.  In mode 1 the
+ * activation scalars are first moved with the MODEL learning rate `lr` as well - the reference's range_wt `else` branch
+ * does exactly that (geta.py:620-629).  fix_bits_*: [layers] fp32 (mode 2) or NULL. */
+int qvit_geta_quant_step(float* const* params, const float* const* grads, float* m1, float* m2, uint8_t* inited,
+                         const float* fix_bits_wt, const float* fix_bits_act, int layers, int variant, int mode,
+                         float lr, float lr_quant, int has_wd, float wd, float beta1, float beta2, float dampening,
+                         double bc1, double bc2, float safe_guard, int clip, float clip_min, float clip_max,
+                         float min_bit_wt, float max_bit_wt, float min_bit_act, float max_bit_act, int32_t* flags,
+                         qvit_stream_t stream);
+
 /* ------------------------------------------------------------------ QuantLinear GEMM
  * Replaces nn.functional.linear(x_q, w_q, bias) on fake-quant values (QL:499, QU:220) by the exact integer
  * contraction  acc[m,n] = sum_k A[m,k] * Wc[n,k]  (int8 x int8 -> int32, tcgen05.mma kind::i8, TMEM

@@ -257,6 +257,97 @@ def golden_ultra_hls():
     np.savez_compressed(os.path.join(OUT, "ultra_hls.npz"), **out)
 
 
+GETA_STEP_CASES = [  # name, hyper-parameters, stages of the consecutive steps
+    ("sgd_range", dict(variant="sgd", lr=0.1, lr_quant=1e-3, first_momentum=0.0, dampening=0.0, weight_decay=None), ["range"] * 3),
+    ("sgdm_wd_descent", dict(variant="sgd", lr=0.05, lr_quant=2e-3, first_momentum=0.9, dampening=0.1, weight_decay=1e-2), ["descent"] * 4),
+    ("adam_range", dict(variant="adam", lr=1e-3, lr_quant=1e-3, first_momentum=0.9, second_momentum=0.999, weight_decay=None), ["descent", "range", "range", "range"]),
+    ("adamw_all", dict(variant="adamw", lr=3e-3, lr_quant=5e-3, first_momentum=0.9, second_momentum=0.99, weight_decay=0.05), ["descent", "range", "range", "fix", "fix"]),
+]
+
+
+def _geta_fake_params(rng, nonlinear):
+    """Six layers: W+A (with and without t), weight-only; values around a 4..8-bit operating point."""
+    params = {}
+    for li in range(6):
+        layer = f"blocks.{li}.fc"
+        qm = float(rng.uniform(0.2, 3.0))
+        params[f"{layer}.d_quant_wt"] = qm / float(rng.choice([3, 7, 15, 127])) * float(rng.uniform(0.8, 1.2))
+        params[f"{layer}.q_m_wt"] = qm * (1 if li % 3 else -1)              # q_m may be negative: |.| is taken
+        if nonlinear and li % 2 == 0:
+            params[f"{layer}.t_quant_wt"] = float(rng.uniform(0.8, 1.2))
+        if li != 5:                                                          # last layer: weight-only
+            qa = float(rng.uniform(0.5, 4.0))
+            params[f"{layer}.d_quant_act"] = qa / float(rng.choice([7, 15, 127]))
+            params[f"{layer}.q_m_act"] = qa
+            if nonlinear and li % 2 == 0:
+                params[f"{layer}.t_quant_act"] = float(rng.uniform(0.8, 1.2))
+    return params
+
+
+def golden_geta_step():
+    """Quantizer-scalar half of GETA.step(), run on the REAL class: the methods are called on a GETA object created without
+    its constructor (no model / graph needed for them), with one hand-made param_group."""
+    import contextlib, importlib, io
+    R._stub_only_train_once()
+    geta_mod = importlib.import_module("only_train_once.optimizer.geta")
+    out = {}
+    rng = np.random.RandomState(21)
+    for name, hp, stages in GETA_STEP_CASES:
+        for nonlinear in (False, True):
+            tag = f"{name}.{'nl' if nonlinear else 'lin'}"
+            init = _geta_fake_params(rng, nonlinear)
+            names = list(init)
+            params = [torch.nn.Parameter(torch.tensor([v], dtype=torch.float32)) for v in init.values()]
+            opt = object.__new__(geta_mod.GETA)
+            group = dict(p_names=names, params=params, grad_variant=dict(), is_prunable=False, active_redundant_idxes=[])
+            group.update(dampening=0.0, second_momentum=0.0, first_momentum=0.0)
+            group.update(hp)
+            opt.param_groups = [group]
+            opt.num_steps, opt.safe_guard = 0, 1e-8
+            opt.first_moment_grads, opt.second_moment_grads = dict(), dict()
+            opt.min_bit_wt, opt.max_bit_wt, opt.min_bit_act, opt.max_bit_act = 4, 8, 3, 6
+            opt.grad_clip_min, opt.grad_clip_max = -1.0, 1.0
+            out[f"{tag}.names"] = np.array(names)
+            out[f"{tag}.init"] = np.array(list(init.values()), dtype=np.float32)
+            bit_dict = None
+            grads_all, after_all = [], []
+            for si, stage in enumerate(stages):
+                g = (rng.randn(len(names)) * rng.choice([0.05, 0.5, 3.0], size=len(names))).astype(np.float32)
+                if si == 1:
+                    g[3] = np.nan if False else g[3]
+                    g[1::5] = 0.0                                            # some exact zeros
+                for p, gi in zip(params, g):
+                    p.grad = torch.tensor([gi], dtype=torch.float32)
+                if si == len(stages) - 1:
+                    params[2].grad = None                                    # "if p.grad is None: continue"
+                    g[2] = np.nan                                            # marker: no gradient
+                opt.grad_clipping_names = None
+                for p in params:                                             # GETA.grad_clipping (geta.py:160-165), None-safe
+                    if p.grad is not None:
+                        p.grad = p.grad.clamp(min=opt.grad_clip_min, max=opt.grad_clip_max)
+                opt.num_steps += 1
+                opt.compute_grad_variant()
+                with contextlib.redirect_stdout(io.StringIO()):
+                    if stage == "descent":
+                        opt.gradient_descent_step(group)
+                    elif stage == "range":
+                        opt.partial_projected_gradient_descent_step_range_wt(group)
+                        opt.partial_projected_gradient_descent_step_range_act(group)
+                    else:
+                        if bit_dict is None:
+                            bit_dict = opt.get_bitwidth_dict(group)
+                            out[f"{tag}.bit_layers"] = np.array(list(bit_dict))
+                            out[f"{tag}.bit_wt"] = np.array([bit_dict[k]["weight"] for k in bit_dict], dtype=np.float64)
+                            out[f"{tag}.bit_act"] = np.array([bit_dict[k].get("activation", -1) for k in bit_dict], dtype=np.float64)
+                        opt.partial_projected_gradient_descent_step_fix(group, bit_dict)
+                grads_all.append(g)
+                after_all.append(np.array([float(p.data) for p in params], dtype=np.float32))
+            out[f"{tag}.grads"] = np.stack(grads_all)
+            out[f"{tag}.after"] = np.stack(after_all)
+            out[f"{tag}.stages"] = np.array(stages)
+    np.savez_compressed(os.path.join(OUT, "geta_step.npz"), **out)
+
+
 def golden_ultranet():
     mm = R.mymodel()
     torch.manual_seed(0)

@@ -4,3 +4,4 @@ from .quant_layers import (LAYER_TO_QUANTLAYER, DGEQuantizer, NanInGradientError
                            QuantizeConv2d, QuantizeLinear, QuantizeMixin, SymQuantizerLinear, SymQuantizerNonLinear,
                            _get_quantizer, check_nan_flags, initialize_quant_layer)  # noqa: F401
 from .quant_model import get_bitwidth_dict, get_quant_param_dict, model_to_quantize_model  # noqa: F401
+from .geta_step import GetaQuantParamStepper  # noqa: F401

@@ -1,0 +1,93 @@
+"""Quantizer-scalar half of GETA.step(): oracle restatement and the fused CUDA step against
+values produced by the REAL reference class (tests/golden/geta_step.npz, oracle/make_golden.py::golden_geta_step).
+
+Four hyper-parameter sets (SGD, SGD + momentum + weight decay, Adam, AdamW) x (linear / non-linear quantizers), sequences
+of 3-5 steps mixing the three stages, six layers each (negative q_m, weight-only layer, a parameter that loses its
+gradient).  Tolerance: these are fp32 scalar updates; the CPU kernels of the reference may or may not contract
+a + alpha*b into an fma, so the bar is 2e-6 relative (well inside the 1e-3 the task states for floating point)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import make_golden, ref_geta_step
+
+CASES = [(name, nl) for name, _, _ in make_golden.GETA_STEP_CASES for nl in ("lin", "nl")]
+
+
+def _hp(name):
+    return next(hp for n, hp, _ in make_golden.GETA_STEP_CASES if n == name)
+
+
+def _close(got, want, what):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    err = np.abs(got - want) / np.maximum(np.abs(want), 1e-12)
+    assert err.max() <= 2e-6, (what, float(err.max()), int(err.argmax()))
+
+
+def _bit_dict(g, tag):
+    if f"{tag}.bit_layers" not in g.files:
+        return None
+    return {str(l): ({"weight": float(w)} if a < 0 else {"weight": float(w), "activation": float(a)})
+            for l, w, a in zip(g[f"{tag}.bit_layers"], g[f"{tag}.bit_wt"], g[f"{tag}.bit_act"])}
+
+
+@pytest.mark.parametrize("name,nl", CASES)
+def test_oracle_matches_reference_class(golden, name, nl):
+    g = golden("geta_step")
+    tag = f"{name}.{nl}"
+    names = [str(n) for n in g[f"{tag}.names"]]
+    params = {n: torch.nn.Parameter(torch.tensor([v], dtype=torch.float32)) for n, v in zip(names, g[f"{tag}.init"])}
+    ref = ref_geta_step.GetaQuantStepRef(min_bit_wt=4, max_bit_wt=8, min_bit_act=3, max_bit_act=6, grad_clip=(-1.0, 1.0), **_hp(name))
+    for stage, grads, after in zip(g[f"{tag}.stages"], g[f"{tag}.grads"], g[f"{tag}.after"]):
+        for n, gi in zip(names, grads):
+            params[n].grad = None if np.isnan(gi) else torch.tensor([gi], dtype=torch.float32)
+        ref.step(params, str(stage), _bit_dict(g, tag))
+        got = np.array([float(params[n].data) for n in names], dtype=np.float32)
+        assert np.array_equal(got, after) or (_close(got, after, (tag, stage)) is None)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,nl", CASES)
+def test_fused_cuda_step_matches_reference_class(golden, name, nl):
+    from quantized_vit_b200.quantization import GetaQuantParamStepper
+    g = golden("geta_step")
+    tag = f"{name}.{nl}"
+    names = [str(n) for n in g[f"{tag}.names"]]
+    params = {n: torch.nn.Parameter(torch.tensor([v], dtype=torch.float32, device="cuda")) for n, v in zip(names, g[f"{tag}.init"])}
+    st = GetaQuantParamStepper(params.items(), min_bit_wt=4, max_bit_wt=8, min_bit_act=3, max_bit_act=6, grad_clip=(-1.0, 1.0),
+                               **_hp(name))
+    assert len(st.layer_names) == 6
+    for stage, grads, after in zip(g[f"{tag}.stages"], g[f"{tag}.grads"], g[f"{tag}.after"]):
+        for n, gi in zip(names, grads):
+            params[n].grad = None if np.isnan(gi) else torch.tensor([gi], dtype=torch.float32, device="cuda")
+        st.step(str(stage), _bit_dict(g, tag))
+        got = torch.cat([params[n].data for n in names]).cpu().numpy()
+        _close(got, after, (tag, str(stage)))
+    assert int(st.flags.item()) == 0
+
+
+@pytest.mark.gpu
+def test_fused_step_on_a_converted_model_and_nan_flag():
+    """End to end: quantizer scalars of a converted model move exactly as the oracle moves them; a NaN gradient raises the flag."""
+    from quantized_vit_b200.quantization import GetaQuantParamStepper, model_to_quantize_model
+    torch.manual_seed(0)
+    model = torch.nn.Sequential(torch.nn.Linear(32, 48), torch.nn.GELU(), torch.nn.Linear(48, 16))
+    model = model_to_quantize_model(model, num_bits=4, quant_type="symmetric+nonlinear", quant_mode="weight_and_activation").cuda()
+    hp = dict(variant="adam", lr=1e-3, lr_quant=1e-2, first_momentum=0.9, second_momentum=0.999)
+    st = GetaQuantParamStepper(model.named_parameters(), **hp)
+    quant = {n: p for n, p in model.named_parameters() if any(t in n for t in ("d_quant", "q_m", "t_quant"))}
+    assert len(quant) == 12 and len(st.layer_names) == 2
+    cpu = {n: torch.nn.Parameter(p.detach().cpu().clone()) for n, p in quant.items()}
+    ref = ref_geta_step.GetaQuantStepRef(**hp)
+    x = torch.randn(64, 32, device="cuda")
+    for step in range(3):
+        model.zero_grad(set_to_none=True)
+        model(x).square().mean().backward()
+        for n in quant:
+            cpu[n].grad = quant[n].grad.detach().cpu().clone()
+        st.step("range")
+        ref.step(cpu, "range")
+        _close(torch.cat([quant[n].data for n in quant]).cpu().numpy(), np.array([float(cpu[n].data) for n in quant]), step)
+    next(iter(quant.values())).grad.fill_(float("nan"))
+    st.step("descent")
+    assert int(st.flags.item()) & 4
