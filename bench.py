@@ -9,7 +9,8 @@ One "step" = one forward pass of ViT-B/16 (quantized patch-embed + 48 QuantizeLi
 weight_and_activation) over one batch of 256 synthetic 224x224 images PER GPU (weak scaling: batch-sharded
 replicas, no collective on the forward path - SURVEY.md section 8e).  `value` is whole-job images/s with the
 batch resident in HBM (CUDA-graph replay, device-timed with CUDA events, max over ranks); `e2e` is the same metric
-through the public host-facing call `ViTInferenceEngine.infer()` with host<->device copies inside the timed region.
+through the public host-facing call `ViTInferenceEngine.infer_many()` (pinned host batches in, host logits out) with the
+host<->device copies inside the timed region.
 `roofline` describes the dominant kernel (the tcgen05 int8 GEMM): algorithmic 2*M*K*N ops of the quantized layers
 divided by the summed CUDA-event duration of the GEMM launches of a step, against 2x the measured dense-bf16 peak
 (MEASURED_PEAKS.json has no int8 entry; int8 tensor throughput is nominally 2x bf16 - DESIGN.md "peaks").
