@@ -187,15 +187,17 @@ __global__ void __launch_bounds__(kThreads)
 patchify_quantize_kernel(const float* __restrict__ x, ConvGeom g, const float* __restrict__ d, const float* __restrict__ qm,
                          const float* __restrict__ t, int8_t* __restrict__ cols, int64_t ld_cols, int32_t* __restrict__ flags) {
   const SymParams p = load_sym_params(d, qm, t);
-  const FastQ fq = make_fastq(p);
+  const FastQ2 fq = make_fastq2(p);
   int fl = 0;
   const int w4 = g.W / 4;                                  // float4 groups per image row
   const int64_t total = (int64_t)g.B * g.C * g.H * w4;
+  const uint32_t hw4 = (uint32_t)(g.H * w4);               // groups per (image, channel) plane: 32-bit index math inside it
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int xg = (int)(i % w4);
-    const int ih = (int)((i / w4) % g.H);
-    const int c = (int)((i / ((int64_t)w4 * g.H)) % g.C);
-    const int b = (int)(i / ((int64_t)w4 * g.H * g.C));
+    // (64-bit divisions cost ~100 instructions each and made this kernel instruction bound: one 64-bit divide, the
+    // rest in 32 bits)
+    const uint32_t plane = (uint32_t)(i / hw4), rem = (uint32_t)(i - (int64_t)plane * hw4);
+    const int ih = (int)(rem / (uint32_t)w4), xg = (int)(rem - (uint32_t)ih * (uint32_t)w4);
+    const int b = (int)(plane / (uint32_t)g.C), c = (int)(plane - (uint32_t)b * (uint32_t)g.C);
     const int iw = xg * 4;
     const int oh = ih / g.kh, ki = ih - oh * g.kh;
     const int ow = iw / g.kw, kj = iw - ow * g.kw;
@@ -203,7 +205,7 @@ patchify_quantize_kernel(const float* __restrict__ x, ConvGeom g, const float* _
     const float4 v = ldg_stream4(x + i * 4);
     const int64_t row = ((int64_t)b * g.OH + oh) * g.OW + ow;
     const int k = (c * g.kh + ki) * g.kw + kj;
-    *reinterpret_cast<uint32_t*>(cols + row * ld_cols + k) = sym_codes4(v.x, v.y, v.z, v.w, p, fq, fl);
+    *reinterpret_cast<uint32_t*>(cols + row * ld_cols + k) = sym_codes4_v2(v.x, v.y, v.z, v.w, p, fq, fl);
   }
   fl = warp_or(fl);
   if (fl && flags && (threadIdx.x & 31) == 0) atomicOr(flags, fl);
