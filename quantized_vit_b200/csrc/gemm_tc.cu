@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                   const EpiParams ep, const int K, const uint32_t idesc, const int tma_store, const int res_tma,
-                  const int mma_only_flags, const int b_wrap) {
+                  const int mma_only_flags, const int b_wrap, const int ksplit) {
   using S = GemmSmem<BN, CG>;
   constexpr int kStages = S::kStages;
   constexpr int kTmemCols = 2 * BN;   // 256 or 512: a power of two >= 32
@@ -243,8 +243,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
 
   const int m_tiles = (ep.M + kTileM - 1) / kTileM;
   const int n_tiles = (ep.N + BN - 1) / BN;
-  const int total_tiles = m_tiles * n_tiles;
+  const int total_tiles = m_tiles * n_tiles * ksplit;       // split-K: `ksplit` consecutive tiles share an output tile
   const int k_blocks = (K + kBK - 1) / kBK;
+  const int k_per_split = (k_blocks + ksplit - 1) / ksplit;
   const int tile_first = blockIdx.x / CG, tile_step = gridDim.x / CG;
 
   if (warp == 0 && lane == 0) {
@@ -284,15 +285,17 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
-        const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+        const int t2 = tile / ksplit, ks = tile - t2 * ksplit;
+        const int m_blk = t2 / n_tiles, n_blk = t2 - m_blk * n_tiles;
         const int a_row = m_blk * kTileM + (int)rank * kBM;          // this CTA's 128 rows of A
         const int w_row = n_blk * BN + (int)rank * (BN / CG);        // this CTA's share of the W rows
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int kb0 = ks * k_per_split, kb1 = min(k_blocks, kb0 + k_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(empty_bar(stage), phase ^ 1u);
           const uint32_t a_dst = smem_base + stage * S::kStageBytes;
           const uint32_t b_dst = a_dst + S::kABytes;
           if (ptx::elect_one()) {
-            if (mma_only && (tile != tile_first || kb >= kStages)) {
+            if (mma_only && (tile != tile_first || kb - kb0 >= kStages)) {
               // benchmark mode: operands stay whatever the first kStages loads brought in - measures the tensor-core
               // issue rate with no L2 / HBM traffic at all
               if (rank == 0) ptx::mbar_arrive(full_bar(stage));
@@ -330,7 +333,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
         ptx::tc_fence_after();
         QVIT_PROF(0);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < k_blocks; ++kb) {
+        const int ks = tile % ksplit;
+        const int kb0 = ks * k_per_split, kb1 = min(k_blocks, kb0 + k_per_split);
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(full_bar(stage), phase);
           ptx::tc_fence_after();
           const uint32_t a_src = smem_base + stage * S::kStageBytes;
@@ -342,22 +347,22 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               // advance both descriptors by k*32 bytes inside the swizzle atom (address field is >>4)
               if (KIND == 0)
                 ptx::mma_i8<CG>(d_tmem, a_desc + (uint64_t)(k * (kUmmaK >> 4)), b_desc + (uint64_t)(k * (kUmmaK >> 4)), idesc,
-                                (uint32_t)((kb | k) != 0));
+                                (uint32_t)(kb != kb0 || k != 0));
               else
                 ptx::mma_bf16<CG>(d_tmem, a_desc + (uint64_t)(k * (kUmmaK >> 4)), b_desc + (uint64_t)(k * (kUmmaK >> 4)), idesc,
-                                  (uint32_t)((kb | k) != 0));
+                                  (uint32_t)(kb != kb0 || k != 0));
             }
             // smem slot free once these MMAs retire (in both CTAs of a pair)
             if (CG == 1) ptx::mma_commit(empty_bar(stage)); else ptx::mma_commit_cg2(empty_bar(stage), 0x3);
             // accumulator complete after the last k-block
-            if (kb == k_blocks - 1) {
+            if (kb == kb1 - 1) {
               if (CG == 1) ptx::mma_commit(tfull_bar(acc)); else ptx::mma_commit_cg2(tfull_bar(acc), 0x3);
             }
           }
           __syncwarp();
           if (++stage == kStages) { stage = 0; phase ^= 1u; }
         }
-        if (k_blocks == 0 && ptx::elect_one()) {             // (K = 0 never reaches this kernel; keep the protocol total)
+        if (kb0 >= kb1 && ptx::elect_one()) {                // (never happens: K > 0 and every split is non-empty; keep the protocol total)
           if (CG == 1) ptx::mma_commit(tfull_bar(acc)); else ptx::mma_commit_cg2(tfull_bar(acc), 0x3);
         }
         QVIT_PROF(1);
@@ -406,7 +411,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // bias of the warp's columns: loaded one tile ahead into registers, parked in shared memory for the tile
     float nb[kChunksPerQuad];
     auto bias_fetch = [&](int t) {
-      const int nblk = t % n_tiles;
+      const int nblk = (t / ksplit) % n_tiles;
 #pragma unroll
       for (int cq = 0; cq < kChunksPerQuad; ++cq) {
         const int col = nblk * BN + (quad * kChunksPerQuad + cq) * 32 + lane;
@@ -415,7 +420,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     };
     bias_fetch(tile_first);
     for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
-      const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+      const int t2 = tile / ksplit;
+      const int m_blk = t2 / n_tiles, n_blk = t2 - m_blk * n_tiles;
 #pragma unroll
       for (int cq = 0; cq < kChunksPerQuad; ++cq)
         asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_sm + (uint32_t)(cq * 128 + lane * 4)), "f"(nb[cq]) : "memory");
@@ -556,7 +562,8 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             ptx::fence_proxy_async_smem();                   // generic-proxy writes -> visible to the TMA engine
             __syncwarp();
             if (lane == 0) {
-              ptx::tma_store_2d(&tmap_out, slab, box_n0, row0);
+              if (ksplit > 1) ptx::tma_reduce_add_2d(&tmap_out, slab, box_n0, row0);   // split-K partials add up in global memory
+              else ptx::tma_store_2d(&tmap_out, slab, box_n0, row0);
               ptx::tma_store_commit();
             }
           }
@@ -701,7 +708,7 @@ struct TcMaps {
 
 template <int BN, int OUT, int CG, int KIND = 0>
 static int launch_tc(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsigned, int max_ctas, cudaStream_t s,
-                     int b_wrap = 1 << 30) {
+                     int b_wrap = 1 << 30, int ksplit = 1) {
   using S = GemmSmem<BN, CG>;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -715,7 +722,7 @@ static int launch_tc(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsign
     attr_set[dev] = true;
   }
   const int m_tiles = (ep.M + kBM * CG - 1) / (kBM * CG), n_tiles = (ep.N + BN - 1) / BN;
-  int grid = m_tiles * n_tiles * CG;
+  int grid = m_tiles * n_tiles * CG * ksplit;
   if (grid > max_ctas) grid = max_ctas;
   if (CG == 2) grid &= ~1;
   const uint32_t idesc = KIND == 0 ? ptx::make_idesc_i8(kBM * CG, BN, !a_unsigned, true) : ptx::make_idesc_bf16_f32(kBM * CG, BN);
@@ -732,7 +739,7 @@ static int launch_tc(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsign
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_i8_tc_kernel<BN, OUT, CG, KIND>, tm.a, tm.w, tm.out, tm.res, ep, K, idesc,
-                                     (tm.tma_store && g_skip_store) ? 2 : tm.tma_store, tm.res_tma, g_mma_only | (g_profile << 1) | (g_force_path == 1 ? 4 : 0) | (g_force_path == 2 ? 8 : 0), b_wrap);
+                                     (tm.tma_store && g_skip_store) ? 2 : tm.tma_store, tm.res_tma, g_mma_only | (g_profile << 1) | (g_force_path == 1 ? 4 : 0) | (g_force_path == 2 ? 8 : 0), b_wrap, ksplit);
   if (e != cudaSuccess) {
     set_error("gemm_i8_tc_kernel launch: %s", cudaGetErrorString(e));
     return QVIT_ERR_CUDA;
@@ -831,8 +838,29 @@ int gemm_tc_launch_bf16_split(const void* a, int64_t lda, int planes, const void
   }
   const int k_bytes = 2 * planes * Kp;          // contraction length of the kernel's byte-wise K loop
   const int b_wrap = (2 * Kp) / kBK;            // k-blocks per plane: the B coordinate wraps, A runs through all planes
-  if (bn == 256) return launch_tc<256, QVIT_OUT_F32, 1, 1>(tm, ep, k_bytes, false, sms, s, b_wrap);
-  return launch_tc<128, QVIT_OUT_F32, 1, 1>(tm, ep, k_bytes, false, sms, s, b_wrap);
+  // Split-K for the weight-gradient shape (small output, very long contraction: [3072 x 768] over 25 216 x 3 planes): with
+  // fewer [128 x 256] tiles than SMs, two CTAs share an output tile, each takes half of the k-blocks and both ADD their
+  // partial tile with a TMA reduce (fp32 add of two partials onto zero is order independent: deterministic).
+  const int64_t tiles256 = (int64_t)((M + kBM - 1) / kBM) * ((N + 255) / 256);
+  const int k_blocks = (k_bytes + kBK - 1) / kBK;
+  const int64_t tiles128 = (int64_t)((M + kBM - 1) / kBM) * ((N + 127) / 128);
+  int ksplit = 1;
+  if (k_blocks >= 64 && !ep.bias && !ep.residual && !ep.col_scale && ep.act == QVIT_ACT_NONE) {
+    if (N > 128 && tiles256 * 2 <= sms && tiles256 * 4 >= sms) { ksplit = 2; bn = 256; }
+    else if (tiles128 * 2 <= sms) { ksplit = 2; bn = 128; }
+  }
+  if (ksplit > 1) {
+    rc = make_tmap_bytes(&tm.w, b, N, (int64_t)2 * Kp, ldb * 2, bn);
+    if (rc) return rc;
+    rc = make_tmap_out(&tm.out, ep.out, M, N, ep.ldo, QVIT_OUT_F32, out_box_bytes(bn, QVIT_OUT_F32), 32);
+    if (rc) return rc;
+    if (cudaMemset2DAsync(ep.out, (size_t)ep.ldo * 4, 0, (size_t)N * 4, (size_t)M, s) != cudaSuccess) {
+      set_error("qvit_gemm_bf16_split: cudaMemset2DAsync failed");
+      return QVIT_ERR_CUDA;
+    }
+  }
+  if (bn == 256) return launch_tc<256, QVIT_OUT_F32, 1, 1>(tm, ep, k_bytes, false, sms, s, b_wrap, ksplit);
+  return launch_tc<128, QVIT_OUT_F32, 1, 1>(tm, ep, k_bytes, false, sms, s, b_wrap, ksplit);
 }
 
 }  // namespace qvit

@@ -85,6 +85,12 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int
                ::"l"(tmap), "r"(src), "r"(c0), "r"(c1)
                : "memory");
 }
+// same box, but added to global memory (fp32): split-K partial tiles
+__device__ __forceinline__ void tma_reduce_add_2d(const void* tmap, uint32_t src, int c0, int c1) {
+  asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(tmap), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void tma_store_wait_read() {
