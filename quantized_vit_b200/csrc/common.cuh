@@ -186,30 +186,8 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
   return r;
 }
 
-// gelu_erf() on a pair, bit-identical to the scalar form: the polynomial runs in t' = -min(|x|, 5.94) with the odd
+// gelu_erf() on pairs, bit-identical to the scalar form: the polynomial runs in t' = -min(|x|, 5.94) with the odd
 // coefficients negated (every Horner step is the exact mirror image), so that the last step is fma(t', h, max(x, 0)).
-__device__ __forceinline__ f32x2 gelu_erf2(f32x2 x) {
-  float x0, x1;
-  unpk2(x, x0, x1);
-  const f32x2 t = pk2(fmaxf(-fabsf(x0), -5.939696788787842f), fmaxf(-fabsf(x1), -5.939696788787842f));
-  f32x2 p = pk1(-2.2758645172871184e-06f);
-  p = fma2(p, t, pk1(-3.296791692264378e-05f));
-  p = fma2(p, t, pk1(-0.0001572782639414072f));
-  p = fma2(p, t, pk1(0.00020248025248292834f));
-  p = fma2(p, t, pk1(0.007142783608287573f));
-  p = fma2(p, t, pk1(0.052546434104442596f));
-  p = fma2(p, t, pk1(-0.45919305086135864f));
-  p = fma2(p, t, pk1(1.1511069536209106f));
-  p = fma2(p, t, pk1(-0.9999999403953552f));
-  float p0, p1, h0, h1, r0, r1;
-  unpk2(p, p0, p1);
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h0) : "f"(p0));
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h1) : "f"(p1));
-  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r0) : "f"(x0), "f"(0.0f));
-  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r1) : "f"(x1), "f"(0.0f));
-  return fma2(t, pk2(h0, h1), pk2(r0, r1));
-}
-
 // Four pairs at once, coefficient-major (four independent Horner chains per thread for the scheduler to interleave).
 __device__ __forceinline__ void gelu_erf2x4(f32x2 (&x)[4]) {
   f32x2 t[4], p[4];
