@@ -575,7 +575,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
     }
-    if (tma_store == 1 && lane == 0) ptx::tma_store_wait<0>();
+    if (tma_store == 1 && lane == 0) ptx::tma_store_wait_read<0>();   // the slab must outlive the reads; the writes complete with the grid
     fl = warp_or(fl);
     if (fl && ep.flags && lane == 0) atomicOr(ep.flags, fl);
   }
