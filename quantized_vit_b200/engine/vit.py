@@ -199,9 +199,10 @@ class ViTInferenceEngine:
     __call__ = forward
 
     # ------------------------------------------------------------------ CUDA-graph replay for a fixed batch size
-    def capture(self, batch: int, img: int = 224):
-        """Capture forward() for [batch, 3, img, img] into a CUDA graph; returns (static_input, static_output, graph)."""
-        key = (batch, img)
+    def capture(self, batch: int, img: int = 224, slot: int = 0):
+        """Capture forward() for [batch, 3, img, img] into a CUDA graph; returns (static_input, static_output, graph).
+        `slot` selects an independent capture (own static input / output): the pipelined host API ping-pongs between two."""
+        key = (batch, img) if slot == 0 else (batch, img, slot)
         if key in self._graphs:
             return self._graphs[key]
         x = torch.zeros((batch, 3, img, img), dtype=torch.float32, device=self.device)
@@ -236,49 +237,47 @@ class ViTInferenceEngine:
 
     def infer_many(self, host_batches) -> list:
         """Pipelined end-to-end inference over a sequence of pinned HOST batches of one shape: the host->device copy
-        of batch i+1 (copy stream, double-buffered staging) and the device->host copy of the logits of batch i-1 run
-        while the captured forward of batch i executes.  Returns one host logits tensor per batch; they live in the
+        of batch i+1 (copy stream, straight into the static input of the second of two captured graphs) and the
+        device->host copy of the logits of batch i-1 run while the captured forward of batch i executes.  Returns one host logits tensor per batch; they live in the
         engine's pinned result pool and stay valid until the next infer_many call (clone to keep them longer)."""
         batches = list(host_batches)
         if not batches:
             return []
         B, _, Hh, _ = batches[0].shape
-        xs, ys, graph = self.capture(B, Hh)
+        caps = [self.capture(B, Hh, slot=j) for j in range(2)]   # two captures: batch i+1 is copied into one graph's static
+        ys = caps[0][1]                                           # input while the other graph runs batch i (no device copy)
         key = ("pipe", B, Hh)
         st = self._pinned.get(key)
         if st is None:
-            st = self._pinned[key] = {
-                "stage": [torch.empty_like(xs) for _ in range(2)], "h2d": torch.cuda.Stream(device=self.device),
-                "d2h": torch.cuda.Stream(device=self.device), "ydev": [torch.empty_like(ys) for _ in range(2)]}
+            st = self._pinned[key] = {"h2d": torch.cuda.Stream(device=self.device), "d2h": torch.cuda.Stream(device=self.device)}
         pool = st.setdefault("outs", [])                      # page-locked allocations cost milliseconds: made once, reused
         while len(pool) < len(batches):
             pool.append(torch.empty(ys.shape, dtype=ys.dtype, pin_memory=True))
         outs = pool[:len(batches)]
         main = torch.cuda.current_stream()
-        copied = [torch.cuda.Event() for _ in range(2)]      # staging[j] filled
-        consumed = [torch.cuda.Event() for _ in range(2)]    # staging[j] read by the compute stream
-        ydone = [torch.cuda.Event() for _ in range(2)]       # ydev[j] written by the compute stream
-        yfree = [torch.cuda.Event() for _ in range(2)]       # ydev[j] copied out
+        copied = [torch.cuda.Event() for _ in range(2)]      # static input j filled
+        consumed = [torch.cuda.Event() for _ in range(2)]    # static input j read by its graph
+        ydone = [torch.cuda.Event() for _ in range(2)]       # static output j written
+        yfree = [torch.cuda.Event() for _ in range(2)]       # static output j copied out
         st["h2d"].wait_stream(main)
         st["d2h"].wait_stream(main)
         for i, xb in enumerate(batches):
             j = i & 1
+            xs_j, ys_j, graph_j = caps[j]
             with torch.cuda.stream(st["h2d"]):
                 if i >= 2:
                     st["h2d"].wait_event(consumed[j])
-                st["stage"][j].copy_(xb, non_blocking=True)
+                xs_j.copy_(xb, non_blocking=True)
                 copied[j].record(st["h2d"])
             main.wait_event(copied[j])
-            xs.copy_(st["stage"][j], non_blocking=True)
-            consumed[j].record(main)
-            graph.replay()
             if i >= 2:
                 main.wait_event(yfree[j])
-            st["ydev"][j].copy_(ys, non_blocking=True)
+            graph_j.replay()
+            consumed[j].record(main)
             ydone[j].record(main)
             with torch.cuda.stream(st["d2h"]):
                 st["d2h"].wait_event(ydone[j])
-                outs[i].copy_(st["ydev"][j], non_blocking=True)
+                outs[i].copy_(ys_j, non_blocking=True)
                 yfree[j].record(st["d2h"])
         main.wait_stream(st["d2h"])
         main.synchronize()
