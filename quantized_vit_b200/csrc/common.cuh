@@ -227,19 +227,41 @@ struct FastQ2 {
   f32x2 inv_hi, inv_lo;
   float t_lo, t_hi;        // 1.5 * 2^23 -+ sat
   float inv_d, d;
-  int generic;
+  int generic;             // no fast path at all: every element through sym_code()
+  int nl;                  // non-linear quantizer on the fast path: |y|^t through MUFU lg2 / ex2, wider doubt band
+  float t, qm, satd;       // exponent, q_m, sat * d (the power-domain value every saturated element is replaced by)
 };
 __device__ __forceinline__ FastQ2 make_fastq2(const SymParams& p) {
   FastQ2 f;
   const float inv_d = __fdiv_rn(1.0f, p.d);
-  f.inv_hi = pk1(fmaf(inv_d, 3.0e-7f, inv_d));
-  f.inv_lo = pk1(fmaf(inv_d, -3.0e-7f, inv_d));
+  const bool base_ok = (p.qm > 0.0f) && (p.sat <= 127.0f) && (p.d > 1.0e-10f) && (p.d < 1.0e10f);
+  // Non-linear quantizer (QL:40-69): the code is rint(exp(t log|y|) / d).  Fast path: |y|^t = ex2(t * lg2|y|) on the MUFU
+  // (relative error ~0.7 * t * |lg2 y| * 2^-22 + 2^-22, i.e. < 1e-5 wherever the code is not trivially 0), the same
+  // interval test with a band of +-1.2e-5; elements it cannot decide go to sym_code() (expf / logf / IEEE division), so
+  // the codes are those of the exact path bit for bit.  Saturation compares |y| with q_m BEFORE the power (QL:65-67):
+  // saturated elements are replaced by sat * d, which rounds to sat under both multipliers.
+  f.nl = (p.nonlinear && base_ok && p.t > 0.0f && p.t < 8.0f && p.d >= 1.0e-6f) ? 1 : 0;
+  const float band = f.nl ? 1.2e-5f : 3.0e-7f;
+  f.inv_hi = pk1(fmaf(inv_d, band, inv_d));
+  f.inv_lo = pk1(fmaf(inv_d, -band, inv_d));
   f.t_lo = kRoundMagic - p.sat;
   f.t_hi = kRoundMagic + p.sat;
   f.inv_d = inv_d;
   f.d = p.d;
-  f.generic = (p.nonlinear || !(p.qm > 0.0f) || !(p.sat <= 127.0f) || !(p.d > 1.0e-10f) || !(p.d < 1.0e10f)) ? 1 : 0;
+  f.t = p.t;
+  f.qm = p.qm;
+  f.satd = p.sat * p.d;
+  f.generic = (!base_ok || (p.nonlinear && !f.nl)) ? 1 : 0;
   return f;
+}
+// power-domain value of one element for the non-linear fast path, sign of y attached (NaN stays NaN -> lands in the doubt set)
+__device__ __forceinline__ float nl_power(float y, const FastQ2& f) {
+  const float a = fabsf(y);
+  float l, pw;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(a));
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(pw) : "f"(f.t * l));
+  pw = (a >= f.qm) ? f.satd : pw;
+  return copysignf(pw, y);
 }
 // Exact code of one element without the division unit, for the elements the interval test could not decide:
 // Markstein's correction (q' = q + (y - q d) * RN(1/d), residual exact in an fma) applied twice turns q0 = RN(y * RN(1/d))
@@ -255,6 +277,13 @@ __device__ __forceinline__ float sym_t_exact(float y, const FastQ2& f) {
 // four elements (two pairs) -> one word of four int8 codes; dacc accumulates (ta - tb)^2
 __device__ __forceinline__ uint32_t sym_codes4_fast2(f32x2 y01, f32x2 y23, const FastQ2& f, f32x2& dacc) {
   const f32x2 magic = pk1(kRoundMagic), mone = pk1(-1.0f);
+  if (f.nl) {
+    float y0, y1, y2, y3;
+    unpk2(y01, y0, y1);
+    unpk2(y23, y2, y3);
+    y01 = pk2(nl_power(y0, f), nl_power(y1, f));
+    y23 = pk2(nl_power(y2, f), nl_power(y3, f));
+  }
   const f32x2 ta01 = fma2(y01, f.inv_hi, magic), tb01 = fma2(y01, f.inv_lo, magic);
   const f32x2 ta23 = fma2(y23, f.inv_hi, magic), tb23 = fma2(y23, f.inv_lo, magic);
   const f32x2 d01 = fma2(tb01, mone, ta01), d23 = fma2(tb23, mone, ta23);
@@ -294,7 +323,9 @@ __device__ __forceinline__ uint4 sym_codes16(const float (&v)[16], const SymPara
     for (int j = 0; j < 4; ++j) w[j] = sym_codes4_fast2(pk2(v[4 * j], v[4 * j + 1]), pk2(v[4 * j + 2], v[4 * j + 3]), f, dacc);
     float d0, d1;
     unpk2(dacc, d0, d1);
-    if (!(d0 + d1 == 0.0f)) {
+    if (!(d0 + d1 == 0.0f) && f.nl) {
+      slow = true;                                           // non-linear: the scalar sequence decides (out of line)
+    } else if (!(d0 + d1 == 0.0f)) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         slow = slow || !(fabsf(v[4 * j]) < 1.0e30f) || !(fabsf(v[4 * j + 1]) < 1.0e30f) || !(fabsf(v[4 * j + 2]) < 1.0e30f) ||
@@ -326,7 +357,9 @@ __device__ __forceinline__ uint32_t sym_codes4_v2(float a0, float a1, float a2, 
     w = sym_codes4_fast2(pk2(a0, a1), pk2(a2, a3), f, dacc);
     float d0, d1;
     unpk2(dacc, d0, d1);
-    if (!(d0 + d1 == 0.0f)) {
+    if (!(d0 + d1 == 0.0f) && f.nl) {
+      slow = true;
+    } else if (!(d0 + d1 == 0.0f)) {
       slow = !(fabsf(a0) < 1.0e30f) || !(fabsf(a1) < 1.0e30f) || !(fabsf(a2) < 1.0e30f) || !(fabsf(a3) < 1.0e30f);
       w = pack4_low_bytes(__float_as_uint(sym_t_exact(a0, f)), __float_as_uint(sym_t_exact(a1, f)),
                           __float_as_uint(sym_t_exact(a2, f)), __float_as_uint(sym_t_exact(a3, f)));

@@ -506,7 +506,19 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 float d0, d1;
                 unpk2(dacc, d0, d1);
                 bool bad = false;
-                if (!(d0 + d1 == 0.0f) || (mma_only_flags & 4)) {
+                if ((!(d0 + d1 == 0.0f) || (mma_only_flags & 4)) && fq.nl) {
+                  // non-linear quantizer: the rows the interval test cannot decide get the scalar sequence (expf / logf /
+                  // IEEE division), out of line, 16 elements per call
+                  float a[32];
+#pragma unroll
+                  for (int j = 0; j < 16; ++j) unpk2(y[j], a[2 * j], a[2 * j + 1]);
+                  const uint4 lo = sym_codes16_slow(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12],
+                                                    a[13], a[14], a[15], nq, &fl);
+                  const uint4 hi = sym_codes16_slow(a[16], a[17], a[18], a[19], a[20], a[21], a[22], a[23], a[24], a[25], a[26],
+                                                    a[27], a[28], a[29], a[30], a[31], nq, &fl);
+                  w[0 % (kChunkBytes / 4)] = lo.x; w[1 % (kChunkBytes / 4)] = lo.y; w[2 % (kChunkBytes / 4)] = lo.z; w[3 % (kChunkBytes / 4)] = lo.w;
+                  w[4 % (kChunkBytes / 4)] = hi.x; w[5 % (kChunkBytes / 4)] = hi.y; w[6 % (kChunkBytes / 4)] = hi.z; w[7 % (kChunkBytes / 4)] = hi.w;
+                } else if (!(d0 + d1 == 0.0f) || (mma_only_flags & 4)) {
                   // some element of this row sits on a rounding boundary (or is NaN / inf): exact codes for the row
                   // (lane-local branch; (mma_only_flags & 4) forces it for the tests)
 #pragma unroll

@@ -187,6 +187,40 @@ def test_cta_pair_mode_bit_exact(ops, cta_group, M, N, K):
         L.qvit_gemm_set_cta_group(0)
 
 
+@pytest.mark.parametrize("t_next", [0.85, 1.3])
+@pytest.mark.parametrize("bits", [4, 8])
+def test_requantize_nonlinear_fast_path_equals_scalar_path(ops, bits, t_next):
+    """Non-linear consumer quantizer (QL:40-69) in the int8-output epilogue: |y|^t through MUFU lg2 / ex2 with an interval test
+    (hot), the out-of-line scalar sequence for rows in doubt (forced by mode 101) and the scalar path for everything (mode
+    201, also the SIMT backend) must produce identical codes, saturation at |y| >= q_m included."""
+    from quantized_vit_b200 import _lib
+    M, N, K = 2000, 384, 768
+    a = _codes(M, K, -7, 7, 51).cuda()
+    w = _codes(N, K, -7, 7, 52).cuda()
+    bias = torch.randn(N).cuda()
+    qm = 2.1
+    sat = 2 ** (bits - 1) - 1
+    d_next = float(torch.exp(torch.tensor(t_next) * torch.log(torch.tensor(qm + 1e-6))) / sat)
+    L = _lib.lib()
+    outs = {}
+    try:
+        for mode in (1, 101, 201):
+            assert L.qvit_gemm_set_cta_group(mode) == 0
+            for act in (ops.QVIT_ACT_NONE, ops.QVIT_ACT_GELU):
+                outs[(mode, act)] = ops.gemm_i8(a, w, K, N, out_kind=ops.QVIT_OUT_I8, bias=bias, act=act, scale_a=0.01, scale_w=0.02,
+                                                next_q=(d_next, qm, t_next), backend=ops.QVIT_GEMM_TCGEN05, acc_abs_max=49 * K)
+    finally:
+        L.qvit_gemm_set_cta_group(0)
+    for act in (ops.QVIT_ACT_NONE, ops.QVIT_ACT_GELU):
+        ref = outs[(201, act)]
+        assert int(ref.abs().max()) == sat and len(torch.unique(ref)) >= 5
+        for mode in (1, 101):
+            assert torch.equal(outs[(mode, act)], ref), (mode, act, int((outs[(mode, act)] != ref).sum()))
+    simt = ops.gemm_i8(a, w, K, N, out_kind=ops.QVIT_OUT_I8, bias=bias, act=ops.QVIT_ACT_GELU, scale_a=0.01, scale_w=0.02,
+                       next_q=(d_next, qm, t_next), backend=ops.QVIT_GEMM_SIMT)
+    assert torch.equal(simt, outs[(1, ops.QVIT_ACT_GELU)])
+
+
 @pytest.mark.parametrize("d_next", [0.3, 2.1 / 127.0])
 def test_requantize_paths_agree(ops, d_next):
     """The int8-output epilogue has three levels: packed interval test (hot), exact two-step Markstein division for rows

@@ -21,7 +21,7 @@ cases = [("none", dict(out_kind=ops.QVIT_OUT_NONE, backend=ops.QVIT_GEMM_TCGEN05
          ("i8+relu", dict(out_kind=ops.QVIT_OUT_I8, bias=bias, act=ops.QVIT_ACT_RELU, next_q=(T(0.3), T(2.1), None))),
          ("i8+gelu", dict(out_kind=ops.QVIT_OUT_I8, bias=bias, act=ops.QVIT_ACT_GELU, next_q=(T(0.3), T(2.1), None))),
          ("i8+gelu A8", dict(out_kind=ops.QVIT_OUT_I8, bias=bias, act=ops.QVIT_ACT_GELU, next_q=(T(2.1 / 127), T(2.1), None))),
-         ("i8+gelu nonlinear-q", dict(out_kind=ops.QVIT_OUT_I8, bias=bias, act=ops.QVIT_ACT_GELU, next_q=(T(0.3), T(2.1), T(1.0))))]
+         ("i8+gelu nonlinear-q", dict(out_kind=ops.QVIT_OUT_I8, bias=bias, act=ops.QVIT_ACT_GELU, next_q=(T(0.3), T(2.1), T(0.9))))]
 from quantized_vit_b200 import _lib
 modes = [int(v) for v in sys.argv[1:]] or [1]
 sel = os.environ.get("EPI_CASES")
