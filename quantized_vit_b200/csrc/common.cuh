@@ -71,63 +71,15 @@ __device__ __forceinline__ int sym_code(float x, const SymParams& p, int& flags)
   return x < 0.0f ? -c : (x > 0.0f ? c : 0);
 }
 
-// Same code, ~4x fewer instructions and NO conversion-unit (XU) instruction for the hot epilogue:
-//   q  = y * RN(1/d)                        differs from the reference's RN(y/d) by at most 3 * 2^-24 |q|
-//   qc = clamp(q, -sat, +sat)               for q_m > 0, "|y| >= q_m -> sat" equals clamping: RN division and rint are monotone,
-//                                           and rint(clamp(q)) == clamp(rint(q)) because sat is an integer
-//   t  = qc + 1.5 * 2^23                    the fp32 add rounds qc to the nearest integer, ties to even, exactly like rintf
-//                                           for |qc| <= 127; the low BYTE of t's bit pattern is the two's-complement int8 code
-//   k  = t - 1.5 * 2^23                     the rounded value back as a float (exact)
-//   m  = |q| * 3e-7 + |qc - k|              >= 0.5 (or NaN) <=> q lies within the 3 * 2^-24 |q| error band (+ the fma's own
-//                                           2^-25 rounding) of a rounding boundary: the exact IEEE division has to decide.
-// Callers fold as_uint(m) into a running unsigned max (NaN = 0x7fffffff sorts above every finite value) and redo only
-// the doubtful elements with sym_code().
+// Fast-path constants shared by the packed quantizers below: adding 1.5 * 2^23 to a value of magnitude < 2^22 rounds it to
+// the nearest integer, ties to even, exactly like rintf; the low BYTE of the sum's bit pattern is then the two's-complement
+// int8 code of that integer.
 constexpr float kRoundMagic = 12582912.0f;      // 1.5 * 2^23
-constexpr uint32_t kDoubtBits = 0x3F000000u;    // bit pattern of 0.5f
-struct FastQ {
-  float inv_d, d, sat;
-  int generic;     // non-linear quantizer, q_m <= 0 or codes beyond int8: use the general path
-};
-__device__ __forceinline__ FastQ make_fastq(const SymParams& p) {
-  FastQ f;
-  f.d = p.d;
-  f.inv_d = __fdiv_rn(1.0f, p.d);
-  f.sat = p.sat;
-  f.generic = (p.nonlinear || !(p.qm > 0.0f) || !(p.sat <= 127.0f) || !(p.d > 0.0f)) ? 1 : 0;
-  return f;
-}
-// returns t (code in the low byte); m_bits = as_uint(m)
-__device__ __forceinline__ float sym_code_fast(float y, const FastQ& f, uint32_t& m_bits) {
-  const float q = y * f.inv_d;
-  const float qc = fminf(fmaxf(q, -f.sat), f.sat);
-  const float t = qc + kRoundMagic;
-  const float k = t - kRoundMagic;
-  m_bits = __float_as_uint(fmaf(fabsf(q), 3.0e-7f, fabsf(qc - k)));
-  return t;
-}
 // low bytes of four 32-bit words -> one little-endian word (3 PRMT)
 __device__ __forceinline__ uint32_t pack4_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 __device__ __forceinline__ uint32_t pack4_i8_fwd(int a, int b, int c, int d);
-
-// four codes packed little-endian into one word: fast path + exact redo of the elements in doubt
-__device__ __forceinline__ uint32_t sym_codes4(float x0, float x1, float x2, float x3, const SymParams& p, const FastQ& f,
-                                               int& flags) {
-  if (f.generic) return pack4_i8_fwd(sym_code(x0, p, flags), sym_code(x1, p, flags), sym_code(x2, p, flags), sym_code(x3, p, flags));
-  uint32_t m0, m1, m2, m3;
-  uint32_t t0 = __float_as_uint(sym_code_fast(x0, f, m0));
-  uint32_t t1 = __float_as_uint(sym_code_fast(x1, f, m1));
-  uint32_t t2 = __float_as_uint(sym_code_fast(x2, f, m2));
-  uint32_t t3 = __float_as_uint(sym_code_fast(x3, f, m3));
-  if (max(max(m0, m1), max(m2, m3)) >= kDoubtBits) {
-    if (m0 >= kDoubtBits) t0 = (uint32_t)sym_code(x0, p, flags);
-    if (m1 >= kDoubtBits) t1 = (uint32_t)sym_code(x1, p, flags);
-    if (m2 >= kDoubtBits) t2 = (uint32_t)sym_code(x2, p, flags);
-    if (m3 >= kDoubtBits) t3 = (uint32_t)sym_code(x3, p, flags);
-  }
-  return pack4_low_bytes(t0, t1, t2, t3);
-}
 
 // fake-quantized value exactly as the reference returns it: sign(x) * (d * round(p/d))
 __device__ __forceinline__ float sym_value(float x, const SymParams& p) {

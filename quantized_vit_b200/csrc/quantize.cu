@@ -30,7 +30,7 @@ quantize_sym_flat_kernel(const float* __restrict__ x, int64_t n, const float* __
                          const float* __restrict__ qm, const float* __restrict__ t,
                          int8_t* __restrict__ codes, int32_t* __restrict__ flags) {
   const SymParams p = load_sym_params(d, qm, t);
-  const FastQ fq = make_fastq(p);
+  const FastQ2 fq = make_fastq2(p);
   int fl = 0;
   const int lane = threadIdx.x & 31;
   const int64_t warp_global = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
@@ -44,7 +44,7 @@ quantize_sym_flat_kernel(const float* __restrict__ x, int64_t n, const float* __
     uint32_t* dst = reinterpret_cast<uint32_t*>(codes + w * kWarpElems);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      dst[j * 32 + lane] = sym_codes4(v[j].x, v[j].y, v[j].z, v[j].w, p, fq, fl);
+      dst[j * 32 + lane] = sym_codes4_v2(v[j].x, v[j].y, v[j].z, v[j].w, p, fq, fl);
     }
   }
   // tail (< 512 elements): first warp of block 0
@@ -99,7 +99,7 @@ quantize_sym_bf16_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows,
                               const float* __restrict__ d, const float* __restrict__ qm, const float* __restrict__ t,
                               int8_t* __restrict__ codes, int64_t ld_codes, int32_t* __restrict__ flags) {
   const SymParams p = load_sym_params(d, qm, t);
-  const FastQ fq = make_fastq(p);
+  const FastQ2 fq = make_fastq2(p);
   int fl = 0;
   // one thread = 8 consecutive columns (16 B in, 8 B out) when everything is 8-aligned
   const bool vec = (cols % 8 == 0) && (ld_x % 8 == 0) && (ld_codes % 8 == 0) &&
@@ -119,8 +119,8 @@ quantize_sym_bf16_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t rows,
           f[2 * j] = __uint_as_float(w[j] << 16);
           f[2 * j + 1] = __uint_as_float(w[j] & 0xffff0000u);
         }
-        o.x = sym_codes4(f[0], f[1], f[2], f[3], p, fq, fl);
-        o.y = sym_codes4(f[4], f[5], f[6], f[7], p, fq, fl);
+        o.x = sym_codes4_v2(f[0], f[1], f[2], f[3], p, fq, fl);
+        o.y = sym_codes4_v2(f[4], f[5], f[6], f[7], p, fq, fl);
       }
       *reinterpret_cast<uint2*>(codes + r * ld_codes + g * 8) = o;
     }
