@@ -227,9 +227,12 @@ __device__ __forceinline__ float sym_t_exact(float y, const FastQ2& f) {
   return fminf(fmaxf(q2 + kRoundMagic, f.t_lo), f.t_hi);
 }
 // four elements (two pairs) -> one word of four int8 codes; dacc accumulates (ta - tb)^2
+// (NL is a template parameter and callers branch OUTSIDE their element loops: with the test inside, the linear hot loop
+// of the GEMM epilogue carried the non-linear fields in registers and lost ~10 %)
+template <bool NL>
 __device__ __forceinline__ uint32_t sym_codes4_fast2(f32x2 y01, f32x2 y23, const FastQ2& f, f32x2& dacc) {
   const f32x2 magic = pk1(kRoundMagic), mone = pk1(-1.0f);
-  if (f.nl) {
+  if (NL) {
     float y0, y1, y2, y3;
     unpk2(y01, y0, y1);
     unpk2(y23, y2, y3);
@@ -271,8 +274,13 @@ __device__ __forceinline__ uint4 sym_codes16(const float (&v)[16], const SymPara
   bool slow = f.generic != 0;
   if (!slow) {
     f32x2 dacc = pk1(0.0f);
+    if (f.nl) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) w[j] = sym_codes4_fast2(pk2(v[4 * j], v[4 * j + 1]), pk2(v[4 * j + 2], v[4 * j + 3]), f, dacc);
+      for (int j = 0; j < 4; ++j) w[j] = sym_codes4_fast2<true>(pk2(v[4 * j], v[4 * j + 1]), pk2(v[4 * j + 2], v[4 * j + 3]), f, dacc);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) w[j] = sym_codes4_fast2<false>(pk2(v[4 * j], v[4 * j + 1]), pk2(v[4 * j + 2], v[4 * j + 3]), f, dacc);
+    }
     float d0, d1;
     unpk2(dacc, d0, d1);
     if (!(d0 + d1 == 0.0f) && f.nl) {
@@ -306,7 +314,7 @@ __device__ __forceinline__ uint32_t sym_codes4_v2(float a0, float a1, float a2, 
   uint32_t w = 0;
   if (!slow) {
     f32x2 dacc = pk1(0.0f);
-    w = sym_codes4_fast2(pk2(a0, a1), pk2(a2, a3), f, dacc);
+    w = f.nl ? sym_codes4_fast2<true>(pk2(a0, a1), pk2(a2, a3), f, dacc) : sym_codes4_fast2<false>(pk2(a0, a1), pk2(a2, a3), f, dacc);
     float d0, d1;
     unpk2(dacc, d0, d1);
     if (!(d0 + d1 == 0.0f) && f.nl) {

@@ -501,8 +501,13 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
               } else {
                 f32x2 dacc = pk1(0.0f);
+                if (fq.nl) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) w[j % (kChunkBytes / 4)] = sym_codes4_fast2(y[2 * j], y[2 * j + 1], fq, dacc);
+                  for (int j = 0; j < 8; ++j) w[j % (kChunkBytes / 4)] = sym_codes4_fast2<true>(y[2 * j], y[2 * j + 1], fq, dacc);
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 8; ++j) w[j % (kChunkBytes / 4)] = sym_codes4_fast2<false>(y[2 * j], y[2 * j + 1], fq, dacc);
+                }
                 float d0, d1;
                 unpk2(dacc, d0, d1);
                 bool bad = false;
