@@ -165,6 +165,12 @@ int qvit_geta_quant_step(float* const* params, const float* const* grads, float*
                          float min_bit_wt, float max_bit_wt, float min_bit_act, float max_bit_act, int32_t* flags,
                          qvit_stream_t stream);
 
+/* Saturation codes round(r / |d|), r = |q_m| or exp(t log(|q_m| + 1e-6)) (QL:159 / QL:62-67), of `layers` weight /
+ * activation quantizers through the same pointer table: out[2l] = weight, out[2l+1] = activation, -1 where absent.
+ * Lets QuantizeMixin follow GETA's bit-width walk (geta.py:895-900) and pick the int8 or the wide path without a host
+ * synchronisation (the result is read back asynchronously, one step late).                                   */
+int qvit_quant_sat_levels(const float* const* params, int layers, float* out, qvit_stream_t stream);
+
 /* ------------------------------------------------------------------ QuantLinear GEMM
  * Replaces nn.functional.linear(x_q, w_q, bias) on fake-quant values (QL:499, QU:220) by the exact integer
  * contraction  acc[m,n] = sum_k A[m,k] * Wc[n,k]  (int8 x int8 -> int32, tcgen05.mma kind::i8, TMEM

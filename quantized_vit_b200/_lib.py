@@ -56,6 +56,7 @@ PROTOTYPES = {
     "qvit_pack_hls_weights": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _p, _p]),
     "qvit_geta_quant_step": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _f, _f, _i, _f, _f, _f, _f, C.c_double, C.c_double, _f, _i, _f, _f,
                                   _f, _f, _f, _f, _p, _p]),
+    "qvit_quant_sat_levels": (_i, [_p, _i, _p, _p]),
     "qvit_gemm_set_cta_group": (_i, [_i]),
     "qvit_gemm_read_profile": (_i, [_p, _i]),
     "qvit_gemm_i8": (_i, [_p, _i64, _i, _p, _i64, _i, _i, _i, _p, _i64, C.POINTER(Epilogue), _i, _p]),

@@ -104,9 +104,31 @@ __global__ void geta_quant_step_kernel(float* const* __restrict__ params, const 
   if (fl && flags) atomicOr(flags, fl);
 }
 
+// Saturation codes round(r / |d|) of every layer's weight / activation quantizer (what QuantizeMixin needs to decide
+// whether the codes fit the int8 tensor-core pipe): out[2 * l] = weight, out[2 * l + 1] = activation (-1 = absent).
+__global__ void quant_sat_levels_kernel(const float* const* __restrict__ params, int layers, float* __restrict__ out) {
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= layers) return;
+  for (int side = 0; side < 2; ++side) {
+    const float* d = params[l * 6 + 3 * side];
+    const float* qm = params[l * 6 + 3 * side + 1];
+    const float* t = params[l * 6 + 3 * side + 2];
+    float v = -1.0f;
+    if (d && qm) v = load_sym_params(d, qm, t).sat;            // same fp32 sequence as the quantize kernels
+    out[2 * l + side] = v;
+  }
+}
+
 }  // namespace qvit
 
 using namespace qvit;
+
+extern "C" int qvit_quant_sat_levels(const float* const* params, int layers, float* out, qvit_stream_t stream) {
+  QVIT_REQUIRE(params && out && layers >= 0, "qvit_quant_sat_levels: null pointer");
+  if (layers == 0) return QVIT_OK;
+  quant_sat_levels_kernel<<<(layers + 127) / 128, 128, 0, (cudaStream_t)stream>>>(params, layers, out);
+  return check_launch("qvit_quant_sat_levels");
+}
 
 extern "C" int qvit_geta_quant_step(float* const* params, const float* const* grads, float* m1, float* m2, uint8_t* inited,
                                     const float* fix_bits_wt, const float* fix_bits_act, int layers, int variant, int mode,

@@ -50,69 +50,151 @@ def gather_outputs(y: torch.Tensor, total: int, group=None) -> Optional[torch.Te
 
 
 class GradientAllReducer:
-    """Bucketed gradient averaging for QAT.  Build once per model; call ``reduce()`` after every backward."""
+    """Bucketed gradient averaging for QAT, overlapped with backward.  Build once per model.
 
-    def __init__(self, named_params: Iterable[Tuple[str, torch.nn.Parameter]], bucket_bytes: int = 64 << 20, group=None):
-        self.group = group
-        self.quant: List[torch.nn.Parameter] = []
-        self.buckets: List[List[torch.nn.Parameter]] = []
+    * Every bucket owns ONE persistent flat fp32 buffer and the parameters' ``.grad`` tensors are VIEWS into it
+      (``zero_grad()`` below zeroes the buffers; a ``.grad`` that the training loop replaced or set to None is copied back
+      in and re-pointed), so no flatten / unflatten copy runs per step.
+    * ``register_post_accumulate_grad_hook`` counts the parameters of a bucket as autograd finishes them and launches the
+      bucket's asynchronous all-reduce as soon as the last one is in - while the rest of backward is still running.
+      Buckets are laid out in reverse parameter order (the order backward produces them).  All quantizer scalars
+      (d_quant_* / q_m_* / t_quant_*) travel in one small extra bucket: "gradients and step sizes" (SURVEY.md 8e).
+    * ``reduce()`` after ``backward()`` launches whatever has not been launched, waits, and applies the weight.  Weighting:
+      every rank's loss is the mean over ITS shard; with ``local_batch`` / ``global_batch`` given each rank pre-scales by
+      n_r / N and the collective sums, which is the gradient of the mean over the concatenated batch also for uneven
+      shards; without them the shards are assumed equal and the collective averages.
+    * Parameters that received no gradient on this rank stay ``None`` when ``keep_none`` (the autograd graph is the same on
+      every data-parallel rank, so all ranks agree on which those are); their slice of the buffer travels as zeros.
+    Must run BEFORE gradient clipping (reference order utils.py:291-292)."""
+
+    def __init__(self, named_params: Iterable[Tuple[str, torch.nn.Parameter]], bucket_bytes: int = 64 << 20, group=None,
+                 overlap: bool = True, keep_none: bool = True):
+        self.group, self.keep_none = group, keep_none
+        named = [(n, p) for n, p in named_params if p.requires_grad]
+        quant = [p for n, p in named if any(tag in n for tag in QUANT_PARAM_TAGS)]
+        rest = [p for n, p in named if not any(tag in n for tag in QUANT_PARAM_TAGS)]
+        groups: List[List[torch.nn.Parameter]] = []
         cur, cur_bytes = [], 0
-        for name, p in named_params:
-            if not p.requires_grad:
-                continue
-            if any(tag in name for tag in QUANT_PARAM_TAGS):
-                self.quant.append(p)
-                continue
+        for p in reversed(rest):                                   # backward reaches the last layers first
             nbytes = p.numel() * 4
             if cur and cur_bytes + nbytes > bucket_bytes:
-                self.buckets.append(cur)
+                groups.append(cur)
                 cur, cur_bytes = [], 0
             cur.append(p)
             cur_bytes += nbytes
         if cur:
-            self.buckets.append(cur)
+            groups.append(cur)
+        self.quant = quant
+        self.buckets = groups
+        self._all = groups + ([quant] if quant else [])
+        self._flat: List[torch.Tensor] = []
+        self._views: List[List[torch.Tensor]] = []
+        self._bucket_of = {}
+        for bi, params in enumerate(self._all):
+            dev = params[0].device
+            flat = torch.zeros(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
+            views, off = [], 0
+            for pi, p in enumerate(params):
+                v = flat[off:off + p.numel()].view_as(p)
+                views.append(v)
+                off += p.numel()
+                self._bucket_of[id(p)] = (bi, pi)
+            self._flat.append(flat)
+            self._views.append(views)
+        self._ready = [0] * len(self._all)
+        self._seen = [set() for _ in self._all]
+        self._work = [None] * len(self._all)
+        self._scale = None
+        self._hooks = []
+        if overlap and hasattr(torch.Tensor, "register_post_accumulate_grad_hook"):
+            for params in self._all:
+                for p in params:
+                    self._hooks.append(p.register_post_accumulate_grad_hook(self._on_grad))
 
-    @staticmethod
-    def _flatten(params: Sequence[torch.nn.Parameter]) -> torch.Tensor:
-        dev = params[0].device
-        flat = torch.empty(sum(p.numel() for p in params), dtype=torch.float32, device=dev)
-        off = 0
-        for p in params:
-            n = p.numel()
-            if p.grad is None:
-                flat[off:off + n].zero_()          # a rank that did not touch a parameter contributes zero
-            else:
-                flat[off:off + n].copy_(p.grad.reshape(-1))
-            off += n
-        return flat
+    # ------------------------------------------------------------------ persistent gradient storage
+    def zero_grad(self) -> None:
+        """Zero the flat buffers and (re-)point every .grad at its view: use instead of model.zero_grad(set_to_none=True)."""
+        for flat, params, views in zip(self._flat, self._all, self._views):
+            flat.zero_()
+            for p, v in zip(params, views):
+                p.grad = v
 
-    @staticmethod
-    def _unflatten(flat: torch.Tensor, params: Sequence[torch.nn.Parameter]) -> None:
-        off = 0
-        for p in params:
-            n = p.numel()
-            g = flat[off:off + n].view_as(p)
-            if p.grad is None:
-                p.grad = g.clone()
-            else:
-                p.grad.copy_(g)
-            off += n
+    def _adopt(self, bi: int, pi: int) -> None:
+        """Make sure parameter (bi, pi)'s gradient lives in its view (the loop may have replaced .grad or left it None)."""
+        p, v = self._all[bi][pi], self._views[bi][pi]
+        g = p.grad
+        if g is None:
+            v.zero_()
+        elif g.data_ptr() != v.data_ptr():
+            v.copy_(g)
+            p.grad = v
+
+    # ------------------------------------------------------------------ collectives
+    def _world(self) -> int:
+        return dist.get_world_size(self.group) if dist.is_initialized() else 1
+
+    def set_batch(self, local_batch: int, global_batch: int) -> None:
+        """Weight of this rank's (shard-mean) gradients in the global mean: n_r / N.  Call when shards are uneven."""
+        self._scale = float(local_batch) / float(global_batch)
+
+    def _launch(self, bi: int) -> None:
+        if self._work[bi] is not None or self._world() == 1:
+            return
+        for pi in range(len(self._all[bi])):
+            if pi not in self._seen[bi] or self._all[bi][pi].grad is None or \
+                    self._all[bi][pi].grad.data_ptr() != self._views[bi][pi].data_ptr():
+                self._adopt(bi, pi)
+        flat = self._flat[bi]
+        if self._scale is not None:
+            flat.mul_(self._scale)
+            op = dist.ReduceOp.SUM
+        else:
+            op = dist.ReduceOp.SUM          # divided by the world size in reduce() (gloo has no AVG)
+            if dist.get_backend(self.group) == "nccl":
+                op = dist.ReduceOp.AVG
+        self._work[bi] = (dist.all_reduce(flat, op=op, group=self.group, async_op=True), op)
+
+    def _on_grad(self, p: torch.nn.Parameter) -> None:
+        if self._world() == 1:
+            return
+        bi, pi = self._bucket_of[id(p)]
+        if pi in self._seen[bi]:
+            return
+        self._seen[bi].add(pi)
+        if len(self._seen[bi]) == len(self._all[bi]):
+            self._launch(bi)                 # the whole bucket is final: its all-reduce runs under the rest of backward
 
     def reduce(self) -> int:
-        """Average gradients over the group in place; returns the number of collectives issued."""
-        world = dist.get_world_size(self.group) if dist.is_initialized() else 1
+        """Finish the step's gradient exchange in place; returns the number of collectives issued."""
+        world = self._world()
         if world == 1:
+            for s in self._seen:
+                s.clear()
             return 0
-        work = []
-        groups = list(self.buckets) + ([self.quant] if self.quant else [])
-        for params in groups:                       # issue everything first: NVSwitch collectives overlap each other
-            flat = self._flatten(params)
-            work.append((dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True), flat, params))
-        for w, flat, params in work:
-            w.wait()
-            flat.div_(world)
-            self._unflatten(flat, params)
-        return len(work)
+        none_mask = [[(p.grad is None) for p in params] for params in self._all]
+        n = 0
+        for bi in range(len(self._all)):
+            self._launch(bi)
+        for bi, params in enumerate(self._all):
+            work, op = self._work[bi]
+            work.wait()
+            if self._scale is None and op == dist.ReduceOp.SUM:
+                self._flat[bi].div_(world)
+            for pi, p in enumerate(params):
+                untouched = (pi not in self._seen[bi]) if self._hooks else none_mask[bi][pi]
+                if self.keep_none and untouched:
+                    p.grad = None            # untouched on every rank: optimizers must keep skipping it
+                else:
+                    p.grad = self._views[bi][pi]
+            self._work[bi] = None
+            self._seen[bi].clear()
+            n += 1
+        return n
+
+    def clip_(self, bound: float = 1.0) -> None:
+        """GETA.grad_clipping (geta.py:160-165) on the flat buffers: one clamp per bucket instead of one per parameter."""
+        for flat in self._flat:
+            flat.clamp_(-bound, bound)
 
 
 def clip_gradients_(params: Iterable[torch.nn.Parameter], bound: float = 1.0) -> None:

@@ -63,7 +63,13 @@ class GetaQuantParamStepper:
         self._inited = torch.zeros(n, dtype=torch.uint8, device=self.device)
         self._ptab = torch.zeros(n, dtype=torch.int64, device=self.device)
         self._gtab = torch.zeros(n, dtype=torch.int64, device=self.device)
-        self._gtab_host = torch.zeros(n, dtype=torch.int64).pin_memory()
+        # the gradient pointers change whenever autograd re-allocates .grad (zero_grad(set_to_none=True)): they are staged
+        # through a RING of pinned tables, each guarded by an event recorded after its host->device copy, so that a host
+        # running several steps ahead never overwrites a table whose DMA has not executed yet
+        self._gtab_ring = [torch.zeros(n, dtype=torch.int64).pin_memory() for _ in range(4)]
+        self._gtab_events = [None] * 4
+        self._gtab_slot = 0
+        self._gtab_key = None
         self._ptab_key = None
         self.flags = torch.zeros(1, dtype=torch.int32, device=self.device)
 
@@ -74,9 +80,35 @@ class GetaQuantParamStepper:
         if key != self._ptab_key:
             self._ptab.copy_(torch.tensor(ptrs, dtype=torch.int64), non_blocking=False)
             self._ptab_key = key
-        self._gtab_host.copy_(torch.tensor([0 if (p is None or p.grad is None) else p.grad.data_ptr()
-                                            for row in self._params for p in row], dtype=torch.int64))
-        self._gtab.copy_(self._gtab_host, non_blocking=True)
+        gptrs = tuple(0 if (p is None or p.grad is None) else p.grad.data_ptr() for row in self._params for p in row)
+        if gptrs != self._gtab_key:                      # persistent .grad buffers (zero_grad(set_to_none=False)): nothing to copy
+            j = self._gtab_slot
+            if self._gtab_events[j] is not None:
+                self._gtab_events[j].synchronize()       # four steps old: complete long ago unless the host is far ahead
+            self._gtab_ring[j].copy_(torch.tensor(gptrs, dtype=torch.int64))
+            self._gtab.copy_(self._gtab_ring[j], non_blocking=True)
+            ev = self._gtab_events[j] = self._gtab_events[j] or torch.cuda.Event()
+            ev.record()
+            self._gtab_slot = (j + 1) % len(self._gtab_ring)
+            self._gtab_key = gptrs
+
+    def _poll_flags(self):
+        """Deferred, sync-free NaN report: the flag word of step N is copied to pinned memory asynchronously and examined
+        at step N+1 (or later) once its event has completed - GETA's scalars turning NaN raises NanInGradientError by
+        default, one step late, without a host synchronisation in the training loop."""
+        from .quant_layers import NanInGradientError
+        st = self.__dict__.setdefault("_poll", {"host": torch.zeros(1, dtype=torch.int32).pin_memory(), "ev": None})
+        if torch.cuda.is_current_stream_capturing():
+            return
+        if st["ev"] is not None and st["ev"].query():
+            bits = int(st["host"][0])
+            st["ev"] = None
+            if bits & _lib.QVIT_FLAG_NAN_GRAD:
+                raise NanInGradientError("Error: NaN appears in gradient! (quantizer-scalar gradients, reported by qvit_geta_quant_step)")
+        if st["ev"] is None:
+            st["host"].copy_(self.flags, non_blocking=True)     # the device word stays sticky: `flags` / explicit checks still see it
+            st["ev"] = torch.cuda.Event()
+            st["ev"].record()
 
     @torch.no_grad()
     def step(self, stage: str = "range", bit_dict: Optional[Dict[str, Dict[str, float]]] = None) -> None:
@@ -106,3 +138,4 @@ class GetaQuantParamStepper:
             self.first_momentum, self.second_momentum, self.dampening if not is_adam else self.first_momentum,
             C.c_double(bc1), C.c_double(bc2), self.safe_guard, 1 if clip else 0, float(cmin), float(cmax), self.min_bit_wt,
             self.max_bit_wt, self.min_bit_act, self.max_bit_act, _lib.ptr(self.flags), _lib.stream()), "qvit_geta_quant_step")
+        self._poll_flags()

@@ -74,14 +74,132 @@ def check_nan_flags(raise_error: bool = True) -> int:
     NaN in the reduced step-size gradient - the deferred equivalent of QL:189-204 / QL:107-123."""
     bits = 0
     for w in _flag_words.values():
-        bits |= int(w.item())
+        bits |= int(w.item())                     # host sync: every asynchronous read-back below has landed as well
         w.zero_()
+    for mon in _monitors.values():
+        bits |= mon.drain()
     if raise_error and bits & ops._lib.QVIT_FLAG_NAN_GRAD:
         raise NanInGradientError("Error: NaN appears in gradient! (reported by the fused quantizer backward)")
     if raise_error and bits & ops._lib.QVIT_FLAG_OVERFLOW:
         raise RuntimeError("a quantizer produced codes beyond +-127 on the int8 path (d_quant shrank below q_m/127): "
                            "call module.invalidate_quant_cache() / re-create the modules so the wide path is selected")
     return bits
+
+
+class _DispatchMonitor:
+    """Sync-free, one-step-late host view of (a) the saturation codes round(r/d) of every registered layer's weight and
+    activation quantizer and (b) the device flag word.
+
+    GETA moves d_quant / q_m / t_quant every step through raw ``.data`` writes (geta.py:571-772) and walks the bit width
+    from the conversion value (32 in train.py:247-250) down to ~4-8 bits (geta.py:895-900).  Whether a layer's codes fit the
+    int8 tensor-core pipe therefore changes DURING training, and asking the device each step would synchronise every
+    layer.  Instead, roughly once per training step one tiny kernel (``qvit_quant_sat_levels``) evaluates all saturation
+    codes through a pointer table, the result and the flag word are copied to pinned memory asynchronously, and the copy is
+    consumed by whichever forward() first finds its event complete.  A layer takes the int8 path only while both codes
+    are <= MARGIN (120 < 127): one step of lag cannot push a code past 127, so the int8 kernels never have to clamp; above
+    the margin the layer runs the wide path, which is exact for any bit width.  NaN-in-gradient bits found in the flag
+    word raise NanInGradientError from that forward (the deferred equivalent of QL:189-204), so an unchanged training loop
+    sees the error without calling check_nan_flags()."""
+    MARGIN = 120.0
+
+    def __init__(self, device: torch.device):
+        import weakref
+        self._weakref = weakref
+        self.device = device
+        self.mods = []                 # weak references, slot = index
+        self.sat = []                  # [2 * n] python floats (weight, activation), lagged
+        self.calls = 0
+        self.pending = None            # CUDA event of the read-back in flight
+        self.key = None
+        self.ptab = self.dev_sat = self.host_sat = None
+        self.host_flags = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.sticky = 0
+
+    def register(self, mod) -> int:
+        slot = len(self.mods)
+        self.mods.append(self._weakref.ref(mod))
+        sw = QuantizeMixin._sat_level(*mod._wt_qparams())             # one host read per quantizer, once per module
+        sa = QuantizeMixin._sat_level(*mod._act_qparams())
+        self.sat += [sw, sa]
+        self.key = None
+        return slot
+
+    def _ptr_key(self):
+        ptrs = []
+        for r in self.mods:
+            m = r()
+            ps = (None,) * 6 if m is None else (*m._wt_qparams(), *m._act_qparams())
+            ptrs += [0 if p is None else p.data_ptr() for p in ps]
+        return tuple(ptrs)
+
+    def _launch(self):
+        n = len(self.mods)
+        key = self._ptr_key()
+        if key != self.key:                                            # parameters re-created (pruning) / new modules
+            self.ptab = torch.tensor(key, dtype=torch.int64).to(self.device)
+            self.dev_sat = torch.empty(2 * n, dtype=torch.float32, device=self.device)
+            self.host_sat = torch.empty(2 * n, dtype=torch.float32).pin_memory()
+            self.key = key
+        ops._lib.check(ops._lib.lib().qvit_quant_sat_levels(self.ptab.data_ptr(), n, self.dev_sat.data_ptr(), ops._lib.stream()),
+                       "qvit_quant_sat_levels")
+        self.host_sat.copy_(self.dev_sat, non_blocking=True)
+        w = _flags_for(self.device)
+        self.host_flags.copy_(w, non_blocking=True)
+        w.zero_()                                                      # stream-ordered after the copy: later bits are kept
+        self.pending = torch.cuda.Event()
+        self.pending.record()
+        self.calls = 0
+
+    def _consume(self) -> int:
+        self.pending = None
+        vals = self.host_sat.tolist()
+        if len(vals) == len(self.sat):
+            self.sat = [v if v >= 0 else s for v, s in zip(vals, self.sat)]
+        bits = int(self.host_flags[0])
+        self.host_flags[0] = 0
+        self.sticky |= bits
+        return bits
+
+    def drain(self) -> int:
+        """After a host sync: fold a landed read-back in and hand the collected flag bits over."""
+        if self.pending is not None and self.pending.query():
+            self._consume()
+        bits, self.sticky = self.sticky, 0
+        return bits
+
+    def tick(self):
+        if torch.cuda.is_current_stream_capturing():
+            return
+        if self.pending is not None and self.pending.query():
+            bits = self._consume()
+            if bits & ops._lib.QVIT_FLAG_OVERFLOW:
+                logger.warning("a quantizer's saturation code moved past 127 within one step; the affected int8 codes were "
+                               "clamped for that step (the layer is on the wide path from now on)")
+            if bits & ops._lib.QVIT_FLAG_NAN_GRAD:
+                self.sticky &= ~ops._lib.QVIT_FLAG_NAN_GRAD
+                raise NanInGradientError("Error: NaN appears in gradient! (reported by the fused quantizer backward)")
+        self.calls += 1
+        if self.pending is None and self.calls >= len(self.mods):
+            self._launch()
+
+    def int8_ok(self, mod) -> bool:
+        slot = mod.__dict__.get("_mon_slot")
+        if slot is None or slot[0] is not self or self.mods[slot[1]]() is not mod:
+            slot = mod.__dict__["_mon_slot"] = (self, self.register(mod))
+        self.tick()
+        i = slot[1]
+        return self.sat[2 * i] <= self.MARGIN and 0 <= self.sat[2 * i + 1] <= self.MARGIN
+
+
+_monitors = {}
+
+
+def _monitor_for(device: torch.device) -> _DispatchMonitor:
+    key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+    m = _monitors.get(key)
+    if m is None:
+        m = _monitors[key] = _DispatchMonitor(torch.device(*key))
+    return m
 
 
 def _clip_pair(clip_val) -> Tuple[float, float]:
@@ -198,23 +316,26 @@ class QuantLinearFunction(torch.autograd.Function):
         g2 = g.reshape(-1, N).contiguous()
         flags = _flags_for(g.device)
         M = g2.shape[0]
+        # the activation quantizer's scalar gradients (QL:177-187 / 89-105) are sums over grad_output of quantize_act whether
+        # or not the layer INPUT needs a gradient (a first layer fed raw data still trains d_quant_act / q_m_act)
+        need_act = any(ctx.needs_input_grad[i] for i in (0, 3, 4, 5))
         if TENSOR_CORE_BACKWARD and K % 4 == 0:
             # grad_x_q = g @ w_q = |d_w| * (g1 + g2 + g3) @ codes_w   and   grad_w_q = g^T @ x_q = |d_a| * (g^T planes) @ codes_a:
             # exact 3-way bf16 split of g, integer codes as bf16, tcgen05 kind::f16 with fp32 accumulation
             grad_xq = ops.gemm_bf16_split(ops.split3_bf16(g2), ops.codes_to_bf16_t(w_codes, K), N, planes=GRADIENT_PLANES, scale=d_w) \
-                if ctx.needs_input_grad[0] else None
+                if need_act else None
             grad_wq = ops.gemm_bf16_split(ops.split3_bf16(g2, transpose=True), ops.codes_to_bf16_t(a_codes, K), M,
                                           planes=GRADIENT_PLANES, scale=d_a)
         else:
             # fake-quant values from the saved codes: value = code * |d| (exactly what the reference forward produced)
             x_q = a_codes[:, :K].to(torch.float32) * d_a.detach().abs()
             w_q = w_codes[:, :K].to(torch.float32) * d_w.detach().abs()
-            grad_xq = g2 @ w_q
+            grad_xq = g2 @ w_q if need_act else None
             grad_wq = g2.t() @ x_q
         if grad_xq is None:
             grad_x, s_a = None, torch.zeros(3, dtype=torch.float32, device=g.device)
         else:
-            grad_x, s_a = ops.sym_backward(x2, grad_xq, d_a, qm_a, t_a, ctx.clip_a, want_grad_x=True, flags=flags)
+            grad_x, s_a = ops.sym_backward(x2, grad_xq, d_a, qm_a, t_a, ctx.clip_a, want_grad_x=ctx.needs_input_grad[0], flags=flags)
         grad_w, s_w = ops.sym_backward(weight.detach(), grad_wq, d_w, qm_w, t_w, ctx.clip_w, flags=flags)
         grad_b = g2.sum(0) if ctx.has_bias else None
         if EAGER_NAN_CHECK:
@@ -327,7 +448,6 @@ class QuantizeMixin:
     # ---- integer-path plumbing -----------------------------------------------------------------
     def invalidate_quant_cache(self) -> None:
         self.__dict__["_qcache"] = _QuantCache()
-        self.__dict__["_train_int8"] = None
 
     def _wt_qparams(self):
         return self.d_quant_wt, self.q_m_wt, getattr(self, "t_quant_wt", None)
@@ -371,18 +491,13 @@ class QuantizeMixin:
                 and c.w_sat <= 127 and c.a_sat is not None and c.a_sat <= 127)
 
     def _int8_train_ok(self) -> bool:
-        """Training dispatch: is the exact int8 forward applicable?  Evaluated once per parameter identity (one host
-        read) - the optimizer changes d / q_m every step, so re-evaluating per version would synchronise every layer
-        every step.  Safety net: the quantize kernels clamp to +-127 and raise QVIT_FLAG_OVERFLOW, which
-        check_nan_flags() turns into an error."""
+        """Training dispatch: is the exact int8 forward applicable?  Decided from the dispatch monitor's one-step-late,
+        sync-free view of the saturation codes (see _DispatchMonitor): a model converted at 16 / 32 bits (train.py:247-250)
+        moves onto the int8 tensor-core path when GETA has walked its bit width down, and back to the wide path should a
+        code approach 127 again."""
         if self.quant_mode != QuantizationMode.WEIGHT_AND_ACTIVATION or self.quant_type == QuantizationType.DGE:
             return False
-        key = tuple(p.data_ptr() for p in (*self._wt_qparams(), *self._act_qparams()) if p is not None)
-        st = self.__dict__.get("_train_int8")
-        if st is None or st[0] != key:
-            ok = self._sat_level(*self._wt_qparams()) <= 127 and self._sat_level(*self._act_qparams()) <= 127
-            st = self.__dict__["_train_int8"] = (key, ok)
-        return st[1]
+        return _monitor_for(self.weight.device).int8_ok(self)
 
     def _weight_codes(self, c: _QuantCache) -> torch.Tensor:
         """[out, pad16(K)] int8 codes, K = in_features or C*kh*kw ordered (c, kh, kw) = weight.reshape(O, -1)."""
@@ -413,7 +528,7 @@ class QuantizeMixin:
 
     def __getstate__(self):
         st = self.__dict__.copy()
-        st["_train_int8"] = None
+        st["_mon_slot"] = None
         st["_qcache"] = None          # whole-model pickles (pruning_compression.py:34) never carry device caches
         return st
 
@@ -542,8 +657,10 @@ class QuantizeConv2d(QuantizeMixin, nn.Conv2d):
             K = self.in_channels * self.kernel_size[0] * self.kernel_size[1]
             y = ops.gemm_i8(cols, self._weight_codes(c), K, self.out_channels, out_kind=ops.QVIT_OUT_F32, scale_a=d_a,
                             scale_w=self.d_quant_wt, bias=self.bias, flags=flags)
-            # [B*OH*OW, O] is NHWC memory; hand back the NCHW view (PatchEmbed's flatten(2).transpose(1,2),
-            # vit_model.py:100, turns it into the contiguous token matrix without a copy)
+            # [B*OH*OW, O] is NHWC memory; hand back the NCHW-shaped view, i.e. a torch.channels_last tensor - the same
+            # memory format cuDNN hands back for channels_last inputs (PatchEmbed's flatten(2).transpose(1,2),
+            # vit_model.py:100, turns it into the contiguous token matrix without a copy; code that calls .view() on a conv
+            # output needs .contiguous() first, exactly as with any channels_last tensor)
             return y.view(input_.shape[0], OH, OW, self.out_channels).permute(0, 3, 1, 2)
         x = input_
         if self.quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION:

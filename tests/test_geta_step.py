@@ -91,3 +91,10 @@ def test_fused_step_on_a_converted_model_and_nan_flag():
     next(iter(quant.values())).grad.fill_(float("nan"))
     st.step("descent")
     assert int(st.flags.item()) & 4
+    # ... and by default the NEXT step raises (deferred, sync-free poll of the flag word)
+    from quantized_vit_b200.quantization import NanInGradientError
+    torch.cuda.synchronize()
+    with pytest.raises(NanInGradientError):
+        st.step("descent")
+        torch.cuda.synchronize()
+        st.step("descent")

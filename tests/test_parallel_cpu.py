@@ -42,29 +42,40 @@ class _Toy(torch.nn.Module):
         return torch.nn.functional.linear(x * self.d_quant_act + torch.sin(x) * self.q_m_act, w, self.bias)
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, n=10):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         torch.manual_seed(1)
-        x = torch.randn(10, 5)
-        y = torch.randn(10, 6)
+        x = torch.randn(n, 5)
+        y = torch.randn(n, 6)
         model = _Toy()
         red = parallel.GradientAllReducer(model.named_parameters(), bucket_bytes=64)      # tiny buckets -> several collectives
         xs, ys = parallel.shard_batch(x, rank, world), parallel.shard_batch(y, rank, world)
-        # mean over the GLOBAL batch = average over ranks of the per-rank mean when shards are equal-sized
-        loss = ((model(xs) - ys) ** 2).mean()
-        loss.backward()
-        n_coll = red.reduce()
-        parallel.clip_gradients_(model.parameters(), 1.0)
+        if n % world:
+            red.set_batch(xs.shape[0], n)          # uneven shards: weight n_r / N instead of 1 / world
+        # step 1 the way an unchanged loop does it (fresh .grad tensors), step 2 on the persistent bucket views
+        for it in range(2):
+            if it == 0:
+                model.zero_grad(set_to_none=True)
+            else:
+                red.zero_grad()
+                assert model.weight.grad.data_ptr() == red._views[red._bucket_of[id(model.weight)][0]][red._bucket_of[id(model.weight)][1]].data_ptr()
+            # mean over the GLOBAL batch = weighted average over ranks of the per-rank mean
+            loss = ((model(xs) - ys) ** 2).mean()
+            loss.backward()
+            n_coll = red.reduce()
+        red.clip_(1.0)
         out = parallel.gather_outputs(model(xs).detach(), x.shape[0])
-        grads = {n: (p.grad.clone() if p.grad is not None else None) for n, p in model.named_parameters()}
-        q.put((rank, n_coll, grads, out))
+        # plain numpy payloads: torch tensors travel through a Queue as shared-memory handles that die with this process
+        grads = {n: (p.grad.numpy().copy() if p.grad is not None else None) for n, p in model.named_parameters()}
+        q.put((rank, n_coll, grads, None if out is None else out.numpy().copy()))
     finally:
         dist.destroy_process_group()
 
 
-def test_two_rank_allreduce_equals_single_process():
+@pytest.mark.parametrize("n", [10, 11])
+def test_two_rank_allreduce_equals_single_process(n):
     world = 2
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
@@ -72,7 +83,7 @@ def test_two_rank_allreduce_equals_single_process():
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, n)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=120) for _ in range(world)], key=lambda t: t[0])
@@ -81,8 +92,8 @@ def test_two_rank_allreduce_equals_single_process():
         assert p.exitcode == 0
     # single-process reference on the concatenated batch
     torch.manual_seed(1)
-    x = torch.randn(10, 5)
-    y = torch.randn(10, 6)
+    x = torch.randn(n, 5)
+    y = torch.randn(n, 6)
     model = _Toy()
     ((model(x) - y) ** 2).mean().backward()
     parallel.clip_gradients_(model.parameters(), 1.0)
@@ -90,8 +101,8 @@ def test_two_rank_allreduce_equals_single_process():
         assert n_coll >= 3                                      # >= 2 weight buckets + the packed quant-scalar buffer
         for n, p in model.named_parameters():
             if n == "unused":
-                assert grads[n] is None or float(grads[n].abs().sum()) == 0.0
+                assert grads[n] is None                          # untouched on every rank: stays None (optimizers skip it)
                 continue
-            assert torch.allclose(grads[n], p.grad, rtol=1e-5, atol=1e-6), n
-    assert torch.allclose(res[0][3], model(x).detach(), rtol=1e-5, atol=1e-6)       # gathered in batch order on rank 0
+            assert torch.allclose(torch.from_numpy(grads[n]), p.grad, rtol=1e-5, atol=1e-6), n
+    assert torch.allclose(torch.from_numpy(res[0][3]), model(x).detach(), rtol=1e-5, atol=1e-6)       # gathered in batch order on rank 0
     assert res[1][3] is None
