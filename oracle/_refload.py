@@ -18,6 +18,14 @@ _GETA_DIR = os.path.join(REFERENCE_ROOT, "QViT_with_GETA")
 _ULTRA_DIR = os.path.join(REFERENCE_ROOT, "4-bit quantization")
 
 
+def use_root(root: str) -> None:
+    """Point the loader at another copy of the reference tree (oracle/_ref on the GPU box, see oracle/make_ref.py)."""
+    global REFERENCE_ROOT, _GETA_DIR, _ULTRA_DIR
+    REFERENCE_ROOT = root
+    _GETA_DIR = os.path.join(root, "QViT_with_GETA")
+    _ULTRA_DIR = os.path.join(root, "4-bit quantization")
+
+
 def available() -> bool:
     return os.path.isdir(os.path.join(_GETA_DIR, "only_train_once", "quantization"))
 

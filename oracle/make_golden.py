@@ -452,6 +452,149 @@ def golden_vit():
     _vit_golden(vm, qm, "vit_b16_w4a4_calib", base, 2, 4, "symmetric+linear", calibrate=True)
 
 
+def golden_vit_large():
+    """Config 4: ViT-L/16 (vit_model.py:419-433), num_bits=4 conversion, 8-bit activation codes.
+    `init`: q_m_act stays max|W| and d_quant_act = q_m_act / 127 (the survey's literal recipe); `calib`: q_m_act = 99.9th
+    percentile of the layer input, d = q_m / 127.  Batch 2; weights are re-created on the GPU box by fill_state_dict_."""
+    vm, qm = R.vit_model(), R.quant_model()
+    large = dict(img_size=224, patch_size=16, embed_dim=1024, depth=24, num_heads=16, num_classes=1000)
+    _vit_golden(vm, qm, "vit_l16_w4a8_calib", large, 2, 4, "symmetric+linear", act_bits=8)
+    # literal recipe: convert at 4 bits, then d_quant_act = q_m_act / 127
+    torch.manual_seed(0)
+    model = vm.vit_large_patch16_224(num_classes=1000)
+    sd = model.state_dict()
+    ref_models.fill_state_dict_(sd, seed=0, weight_std=0.02)
+    model.load_state_dict(sd)
+    model = qm.model_to_quantize_model(model, num_bits=4, quant_type="symmetric+linear", quant_mode="weight_and_activation").eval()
+    with torch.no_grad():
+        for m in model.modules():
+            if hasattr(m, "q_m_act"):
+                m.d_quant_act.copy_(m.q_m_act / 127)
+    x = torch.randn(2, 3, 224, 224, generator=_gen(1))
+    with torch.no_grad():
+        logits = model(x)
+    out = {"logits": _np(logits), "x_sum": np.float64(x.double().sum().item()),
+           "cfg": np.array([224, 16, 1024, 24, 16, 1000], dtype=np.int64), "batch": np.int64(2), "fill_seed": np.int64(0)}
+    qn = [k for k in model.state_dict() if any(t in k for t in ("d_quant", "q_m", "t_quant"))]
+    out["q.names"] = np.array(qn)
+    out["q.values"] = np.array([model.state_dict()[k].item() for k in qn], dtype=np.float32)
+    top2 = torch.topk(logits, 2, dim=-1).values
+    out["top1"], out["margin"] = _np(logits.argmax(-1)), _np(top2[:, 0] - top2[:, 1])
+    np.savez_compressed(os.path.join(OUT, "vit_l16_w4a8_init.npz"), **out)
+    print("vit_l16_w4a8_init logits[0,:4]", logits[0, :4].tolist())
+
+
+def golden_vit_b16_w8a8():
+    vm, qm = R.vit_model(), R.quant_model()
+    base = dict(img_size=224, patch_size=16, embed_dim=768, depth=12, num_heads=12, num_classes=1000)
+    _vit_golden(vm, qm, "vit_b16_w8a8_calib", base, 2, 8, "symmetric+linear", calibrate=True)
+
+
+def golden_qat():
+    """Config 3 parity: the REFERENCE's autograd (SymQuantizerLinear / NonLinear.backward through QuantizeLinear /
+    QuantizeConv2d inside the reference VisionTransformer) on a depth-2, D = 768 ViT, W&A 4-bit, batch 2, cross-entropy.
+    Committed: loss, logits, every quantizer-scalar gradient, and a digest (sum, abs-sum, l2, 256 strided samples) of every
+    other parameter's gradient."""
+    vm, qm = R.vit_model(), R.quant_model()
+    ql = R.quant_layers()
+    cfg = dict(img_size=224, patch_size=16, embed_dim=768, depth=2, num_heads=12, num_classes=10)
+    for tag, qtype in (("lin", "symmetric+linear"), ("nl", "symmetric+nonlinear")):
+        torch.manual_seed(0)
+        model = vm.VisionTransformer(**cfg)
+        sd = model.state_dict()
+        ref_models.fill_state_dict_(sd, seed=5, weight_std=0.02)
+        model.load_state_dict(sd)
+        model = qm.model_to_quantize_model(model, num_bits=4, quant_type=qtype, quant_mode="weight_and_activation")
+        x = torch.randn(2, 3, 224, 224, generator=_gen(1))
+        labels = torch.randint(0, 10, (2,), generator=_gen(2))
+        # calibrated activation ranges (fixture B recipe), two passes
+        stats, hooks = {}, []
+
+        def mk(nm):
+            def hook(mod, inp):
+                a = inp[0].detach().abs().flatten()
+                stats[nm] = a.kthvalue(max(1, int(round(0.999 * a.numel())))).values.item()
+            return hook
+        for nm, mod in model.named_modules():
+            if isinstance(mod, (ql.QuantizeLinear, ql.QuantizeConv2d)):
+                hooks.append(mod.register_forward_pre_hook(mk(nm)))
+        model.eval()
+        for _ in range(2):
+            with torch.no_grad():
+                model(x)
+            for nm, mod in model.named_modules():
+                if nm in stats:
+                    with torch.no_grad():
+                        mod.q_m_act.fill_(stats[nm])
+                        mod.d_quant_act.fill_(stats[nm] / 7)
+        for h in hooks:
+            h.remove()
+        if tag == "nl":
+            with torch.no_grad():
+                for mod in model.modules():
+                    if hasattr(mod, "t_quant_act"):
+                        mod.t_quant_act.fill_(0.9)
+                        mod.t_quant_wt.fill_(1.05)
+        model.train()
+        logits = model(x)
+        loss = torch.nn.functional.cross_entropy(logits, labels)
+        loss.backward()
+        out = {"cfg": np.array([224, 16, 768, 2, 12, 10], dtype=np.int64), "fill_seed": np.int64(5), "batch": np.int64(2),
+               "labels": _np(labels), "loss": np.float64(loss.item()), "logits": _np(logits),
+               "x_sum": np.float64(x.double().sum().item())}
+        qn = [k for k in model.state_dict() if any(t in k for t in ("d_quant", "q_m", "t_quant"))]
+        out["q.names"] = np.array(qn)
+        out["q.values"] = np.array([model.state_dict()[k].item() for k in qn], dtype=np.float32)
+        names = []
+        for n, p in model.named_parameters():
+            assert p.grad is not None, n
+            names.append(n)
+            st, smp = ref_models.grad_digest(p.grad)
+            out[f"g.{n}.stats"], out[f"g.{n}.samples"] = st, smp
+        out["g.names"] = np.array(names)
+        np.savez_compressed(os.path.join(OUT, f"qat_vit_d768_{tag}.npz"), **out)
+        print("qat", tag, "loss", loss.item(), "grad d_quant_act blocks.0.attn.qkv",
+              dict(model.named_parameters())["blocks.0.attn.qkv.d_quant_act"].grad.item())
+
+
+def golden_bnq():
+    """BatchNorm2d_Q / BatchNorm1d_Q (QU:94-207).  Their forward ends in F.batch_norm(eps = eps * 0); torch >= 2 added a
+    PYTHON-level guard (eps <= 0 raises) in front of the unchanged ATen op.  The golden runs the unmodified reference
+    classes with that guard bypassed: the module's `F.batch_norm` is pointed at a shim that forwards the very same
+    arguments to torch.batch_norm (what F.batch_norm did when the reference was written)."""
+    qu = R.quant_ultra()
+
+    class _F:
+        def __getattr__(self, k):
+            return getattr(torch.nn.functional, k)
+
+        @staticmethod
+        def batch_norm(input, running_mean, running_var, weight=None, bias=None, training=False, momentum=0.1, eps=1e-5):
+            return torch.batch_norm(input, weight, bias, running_mean, running_var, training, momentum, eps, False)
+    saved = qu.F
+    qu.F = _F()
+    out = {}
+    try:
+        for dim, fn, shape in ((2, qu.batchNorm2d_Q_fn, (2, 6, 4, 5)), (1, qu.batchNorm1d_Q_fn, (7, 6))):
+            for bits in (2, 4, 8):
+                bn = fn(bits)(6).eval()
+                with torch.no_grad():
+                    bn.weight.copy_(torch.rand(6, generator=_gen(405)) * 1.5)
+                    bn.bias.copy_(torch.randn(6, generator=_gen(406)) * 0.5)
+                    bn.running_mean.copy_(torch.randn(6, generator=_gen(407)) * 0.3)
+                    bn.running_var.copy_(torch.rand(6, generator=_gen(408)) * 2 + 0.2)
+                xb = torch.randn(shape, generator=_gen(409 + dim))
+                with torch.no_grad():
+                    y = bn(xb)
+                for k in ("weight", "bias", "running_mean", "running_var"):
+                    out[f"bn{dim}d.{k}"] = _np(getattr(bn, k))
+                out[f"bn{dim}d.x"] = _np(xb)
+                out[f"bn{dim}d.bit{bits}.y"] = _np(y)
+    finally:
+        qu.F = saved
+    np.savez_compressed(os.path.join(OUT, "ultra_bnq.npz"), **out)
+
+
 if __name__ == "__main__":
     if not R.available():
         raise SystemExit("reference tree not found (this script only runs in the build container)")

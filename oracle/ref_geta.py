@@ -211,3 +211,42 @@ def int_conv2d(a_codes: torch.Tensor, w_codes: torch.Tensor, stride=1, padding=0
     OH = (H + 2 * ph - dh * (kh - 1) - 1) // sh + 1
     OW = (W + 2 * pw - dw * (kw - 1) - 1) // sw + 1
     return acc.reshape(B, O, OH, OW)
+
+
+# --------------------------------------------------------------------------------------------
+# autograd view of the quantizers (QAT parity): the oracle's forward / backward restatements above wired
+# into torch.autograd so that a whole model can be differentiated exactly the way the reference's
+# autograd.Functions do it (QL:33-205), without the reference's classes being present.
+# --------------------------------------------------------------------------------------------
+
+class SymQuantFn(torch.autograd.Function):
+    """forward = sym_forward, backward = sym_backward (STE inside clip, fused reductions for d / q_m / t)."""
+
+    @staticmethod
+    def forward(ctx, x, d, q_m, t, clip_lo, clip_hi):
+        ctx.save_for_backward(x, d, q_m) if t is None else ctx.save_for_backward(x, d, q_m, t)
+        ctx.nl, ctx.clip = t is not None, (clip_lo, clip_hi)
+        return sym_forward(x, d, q_m, t)
+
+    @staticmethod
+    def backward(ctx, g):
+        if ctx.nl:
+            x, d, q_m, t = ctx.saved_tensors
+        else:
+            (x, d, q_m), t = ctx.saved_tensors, None
+        r = sym_backward(x, g, d, q_m, t, ctx.clip)
+        return r["grad_x"], r["grad_d"], r["grad_qm"], r.get("grad_t"), None, None
+
+
+def quantize_linear_autograd(x, weight, bias, wq, aq, clip=(-2.0, 2.0)):
+    """QuantizeLinear.forward (QL:495-499) under autograd: F.linear(Q_a(x), Q_w(W), b)."""
+    w_q = SymQuantFn.apply(weight, wq["d"], wq["q_m"], wq.get("t"), clip[0], clip[1])
+    x_q = x if aq is None else SymQuantFn.apply(x, aq["d"], aq["q_m"], aq.get("t"), clip[0], clip[1])
+    return F.linear(x_q, w_q, bias)
+
+
+def quantize_conv2d_autograd(x, weight, bias, wq, aq, stride=1, padding=1, dilation=1, groups=1, clip=(-2.0, 2.0)):
+    """QuantizeConv2d.forward (QL:575-587) under autograd."""
+    w_q = SymQuantFn.apply(weight, wq["d"], wq["q_m"], wq.get("t"), clip[0], clip[1])
+    x_q = x if aq is None else SymQuantFn.apply(x, aq["d"], aq["q_m"], aq.get("t"), clip[0], clip[1])
+    return F.conv2d(x_q, w_q, bias, stride, padding, dilation, groups)

@@ -120,6 +120,60 @@ def vit_forward(sd: Dict[str, torch.Tensor], x: torch.Tensor, depth: int, num_he
     return _qlinear(sd, "head", h[:, 0], taps)                                    # VIT:312, 327
 
 
+def vit_forward_autograd(params: Dict[str, torch.Tensor], x: torch.Tensor, depth: int, num_heads: int,
+                         patch: int = 16, ln_eps: float = 1e-6, taps: Optional[dict] = None) -> torch.Tensor:
+    """vit_forward under autograd (QAT parity, config 3): ``params`` are fp32 CPU leaf tensors (requires_grad as the
+    caller set it); the quantizers differentiate through ref_geta.SymQuantFn, i.e. the reference's autograd.Functions
+    (QL:71-125, 163-205).  ``taps`` receives every quantized layer's input and output with retain_grad(), so that after
+    backward() ``taps[name + ".in"].grad`` / ``taps[name + ".y"].grad`` are the reference's per-layer gradients."""
+    def q(prefix, which):
+        return _qparams(params, prefix, which)
+
+    def qlin(prefix, y):
+        if taps is not None and y.requires_grad:
+            y.retain_grad()
+        out = ref_geta.quantize_linear_autograd(y, params[f"{prefix}.weight"], params.get(f"{prefix}.bias"), q(prefix, "wt"),
+                                                q(prefix, "act"))
+        if taps is not None:
+            out.retain_grad()
+            taps[f"{prefix}.in"], taps[f"{prefix}.y"] = y, out
+        return out
+
+    h = ref_geta.quantize_conv2d_autograd(x, params["patch_embed.proj.weight"], params.get("patch_embed.proj.bias"),
+                                          q("patch_embed.proj", "wt"), q("patch_embed.proj", "act"), stride=patch, padding=0)
+    if taps is not None:
+        h.retain_grad()
+        taps["patch_embed.proj.in"], taps["patch_embed.proj.y"] = x, h
+    h = h.flatten(2).transpose(1, 2)
+    B = h.shape[0]
+    h = torch.cat((params["cls_token"].expand(B, -1, -1), h), dim=1) + params["pos_embed"]
+    D = h.shape[-1]
+    for i in range(depth):
+        p = f"blocks.{i}"
+        y = F.layer_norm(h, (D,), params[f"{p}.norm1.weight"], params[f"{p}.norm1.bias"], ln_eps)
+        qkv = qlin(f"{p}.attn.qkv", y)
+        N = qkv.shape[1]
+        qkv = qkv.reshape(B, N, 3, num_heads, -1).permute(2, 0, 3, 1, 4)
+        attn = ((qkv[0] @ qkv[1].transpose(-2, -1)) * (qkv.shape[-1] ** -0.5)).softmax(dim=-1)
+        y = (attn @ qkv[2]).transpose(1, 2).reshape(B, N, -1)
+        h = h + qlin(f"{p}.attn.proj", y)
+        y = F.layer_norm(h, (D,), params[f"{p}.norm2.weight"], params[f"{p}.norm2.bias"], ln_eps)
+        y = F.gelu(qlin(f"{p}.mlp.fc1", y))
+        h = h + qlin(f"{p}.mlp.fc2", y)
+    h = F.layer_norm(h, (D,), params["norm.weight"], params["norm.bias"], ln_eps)
+    return qlin("head", h[:, 0])
+
+
+def grad_digest(g: torch.Tensor, n_samples: int = 256):
+    """(stats[3] = sum, abs-sum, l2 in float64; samples at a fixed pseudo-random stride) of a gradient tensor - the
+    committed fingerprint of tensors too large to commit (oracle/make_golden.py::golden_qat and its tests)."""
+    flat = g.detach().double().reshape(-1).cpu()
+    n = flat.numel()
+    idx = (torch.arange(min(n_samples, n), dtype=torch.int64) * 7919) % n
+    stats = torch.stack([flat.sum(), flat.abs().sum(), flat.pow(2).sum().sqrt()])
+    return stats.numpy(), flat[idx].float().numpy()
+
+
 # ------------------------------------------------------------------------------------------
 # UltraNet
 # ------------------------------------------------------------------------------------------

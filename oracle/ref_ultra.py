@@ -102,10 +102,18 @@ def batchnorm2d_q_scale_bias(gamma, beta, mean, var, eps: float, w_bit: int) -> 
 
 
 def batchnorm2d_q_forward(x, gamma, beta, mean, var, eps: float, w_bit: int) -> torch.Tensor:
-    """BatchNorm2d_Q.forward (QU:125-130): F.batch_norm with zero mean, unit var, eps 0."""
+    """BatchNorm2d_Q.forward (QU:125-130): batch_norm with zero mean, unit var, eps 0.  The ATen op is called directly:
+    torch >= 2 put a Python guard (eps <= 0 raises) in front of it that did not exist when the reference was written."""
     w_q, b_q = batchnorm2d_q_scale_bias(gamma, beta, mean, var, eps, w_bit)
-    return F.batch_norm(x, running_mean=mean * 0, running_var=torch.sign(torch.abs(var) + 1),
-                        weight=w_q, bias=b_q, eps=eps * 0)
+    return torch.batch_norm(x, w_q, b_q, mean * 0, torch.sign(torch.abs(var) + 1), False, 0.1, eps * 0, False)
+
+
+def batchnorm1d_q_forward(x, gamma, beta, mean, var, eps: float, w_bit: int) -> torch.Tensor:
+    """BatchNorm1d_Q.forward (QU:185-206): the folded scale is quantised (w_q, QU:196) but the UN-quantised fold (w, b) is
+    what reaches batch_norm (QU:203-206); zero mean, unit var (sign(var + 1)), eps 0."""
+    w = gamma / (torch.sqrt(var) + eps)
+    b = beta - (mean / (torch.sqrt(var) + eps)) * gamma
+    return torch.batch_norm(x, w, b, mean * 0, torch.sign(var + 1), False, 0.1, eps * 0, False)
 
 
 # ---------------------------------------------------------------- NumPy export path (QZ)

@@ -109,6 +109,7 @@ class _DispatchMonitor:
         self.mods = []                 # weak references, slot = index
         self.sat = []                  # [2 * n] python floats (weight, activation), lagged
         self.calls = 0
+        self.n_live = 0                # registered modules still alive (a refresh is due every n_live forward calls)
         self.pending = None            # CUDA event of the read-back in flight
         self.key = None
         self.ptab = self.dev_sat = self.host_sat = None
@@ -117,12 +118,16 @@ class _DispatchMonitor:
 
     def register(self, mod) -> int:
         slot = len(self.mods)
-        self.mods.append(self._weakref.ref(mod))
+        self.mods.append(self._weakref.ref(mod, self._on_dead))
+        self.n_live += 1
         sw = QuantizeMixin._sat_level(*mod._wt_qparams())             # one host read per quantizer, once per module
         sa = QuantizeMixin._sat_level(*mod._act_qparams())
         self.sat += [sw, sa]
         self.key = None
         return slot
+
+    def _on_dead(self, _ref):
+        self.n_live -= 1
 
     def _ptr_key(self):
         ptrs = []
@@ -179,7 +184,7 @@ class _DispatchMonitor:
                 self.sticky &= ~ops._lib.QVIT_FLAG_NAN_GRAD
                 raise NanInGradientError("Error: NaN appears in gradient! (reported by the fused quantizer backward)")
         self.calls += 1
-        if self.pending is None and self.calls >= len(self.mods):
+        if self.pending is None and self.calls >= max(1, self.n_live):
             self._launch()
 
     def int8_ok(self, mod) -> bool:
@@ -497,7 +502,8 @@ class QuantizeMixin:
         code approach 127 again."""
         if self.quant_mode != QuantizationMode.WEIGHT_AND_ACTIVATION or self.quant_type == QuantizationType.DGE:
             return False
-        return _monitor_for(self.weight.device).int8_ok(self)
+        ok = _monitor_for(self.weight.device).int8_ok(self)
+        return ok and not self.__dict__.get("_force_wide", False)      # (_force_wide: tests compare the two paths)
 
     def _weight_codes(self, c: _QuantCache) -> torch.Tensor:
         """[out, pad16(K)] int8 codes, K = in_features or C*kh*kw ordered (c, kh, kw) = weight.reshape(O, -1)."""

@@ -147,9 +147,10 @@ def _folded_bn(mod):
 
 def batchNorm2d_Q_fn(w_bit):
     """QU:94-132.  The fold is clamped to [-1, 1], mapped to [0, 1], quantised on the 2^w_bit-1 grid and mapped back; the
-    layer then applies y = x * w_q + b_q (upstream calls F.batch_norm with zero mean, unit variance and eps = 0, which
-    torch >= 2 rejects with a ValueError - that forward cannot run there, so this class is 'parity unpinned':
-    checked against the oracle restatement only).  Unused by mymodel.py (it uses nn.BatchNorm2d, MM:74)."""
+    layer then applies y = x * w_q + b_q (upstream calls F.batch_norm with zero mean, unit variance and eps = 0; torch >= 2
+    put a Python-level `eps <= 0` guard in front of the unchanged ATen op, so the golden outputs this class is tested
+    against were produced by the reference class with that guard bypassed - oracle/make_golden.py::golden_bnq).
+    Unused by mymodel.py (it uses nn.BatchNorm2d, MM:74)."""
 
     class BatchNorm2d_Q(nn.BatchNorm2d):
         def __init__(self, num_features, eps=1e-5, momentum=0.1, affine=True, track_running_stats=True):

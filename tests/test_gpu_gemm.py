@@ -221,6 +221,41 @@ def test_requantize_nonlinear_fast_path_equals_scalar_path(ops, bits, t_next):
     assert torch.equal(simt, outs[(1, ops.QVIT_ACT_GELU)])
 
 
+@pytest.mark.parametrize("t_next", [None, 0.85, 1.3])
+@pytest.mark.parametrize("bits", [4, 8])
+def test_requantize_epilogue_codes_equal_oracle(ops, bits, t_next):
+    """The int8-output epilogue against the ORACLE (ref_geta.sym_codes = the reference's quantize_act, QL:40-69 / 136-161):
+    the fp32 pre-activation y is taken from the fp32-output run of the same GEMM (bit-identical to what the int8 epilogue
+    quantizes), the oracle quantizes it on the CPU, and the kernel's codes must be those integers.  Linear consumer:
+    bit-exact.  Non-linear consumer: equal except where CPU and GPU libm (expf / logf) round a value across a code
+    boundary - at most a single level, rate <= 2e-3 (the allowance SURVEY.md section 7 states for rows 3 / 11)."""
+    from oracle import ref_geta
+    M, N, K = 1500, 384, 768
+    a = _codes(M, K, -7, 7, 61).cuda()
+    w = _codes(N, K, -7, 7, 62).cuda()
+    bias = torch.randn(N).cuda() * 0.3
+    qm = 1.7
+    sat = 2 ** (bits - 1) - 1
+    if t_next is None:
+        d_next = qm / sat
+    else:
+        d_next = float(torch.exp(torch.tensor(t_next) * torch.log(torch.tensor(qm + 1e-6))) / sat)
+    for act in (ops.QVIT_ACT_NONE, ops.QVIT_ACT_GELU):
+        y = ops.gemm_i8(a, w, K, N, out_kind=ops.QVIT_OUT_F32, bias=bias, act=act, scale_a=0.01, scale_w=0.02,
+                        backend=ops.QVIT_GEMM_TCGEN05, acc_abs_max=49 * K)
+        c = ops.gemm_i8(a, w, K, N, out_kind=ops.QVIT_OUT_I8, bias=bias, act=act, scale_a=0.01, scale_w=0.02,
+                        next_q=(d_next, qm, t_next), backend=ops.QVIT_GEMM_TCGEN05, acc_abs_max=49 * K)
+        want = ref_geta.sym_codes(y.cpu(), torch.tensor([d_next]), torch.tensor([qm]), None if t_next is None else torch.tensor([t_next]))
+        diff = (c.cpu().long() - want)
+        assert int(want.abs().max()) == sat and len(torch.unique(want)) >= 5
+        if t_next is None:
+            assert int((diff != 0).sum()) == 0, f"linear consumer: {int((diff != 0).sum())} codes differ from the oracle"
+        else:
+            rate = float((diff != 0).float().mean())
+            print(f"non-linear requantize (bits={bits}, t={t_next}, act={act}): {int((diff != 0).sum())} of {diff.numel()} codes off by one level")
+            assert int(diff.abs().max()) <= 1 and rate <= 2e-3, rate
+
+
 @pytest.mark.parametrize("d_next", [0.3, 2.1 / 127.0])
 def test_requantize_paths_agree(ops, d_next):
     """The int8-output epilogue has three levels: packed interval test (hot), exact two-step Markstein division for rows

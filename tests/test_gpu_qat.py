@@ -1,0 +1,336 @@
+"""Config 3 (QAT) parity on the GPU: gradients through the drop-in modules (QuantLinearFunction: exact int8 forward GEMM on
+tcgen05, split-bf16 gradient GEMMs, fused quantizer backward) against the REFERENCE's autograd.
+
+Evidence chain: tests/golden/qat_vit_d768_{lin,nl}.npz hold loss / logits / every quantizer-scalar gradient / a digest of
+every other gradient produced by the unmodified reference (oracle/make_golden.py::golden_qat) on a depth-2, D = 768 ViT
+(W&A 4-bit, linear and non-linear quantizers, batch 2).  The oracle's autograd restatement reproduces them bit for bit on
+the CPU (tests/test_oracle_golden.py::test_qat_autograd_matches_reference), so on the GPU box it supplies what the golden
+file is too small to hold: every layer's input, grad_output and full gradient tensors.
+
+Tolerances: tensors norm-wise 1e-3; scalar gradients |delta| <= 1e-3 |ref| + 1e-6 max(1, sum|terms|)
+against a float64 re-summation of the reference formula (the fp32 sums of ~3e5 signed terms carry that much rounding noise
+in either implementation)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ref_geta, ref_models
+from tests import fixtures
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(x):
+    return torch.from_numpy(np.ascontiguousarray(x))
+
+
+def _setup(golden, tag):
+    g = golden(f"qat_vit_d768_{tag}")
+    img, patch, dim, depth, heads, classes = [int(v) for v in g["cfg"]]
+    sd = fixtures.vit_state_dict(img, patch, dim, depth, heads, classes, seed=int(g["fill_seed"]))
+    for k, v in zip(g["q.names"], g["q.values"]):
+        sd[str(k)] = torch.tensor([float(v)], dtype=torch.float32)
+    x = fixtures.vit_input(int(g["batch"]), img, seed=1)
+    return g, sd, x, dict(img=img, patch=patch, dim=dim, depth=depth, heads=heads, classes=classes)
+
+
+def _our_model(sd, cfg, tag):
+    from quantized_vit_b200.engine.vit_module import VisionTransformer
+    from quantized_vit_b200.quantization import model_to_quantize_model
+    m = VisionTransformer(img_size=cfg["img"], patch_size=cfg["patch"], num_classes=cfg["classes"], embed_dim=cfg["dim"],
+                          depth=cfg["depth"], num_heads=cfg["heads"])
+    m = model_to_quantize_model(m, num_bits=4, quant_type="symmetric+linear" if tag == "lin" else "symmetric+nonlinear",
+                                quant_mode="weight_and_activation")
+    missing, unexpected = m.load_state_dict(sd, strict=True), None
+    return m.cuda().train()
+
+
+def _f64_scalar_grads(x, g, d, q_m, t):
+    """float64 re-summation of QL:177-187 / QL:89-105 with the reference's fp32 per-element terms; returns
+    {name: (sum, sum|terms|)}."""
+    x = x.detach().float().cpu()
+    g = g.detach().float().cpu()
+    one = ref_geta.sym_backward  # noqa: F841  (formulas below follow it term by term)
+    d, q_m = ref_geta._as_param(d), ref_geta._as_param(q_m)
+    t = None if t is None else ref_geta._as_param(t)
+    a, sgn = x.abs(), torch.sign(x)
+    p, r = ref_geta._domain(a, q_m, t)
+    resid = torch.round(p.div(d)) - p.div(d)
+    resid[a >= q_m] = torch.round(r.div(d)) - r.div(d)
+    resid[a <= 0.0] = 0
+    out = {}
+    td = (g * (sgn * resid)).double()
+    out["d"] = (float(td.sum()), float(td.abs().sum()))
+    if t is None:
+        dq = sgn.clone()
+    else:
+        dq = sgn * (t * torch.exp((t - 1) * torch.log(q_m.abs() + 1e-6))).expand_as(x)
+    dq[a <= q_m] = 0
+    tq = (g * dq).double()
+    out["q_m"] = (float(tq.sum()), float(tq.abs().sum()))
+    if t is not None:
+        dt = p * torch.log(a)
+        dt[a >= q_m] = r * torch.log(q_m.abs() + 1e-6)
+        dt[a <= 0.0] = 0
+        tt = (g * (sgn * dt)).double()
+        out["t"] = (float(tt.sum()), float(tt.abs().sum()))
+    return out
+
+
+def _scalar_ok(got, ref_sum, ref_abs):
+    return abs(got - ref_sum) <= 1e-3 * abs(ref_sum) + 1e-6 * max(1.0, ref_abs)
+
+
+@pytest.mark.parametrize("tag", ["lin", "nl"])
+def test_qat_layers_teacher_forced_vs_reference_autograd(golden, tag):
+    """Every quantized layer of the depth-2, D = 768 ViT, fed the reference's own input and grad_output: grad_x, grad_W,
+    grad_b norm-wise 1e-3 and the six quantizer-scalar gradients at the stated scalar tolerance."""
+    from quantized_vit_b200.quantization import QuantizeConv2d, QuantizeLinear, check_nan_flags
+    g, sd, x, cfg = _setup(golden, tag)
+    torch.set_num_threads(os.cpu_count() or 1)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    taps = {}
+    xr = x.clone().requires_grad_(True)
+    logits = ref_models.vit_forward_autograd(params, xr, cfg["depth"], cfg["heads"], cfg["patch"], taps=taps)
+    loss = torch.nn.functional.cross_entropy(logits, _t(g["labels"]))
+    loss.backward()
+    assert np.array_equal(logits.detach().numpy(), g["logits"]), "the oracle taps must come from the reference-equal forward"
+    model = _our_model(sd, cfg, tag)
+    worst_t, worst_s, n_layers = 0.0, 0.0, 0
+    for name, mod in model.named_modules():
+        if not isinstance(mod, (QuantizeLinear, QuantizeConv2d)):
+            continue
+        n_layers += 1
+        x_in, y_ref = taps[f"{name}.in"], taps[f"{name}.y"]
+        go = y_ref.grad
+        xg = x_in.detach().cuda().requires_grad_(True)
+        mod.zero_grad(set_to_none=True)
+        y = mod(xg)
+        ref_y = y_ref.detach()
+        assert (y.detach().cpu() - ref_y).abs().max() <= 1e-3 * ref_y.abs().max(), f"{name}: forward"
+        y.backward(go.cuda())
+        torch.cuda.synchronize()
+
+        def tens(got, ref, what):
+            nonlocal worst_t
+            e = float((got.detach().cpu().double() - ref.double()).abs().max() / max(float(ref.abs().max()), 1e-30))
+            worst_t = max(worst_t, e)
+            assert e <= 1e-3, f"{name} {what}: {e:.2e}"
+        tens(xg.grad, x_in.grad, "grad_x")
+        tens(mod.weight.grad, params[f"{name}.weight"].grad, "grad_w")
+        if mod.bias is not None:
+            tens(mod.bias.grad, params[f"{name}.bias"].grad, "grad_b")
+        # scalar gradients: float64 re-summation of the reference's terms, from the reference's tensors
+        w_q = ref_geta.sym_forward(sd[f"{name}.weight"], sd[f"{name}.d_quant_wt"], sd[f"{name}.q_m_wt"], sd.get(f"{name}.t_quant_wt"))
+        x_q = ref_geta.sym_forward(x_in, sd[f"{name}.d_quant_act"], sd[f"{name}.q_m_act"], sd.get(f"{name}.t_quant_act"))
+        if isinstance(mod, QuantizeLinear):
+            g2, xq2 = go.reshape(-1, go.shape[-1]).double(), x_q.reshape(-1, x_q.shape[-1]).double()
+            g_wq, g_xq = (g2.t() @ xq2).float(), (g2 @ w_q.double()).float().reshape(x_in.shape)
+        else:
+            xq_r = x_q.detach().requires_grad_(True)
+            wq_r = w_q.detach().requires_grad_(True)
+            torch.nn.functional.conv2d(xq_r, wq_r, None, mod.stride, mod.padding, mod.dilation, mod.groups).backward(go)
+            g_wq, g_xq = wq_r.grad, xq_r.grad
+        for side, xx, gg in (("wt", sd[f"{name}.weight"], g_wq), ("act", x_in.detach(), g_xq)):
+            want = _f64_scalar_grads(xx, gg, sd[f"{name}.d_quant_{side}"], sd[f"{name}.q_m_{side}"], sd.get(f"{name}.t_quant_{side}"))
+            for key, (rs, ra) in want.items():
+                pname = {"d": "d_quant", "q_m": "q_m", "t": "t_quant"}[key] + "_" + side
+                got = float(getattr(mod, pname).grad.item())
+                # the reference's own fp32 value must satisfy the same bound (sanity of the bound itself)
+                ref32 = float(params[f"{name}.{pname}"].grad.item())
+                assert _scalar_ok(ref32, rs, ra), f"{name}.{pname}: reference fp32 {ref32} vs float64 {rs}"
+                worst_s = max(worst_s, abs(got - rs) / (1e-3 * abs(rs) + 1e-6 * max(1.0, ra)))
+                assert _scalar_ok(got, rs, ra), f"{name}.{pname}: {got} vs {rs} (reference fp32 {ref32}, sum|terms| {ra})"
+    assert n_layers == 2 + 4 * cfg["depth"]
+    check_nan_flags()
+    print(f"qat {tag}: {n_layers} layers teacher-forced; worst tensor error {worst_t:.2e} (bar 1e-3), worst scalar error "
+          f"{worst_s:.2f} x the stated tolerance")
+
+
+@pytest.mark.parametrize("tag", ["lin", "nl"])
+def test_qat_model_gradients_vs_reference_golden(golden, tag):
+    """The whole model (our VisionTransformer caller + drop-in modules) against the reference-generated golden: loss,
+    logits, and the digest of every parameter gradient.  A single activation code flipping at a rounding tie (GPU vs CPU
+    LayerNorm / softmax rounding) moves individual scalar gradients by up to ~1e-2 of their value, so the model-level
+    bound on the quantizer scalars is 5e-2 (the per-layer bound above is the tight one); tensors stay at 1e-3 norm-wise
+    on their sampled entries and l2."""
+    from quantized_vit_b200.quantization import check_nan_flags
+    g, sd, x, cfg = _setup(golden, tag)
+    model = _our_model(sd, cfg, tag)
+    logits = model(x.cuda())
+    loss = torch.nn.functional.cross_entropy(logits, _t(g["labels"]).cuda())
+    loss.backward()
+    torch.cuda.synchronize()
+    check_nan_flags()
+    ref_logits = g["logits"]
+    assert np.abs(logits.detach().cpu().numpy() - ref_logits).max() <= 1e-3 * np.abs(ref_logits).max()
+    assert abs(loss.item() - float(g["loss"])) <= 1e-4
+    worst_t = worst_s = 0.0
+    named = dict(model.named_parameters())
+    for n in [str(s) for s in g["g.names"]]:
+        st, smp = ref_models.grad_digest(named[n].grad)
+        ref_st, ref_smp = g[f"g.{n}.stats"], g[f"g.{n}.samples"]
+        if any(tq in n for tq in ("d_quant", "q_m", "t_quant")):
+            e = abs(st[0] - ref_st[0]) / (abs(ref_st[0]) + 1e-6)
+            worst_s = max(worst_s, e)
+            assert e <= 5e-2, f"{n}: {st[0]} vs {ref_st[0]}"
+        else:
+            e = max(np.abs(smp - ref_smp).max() / max(np.abs(ref_smp).max(), 1e-30), abs(st[2] - ref_st[2]) / max(ref_st[2], 1e-30))
+            worst_t = max(worst_t, e)
+            assert e <= 1e-3, f"{n}: {e:.2e}"
+    print(f"qat {tag} model level: loss {loss.item():.6f} vs {float(g['loss']):.6f}; worst tensor-gradient deviation {worst_t:.2e}, "
+          f"worst quantizer-scalar deviation {worst_s:.2e}")
+
+
+def test_activation_quantizer_trains_when_input_needs_no_grad():
+    """A QuantizeLinear fed raw data (first layer): d_quant_act / q_m_act gradients come from grad_output of quantize_act
+    whether or not the input requires grad (QL:163-205)."""
+    from quantized_vit_b200.quantization import QuantizeLinear, QuantizationMode, QuantizationType
+    torch.manual_seed(3)
+    lin = torch.nn.Linear(64, 48)
+    m = QuantizeLinear.from_module(lin, quant_type=QuantizationType.SYMMETRIC_LINEAR, quant_mode=QuantizationMode.WEIGHT_AND_ACTIVATION,
+                                   num_bits=4).cuda().train()
+    with torch.no_grad():
+        m.q_m_act.fill_(1.5)
+        m.d_quant_act.fill_(1.5 / 7)
+    x = torch.randn(9, 64)
+    go = torch.randn(9, 48)
+    grads = []
+    for needs in (True, False):
+        m.zero_grad(set_to_none=True)
+        xg = x.cuda().requires_grad_(needs)
+        m(xg).backward(go.cuda())
+        grads.append((m.d_quant_act.grad.clone(), m.q_m_act.grad.clone(), m.weight.grad.clone()))
+        assert (xg.grad is not None) == needs
+    for a, b in zip(*grads):
+        assert torch.equal(a, b)
+    assert float(grads[1][0].abs()) > 0
+
+
+def test_dispatch_follows_bit_walk():
+    """GETA walks the bit width down during training (train.py:247-250 converts at 32 bits, geta.py:895-900): a layer that
+    starts on the wide path must move to the int8 tensor-core path once its codes fit, without a host sync and with the
+    same results; and back when a code approaches 127 again."""
+    from quantized_vit_b200.quantization import QuantizeLinear, QuantizationMode, QuantizationType
+    torch.manual_seed(5)
+    lin = torch.nn.Linear(96, 80)
+    m = QuantizeLinear.from_module(lin, quant_type=QuantizationType.SYMMETRIC_LINEAR, quant_mode=QuantizationMode.WEIGHT_AND_ACTIVATION,
+                                   num_bits=16).cuda().train()
+    x = torch.randn(33, 96, device="cuda")
+    go = torch.randn(33, 80, device="cuda")
+
+    def run():
+        m.zero_grad(set_to_none=True)
+        xg = x.clone().requires_grad_(True)
+        y = m(xg)
+        y.backward(go)
+        torch.cuda.synchronize()
+        return y.detach().clone(), xg.grad.clone(), m.weight.grad.clone(), m.d_quant_act.grad.clone()
+
+    assert not m._int8_train_ok()                       # 16-bit codes: wide path
+    wide16 = run()
+    with torch.no_grad():                               # the optimizer shrinks the bit width through .data (geta.py:571-772)
+        for p, qm in ((m.d_quant_wt, m.q_m_wt), (m.d_quant_act, m.q_m_act)):
+            p.data.copy_(qm.data / 7)
+    paths = []
+    for _ in range(4):                                  # at most a couple of steps of lag: launch, land, consume
+        paths.append(m._int8_train_ok())
+        out = run()
+    assert paths[-1], f"layer never moved onto the int8 path: {paths}"
+    # same parameters, wide path forced: results must agree (1e-3 norm-wise; the two paths differ by fp32 rounding only)
+    m.__dict__["_force_wide"] = True
+    assert not m._int8_train_ok()
+    wide4 = run()
+    m.__dict__["_force_wide"] = False
+    for a, b, what in zip(out, wide4, ("y", "grad_x", "grad_w", "grad_d_act")):
+        assert (a - b).abs().max() <= 1e-3 * b.abs().max() + 1e-6, what
+    with torch.no_grad():                               # growing again past the margin: back to the wide path
+        m.d_quant_act.data.copy_(m.q_m_act.data / 126)
+    paths = []
+    for _ in range(4):
+        paths.append(m._int8_train_ok())
+        run()
+    assert not paths[-1], f"layer stayed on the int8 path with saturation code 126: {paths}"
+    assert wide16[0].shape == out[0].shape
+
+
+# ---------------------------------------------------------------------------------------------- multi-GPU
+def _ddp_worker(rank, world, port, tag, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    try:
+        from quantized_vit_b200 import parallel
+        g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"qat_vit_d768_{tag}.npz"))
+        img, patch, dim, depth, heads, classes = [int(v) for v in g["cfg"]]
+        cfg = dict(img=img, patch=patch, dim=dim, depth=depth, heads=heads, classes=classes)
+        sd = fixtures.vit_state_dict(img, patch, dim, depth, heads, classes, seed=int(g["fill_seed"]))
+        for k, v in zip(g["q.names"], g["q.values"]):
+            sd[str(k)] = torch.tensor([float(v)], dtype=torch.float32)
+        model = _our_model(sd, cfg, tag)
+        n = 8
+        x = torch.randn(n, 3, img, img, generator=torch.Generator().manual_seed(11))
+        y = torch.randint(0, classes, (n,), generator=torch.Generator().manual_seed(12))
+        red = parallel.GradientAllReducer(model.named_parameters(), bucket_bytes=8 << 20)
+        xs, ys = parallel.shard_batch(x, rank, world).cuda(), parallel.shard_batch(y, rank, world).cuda()
+        red.zero_grad()
+        torch.nn.functional.cross_entropy(model(xs), ys).backward()
+        n_coll = red.reduce()
+        torch.cuda.synchronize()
+        if rank == 0:
+            q.put((n_coll, {k: p.grad.detach().cpu().numpy().copy() for k, p in model.named_parameters() if p.grad is not None}))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_n_gpu_gradients_equal_single_gpu_on_the_concatenated_batch(world):
+    """N-GPU averaged gradients (weights AND quantizer step sizes, all-reduced over NCCL by
+    GradientAllReducer, launched from backward hooks) == 1-GPU gradients on the concatenated batch, up to fp32
+    reassociation: tensors 1e-3 norm-wise, scalars 1e-3 |ref| + 1e-5."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    import torch.multiprocessing as mp
+    tag = "lin"
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, world, port, tag, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    n_coll, grads = q.get(timeout=600)
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    # single GPU, whole batch
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", f"qat_vit_d768_{tag}.npz"))
+    img, patch, dim, depth, heads, classes = [int(v) for v in g["cfg"]]
+    cfg = dict(img=img, patch=patch, dim=dim, depth=depth, heads=heads, classes=classes)
+    sd = fixtures.vit_state_dict(img, patch, dim, depth, heads, classes, seed=int(g["fill_seed"]))
+    for k, v in zip(g["q.names"], g["q.values"]):
+        sd[str(k)] = torch.tensor([float(v)], dtype=torch.float32)
+    model = _our_model(sd, cfg, tag)
+    x = torch.randn(8, 3, img, img, generator=torch.Generator().manual_seed(11))
+    y = torch.randint(0, classes, (8,), generator=torch.Generator().manual_seed(12))
+    torch.nn.functional.cross_entropy(model(x.cuda()), y.cuda()).backward()
+    torch.cuda.synchronize()
+    assert n_coll >= 2
+    worst = 0.0
+    for k, p in model.named_parameters():
+        ref = p.grad.detach().cpu().double()
+        got = torch.from_numpy(grads[k]).double()
+        if ref.numel() == 1:
+            assert abs(float(got) - float(ref)) <= 1e-3 * abs(float(ref)) + 1e-5, k
+        else:
+            e = float((got - ref).abs().max() / max(float(ref.abs().max()), 1e-30))
+            worst = max(worst, e)
+            assert e <= 1e-3, f"{k}: {e:.2e}"
+    print(f"{world} GPUs vs 1 GPU: {n_coll} collectives, worst tensor deviation {worst:.2e}")

@@ -7,6 +7,10 @@ import torch
 from oracle import ref_geta, ref_ultra, ref_models
 
 
+def _t(a):
+    return torch.from_numpy(np.ascontiguousarray(a))
+
+
 def T(a):
     return torch.from_numpy(np.asarray(a))
 
@@ -189,7 +193,8 @@ def test_vit_tiny_whole_model(golden, name):
     assert np.array_equal(logits.numpy(), g["logits"])
 
 
-@pytest.mark.parametrize("name", ["vit_b16_w4a4_init", "vit_b16_w4a4_calib"])
+@pytest.mark.parametrize("name", ["vit_b16_w4a4_init", "vit_b16_w4a4_calib", "vit_b16_w8a8_calib", "vit_l16_w4a8_init",
+                                  "vit_l16_w4a8_calib"])
 def test_vit_b16_whole_model(golden, name):
     """ViT-B/16 at batch 2: weights come from the seeded fill, quantizer params from the fixture
     (they were produced by the reference's own initialize_quant_layer / calibration)."""
@@ -198,7 +203,7 @@ def test_vit_b16_whole_model(golden, name):
     img, patch, dim, depth, heads, classes = [int(v) for v in g["cfg"]]
     sd = vit_state_dict(img, patch, dim, depth, heads, classes, seed=int(g["fill_seed"]))
     qref = dict(zip(g["q.names"].tolist(), g["q.values"].tolist()))
-    if name.endswith("init"):   # our own restatement of initialize_quant_layer must give the same params
+    if name == "vit_b16_w4a4_init":   # our own restatement of initialize_quant_layer must give the same params
         for k, v in qref.items():
             if k.endswith("d_quant_wt"):
                 d, q_m = ref_geta.init_quant_params(sd[k.replace("d_quant_wt", "weight")], 4)
@@ -209,3 +214,47 @@ def test_vit_b16_whole_model(golden, name):
     assert abs(x.double().sum().item() - float(g["x_sum"])) < 1e-6
     logits = ref_models.vit_forward(sd, x, depth, heads, patch)
     assert np.array_equal(logits.numpy(), g["logits"])
+
+
+def test_batchnorm_q_pinned_to_reference(golden):
+    """QU:94-207: outputs of the UNMODIFIED reference classes with only torch >= 2's Python-level
+    `eps <= 0` guard bypassed (oracle/make_golden.py::golden_bnq) - bit for bit."""
+    g = golden("ultra_bnq")
+    for dim, fwd in ((2, ref_ultra.batchnorm2d_q_forward), (1, ref_ultra.batchnorm1d_q_forward)):
+        gam, bet, mu, var = (_t(g[f"bn{dim}d.{k}"]) for k in ("weight", "bias", "running_mean", "running_var"))
+        x = _t(g[f"bn{dim}d.x"])
+        for bits in (2, 4, 8):
+            assert np.array_equal(fwd(x, gam, bet, mu, var, 1e-5, bits).numpy(), g[f"bn{dim}d.bit{bits}.y"]), (dim, bits)
+
+
+@pytest.mark.parametrize("tag", ["lin", "nl"])
+def test_qat_autograd_matches_reference(golden, tag):
+    """Config 3 parity of the ORACLE: ref_models.vit_forward_autograd (quantizers differentiated by ref_geta.SymQuantFn)
+    against the reference's own autograd on the depth-2, D = 768 ViT (tests/golden/qat_vit_d768_*.npz): loss, logits, every
+    quantizer-scalar gradient and the digest of every other gradient."""
+    import os
+    from tests import fixtures
+    g = golden(f"qat_vit_d768_{tag}")
+    img, patch, dim, depth, heads, classes = [int(v) for v in g["cfg"]]
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = fixtures.vit_state_dict(img, patch, dim, depth, heads, classes, seed=int(g["fill_seed"]))
+    for k, v in zip(g["q.names"], g["q.values"]):
+        sd[str(k)] = torch.tensor([float(v)], dtype=torch.float32)
+    params = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    x = fixtures.vit_input(int(g["batch"]), img, seed=1)
+    assert abs(float(x.double().sum()) - float(g["x_sum"])) < 1e-6
+    logits = ref_models.vit_forward_autograd(params, x, depth, heads, patch)
+    loss = torch.nn.functional.cross_entropy(logits, _t(g["labels"]))
+    loss.backward()
+    assert np.array_equal(logits.detach().numpy(), g["logits"])
+    assert abs(loss.item() - float(g["loss"])) <= 1e-6
+    worst = 0.0
+    for n in [str(s) for s in g["g.names"]]:
+        st, smp = ref_models.grad_digest(params[n].grad)
+        ref_st, ref_smp = g[f"g.{n}.stats"], g[f"g.{n}.samples"]
+        tol = 1e-5 * max(abs(ref_st[1]), 1e-30)
+        assert abs(st[0] - ref_st[0]) <= tol and abs(st[1] - ref_st[1]) <= tol and abs(st[2] - ref_st[2]) <= 1e-5 * ref_st[2] + 1e-12, n
+        err = np.abs(smp - ref_smp).max() / max(np.abs(ref_smp).max(), 1e-30)
+        worst = max(worst, err)
+        assert err <= 1e-5, (n, err)
+    print(f"qat {tag}: {len(g['g.names'])} gradients, worst sampled deviation {worst:.2e}")
