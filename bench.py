@@ -329,9 +329,9 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         tc = time.perf_counter()
-        ips, sec, threads, kind = cpu_arm(16, repeats=12, warmup=1)
+        ips, sec, threads, kind = cpu_arm(32, repeats=12, warmup=1)
         cpu = {"value": ips, "unit": UNIT, "cores": threads, "kind": kind,
-               "sample": f"16-image sub-batch of the 256-image step, median of 12 forwards ({time.perf_counter() - tc:.0f} s of CPU work)"}
+               "sample": f"32-image sub-batch of the 256-image step, median of 12 forwards ({time.perf_counter() - tc:.0f} s of CPU work)"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "int8 codes x int8 codes -> int32 (tcgen05 kind::i8); fp32 epilogues, LayerNorm, residual stream and attention",

@@ -234,7 +234,7 @@ def test_requantize_epilogue_codes_equal_oracle(ops, bits, t_next):
     a = _codes(M, K, -7, 7, 61).cuda()
     w = _codes(N, K, -7, 7, 62).cuda()
     bias = torch.randn(N).cuda() * 0.3
-    qm = 1.7
+    qm = 0.8                         # |y| reaches ~1.5: saturation (|y| >= q_m) is exercised
     sat = 2 ** (bits - 1) - 1
     if t_next is None:
         d_next = qm / sat
