@@ -181,7 +181,11 @@ enum {
   QVIT_OUT_F32 = 1,   /* y                                                       out: fp32   [M, ldo] */
   QVIT_OUT_BF16 = 2,  /* y rounded to bf16                                         out: bf16   [M, ldo] */
   QVIT_OUT_I8 = 3,    /* y re-quantised with (next_d, next_qm[, next_t]) -> int8 codes  out: int8 [M, ldo] */
-  QVIT_OUT_NONE = 4   /* nothing is stored (out may be NULL): times the TMA/MMA main loop alone (bench only)  */
+  QVIT_OUT_NONE = 4,  /* nothing is stored (out may be NULL): times the TMA/MMA main loop alone (bench only)  */
+  QVIT_OUT_F16X2 = 5  /* y as TWO fp16 planes, hi = fp16(y), lo = fp16(y - hi): 22 significant bits in the bytes of one
+                         fp32, directly consumable by fp16 tensor-core MMAs (qvit_attention_f16x2).  out: fp16 [M, ldo],
+                         hi in columns [0, N), lo in columns [ldo/2, ldo/2 + N); N % 32 == 0, ldo % 16 == 0.  The caller
+                         keeps |y| < 65504 through col_scale (a power of two per column scales y exactly).      */
 };
 enum { QVIT_ACT_NONE = 0, QVIT_ACT_GELU = 1, QVIT_ACT_RELU = 2 };
 enum { QVIT_GEMM_AUTO = 0, QVIT_GEMM_TCGEN05 = 1, QVIT_GEMM_SIMT = 2 };
@@ -267,6 +271,21 @@ int qvit_attention_quantize_sym(const float* qkv, int B, int T, int H, int head_
                                 int32_t* flags, qvit_stream_t stream);
 int qvit_attention_f32_debug(const float* qkv, int B, int T, int H, int head_dim, float scale, float* out,
                              float* dbg, int diag, qvit_stream_t stream);
+
+/* Attention core from the TWO-PLANE fp16 form of qkv (what qvit_gemm_i8 writes with QVIT_OUT_F16X2): planes fp16 [B, T, ld],
+ * hi plane in columns [0, 3*H*64) (q | k | v, head-major inside a part), lo plane in [plane_off, plane_off + 3*H*64);
+ * exp_q / exp_k / exp_v = the powers of two q / k / v were multiplied by.  Products are evaluated as hi*hi' + hi*lo' + lo*hi' on
+ * tcgen05 kind::f16 with fp32 accumulation (fp32-equivalent accuracy, half the tensor-core work of the 3 x bf16 split and no
+ * conversion work: operand tiles arrive by TMA).  codes (the consumer's quantize_act, QL:356-381) and / or out (fp32 context
+ * [B, T, H*64]) as in qvit_attention_quantize_sym; prof: optional device buffer of 128 clock stamps (developer timeline).
+ * head_dim == 64, T <= 208.                                                                                              */
+int qvit_attention_f16x2(const void* planes, int64_t ld, int plane_off, int B, int T, int H, int head_dim, float scale,
+                         int exp_q, int exp_k, int exp_v, const float* d, const float* q_m, const float* t, int8_t* codes,
+                         int64_t ld_codes, float* out, int32_t* flags, long long* prof, qvit_stream_t stream);
+/* fp32 [rows, ldx] -> the two-plane fp16 form, x * 2^col_exp[c] = hi + lo: out fp16 [rows, ld], hi in columns [0, cols), lo in
+ * [plane_off, plane_off + cols).  For callers that hold qkv in fp32 (drop-in modules); sets QVIT_FLAG_OVERFLOW on |x| >= 65504. */
+int qvit_split2_f16(const float* x, int64_t rows, int cols, int64_t ldx, const int* col_exp, void* out, int64_t ld,
+                    int plane_off, int32_t* flags, qvit_stream_t stream);
 
 #ifdef __cplusplus
 }

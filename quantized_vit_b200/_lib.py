@@ -14,7 +14,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libqvit_b200.so")
 
-QVIT_OUT_I32, QVIT_OUT_F32, QVIT_OUT_BF16, QVIT_OUT_I8, QVIT_OUT_NONE = 0, 1, 2, 3, 4
+QVIT_OUT_I32, QVIT_OUT_F32, QVIT_OUT_BF16, QVIT_OUT_I8, QVIT_OUT_NONE, QVIT_OUT_F16X2 = 0, 1, 2, 3, 4, 5
 QVIT_ACT_NONE, QVIT_ACT_GELU, QVIT_ACT_RELU = 0, 1, 2
 QVIT_GEMM_AUTO, QVIT_GEMM_TCGEN05, QVIT_GEMM_SIMT = 0, 1, 2
 QVIT_FLAG_NAN, QVIT_FLAG_OVERFLOW, QVIT_FLAG_NAN_GRAD = 1, 2, 4
@@ -67,6 +67,8 @@ PROTOTYPES = {
     "qvit_attention_f32": (_i, [_p, _i, _i, _i, _i, _f, _p, _p]),
     "qvit_attention_quantize_sym": (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "qvit_attention_f32_debug": (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _i, _p]),
+    "qvit_attention_f16x2": (_i, [_p, _i64, _i, _i, _i, _i, _i, _f, _i, _i, _i, _p, _p, _p, _p, _i64, _p, _p, _p, _p]),
+    "qvit_split2_f16": (_i, [_p, _i64, _i, _i64, _p, _p, _i64, _i, _p, _p]),
     "qvit_quantize_sym_bf16": (_i, [_p, _i64, _i64, _i64, _p, _p, _p, _p, _i64, _p, _p]),
 }
 

@@ -5,6 +5,8 @@
 // F.linear adds the bias), nn.GELU of Mlp.forward (vit_model.py:173), the residual adds of Block.forward
 // (vit_model.py:206-207) and the next layer's quantize_act (quant_layers.py:356-381).
 #pragma once
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace qvit {
@@ -60,6 +62,13 @@ __device__ __forceinline__ void epi_store_one(const EpiParams& e, const SymParam
     return;
   }
   const float y = epi_value(e, acc, scale, m, n);
+  if (e.out_kind == QVIT_OUT_F16X2) {
+    const __half hi = __float2half_rn(y);
+    __half* o = reinterpret_cast<__half*>(e.out);
+    o[m * e.ldo + n] = hi;
+    o[m * e.ldo + e.ldo / 2 + n] = __float2half_rn(y - __half2float(hi));
+    return;
+  }
   if (e.out_kind == QVIT_OUT_F32) reinterpret_cast<float*>(e.out)[m * e.ldo + n] = y;
   else if (e.out_kind == QVIT_OUT_BF16) reinterpret_cast<__nv_bfloat16*>(e.out)[m * e.ldo + n] = __float2bfloat16_rn(y);
   else reinterpret_cast<int8_t*>(e.out)[m * e.ldo + n] = (int8_t)sym_code(y, *nq, fl);

@@ -124,7 +124,9 @@ extern "C" int qvit_gemm_i8(const void* a, int64_t lda, int a_unsigned, const in
   QVIT_REQUIRE(epi->out_kind == QVIT_OUT_NONE || (out != nullptr && ldo >= N), "qvit_gemm_i8: bad output (ldo=%lld < N=%d?)",
                (long long)ldo, N);
   QVIT_REQUIRE(K == 0 || (a != nullptr && w != nullptr && lda >= K && ldw >= K), "qvit_gemm_i8: bad operands");
-  QVIT_REQUIRE(epi->out_kind >= QVIT_OUT_I32 && epi->out_kind <= QVIT_OUT_NONE, "qvit_gemm_i8: bad out_kind %d", epi->out_kind);
+  QVIT_REQUIRE(epi->out_kind >= QVIT_OUT_I32 && epi->out_kind <= QVIT_OUT_F16X2, "qvit_gemm_i8: bad out_kind %d", epi->out_kind);
+  QVIT_REQUIRE(epi->out_kind != QVIT_OUT_F16X2 || (N % 32 == 0 && ldo % 16 == 0 && ldo / 2 >= N && !epi->residual),
+               "qvit_gemm_i8: QVIT_OUT_F16X2 needs N %% 32 == 0, ldo %% 16 == 0, ldo / 2 >= N and no residual");
   QVIT_REQUIRE(epi->act >= QVIT_ACT_NONE && epi->act <= QVIT_ACT_RELU, "qvit_gemm_i8: bad act %d", epi->act);
   QVIT_REQUIRE(epi->out_kind != QVIT_OUT_I8 || (epi->next_d && epi->next_qm), "qvit_gemm_i8: QVIT_OUT_I8 needs next_d/next_qm");
   QVIT_REQUIRE(!epi->residual || epi->ld_res >= N, "qvit_gemm_i8: ld_res < N");

@@ -41,17 +41,34 @@ struct GemmSmem {
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOutBytes = 4 * kBoxBytes;     // one buffer per quad
   static constexpr int kBarBytes = 512;
-  static constexpr int kBiasBytes = kEpiWarps * 256;   // per epilogue warp: the 64 bias values of its columns of the current tile
+  // per epilogue warp: the 64 bias values and the 64 column scales of its columns, for the current and the next tile
+  static constexpr int kBiasBytes = kEpiWarps * 512 * 2;
   static constexpr int kTotal = kStages * kStageBytes + kOutBytes + kBarBytes + kBiasBytes + 1024;   // +1024 for manual alignment
 };
 
 __host__ __device__ constexpr int out_elem_size(int out_kind) {
-  return out_kind == QVIT_OUT_BF16 ? 2 : (out_kind == QVIT_OUT_I8 ? 1 : 4);
+  return (out_kind == QVIT_OUT_BF16 || out_kind == QVIT_OUT_F16X2) ? 2 : (out_kind == QVIT_OUT_I8 ? 1 : 4);
 }
 // bytes one quad contributes per output row and tile, capped at the 128 B of a swizzle atom: the TMA-store box width
+// (two fp16 planes: one 64-byte box per plane and 32-column chunk, both staged in the warp's 4 KiB slab)
 __host__ __device__ constexpr int out_box_bytes(int bn, int out_kind) {
-  return (bn / 4) * out_elem_size(out_kind) > 128 ? 128 : (bn / 4) * out_elem_size(out_kind);
+  return out_kind == QVIT_OUT_F16X2 ? 64
+                                    : ((bn / 4) * out_elem_size(out_kind) > 128 ? 128 : (bn / 4) * out_elem_size(out_kind));
 }
+
+// SPEC: 0 = every epilogue option is decided at run time (warp-uniform branches).  Otherwise the hot configurations of the
+// ViT step with the options as compile-time constants - bit 0 = specialised, bits 1-2 = activation, bit 3 = bias, bit 4 =
+// col_scale - so that the chunk loop carries no branches, no reconvergence scopes and none of the register shuffling the
+// merged paths cost (the profile of the generic kernel: ~110 of 674 instructions per chunk).  The host picks a specialised
+// instance only when acc_abs_max < 2^22 was promised and (int8 output) the consumer quantizer is linear.
+template <int SPEC>
+struct EpiSpec {
+  static constexpr bool on = (SPEC & 1) != 0;
+  static constexpr int act = (SPEC >> 1) & 3;
+  static constexpr bool bias = ((SPEC >> 3) & 1) != 0;
+  static constexpr bool cs = ((SPEC >> 4) & 1) != 0;
+};
+constexpr int make_spec(int act, bool bias, bool cs) { return 1 | (act << 1) | ((bias ? 1 : 0) << 3) | ((cs ? 1 : 0) << 4); }
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -67,14 +84,15 @@ __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, ui
 __device__ __forceinline__ void lds_pair2(uint32_t addr, f32x2& a, f32x2& b) {
   asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(a), "=l"(b) : "r"(addr));
 }
-template <bool FACC>
-__device__ __forceinline__ void epi_math32(const EpiParams& e, const uint32_t (&acc)[32], float scale, int n0, uint32_t bias_sm,
+template <bool FACC, int SPEC>
+__device__ __forceinline__ void epi_math32(const EpiParams& e, const uint32_t (&acc)[32], float scale, uint32_t bias_sm, uint32_t cs_sm,
                                            f32x2 (&y)[16]) {
+  using SP = EpiSpec<SPEC>;
   // accumulator -> fp32
   if (FACC) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) y[j] = pk2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
-  } else if (e.acc_abs_max > 0 && e.acc_abs_max < (1 << 22)) {
+  } else if (SP::on || (e.acc_abs_max > 0 && e.acc_abs_max < (1 << 22))) {
     // |acc| < 2^22: as_float(0x4B400000 + acc) = 1.5 * 2^23 + acc exactly, so one integer add and one fp32 subtract give
     // float(acc) without the quarter-rate conversion unit
     const f32x2 mm = pk1(-kRoundMagic);
@@ -85,25 +103,30 @@ __device__ __forceinline__ void epi_math32(const EpiParams& e, const uint32_t (&
 #pragma unroll
     for (int j = 0; j < 16; ++j) y[j] = pk2((float)(int32_t)acc[2 * j], (float)(int32_t)acc[2 * j + 1]);
   }
-  // y = fma(acc, scale * col_scale[n], bias[n])  (the canonical sequence of epilogue.cuh)
+  // y = fma(acc, scale * col_scale[n], bias[n])  (the canonical sequence of epilogue.cuh); bias and column scales of the
+  // chunk come from the warp's shared-memory prefetch
   const f32x2 s2 = pk1(scale);
-  if (e.col_scale) {
+  const bool has_cs = SP::on ? SP::cs : (e.col_scale != nullptr);
+  const bool has_bias = SP::on ? SP::bias : (e.bias != nullptr);
+  const int act = SP::on ? SP::act : e.act;
+  if (has_cs) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
-      const float4 c = __ldg(reinterpret_cast<const float4*>(e.col_scale + n0) + j);
-      y[2 * j] = mul2(y[2 * j], mul2(s2, pk2(c.x, c.y)));          // (acc * (scale * cs)): same product as fma(acc, s, 0)
-      y[2 * j + 1] = mul2(y[2 * j + 1], mul2(s2, pk2(c.z, c.w)));
-    }
-    if (e.bias) {
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      f32x2 c0, c1;
+      lds_pair2(cs_sm + 16u * j, c0, c1);
+      c0 = mul2(s2, c0);                                         // (scale * cs): same product as epi_value_f
+      c1 = mul2(s2, c1);
+      if (has_bias) {
         f32x2 b0, b1;
         lds_pair2(bias_sm + 16u * j, b0, b1);
-        y[2 * j] = add2(y[2 * j], b0);
-        y[2 * j + 1] = add2(y[2 * j + 1], b1);
+        y[2 * j] = fma2(y[2 * j], c0, b0);
+        y[2 * j + 1] = fma2(y[2 * j + 1], c1, b1);
+      } else {
+        y[2 * j] = mul2(y[2 * j], c0);
+        y[2 * j + 1] = mul2(y[2 * j + 1], c1);
       }
     }
-  } else if (e.bias) {
+  } else if (has_bias) {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       f32x2 b0, b1;
@@ -115,10 +138,10 @@ __device__ __forceinline__ void epi_math32(const EpiParams& e, const uint32_t (&
 #pragma unroll
     for (int j = 0; j < 16; ++j) y[j] = mul2(y[j], s2);
   }
-  if (e.act == QVIT_ACT_GELU) {
+  if (act == QVIT_ACT_GELU) {
 #pragma unroll
     for (int g = 0; g < 4; ++g) gelu_erf2x4(reinterpret_cast<f32x2(&)[4]>(y[4 * g]));
-  } else if (e.act == QVIT_ACT_RELU) {
+  } else if (act == QVIT_ACT_RELU) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) {
       float a, b;
@@ -198,7 +221,7 @@ __device__ __forceinline__ long long global_ns() {
 // KIND 0: int8 x int8 -> int32 (tcgen05 kind::i8).  KIND 1: bf16 x bf16 -> fp32 (kind::f16) for the QAT gradient GEMMs:
 // the fp32 gradient operand arrives as three exact bf16 planes concatenated along K, the integer codes as one bf16
 // plane that is re-read for every A plane (`b_wrap` k-blocks), i.e. D = (A1 + A2 + A3) * B^T with fp32 accumulation.
-template <int BN, int OUT, int CG, int KIND>
+template <int BN, int OUT, int CG, int KIND, int SPEC>
 // (96 registers is the ceiling for 18 warps: the register file is allocated per warp in units that put 104..112 out of reach)
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
@@ -378,6 +401,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // the row goes to the warp's PRIVATE staging slab (XOR-swizzled, conflict free) -> one lane issues a TMA store of
     // the [32 rows x <= 128 B] box.  Nothing wider than the warp synchronises; the slab drains asynchronously while the
     // warp loads and converts its next chunk.
+    using SP = EpiSpec<SPEC>;
     const int lane_grp = warp & 3;                           // TMEM lanes [32*lane_grp, +32) are this warp's
     const int ew = warp - 2;                                 // 0..15
     const int quad = ew >> 2;                                // 0..3: which quarter of the tile's columns
@@ -391,6 +415,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     SymParams nq;
     FastQ2 fq;
     fq.generic = 0;
+    fq.nl = 0;
     if (OUT == QVIT_OUT_I8) {
       nq = load_sym_params(ep.next_d, ep.next_qm, ep.next_t);
       fq = make_fastq2(nq);
@@ -403,30 +428,51 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     const uint32_t slab = out_base + (uint32_t)(ew * 4096);
     const uint32_t row_off = (uint32_t)(lane * kBoxW);
     const uint32_t sw = (row_off >> 7) & kSwzMask;
-    const uint32_t bias_sm = bar_base + (uint32_t)S::kBarBytes + (uint32_t)(ew * 256);   // this warp's 64 bias values of the tile
+    // this warp's prefetch area: [buffer][bias 64 floats | col_scale 64 floats]
+    const uint32_t pre_sm = bar_base + (uint32_t)S::kBarBytes + (uint32_t)(ew * 1024);
+    const bool has_bias = SP::on ? SP::bias : (ep.bias != nullptr);
+    const bool has_cs = SP::on ? SP::cs : (ep.col_scale != nullptr);
     // hot path = packed-pair math on whole, aligned chunks; anything else (warp-uniform conditions only) takes
     // epi_chunk_generic.  tma_store: the output is TMA-addressable (16-byte pointer and pitch); 2 = benchmark, store nothing.
-    const bool hot_ok = tma_store && !fq.generic && (!ep.col_scale || ((reinterpret_cast<uintptr_t>(ep.col_scale) & 15) == 0)) &&
-                        (!ep.residual || use_res_tma) && !(mma_only_flags & 8);
-    // bias of the warp's columns: loaded one tile ahead into registers, parked in shared memory for the tile
-    float nb[kChunksPerQuad];
-    auto bias_fetch = [&](int t) {
-      const int nblk = (t / ksplit) % n_tiles;
+    // (A specialised instance still checks the consumer quantizer: q_m <= 0 or codes beyond 127 are device-side facts.)
+    const bool hot_ok = (OUT == QVIT_OUT_F16X2) ||
+                        (tma_store && !fq.generic && (SP::on ? !fq.nl : true) && (!ep.residual || use_res_tma) && !(mma_only_flags & 8));
+    // tile -> (m_blk, n_blk): one division at the start, then incremental (the per-tile division cost ~60 instructions)
+    const int step_m = tile_step / n_tiles, step_n = tile_step - step_m * n_tiles;
+    int tile = tile_first;
+    int m_blk = (tile / ksplit) / n_tiles, n_blk = (tile / ksplit) - m_blk * n_tiles;
+    // bias / column scales of the warp's columns: copied one tile ahead straight into shared memory (cp.async, no
+    // registers held across the tile; a global load inside the chunk loop would queue behind the warp's own stores)
+    auto prefetch_cols = [&](int nblk, int buf) {
 #pragma unroll
       for (int cq = 0; cq < kChunksPerQuad; ++cq) {
         const int col = nblk * BN + (quad * kChunksPerQuad + cq) * 32 + lane;
-        nb[cq] = (ep.bias && t < total_tiles && col < ep.N) ? __ldg(ep.bias + col) : 0.0f;
+        const uint32_t dst = pre_sm + (uint32_t)(buf * 512 + cq * 128 + lane * 4);
+        const uint32_t nbytes = (col < ep.N) ? 4u : 0u;          // beyond N: zero fill
+        if (has_bias)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(ep.bias + (col < ep.N ? col : 0)), "r"(nbytes) : "memory");
+        if (has_cs)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 256u), "l"(ep.col_scale + (col < ep.N ? col : 0)), "r"(nbytes) : "memory");
       }
     };
-    bias_fetch(tile_first);
-    for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
-      const int t2 = tile / ksplit;
-      const int m_blk = t2 / n_tiles, n_blk = t2 - m_blk * n_tiles;
-#pragma unroll
-      for (int cq = 0; cq < kChunksPerQuad; ++cq)
-        asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_sm + (uint32_t)(cq * 128 + lane * 4)), "f"(nb[cq]) : "memory");
-      bias_fetch(tile + tile_step);                          // lands while this tile is processed
+    int pbuf = 0;
+    if (tile < total_tiles) prefetch_cols(n_blk, 0);
+    for (; tile < total_tiles; tile += tile_step) {
+      // next tile's coordinates
+      int m_next, n_next;
+      if (ksplit == 1) {
+        n_next = n_blk + step_n;
+        m_next = m_blk + step_m;
+        if (n_next >= n_tiles) { n_next -= n_tiles; ++m_next; }
+      } else {
+        const int t2n = (tile + tile_step) / ksplit;
+        m_next = t2n / n_tiles;
+        n_next = t2n - m_next * n_tiles;
+      }
+      asm volatile("cp.async.wait_all;" ::: "memory");         // this tile's bias / scales have landed (issued a tile ago)
       __syncwarp();
+      if (tile + tile_step < total_tiles) prefetch_cols(n_next, pbuf ^ 1);
+      const uint32_t bias_sm = pre_sm + (uint32_t)(pbuf * 512);
       ptx::mbar_wait(tfull_bar(acc), acc_phase);
       ptx::tc_fence_after();
       QVIT_PROF(2);
@@ -471,7 +517,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               for (int j = 0; j < 32; ++j) w[j % (kChunkBytes / 4)] = r[j];      // kChunkBytes/4 == 32 here
             } else {
               f32x2 y[16];
-              epi_math32<KIND == 1>(ep, r, scale, n0, bias_sm + (uint32_t)(cq * 128), y);
+              epi_math32<KIND == 1, SPEC>(ep, r, scale, bias_sm + (uint32_t)(cq * 128), bias_sm + 256u + (uint32_t)(cq * 128), y);
               if (use_res_tma) {
                 ptx::mbar_wait(res_bar(ew), res_phase);
                 res_phase ^= 1u;
@@ -499,9 +545,30 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                   const __nv_bfloat162 p2 = __floats2bfloat162_rn(a, b);
                   w[j % (kChunkBytes / 4)] = *reinterpret_cast<const uint32_t*>(&p2);
                 }
+              } else if (OUT == QVIT_OUT_F16X2) {
+                // hi = fp16(y), lo = fp16(y - hi): the residual is exact in fp32, so hi + lo carries 22 significant bits of y.
+                // The lo plane is staged in the upper half of the slab and leaves with its own TMA store.
+                uint32_t wl[16];
+                const f32x2 mone = pk1(-1.0f);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                  float a, b;
+                  unpk2(y[j], a, b);
+                  const __half2 h2 = __floats2half2_rn(a, b);
+                  const float2 hf = __half22float2(h2);
+                  float ra, rb;
+                  unpk2(fma2(pk2(hf.x, hf.y), mone, y[j]), ra, rb);
+                  const __half2 l2 = __floats2half2_rn(ra, rb);
+                  w[j % (kChunkBytes / 4)] = *reinterpret_cast<const uint32_t*>(&h2);
+                  wl[j] = *reinterpret_cast<const uint32_t*>(&l2);
+                  if (!(fabsf(hf.x) <= 65504.0f) || !(fabsf(hf.y) <= 65504.0f)) fl |= kFlagOverflow;   // inf / NaN: the caller's scale is wrong
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                  sts_v4(slab + 2048u + row_off + ((((uint32_t)j) ^ sw) << 4), wl[4 * j], wl[4 * j + 1], wl[4 * j + 2], wl[4 * j + 3]);
               } else {
                 f32x2 dacc = pk1(0.0f);
-                if (fq.nl) {
+                if (!SP::on && fq.nl) {
 #pragma unroll
                   for (int j = 0; j < 8; ++j) w[j % (kChunkBytes / 4)] = sym_codes4_fast2<true>(y[2 * j], y[2 * j + 1], fq, dacc);
                 } else {
@@ -511,7 +578,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 float d0, d1;
                 unpk2(dacc, d0, d1);
                 bool bad = false;
-                if ((!(d0 + d1 == 0.0f) || (mma_only_flags & 4)) && fq.nl) {
+                if (!SP::on && (!(d0 + d1 == 0.0f) || (mma_only_flags & 4)) && fq.nl) {
                   // non-linear quantizer: the rows the interval test cannot decide get the scalar sequence (expf / logf /
                   // IEEE division), out of line, 16 elements per call
                   float a[32];
@@ -559,9 +626,11 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             ptx::mbar_wait(res_bar(ew), res_phase);
             res_phase ^= 1u;
           }
-          if (redo && tma_store != 2)
-            epi_chunk_generic<OUT, KIND == 1>(ep, nq, t_row + (uint32_t)(c * 32), scale, m, n0, row_ok,
-                                              tma_store ? slab + row_off : 0u, sw, byte0, &fl);
+          if (OUT != QVIT_OUT_F16X2) {
+            if (redo && tma_store != 2)
+              epi_chunk_generic<OUT, KIND == 1>(ep, nq, t_row + (uint32_t)(c * 32), scale, m, n0, row_ok,
+                                                tma_store ? slab + row_off : 0u, sw, byte0, &fl);
+          }
         }
         if (last) {                                          // all TMEM reads of this warp for this tile are done
           QVIT_PROF(6);
@@ -581,6 +650,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             if (lane == 0) {
               if (ksplit > 1) ptx::tma_reduce_add_2d(&tmap_out, slab, box_n0, row0);   // split-K partials add up in global memory
               else ptx::tma_store_2d(&tmap_out, slab, box_n0, row0);
+              if (OUT == QVIT_OUT_F16X2) ptx::tma_store_2d(&tmap_out, slab + 2048u, box_n0 + (int)(ep.ldo >> 1), row0);
               ptx::tma_store_commit();
             }
           }
@@ -591,6 +661,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       ++prof_tile;
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1u;
+      pbuf ^= 1;
+      m_blk = m_next;
+      n_blk = n_next;
     }
     if (tma_store == 1 && lane == 0) ptx::tma_store_wait_read<0>();   // the slab must outlive the reads; the writes complete with the grid
     fl = warp_or(fl);
@@ -668,6 +741,7 @@ static int make_tmap_out(CUtensorMap* map, void* base, int64_t M, int64_t N, int
   const int esz = out_elem_size(out_kind);
   if (out_kind == QVIT_OUT_I32) dt = CU_TENSOR_MAP_DATA_TYPE_INT32;
   else if (out_kind == QVIT_OUT_BF16) dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  else if (out_kind == QVIT_OUT_F16X2) dt = CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   else if (out_kind == QVIT_OUT_I8) dt = CU_TENSOR_MAP_DATA_TYPE_UINT8;
   const CUtensorMapSwizzle swz = box_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
                                                   : (box_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
@@ -723,7 +797,7 @@ struct TcMaps {
   int tma_store, res_tma;
 };
 
-template <int BN, int OUT, int CG, int KIND = 0>
+template <int BN, int OUT, int CG, int KIND = 0, int SPEC = 0>
 static int launch_tc(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsigned, int max_ctas, cudaStream_t s,
                      int b_wrap = 1 << 30, int ksplit = 1) {
   using S = GemmSmem<BN, CG>;
@@ -731,7 +805,7 @@ static int launch_tc(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsign
   int dev = 0;
   cudaGetDevice(&dev);
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel<BN, OUT, CG, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
+    cudaError_t e = cudaFuncSetAttribute(gemm_i8_tc_kernel<BN, OUT, CG, KIND, SPEC>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::kTotal);
     if (e != cudaSuccess) {
       set_error("cudaFuncSetAttribute(smem=%d): %s", S::kTotal, cudaGetErrorString(e));
       return QVIT_ERR_CUDA;
@@ -755,7 +829,7 @@ static int launch_tc(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsign
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_i8_tc_kernel<BN, OUT, CG, KIND>, tm.a, tm.w, tm.out, tm.res, ep, K, idesc,
+  cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_i8_tc_kernel<BN, OUT, CG, KIND, SPEC>, tm.a, tm.w, tm.out, tm.res, ep, K, idesc,
                                      (tm.tma_store && g_skip_store) ? 2 : tm.tma_store, tm.res_tma, g_mma_only | (g_profile << 1) | (g_force_path == 1 ? 4 : 0) | (g_force_path == 2 ? 8 : 0), b_wrap, ksplit);
   if (e != cudaSuccess) {
     set_error("gemm_i8_tc_kernel launch: %s", cudaGetErrorString(e));
@@ -766,11 +840,25 @@ static int launch_tc(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsign
 
 template <int BN, int CG>
 static int launch_tc_kind(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsigned, int max_ctas, cudaStream_t s) {
+  // Specialised instances for the configurations of the ViT step (all on [128 x 256] tiles): options known on the host become
+  // template constants.  Requirements: the caller's acc_abs_max promise (< 2^22), staged TMA stores, no forced test path, a
+  // linear consumer quantizer for int8 output and a TMA-staged residual where there is one.
+  if constexpr (BN == 256) if (tm.tma_store == 1 && g_force_path == 0 && ep.acc_abs_max > 0 && ep.acc_abs_max < (1 << 22)) {
+    const bool b = ep.bias != nullptr, c = ep.col_scale != nullptr;
+    const bool res_ok = (ep.residual == nullptr) || tm.res_tma;
+    if (ep.out_kind == QVIT_OUT_I8 && ep.act == QVIT_ACT_GELU && b && !c && !ep.next_t && !ep.residual)
+      return launch_tc<BN, QVIT_OUT_I8, CG, 0, make_spec(QVIT_ACT_GELU, true, false)>(tm, ep, K, a_unsigned, max_ctas, s);
+    if (ep.out_kind == QVIT_OUT_F32 && ep.act == QVIT_ACT_NONE && b && !c && res_ok)
+      return launch_tc<BN, QVIT_OUT_F32, CG, 0, make_spec(QVIT_ACT_NONE, true, false)>(tm, ep, K, a_unsigned, max_ctas, s);
+    if (ep.out_kind == QVIT_OUT_F16X2 && ep.act == QVIT_ACT_NONE && b && c)
+      return launch_tc<BN, QVIT_OUT_F16X2, CG, 0, make_spec(QVIT_ACT_NONE, true, true)>(tm, ep, K, a_unsigned, max_ctas, s);
+  }
   switch (ep.out_kind) {
     case QVIT_OUT_I32: return launch_tc<BN, QVIT_OUT_I32, CG>(tm, ep, K, a_unsigned, max_ctas, s);
     case QVIT_OUT_F32: return launch_tc<BN, QVIT_OUT_F32, CG>(tm, ep, K, a_unsigned, max_ctas, s);
     case QVIT_OUT_BF16: return launch_tc<BN, QVIT_OUT_BF16, CG>(tm, ep, K, a_unsigned, max_ctas, s);
     case QVIT_OUT_I8: return launch_tc<BN, QVIT_OUT_I8, CG>(tm, ep, K, a_unsigned, max_ctas, s);
+    case QVIT_OUT_F16X2: return launch_tc<BN, QVIT_OUT_F16X2, CG>(tm, ep, K, a_unsigned, max_ctas, s);
     default: return launch_tc<BN, QVIT_OUT_NONE, CG>(tm, ep, K, a_unsigned, max_ctas, s);
   }
 }
@@ -809,7 +897,15 @@ int gemm_tc_launch(const void* a, int64_t lda, int a_unsigned, const int8_t* w, 
                  (((ep.ldo * esz) & 15) == 0) && !g_no_tma_store;
   tm.out = tm.a;
   tm.res = tm.a;
-  if (tm.tma_store) {
+  if (ep.out_kind == QVIT_OUT_F16X2) {
+    if (!tm.tma_store || (ep.col_scale && (reinterpret_cast<uintptr_t>(ep.col_scale) & 3))) {
+      set_error("qvit_gemm_i8: QVIT_OUT_F16X2 needs a 16-byte aligned output with a pitch that is a multiple of 8 halves");
+      return QVIT_ERR_UNSUPPORTED;
+    }
+    // one map over both planes: hi in columns [0, N), lo in [ldo / 2, ldo / 2 + N)
+    rc = make_tmap_out(&tm.out, ep.out, M, ep.ldo / 2 + N, ep.ldo, ep.out_kind, 64, 32);
+    if (rc) return rc;
+  } else if (tm.tma_store) {
     rc = make_tmap_out(&tm.out, ep.out, M, N, ep.ldo, ep.out_kind, out_box_bytes(bn, ep.out_kind), 32);
     if (rc) return rc;
   }

@@ -5,8 +5,8 @@ VisionTransformer.forward :290-328 with every Linear/Conv2d swapped by ``model_t
 What is fused around the integer GEMMs (per Block):
     LayerNorm1 + quantize(qkv)            one kernel   (qvit_layernorm_quantize)
     qkv GEMM + bias                       tcgen05 int8 (qvit_gemm_i8, fp32 or bf16 out)
-    softmax(QK^T)V                        library fused attention (NOT quantized upstream; out of the hot path)
-    quantize(proj)                        one kernel   (qvit_quantize_sym / _bf16)
+    qkv GEMM epilogue                     q / k / v as two fp16 planes (hi + lo, QVIT_OUT_F16X2) in the attention kernel's operand layout
+    softmax(QK^T)V + quantize(proj)       own pipelined tcgen05 kernel (qvit_attention_f16x2; NOT quantized upstream: fp32-equivalent)
     proj GEMM + bias + residual           tcgen05 int8, residual added in the epilogue, in place on the stream
     LayerNorm2 + quantize(fc1)            one kernel
     fc1 GEMM + bias + GELU + quantize(fc2)  tcgen05 int8 -> int8 codes straight out of the epilogue
@@ -35,7 +35,8 @@ VIT_CONFIGS = {
 
 
 class _QLayer:
-    __slots__ = ("w_codes", "bias", "d_wt", "d_act", "qm_act", "t_act", "K", "N", "acc_abs_max")
+    __slots__ = ("w_codes", "bias", "d_wt", "d_act", "qm_act", "t_act", "K", "N", "acc_abs_max", "sat_act", "f16_exps",
+                 "f16_col_scale", "f16_bias")
 
 
 class ViTInferenceEngine:
@@ -50,9 +51,10 @@ class ViTInferenceEngine:
         if self.device.type != "cuda":
             raise RuntimeError("ViTInferenceEngine runs on CUDA (sm_100a) only - there is no CPU fallback")
         self.depth, self.num_heads, self.patch, self.eps, self.precision = depth, num_heads, patch_size, ln_eps, precision
-        if attention not in ("auto", "tc3x", "sdpa", "math"):
-            raise ValueError("attention must be 'auto', 'tc3x' (own tcgen05 kernel, exact 3 x bf16 split), 'sdpa' (library fused kernel) "
-                             "or 'math' (explicit fp32 matmul/softmax)")
+        if attention not in ("auto", "tc2x", "tc3x", "sdpa", "math"):
+            raise ValueError("attention must be 'auto', 'tc2x' (own pipelined tcgen05 kernel on the two-plane fp16 qkv the GEMM epilogue "
+                             "writes), 'tc3x' (own tcgen05 kernel, exact 3 x bf16 split of an fp32 qkv), 'sdpa' (library fused kernel) or "
+                             "'math' (explicit fp32 matmul/softmax)")
         self.attention = attention
         sd = {k: v.detach().to(self.device) for k, v in state_dict.items()}
         self.sd = sd
@@ -91,6 +93,8 @@ class ViTInferenceEngine:
                 raise ValueError(f"{name}: {what} codes reach {sat} > 127 - not representable on the int8 pipe")
             sats.append(int(sat))
         L.acc_abs_max = sats[0] * sats[1] * L.K      # |int32 accumulator| can never exceed this (epilogue hint)
+        L.sat_act = sats[1]
+        L.f16_exps = L.f16_col_scale = L.f16_bias = None
         flags = ops.new_flags(self.device)
         L.w_codes = ops.quantize_sym(w2, d, q, t, ld_codes=ops.pad16(L.K), flags=flags)
         L.bias = sd[f"{name}.bias"].float().contiguous() if f"{name}.bias" in sd else None
@@ -99,19 +103,39 @@ class ViTInferenceEngine:
         L.qm_act = sd[f"{name}.q_m_act"].float().reshape(1).contiguous()
         t_act = sd.get(f"{name}.t_quant_act")
         L.t_act = None if t_act is None else t_act.float().reshape(1).contiguous()
+        if name.endswith(".attn.qkv") and L.N % 96 == 0:
+            self._prepare_f16x2(L)
         return L
+
+    def _prepare_f16x2(self, L: _QLayer) -> None:
+        """Static power-of-two scales for the two-plane fp16 form of q / k / v (QVIT_OUT_F16X2 -> qvit_attention_f16x2).
+        Activations and weights are integer codes, so every output is bounded ahead of time:
+        |y_n| <= |d_a| |d_w| sat_a sum_k |w_code[n, k]| + |bias_n|.  With 2^e = 2^(15 - ceil(log2(max bound of the part)))
+        folded into the epilogue's column scale (exact: a power of two) no value can reach the fp16 limit, whatever the
+        input, and typical values (an order of magnitude or two below the bound) sit around 2^9 .. 2^11 where both planes
+        keep their full 11 significant bits."""
+        import math
+        bound = L.w_codes[:, :L.K].to(torch.float32).abs().sum(1) * (float(L.d_act.abs()) * float(L.d_wt.abs()) * L.sat_act)
+        if L.bias is not None:
+            bound = bound + L.bias.abs()
+        part = L.N // 3
+        exps = [ops.f16x2_exponent(float(bound[i * part:(i + 1) * part].max())) for i in range(3)]
+        cs = torch.cat([torch.full((part,), math.ldexp(1.0, e), dtype=torch.float32, device=self.device) for e in exps])
+        L.f16_exps, L.f16_col_scale = tuple(exps), cs
+        L.f16_bias = (L.bias if L.bias is not None else torch.zeros(L.N, dtype=torch.float32, device=self.device)) * cs
 
     def weight_bytes(self) -> int:
         return sum(L.w_codes.numel() for L in self.layers.values())
 
     # ------------------------------------------------------------------ forward
     def _gemm(self, a_codes, L: _QLayer, **kw):
+        kw.setdefault("bias", L.bias)
         if self.gemm_events is None:
-            return ops.gemm_i8(a_codes, L.w_codes, L.K, L.N, scale_a=L.d_act, scale_w=L.d_wt, bias=L.bias, flags=self.flags,
+            return ops.gemm_i8(a_codes, L.w_codes, L.K, L.N, scale_a=L.d_act, scale_w=L.d_wt, flags=self.flags,
                                acc_abs_max=L.acc_abs_max, **kw)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        y = ops.gemm_i8(a_codes, L.w_codes, L.K, L.N, scale_a=L.d_act, scale_w=L.d_wt, bias=L.bias, flags=self.flags,
+        y = ops.gemm_i8(a_codes, L.w_codes, L.K, L.N, scale_a=L.d_act, scale_w=L.d_wt, flags=self.flags,
                                acc_abs_max=L.acc_abs_max, **kw)
         e1.record()
         self.gemm_events.append((L, 2.0 * a_codes.shape[0] * L.K * L.N, e0, e1))
@@ -129,6 +153,19 @@ class ViTInferenceEngine:
         fc1_l, fc2_l = self.layers[f"{pre}.mlp.fc1"], self.layers[f"{pre}.mlp.fc2"]
         c1, _ = ops.layernorm_quantize(h2, sd[f"{pre}.norm1.weight"], sd[f"{pre}.norm1.bias"], self.eps, qkv_l.d_act,
                                        qkv_l.qm_act, qkv_l.t_act, flags=self.flags)
+        use_tc2x = (self.attention == "tc2x" or (self.attention == "auto" and not bf16)) and ops.attention_f32_supported(NT, hd) \
+            and qkv_l.f16_exps is not None
+        if use_tc2x:
+            # qkv leaves its GEMM as two fp16 planes (hi + lo = 22 significant bits, scaled by a static power of two per part)
+            # in the layout the attention kernel's TMA loads and MMAs consume; proj's quantize_act is fused into its epilogue
+            planes = self._gemm(c1, qkv_l, out_kind=ops.QVIT_OUT_F16X2, col_scale=qkv_l.f16_col_scale, bias=qkv_l.f16_bias)
+            cp, o = ops.attention_f16x2(planes, B, NT, H, qkv_l.f16_exps, proj_l.d_act, proj_l.qm_act, proj_l.t_act,
+                                        want_context=taps is not None, flags=self.flags)
+            if taps is not None:
+                taps[f"{pre}.attn.proj.in"] = o.clone()
+            self._gemm(cp, proj_l, out_kind=ops.QVIT_OUT_F32, residual=h2, out=h2)
+            self._mlp(pre, h, h2, taps)
+            return
         qkv = self._gemm(c1, qkv_l, out_kind=ops.QVIT_OUT_BF16 if bf16 else ops.QVIT_OUT_F32)
         # own tensor-core kernel (exact 3-way bf16 split, fp32 accumulation in TMEM): 2.2x faster than the library fp32
         # kernel at 3e-6 vs 1e-6 max-norm error (tensor-core accumulation rounding), i.e. 0-5 proj-input code flips per
@@ -154,6 +191,11 @@ class ViTInferenceEngine:
         if cp is None:
             cp = ops.quantize_sym(o, proj_l.d_act, proj_l.qm_act, proj_l.t_act, ld_codes=ops.pad16(D), flags=self.flags)
         self._gemm(cp, proj_l, out_kind=ops.QVIT_OUT_F32, residual=h2, out=h2)  # h += proj(o)   (vit_model.py:206)
+        self._mlp(pre, h, h2, taps)
+
+    def _mlp(self, pre: str, h: torch.Tensor, h2: torch.Tensor, taps: Optional[dict]) -> None:
+        sd = self.sd
+        fc1_l, fc2_l = self.layers[f"{pre}.mlp.fc1"], self.layers[f"{pre}.mlp.fc2"]
         c2, _ = ops.layernorm_quantize(h2, sd[f"{pre}.norm2.weight"], sd[f"{pre}.norm2.bias"], self.eps, fc1_l.d_act,
                                        fc1_l.qm_act, fc1_l.t_act, flags=self.flags)
         c3 = self._gemm(c2, fc1_l, out_kind=ops.QVIT_OUT_I8, act=ops.QVIT_ACT_GELU,

@@ -14,16 +14,16 @@ import torch
 
 from . import _lib
 from ._lib import (QVIT_ACT_GELU, QVIT_ACT_NONE, QVIT_ACT_RELU, QVIT_GEMM_AUTO, QVIT_GEMM_SIMT, QVIT_GEMM_TCGEN05,
-                   QVIT_OUT_BF16, QVIT_OUT_F32, QVIT_OUT_I8, QVIT_OUT_I32, QVIT_OUT_NONE)
+                   QVIT_OUT_BF16, QVIT_OUT_F16X2, QVIT_OUT_F32, QVIT_OUT_I8, QVIT_OUT_I32, QVIT_OUT_NONE)
 
 __all__ = ["pad16", "quantize_sym", "fake_quantize_sym", "sym_backward", "absmax", "im2col_quantize_sym", "gemm_i8",
            "layernorm_quantize", "attention_f32", "attention_f32_supported", "split3_bf16", "codes_to_bf16_t", "gemm_bf16_split", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "bn_fold",
            "bn_act_quantize_int", "pack_int4", "unpack_int4", "new_flags", "QVIT_OUT_I32", "QVIT_OUT_F32",
-           "QVIT_OUT_BF16", "QVIT_OUT_I8", "QVIT_OUT_NONE", "QVIT_ACT_NONE", "QVIT_ACT_GELU", "QVIT_ACT_RELU", "QVIT_GEMM_AUTO",
+           "QVIT_OUT_BF16", "QVIT_OUT_I8", "QVIT_OUT_NONE", "QVIT_OUT_F16X2", "attention_f16x2", "split2_f16", "f16x2_exponent", "QVIT_ACT_NONE", "QVIT_ACT_GELU", "QVIT_ACT_RELU", "QVIT_GEMM_AUTO",
            "QVIT_GEMM_TCGEN05", "QVIT_GEMM_SIMT"]
 
 _OUT_DTYPE = {QVIT_OUT_I32: torch.int32, QVIT_OUT_F32: torch.float32, QVIT_OUT_BF16: torch.bfloat16,
-              QVIT_OUT_I8: torch.int8}
+              QVIT_OUT_I8: torch.int8, QVIT_OUT_F16X2: torch.float16}
 
 
 def pad16(k: int) -> int:
@@ -205,6 +205,59 @@ def attention_quantize_sym(qkv: torch.Tensor, num_heads: int, d, q_m, t=None, *,
     return codes, ctx
 
 
+def f16x2_exponent(bound: float) -> int:
+    """Power of two e such that |x| <= bound implies |x * 2^e| <= 2^15 (< 65504, the largest fp16): the scale the producer of
+    a two-plane fp16 tensor applies."""
+    import math
+    if not (bound > 0.0) or not math.isfinite(bound):
+        return 0
+    return 15 - int(math.ceil(math.log2(bound)))
+
+
+def split2_f16(x: torch.Tensor, col_exp: torch.Tensor, flags: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [rows, cols] -> two-plane fp16 [rows, 2*cols] (hi | lo) of x * 2^col_exp[c]."""
+    x = _f32c(x, "split2_f16")
+    x2 = x.reshape(-1, x.shape[-1])
+    rows, cols = x2.shape
+    _lib.require_cuda(col_exp)
+    ce = col_exp.to(torch.int32).contiguous()
+    out = torch.empty((rows, 2 * cols), dtype=torch.float16, device=x.device)
+    _lib.check(_lib.lib().qvit_split2_f16(_lib.ptr(x2), rows, cols, x2.stride(0), _lib.ptr(ce), _lib.ptr(out), 2 * cols, cols,
+                                          _lib.ptr(flags), _lib.stream()), "qvit_split2_f16")
+    return out
+
+
+def attention_f16x2(planes: torch.Tensor, B: int, T: int, num_heads: int, exps, d=None, q_m=None, t=None, *,
+                    plane_off: Optional[int] = None, scale: Optional[float] = None, want_codes: bool = True,
+                    want_context: bool = False, flags: Optional[torch.Tensor] = None, prof: Optional[torch.Tensor] = None):
+    """softmax(q k^T * scale) v from the two-plane fp16 qkv [B*T, ld] (QVIT_OUT_F16X2 of the qkv GEMM); exps = (eq, ek, ev).
+    Returns (codes [B*T, pad16(H*64)] int8 | None, context [B, T, H*64] fp32 | None)."""
+    _lib.require_cuda(planes)
+    if planes.dtype != torch.float16 or planes.dim() != 2 or planes.stride(1) != 1:
+        raise TypeError("attention_f16x2: planes must be a 2-D fp16 tensor with unit inner stride")
+    ld = planes.stride(0)
+    hd = 64
+    C = num_heads * hd
+    plane_off = ld // 2 if plane_off is None else int(plane_off)
+    dev = planes.device
+    codes = ctx = None
+    ldc = pad16(C)
+    d_ = q_ = t_ = None
+    if want_codes:
+        codes = torch.empty((B * T, ldc), dtype=torch.int8, device=dev)
+        if ldc > C:
+            codes[:, C:].zero_()
+        d_, q_ = _scalar_param(d, dev, "d_quant"), _scalar_param(q_m, dev, "q_m")
+        t_ = None if t is None else _scalar_param(t, dev, "t_quant")
+    if want_context:
+        ctx = torch.empty((B, T, C), dtype=torch.float32, device=dev)
+    sc = float(hd) ** -0.5 if scale is None else float(scale)
+    _lib.check(_lib.lib().qvit_attention_f16x2(_lib.ptr(planes), ld, plane_off, B, T, num_heads, hd, sc, int(exps[0]), int(exps[1]),
+                                               int(exps[2]), _lib.ptr(d_), _lib.ptr(q_), _lib.ptr(t_), _lib.ptr(codes), ldc,
+                                               _lib.ptr(ctx), _lib.ptr(flags), _lib.ptr(prof), _lib.stream()), "qvit_attention_f16x2")
+    return codes, ctx
+
+
 def attention_f32_supported(T: int, head_dim: int) -> bool:
     return head_dim == 64 and T <= 208
 
@@ -236,6 +289,8 @@ def gemm_i8(a: torch.Tensor, w: torch.Tensor, K: int, N: Optional[int] = None, *
     if out_kind == QVIT_OUT_NONE:
         out, ldo = None, N
     elif out is None:
+        if out_kind == QVIT_OUT_F16X2:
+            ldo = 2 * N if ldo is None else int(ldo)          # two fp16 planes: hi in [0, N), lo in [ldo/2, ldo/2 + N)
         ldo = N if ldo is None else int(ldo)
         out = torch.empty((M, ldo), dtype=_OUT_DTYPE[out_kind], device=dev)
         if ldo > N and out_kind == QVIT_OUT_I8:

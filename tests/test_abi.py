@@ -94,7 +94,7 @@ def test_bench_reference_arm_contract_keys(monkeypatch, capsys):
     import json
     import sys
     import bench
-    monkeypatch.setattr(bench, "cpu_reference_throughput", lambda sub, repeats, warmup=1: (5.0, 3.2, 8))
+    monkeypatch.setattr(bench, "cpu_arm", lambda sub, repeats, warmup=1: (5.0, 3.2, 8, "port"))
     monkeypatch.setattr(sys, "argv", ["bench.py", "--impl", "reference", "--steps", "2", "--warmup", "1"])
     bench.main()
     line = json.loads(capsys.readouterr().out.strip().splitlines()[-1])

@@ -56,3 +56,52 @@ def test_fused_quantizer_equals_separate_quantize(B, T, H, nonlinear):
     assert torch.equal(codes, want)
     codes_only, none = ops.attention_quantize_sym(qkv, H, d, qm, t)
     assert none is None and torch.equal(codes_only, want)
+
+
+# ------------------------------------------------------------------------------------------ two-plane fp16 kernel (pipelined)
+def _planes(qkv, H):
+    """fp32 qkv [B, T, 3*H*64] -> two-plane fp16 [B*T, 2*3*H*64] with one power of two per part from the data's own range
+    (the engine derives it from a static bound instead; any exponent that keeps |x 2^e| < 65504 is exact)."""
+    from quantized_vit_b200 import ops
+    B, T, C3 = qkv.shape
+    D = C3 // 3
+    exps = [ops.f16x2_exponent(float(qkv[..., i * D:(i + 1) * D].abs().max())) for i in range(3)]
+    col_exp = torch.cat([torch.full((D,), e, dtype=torch.int32) for e in exps]).cuda()
+    fl = ops.new_flags(qkv.device)
+    planes = ops.split2_f16(qkv.reshape(B * T, C3), col_exp, flags=fl)
+    assert int(fl.item()) == 0
+    return planes, exps
+
+
+@pytest.mark.parametrize("B,T,H", [(2, 197, 12), (1, 50, 3), (3, 128, 2), (1, 208, 1), (2, 129, 4), (1, 1, 1), (5, 17, 16), (40, 197, 12)])
+def test_attention_f16x2_matches_fp64(B, T, H):
+    """qvit_attention_f16x2: hi/lo fp16 planes, three product terms, fp32 accumulation in TMEM, TMA-fed, pipelined over two
+    S/P buffers.  Same bar as the 3 x bf16 kernel (6e-6 of max|ref| on a deliberately sharp softmax); (40, 197, 12) gives
+    every CTA several (batch, head) units so that all buffer rotations of the pipeline are exercised."""
+    from quantized_vit_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    qkv = torch.randn(B, T, 3 * H * 64, generator=g).cuda()
+    qkv[..., : H * 64] *= 3.0
+    planes, exps = _planes(qkv, H)
+    sums = planes.float().view(B * T, 2, -1).sum(1)
+    scale = torch.cat([torch.full((H * 64,), 2.0 ** e) for e in exps]).cuda()
+    assert (sums / scale - qkv.view(B * T, -1)).abs().max() <= 2.0 ** -21 * qkv.abs().max()      # hi + lo carries >= 22 bits
+    _, out = ops.attention_f16x2(planes, B, T, H, exps, want_codes=False, want_context=True)
+    ref = _ref(qkv, H)
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    print(f"B={B} T={T} H={H}: two-plane fp16 tensor-core err {err:.2e}")
+    assert err <= 6e-6
+
+
+@pytest.mark.parametrize("nonlinear", [False, True])
+def test_attention_f16x2_fused_quantizer(nonlinear):
+    from quantized_vit_b200 import ops
+    B, T, H = 3, 197, 4
+    qkv = torch.randn(B, T, 3 * H * 64, generator=torch.Generator().manual_seed(9)).cuda()
+    planes, exps = _planes(qkv, H)
+    d, qm, t = 0.031, 0.217, (0.9 if nonlinear else None)
+    codes, ctx = ops.attention_f16x2(planes, B, T, H, exps, d, qm, t, want_context=True)
+    want = ops.quantize_sym(ctx.view(B * T, H * 64), d, qm, t, ld_codes=ops.pad16(H * 64))
+    assert torch.equal(codes, want)
+    codes_only, none = ops.attention_f16x2(planes, B, T, H, exps, d, qm, t)
+    assert none is None and torch.equal(codes_only, want)

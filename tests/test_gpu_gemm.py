@@ -333,3 +333,28 @@ def test_bf16_split_gemm_matches_fp64(ops, M, N, K):
     assert torch.equal(at.float().view(K, 3, -1)[:, :, :M].sum(1), x.t())
     ct = ops.codes_to_bf16_t(codes, K)                       # [K, pad64(N)]
     assert torch.equal(ct[:, :N].float(), codes[:, :K].float().t()) and float(ct[:, N:].abs().sum()) == 0.0
+
+
+@pytest.mark.parametrize("M,N,K", [(394, 2304, 768), (50, 96, 64), (1000, 3072, 1024)])
+def test_f16x2_output_planes(ops, M, N, K):
+    """QVIT_OUT_F16X2: y * 2^e as two fp16 planes (hi | lo).  hi + lo must reproduce the fp32 epilogue value of the same
+    GEMM (col_scale = 2^e scales it exactly) to 22 significant bits, on both backends, and hi must be fp16(y 2^e) exactly."""
+    a = _codes(M, K, -7, 7, 71).cuda()
+    w = _codes(N, K, -7, 7, 72).cuda()
+    bias = torch.randn(N).cuda()
+    cs = torch.full((N,), 2.0 ** 7).cuda()
+    cs[N // 3:] = 2.0 ** 9
+    kw = dict(scale_a=0.013, scale_w=0.021, col_scale=cs, bias=bias * cs, acc_abs_max=49 * K)
+    y = ops.gemm_i8(a, w, K, N, out_kind=ops.QVIT_OUT_F32, backend=ops.QVIT_GEMM_TCGEN05, **kw)
+    fl = ops.new_flags(a.device)
+    for be in (ops.QVIT_GEMM_TCGEN05, ops.QVIT_GEMM_SIMT):
+        p = ops.gemm_i8(a, w, K, N, out_kind=ops.QVIT_OUT_F16X2, backend=be, flags=fl, **kw)
+        assert p.shape == (M, 2 * N) and p.dtype == torch.float16
+        hi, lo = p[:, :N], p[:, N:]
+        assert torch.equal(hi, y.to(torch.float16)), be
+        assert torch.equal(lo, (y - hi.float()).to(torch.float16)), be
+        assert ((hi.float() + lo.float()) - y).abs().max() <= 2.0 ** -21 * y.abs().max()
+    assert int(fl.item()) == 0
+    # the unscaled value equals the plain fp32 epilogue exactly (a power-of-two column scale commutes with the rounding)
+    y0 = ops.gemm_i8(a, w, K, N, out_kind=ops.QVIT_OUT_F32, scale_a=0.013, scale_w=0.021, bias=bias, acc_abs_max=49 * K)
+    assert torch.equal(y / cs, y0)

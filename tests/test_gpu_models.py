@@ -150,16 +150,23 @@ def test_vit_b16_layers_teacher_forced(golden, name):
         # own tensor-core attention kernel (exact 3-way bf16 split, fp32 accumulation in TMEM) on the same qkv
         o_tc = ops.attention_f32(qkv.reshape(B, NT, 3 * D).contiguous(), H).cpu()
         assert (o_tc - o_ref).abs().max() <= 1e-5 * o_ref.abs().max(), f"tc attention: {(o_tc - o_ref).abs().max() / o_ref.abs().max():.2e}"
+        # the engine's path: qkv as two fp16 planes out of the GEMM epilogue (static bound-derived scales) -> pipelined kernel
+        c1 = ops.quantize_sym(ln_ref.cuda(), qkv_l.d_act, qkv_l.qm_act, qkv_l.t_act, ld_codes=ops.pad16(D))
+        planes = eng._gemm(c1, qkv_l, out_kind=ops.QVIT_OUT_F16X2, col_scale=qkv_l.f16_col_scale, bias=qkv_l.f16_bias)
+        _, o_2x = ops.attention_f16x2(planes, B, NT, H, qkv_l.f16_exps, want_codes=False, want_context=True)
+        o_2x = o_2x.cpu()
+        assert (o_2x - o_ref).abs().max() <= 1e-5 * o_ref.abs().max(), f"two-plane attention: {(o_2x - o_ref).abs().max() / o_ref.abs().max():.2e}"
         pl = eng.layers[f"{p}.attn.proj"]
         want_p = ref_geta.sym_codes(o_ref.reshape(-1, D), sd[f"{p}.attn.proj.d_quant_act"], sd[f"{p}.attn.proj.q_m_act"])
         fl = {}
-        for nm, oo in (("library-fp32", o), ("tensor-core", o_tc)):
+        for nm, oo in (("library-fp32", o), ("tensor-core", o_tc), ("two-plane-fp16", o_2x)):
             cc = ops.quantize_sym(oo.reshape(-1, D).cuda(), pl.d_act, pl.qm_act, pl.t_act).cpu().long()
             fl[nm] = int((cc != want_p).sum())
             assert (cc - want_p).abs().max() <= 1
         print(f"{name} {p}: attention err library {float((o - o_ref).abs().max() / o_ref.abs().max()):.1e} / tensor-core "
               f"{float((o_tc - o_ref).abs().max() / o_ref.abs().max()):.1e}; proj-input code flips {fl} of {want_p.numel()}")
         assert fl["tensor-core"] <= 5e-4 * lv(f"{p}.attn.proj") * want_p.numel()
+        assert fl["two-plane-fp16"] <= 5e-4 * lv(f"{p}.attn.proj") * want_p.numel()
         # proj epilogue adds the residual; fc1 epilogue applies GELU and the consumer's quantizer
         proj_l, fc1_l, fc2_l = eng.layers[f"{p}.attn.proj"], eng.layers[f"{p}.mlp.fc1"], eng.layers[f"{p}.mlp.fc2"]
         cp = ops.quantize_sym(o_ref.reshape(-1, D).cuda(), proj_l.d_act, proj_l.qm_act, proj_l.t_act, ld_codes=ops.pad16(D))
