@@ -20,6 +20,8 @@
 #include <cuda.h>
 #include <cuda_fp16.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -39,7 +41,8 @@ constexpr int kOffK = kOffQ + 4 * kQPlane;                // [plane 2]
 constexpr int kOffV = kOffK + 2 * kKVPlane;               // [slot 2][plane 2]
 constexpr int kOffStat = kOffV + 4 * kKVPlane;            // red_max [4][128], red_sum [4][128]
 constexpr int kOffBar = kOffStat + 2 * 4 * kMQ * 4;
-constexpr int kSmem = kOffBar + 256 + 1024;
+constexpr int kOffQuant = kOffBar + 256;                   // consumer quantizer constants (SymParams, FastQ2)
+constexpr int kSmem = kOffQuant + 256 + 1024;
 constexpr int kPCols = kNK / 2;       // TMEM columns of one packed-fp16 P plane (104)
 constexpr int kSB1 = 208, kOCol = 416;
 constexpr float kPScaleLog2 = 10.0f;  // probabilities are carried as p * 2^10 (keeps the lo plane of small p normal)
@@ -125,8 +128,9 @@ __device__ __forceinline__ void split2_pair(f32x2 v, uint32_t& hi, uint32_t& lo)
 
 // planes: fp16 [B, T, ld] with hi in columns [0, 3*H*64) and lo in [plane_off, plane_off + 3*H*64) (part-major: q | k | v,
 // head-major inside a part), as the qkv GEMM writes them.  s_scale = softmax scale * log2(e) * 2^-(sq + sk); o_scale = 2^-sv.
-// (112 registers x 17 warps = 60 928 of the 65 536: __launch_bounds__(544, 1) alone makes the compiler stop at 96 and spill)
-__global__ void __maxnreg__(112)
+// (17 warps are allocated as 20 - registers come in units of four warps - so 96 registers per thread is the ceiling; the
+// softmax below is written in column groups so that it fits)
+__global__ void __launch_bounds__(a2::kThreads, 1)
 attention_f16x2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, float* __restrict__ out,
                        int T, int H, int plane_off, int total_pairs, float s_scale, float o_scale, int8_t* __restrict__ codes,
                        int64_t ld_codes, const float* __restrict__ q_d, const float* __restrict__ q_qm, const float* __restrict__ q_t,
@@ -167,6 +171,11 @@ attention_f16x2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   if (warp == 1) {
     ptx::tmem_alloc<1>(ptx::smem_u32(const_cast<uint32_t*>(tmem_slot)), 512);
     ptx::tmem_relinquish<1>();
+  }
+  if (threadIdx.x == 64 && codes) {
+    const SymParams qp = load_sym_params(q_d, q_qm, q_t);
+    *reinterpret_cast<SymParams*>(gen + kOffQuant) = qp;
+    *reinterpret_cast<FastQ2*>(gen + kOffQuant + 64) = make_fastq2(qp);
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -277,13 +286,11 @@ attention_f16x2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
     }
   } else {
     // ------------------------------------------------------------------------------------------ compute warps
-    SymParams qp;
-    FastQ2 qf;
+    // the consumer quantizer's constants live in shared memory (written once by thread 0 below, read back in the epilogue):
+    // ~20 registers that would otherwise stay live across the softmax
+    const SymParams* qp_s = reinterpret_cast<const SymParams*>(gen + kOffQuant);
+    const FastQ2* qf_s = reinterpret_cast<const FastQ2*>(gen + kOffQuant + 64);
     int qfl = 0;
-    if (codes) {
-      qp = load_sym_params(q_d, q_qm, q_t);
-      qf = make_fastq2(qp);
-    }
     const int row = (warp & 3) * 32 + lane;
     const int cq = warp >> 2;
     const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
@@ -317,6 +324,8 @@ attention_f16x2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         }
         if (codes) {                                             // quantize_act of the consumer layer (quant_layers.py:356-381)
           int8_t* dst = codes + ((int64_t)b * T + tq) * ld_codes + h * kHd + cq * 16;
+          const SymParams qp = *qp_s;
+          const FastQ2 qf = *qf_s;
           const uint4 w = sym_codes16(v, qp, qf, qfl);
           stg_v4_b32(dst, w.x, w.y, w.z, w.w);
         }
@@ -362,25 +371,31 @@ attention_f16x2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         // p' = 2^10 * exp((s - max) * scale): the exponent offset is folded into the constant term
         const f32x2 sc2 = pk1(s_scale), nb2 = pk1(kPScaleLog2 - mx * s_scale);
         f32x2 sum2 = pk1(0.0f);
-        uint32_t w1[26], w2[26];
+        // probabilities -> two packed-fp16 planes, written back over the scores: plane q occupies TMEM columns [q * 104, +104) of
+        // the buffer and this thread owns 26 of them.  Done in column groups of 32 / 16 / 4 scores (16 / 8 / 2 packed words per
+        // plane = one tcgen05.st each) so that only one group's words are live at a time.
+        const uint32_t cbase = sb + lane_addr + (uint32_t)(cq * 26);
+        auto group = [&](auto n_words, int first_pair) {
+          constexpr int NW = decltype(n_words)::value;
+          uint32_t w1[NW], w2[NW];
 #pragma unroll
-        for (int j = 0; j < kColQ / 2; ++j) {
-          float a0, a1;
-          unpk2(fma2(pk2(p[2 * j], p[2 * j + 1]), sc2, nb2), a0, a1);
-          const f32x2 e = pk2(ex2_approx(a0), ex2_approx(a1));   // <= 2 ulp, argument <= 10
-          sum2 = add2(sum2, e);
-          split2_pair(e, w1[j], w2[j]);
-        }
+          for (int j = 0; j < NW; ++j) {
+            float a0, a1;
+            unpk2(fma2(pk2(p[2 * (first_pair + j)], p[2 * (first_pair + j) + 1]), sc2, nb2), a0, a1);
+            const f32x2 e = pk2(ex2_approx(a0), ex2_approx(a1));   // <= 2 ulp, argument <= 10
+            sum2 = add2(sum2, e);
+            split2_pair(e, w1[j], w2[j]);
+          }
+          tmem_st<NW>(cbase + (uint32_t)first_pair, w1);
+          tmem_st<NW>(cbase + (uint32_t)(kPCols + first_pair), w2);
+        };
+        group(std::integral_constant<int, 16>{}, 0);
+        group(std::integral_constant<int, 8>{}, 16);
+        group(std::integral_constant<int, 2>{}, 24);
+        tmem_st_wait();
         float sum, sum_hi;
         unpk2(sum2, sum, sum_hi);
         red_sum[cq * kMQ + row] = sum + sum_hi;
-        {
-          // two packed-fp16 planes: plane q occupies TMEM columns [q * 104, q * 104 + 104) of the buffer; this thread owns 26 of them
-          const uint32_t cbase = sb + lane_addr + (uint32_t)(cq * 26);
-          tmem_st<16>(cbase, w1);          tmem_st<8>(cbase + 16, w1 + 16);          tmem_st<2>(cbase + 24, w1 + 24);
-          tmem_st<16>(cbase + kPCols, w2); tmem_st<8>(cbase + kPCols + 16, w2 + 16); tmem_st<2>(cbase + kPCols + 24, w2 + 24);
-          tmem_st_wait();
-        }
         asm volatile("bar.sync %0, 128;" ::"r"(1 + (warp & 3)) : "memory");
         const float rs = (red_sum[row] + red_sum[kMQ + row]) + (red_sum[2 * kMQ + row] + red_sum[3 * kMQ + row]);
         inv = __fdiv_rn(o_scale, rs);                            // O' / sum(p') * 2^-sv  (the 2^10 of p' cancels)
