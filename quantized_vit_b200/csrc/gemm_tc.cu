@@ -92,7 +92,14 @@ __device__ __forceinline__ void epi_math32(const EpiParams& e, const uint32_t (&
   if (FACC) {
 #pragma unroll
     for (int j = 0; j < 16; ++j) y[j] = pk2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1]));
-  } else if (SP::on || (e.acc_abs_max > 0 && e.acc_abs_max < (1 << 22))) {
+  } else if (SP::on) {
+    // specialised instances keep the accumulators PRE-BIASED: the epilogue re-initialises every column it has read with the
+    // bit pattern of 1.5 * 2^23 and the MMAs accumulate on top, so the word that comes out of TMEM already is the float
+    // 1.5 * 2^23 + acc (|acc| < 2^22) - one packed subtract instead of an integer add per element plus the subtract
+    const f32x2 mm = pk1(-kRoundMagic);
+#pragma unroll
+    for (int j = 0; j < 16; ++j) y[j] = add2(pk2(__uint_as_float(acc[2 * j]), __uint_as_float(acc[2 * j + 1])), mm);
+  } else if (e.acc_abs_max > 0 && e.acc_abs_max < (1 << 22)) {
     // |acc| < 2^22: as_float(0x4B400000 + acc) = 1.5 * 2^23 + acc exactly, so one integer add and one fp32 subtract give
     // float(acc) without the quarter-rate conversion unit
     const f32x2 mm = pk1(-kRoundMagic);
@@ -156,7 +163,7 @@ __device__ __forceinline__ void epi_math32(const EpiParams& e, const uint32_t (&
 // IEEE division).  Writes into the warp's staging slab when `stage` != 0 (address of this row inside the slab, `byte0` =
 // first byte of the chunk inside the row, `swz` = XOR of the 16-byte piece index), else straight to global memory.
 // Warp-collective (tcgen05.ld): call in uniform control flow.
-template <int OUT, bool FACC>
+template <int OUT, bool FACC, bool PRE = false>
 __device__ __noinline__ void epi_chunk_generic(const EpiParams& e_in, const SymParams& nq_in, uint32_t taddr, float scale, int64_t m,
                                                int n0, bool row_ok, uint32_t stage, uint32_t swz, uint32_t byte0, int* flags) {
   constexpr int kEsz = out_elem_size(OUT);
@@ -168,6 +175,10 @@ __device__ __noinline__ void epi_chunk_generic(const EpiParams& e_in, const SymP
     uint32_t r[8];
     ptx::tmem_ld_32x32_x8(taddr + (uint32_t)(8 * g), r);
     ptx::tmem_ld_wait();
+    if (PRE) {                                                 // pre-biased accumulators (specialised instances): back to int32
+#pragma unroll
+      for (int j = 0; j < 8; ++j) r[j] -= 0x4B400000u;
+    }
     uint32_t bits[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -213,10 +224,14 @@ __device__ __forceinline__ long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#ifdef QVIT_GEMM_PROFILE      // developer builds only (tools/gemm_timeline.py): the stamps cost ~10 instructions per chunk
 #define QVIT_PROF(slot)                                                                        \
   do {                                                                                         \
     if (prof && prof_tile < kProfTiles) g_gemm_prof[prof_tile * 8 + (slot)] = clock64();       \
   } while (0)
+#else
+#define QVIT_PROF(slot) do { (void)prof; (void)prof_tile; } while (0)
+#endif
 
 // KIND 0: int8 x int8 -> int32 (tcgen05 kind::i8).  KIND 1: bf16 x bf16 -> fp32 (kind::f16) for the QAT gradient GEMMs:
 // the fp32 gradient operand arrives as three exact bf16 planes concatenated along K, the integer codes as one bf16
@@ -231,6 +246,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
   using S = GemmSmem<BN, CG>;
   constexpr int kStages = S::kStages;
   constexpr int kTmemCols = 2 * BN;   // 256 or 512: a power of two >= 32
+  constexpr bool kPre = EpiSpec<SPEC>::on && KIND == 0;   // accumulators pre-biased with the bits of 1.5 * 2^23 (see epi_math32)
   constexpr int kTileM = kBM * CG;    // rows of the (pair) tile
   const uint32_t rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;   // 0 = leader (issues the MMAs)
 
@@ -352,7 +368,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int tile = tile_first; tile < total_tiles; tile += tile_step) {
-        ptx::mbar_wait(tempty_bar(acc), acc_phase ^ 1u);     // epilogue has drained this accumulator
+        // epilogue has drained this accumulator (pre-biased instances: and re-initialised it - the first use waits for the
+        // epilogue's initial fill, so the parity is that of the use count itself)
+        ptx::mbar_wait(tempty_bar(acc), kPre ? acc_phase : (acc_phase ^ 1u));
         ptx::tc_fence_after();
         QVIT_PROF(0);
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
@@ -370,7 +388,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               // advance both descriptors by k*32 bytes inside the swizzle atom (address field is >>4)
               if (KIND == 0)
                 ptx::mma_i8<CG>(d_tmem, a_desc + (uint64_t)(k * (kUmmaK >> 4)), b_desc + (uint64_t)(k * (kUmmaK >> 4)), idesc,
-                                (uint32_t)(kb != kb0 || k != 0));
+                                (uint32_t)(kPre || kb != kb0 || k != 0));
               else
                 ptx::mma_bf16<CG>(d_tmem, a_desc + (uint64_t)(k * (kUmmaK >> 4)), b_desc + (uint64_t)(k * (kUmmaK >> 4)), idesc,
                                   (uint32_t)(kb != kb0 || k != 0));
@@ -411,6 +429,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     constexpr int kChunkBytes = 32 * kEsz;
     constexpr int kChunksPerBox = kBoxW / kChunkBytes;       // 1 or 2
     constexpr uint32_t kSwzMask = kBoxW / 16 - 1;            // TMA swizzle: 16B-piece index ^= (byte offset >> 7) & mask
+    // a specialised instance is only launched with staged TMA stores and without any test / benchmark mode
+    const int ts = SP::on ? 1 : tma_store;
+    const int mflags = SP::on ? 0 : mma_only_flags;
     const float scale = epi_scale(ep);
     SymParams nq;
     FastQ2 fq;
@@ -436,7 +457,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
     // epi_chunk_generic.  tma_store: the output is TMA-addressable (16-byte pointer and pitch); 2 = benchmark, store nothing.
     // (A specialised instance still checks the consumer quantizer: q_m <= 0 or codes beyond 127 are device-side facts.)
     const bool hot_ok = (OUT == QVIT_OUT_F16X2) ||
-                        (tma_store && !fq.generic && (SP::on ? !fq.nl : true) && (!ep.residual || use_res_tma) && !(mma_only_flags & 8));
+                        (ts && !fq.generic && (SP::on ? !fq.nl : true) && (!ep.residual || use_res_tma) && !(mflags & 8));
     // tile -> (m_blk, n_blk): one division at the start, then incremental (the per-tile division cost ~60 instructions)
     const int step_m = tile_step / n_tiles, step_n = tile_step - step_m * n_tiles;
     int tile = tile_first;
@@ -455,6 +476,28 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst + 256u), "l"(ep.col_scale + (col < ep.N ? col : 0)), "r"(nbytes) : "memory");
       }
     };
+    auto fill_magic = [&](uint32_t taddr32) {                   // 32 columns of this warp's 32 lanes <- bits of 1.5 * 2^23
+#pragma unroll
+      for (int g = 0; g < 8; ++g)
+        asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %1, %1, %1};" ::"r"(taddr32 + (uint32_t)(4 * g)), "r"(0x4B400000u) : "memory");
+    };
+    if (kPre) {
+      // initial fill of both accumulators (this warp's lanes and columns), then the first "accumulator free" signal
+      for (int a = 0; a < 2; ++a) {
+#pragma unroll
+        for (int cq = 0; cq < kChunksPerQuad; ++cq)
+          fill_magic(tmem_base + ((uint32_t)(lane_grp * 32) << 16) + (uint32_t)(a * BN + (quad * kChunksPerQuad + cq) * 32));
+      }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        for (int a = 0; a < 2; ++a) {
+          if (CG == 1) ptx::mbar_arrive(tempty_bar(a));
+          else ptx::mbar_arrive_cluster(tempty_bar(a), 0);
+        }
+      }
+    }
     int pbuf = 0;
     if (tile < total_tiles) prefetch_cols(n_blk, 0);
     for (; tile < total_tiles; tile += tile_step) {
@@ -493,24 +536,31 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           ptx::tmem_ld_wait();
         } else if (n0 < ep.N) {
           const bool hot = hot_ok && (n0 + 32 <= ep.N);
-          if (tma_store && in_box == 0) {
+          if (use_res_tma) {
             if (lane == 0) {
-              if (tma_store == 1) ptx::tma_store_wait_read<0>();   // the warp's previous box has left the slab
-              if (use_res_tma) {
-                // fetch this warp's [32 x 32] fp32 residual rows while the accumulator is loaded and converted
-                // (rows beyond M are zero filled)
-                ptx::mbar_expect_tx(res_bar(ew), 4096u);
-                ptx::tma_load_2d(slab, &tmap_res, res_bar(ew), n0, row0);
-              }
+              ptx::tma_store_wait_read<0>();                 // the warp's previous box has left the slab
+              // fetch this warp's [32 x 32] fp32 residual rows while the accumulator is loaded and converted
+              // (rows beyond M are zero filled)
+              ptx::mbar_expect_tx(res_bar(ew), 4096u);
+              ptx::tma_load_2d(slab, &tmap_res, res_bar(ew), n0, row0);
             }
             __syncwarp();
           }
+          // (without a staged residual the slab is first touched when the converted chunk is staged: the wait for the
+          // previous box is deferred to that point, so that this chunk's TMEM load and math overlap the store's drain)
+          auto slab_free = [&]() {
+            if (ts == 1 && in_box == 0 && !use_res_tma) {
+              if (lane == 0) ptx::tma_store_wait_read<0>();
+              __syncwarp();
+            }
+          };
           bool redo = !hot;
           if (hot) {
             uint32_t w[kChunkBytes / 4];
             uint32_t r[32];
             ptx::tmem_ld_32x32(t_row + (uint32_t)(c * 32), r);
             ptx::tmem_ld_wait();
+            if (kPre) fill_magic(t_row + (uint32_t)(c * 32));  // re-initialise what was just read (completes before the release below)
             QVIT_PROF(cq == 0 ? 3 : 6);
             if (OUT == QVIT_OUT_I32) {
 #pragma unroll
@@ -563,6 +613,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                   wl[j] = *reinterpret_cast<const uint32_t*>(&l2);
                   if (!(fabsf(hf.x) <= 65504.0f) || !(fabsf(hf.y) <= 65504.0f)) fl |= kFlagOverflow;   // inf / NaN: the caller's scale is wrong
                 }
+                slab_free();
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                   sts_v4(slab + 2048u + row_off + ((((uint32_t)j) ^ sw) << 4), wl[4 * j], wl[4 * j + 1], wl[4 * j + 2], wl[4 * j + 3]);
@@ -578,7 +629,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 float d0, d1;
                 unpk2(dacc, d0, d1);
                 bool bad = false;
-                if (!SP::on && (!(d0 + d1 == 0.0f) || (mma_only_flags & 4)) && fq.nl) {
+                if (!SP::on && (!(d0 + d1 == 0.0f) || (mflags & 4)) && fq.nl) {
                   // non-linear quantizer: the rows the interval test cannot decide get the scalar sequence (expf / logf /
                   // IEEE division), out of line, 16 elements per call
                   float a[32];
@@ -590,7 +641,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                                                     a[27], a[28], a[29], a[30], a[31], nq, &fl);
                   w[0 % (kChunkBytes / 4)] = lo.x; w[1 % (kChunkBytes / 4)] = lo.y; w[2 % (kChunkBytes / 4)] = lo.z; w[3 % (kChunkBytes / 4)] = lo.w;
                   w[4 % (kChunkBytes / 4)] = hi.x; w[5 % (kChunkBytes / 4)] = hi.y; w[6 % (kChunkBytes / 4)] = hi.z; w[7 % (kChunkBytes / 4)] = hi.w;
-                } else if (!(d0 + d1 == 0.0f) || (mma_only_flags & 4)) {
+                } else if (!(d0 + d1 == 0.0f) || (mflags & 4)) {
                   // some element of this row sits on a rounding boundary (or is NaN / inf): exact codes for the row
                   // (lane-local branch; (mma_only_flags & 4) forces it for the tests)
 #pragma unroll
@@ -605,17 +656,18 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
                 }
                 // NaN / inf / absurd magnitudes: the scalar reference sequence decides (and raises the flag bits)
                 redo = __any_sync(0xffffffffu, bad);
-                if ((mma_only_flags & 2) && lane == 0 && !(d0 + d1 == 0.0f))
+                if ((mflags & 2) && lane == 0 && !(d0 + d1 == 0.0f))
                   atomicAdd(reinterpret_cast<unsigned long long*>(&g_gemm_prof[kProfTiles * 8 + 4 + 3 * 159]), 1ull);
               }
             }
             if (cq == 0) QVIT_PROF(4);
-            if (tma_store == 2) {                            // benchmark: math only (keep it alive, store nothing)
+            if (ts == 2) {                                   // benchmark: math only (keep it alive, store nothing)
               uint32_t x = redo ? 1u : 0u;
 #pragma unroll
               for (int j = 0; j < kChunkBytes / 4; ++j) x ^= w[j];
               if (x == 0x9e3779b9u && ep.flags) atomicOr(ep.flags, 8);
             } else if (!redo) {
+              if (OUT != QVIT_OUT_F16X2) slab_free();
 #pragma unroll
               for (int j = 0; j < kChunkBytes / 16; ++j) {
                 const uint32_t piece = (uint32_t)(in_box * (kChunkBytes / 16) + j);
@@ -627,13 +679,17 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             res_phase ^= 1u;
           }
           if (OUT != QVIT_OUT_F16X2) {
-            if (redo && tma_store != 2)
-              epi_chunk_generic<OUT, KIND == 1>(ep, nq, t_row + (uint32_t)(c * 32), scale, m, n0, row_ok,
-                                                tma_store ? slab + row_off : 0u, sw, byte0, &fl);
+            if (redo && ts != 2) {
+              slab_free();
+              epi_chunk_generic<OUT, KIND == 1, kPre>(ep, nq, t_row + (uint32_t)(c * 32), scale, m, n0, row_ok,
+                                                      ts ? slab + row_off : 0u, sw, byte0, &fl);
+              if (kPre && !hot) fill_magic(t_row + (uint32_t)(c * 32));   // (hot chunks were re-initialised right after their load)
+            }
           }
         }
         if (last) {                                          // all TMEM reads of this warp for this tile are done
           QVIT_PROF(6);
+          if (kPre) asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
           ptx::tc_fence_before();
           __syncwarp();
           if (lane == 0) {
@@ -641,7 +697,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             else ptx::mbar_arrive_cluster(tempty_bar(acc), 0);   // the leader's MMA warp waits for both CTAs
           }
         }
-        if (OUT != QVIT_OUT_NONE && tma_store == 1 && (in_box == kChunksPerBox - 1 || last)) {
+        if (OUT != QVIT_OUT_NONE && ts == 1 && (in_box == kChunksPerBox - 1 || last)) {
           // (a box whose later chunks lie beyond N is stored as soon as its last in-range chunk is staged: TMA clips it)
           const int box_n0 = n_blk * BN + (c - in_box) * 32;
           if (box_n0 < ep.N) {
@@ -665,7 +721,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
       m_blk = m_next;
       n_blk = n_next;
     }
-    if (tma_store == 1 && lane == 0) ptx::tma_store_wait_read<0>();   // the slab must outlive the reads; the writes complete with the grid
+    if (ts == 1 && lane == 0) ptx::tma_store_wait_read<0>();   // the slab must outlive the reads; the writes complete with the grid
     fl = warp_or(fl);
     if (fl && ep.flags && lane == 0) atomicOr(ep.flags, fl);
   }
@@ -775,6 +831,7 @@ static int g_no_tma_store = 0;   // benchmark: per-thread vector stores instead 
 static int g_skip_store = 0;     // benchmark: epilogue math only, nothing staged or stored
 static int g_profile = 0;        // developer timeline into g_gemm_prof
 static int g_force_path = 0;     // tests: 1 = exact redo of every int8-output chunk, 2 = scalar reference path for every chunk
+static int g_no_spec = 0;        // tests / benchmarks: never pick a specialised instance (mode digit 6 in the tens place)
 int gemm_tc_read_profile(long long* host, int n) {
   if (n > kProfTiles * 8 + 4 + 3 * kProfCtas) n = kProfTiles * 8 + 4 + 3 * kProfCtas;
   return cudaMemcpyFromSymbol(host, g_gemm_prof, sizeof(long long) * n) == cudaSuccess ? n : -1;
@@ -784,6 +841,8 @@ void gemm_tc_force_cta_group(int cg) {
   g_force_path = (cg / 100) % 10;   // hundreds digit
   cg %= 100;
   int t = cg / 10;
+  g_no_spec = (t == 6) ? 1 : 0;      // 60: generic instances only (A/B against the specialised ones)
+  if (t == 6) t = 0;
   g_profile = (t >= 5) ? 1 : 0;      // +50: same modes with the timeline switched on
   if (t >= 5) t -= 5;
   g_no_tma_store = (t == 2) ? 1 : 0;
@@ -843,7 +902,8 @@ static int launch_tc_kind(const TcMaps& tm, const EpiParams& ep, int K, bool a_u
   // Specialised instances for the configurations of the ViT step (all on [128 x 256] tiles): options known on the host become
   // template constants.  Requirements: the caller's acc_abs_max promise (< 2^22), staged TMA stores, no forced test path, a
   // linear consumer quantizer for int8 output and a TMA-staged residual where there is one.
-  if constexpr (BN == 256) if (tm.tma_store == 1 && g_force_path == 0 && ep.acc_abs_max > 0 && ep.acc_abs_max < (1 << 22)) {
+  if constexpr (BN == 256) if (tm.tma_store == 1 && g_force_path == 0 && !g_skip_store && !g_mma_only && !g_profile && !g_no_spec &&
+                               ep.acc_abs_max > 0 && ep.acc_abs_max < (1 << 22)) {
     const bool b = ep.bias != nullptr, c = ep.col_scale != nullptr;
     const bool res_ok = (ep.residual == nullptr) || tm.res_tma;
     if (ep.out_kind == QVIT_OUT_I8 && ep.act == QVIT_ACT_GELU && b && !c && !ep.next_t && !ep.residual)
