@@ -277,7 +277,7 @@ int qvit_attention_f32_debug(const float* qkv, int B, int T, int H, int head_dim
  * exp_q / exp_k / exp_v = the powers of two q / k / v were multiplied by.  Products are evaluated as hi*hi' + hi*lo' + lo*hi' on
  * tcgen05 kind::f16 with fp32 accumulation (fp32-equivalent accuracy, half the tensor-core work of the 3 x bf16 split and no
  * conversion work: operand tiles arrive by TMA).  codes (the consumer's quantize_act, QL:356-381) and / or out (fp32 context
- * [B, T, H*64]) as in qvit_attention_quantize_sym; prof: optional device buffer of 128 clock stamps (developer timeline).
+ * [B, T, H*64]) as in qvit_attention_quantize_sym; prof: optional device buffer of 256 clock stamps (developer timeline).
  * head_dim == 64, T <= 208.                                                                                              */
 int qvit_attention_f16x2(const void* planes, int64_t ld, int plane_off, int B, int T, int H, int head_dim, float scale,
                          int exp_q, int exp_k, int exp_v, const float* d, const float* q_m, const float* t, int8_t* codes,

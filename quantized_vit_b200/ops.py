@@ -17,7 +17,7 @@ from ._lib import (QVIT_ACT_GELU, QVIT_ACT_NONE, QVIT_ACT_RELU, QVIT_GEMM_AUTO, 
                    QVIT_OUT_BF16, QVIT_OUT_F16X2, QVIT_OUT_F32, QVIT_OUT_I8, QVIT_OUT_I32, QVIT_OUT_NONE)
 
 __all__ = ["pad16", "quantize_sym", "fake_quantize_sym", "sym_backward", "absmax", "im2col_quantize_sym", "gemm_i8",
-           "layernorm_quantize", "attention_f32", "attention_f32_supported", "split3_bf16", "codes_to_bf16_t", "gemm_bf16_split", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "bn_fold",
+           "layernorm_quantize", "attention_f32", "attention_f32_supported", "split3_bf16", "codes_to_bf16_t", "gemm_bf16_split", "matmul_f32_tc", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "bn_fold",
            "bn_act_quantize_int", "pack_int4", "unpack_int4", "new_flags", "QVIT_OUT_I32", "QVIT_OUT_F32",
            "QVIT_OUT_BF16", "QVIT_OUT_I8", "QVIT_OUT_NONE", "QVIT_OUT_F16X2", "attention_f16x2", "split2_f16", "f16x2_exponent", "QVIT_ACT_NONE", "QVIT_ACT_GELU", "QVIT_ACT_RELU", "QVIT_GEMM_AUTO",
            "QVIT_GEMM_TCGEN05", "QVIT_GEMM_SIMT"]
@@ -363,8 +363,10 @@ def codes_to_bf16_t(codes: torch.Tensor, cols: int) -> torch.Tensor:
 
 
 def gemm_bf16_split(a_planes: torch.Tensor, b: torch.Tensor, K: int, planes: int = 3, scale=None,
-                    out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[M, N] fp32 = |scale| * sum_p A_p[M, :K] @ B[N, :K]^T on tcgen05 kind::f16 (fp32 accumulation in TMEM)."""
+                    out: Optional[torch.Tensor] = None, bias: Optional[torch.Tensor] = None,
+                    residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M, N] fp32 = |scale| * sum_p A_p[M, :K] @ B[N, :K]^T (+ bias[n]) (+ residual[m, n]) on tcgen05 kind::f16 (fp32
+    accumulation in TMEM)."""
     _lib.require_cuda(a_planes, b)
     M, N = a_planes.shape[0], b.shape[0]
     if out is None:
@@ -375,9 +377,43 @@ def gemm_bf16_split(a_planes: torch.Tensor, b: torch.Tensor, K: int, planes: int
     if scale is not None:
         keep = _scalar_param(scale, a_planes.device, "scale")
         epi.scale_a = keep.data_ptr()
+    if bias is not None:
+        bias = _f32c(bias.detach(), "bias")
+        epi.bias = bias.data_ptr()
+    if residual is not None:
+        _lib.require_cuda(residual)
+        if residual.dtype != torch.float32 or residual.dim() != 2 or residual.stride(1) != 1:
+            raise TypeError("gemm_bf16_split: residual must be a 2-D fp32 tensor with unit inner stride")
+        epi.residual, epi.ld_res = residual.data_ptr(), residual.stride(0)
     _lib.check(_lib.lib().qvit_gemm_bf16_split(_lib.ptr(a_planes), a_planes.stride(0), planes, _lib.ptr(b), b.stride(0), M, N, int(K),
                                                _lib.ptr(out), out.stride(0), C.byref(epi), _lib.stream()), "qvit_gemm_bf16_split")
     return out
+
+
+def matmul_f32_tc(a: torch.Tensor, b: torch.Tensor, bias: Optional[torch.Tensor] = None, *, a_transposed: bool = False,
+                  b_transposed: bool = False) -> torch.Tensor:
+    """fp32-equivalent  op(a) @ op(b)^T (+ bias)  on the tensor cores, for the layers whose codes do not fit the int8 pipe
+    (> 8-bit quantizers, weight-only mode - what GETA trains through before it has walked the bit width down, train.py:247-250).
+
+    Both fp32 operands are split EXACTLY into three bf16 planes (8 + 8 + 8 significant bits) and the six plane products
+    with index sum <= 2 are accumulated in fp32 TMEM (dropped terms <= 2^-24 relative): three launches of the split-bf16
+    GEMM - B plane 0 against A planes {0, 1, 2}, plane 1 against {0, 1}, plane 2 against {0} - the later ones adding onto the
+    earlier result through the epilogue's residual.  op(x) = x^T when *_transposed (the split kernel transposes while it
+    splits).  a: [M, K] (or [K, M] transposed), b: [N, K] (or [K, N] transposed) -> [M, N] fp32."""
+    ap = split3_bf16(a, transpose=a_transposed)
+    bp = split3_bf16(b, transpose=b_transposed)
+    K = a.shape[0] if a_transposed else a.shape[1]
+    Kb = b.shape[0] if b_transposed else b.shape[1]
+    if K != Kb:
+        raise ValueError("matmul_f32_tc: contraction lengths differ")
+    kp = _pad64(K)
+    M, N = ap.shape[0], bp.shape[0]
+    buf = torch.empty((M, (N + 3) // 4 * 4), dtype=torch.float32, device=ap.device)      # TMA stores need a 16-byte row pitch
+    out = buf[:, :N]
+    gemm_bf16_split(ap, bp[:, 0:kp], K, planes=3, out=out, bias=bias)
+    gemm_bf16_split(ap, bp[:, kp:2 * kp], K, planes=2, out=out, residual=out)
+    gemm_bf16_split(ap, bp[:, 2 * kp:3 * kp], K, planes=1, out=out, residual=out)
+    return out if buf.shape[1] == N else out.contiguous()
 
 
 # ------------------------------------------------------------------------------------------ UltraNet (DoReFa)

@@ -8,11 +8,14 @@ behaviour, so ``model_to_quantize_model`` / GETA / checkpoints keep working unch
   parameter version, exact integer contraction on the tcgen05 ``kind::i8`` pipe with TMEM int32 accumulators and
   a fused dequant + bias epilogue (``qvit_gemm_i8``).  The reference runs ~11 elementwise ATen kernels per
   quantizer and an fp32 GEMM on fake-quant values (QL:495-499).
-* training (autograd): fake-quant values from ONE fused kernel per quantizer and the fused STE/step-size
-  backward (``qvit_sym_backward``); the two fp32 gradient GEMMs stay on cuBLAS (their ``grad_output`` operand is
-  never quantized by the reference).
-* configurations the int8 pipe cannot carry (weight-only mode, > 8-bit codes, grouped conv) use the same
-  fused quantizer kernels and a library fp32 GEMM/conv on the GPU.  There is no CPU path.
+* training (autograd): ``QuantLinearFunction`` - exact int8 tensor-core forward, the two gradient GEMMs on tcgen05
+  ``kind::f16`` with the fp32 gradient split exactly into three bf16 planes (the reference never quantizes
+  ``grad_output``), ONE fused kernel per quantizer for the STE mask and the step-size / range /
+  exponent reductions (``qvit_sym_backward``).  QuantizeConv2d trains through the same Functions on the im2col matrix.
+* configurations the int8 pipe cannot carry (> 8-bit codes - where GETA starts, train.py:247-250 - and weight-only mode)
+  run ``WideQuantLinearFunction`` / ``ops.matmul_f32_tc``: fp32-equivalent tensor-core GEMMs (both operands as three
+  exact bf16 planes).  A sync-free monitor (``_DispatchMonitor``) moves a layer between the two paths as GETA walks its
+  bit width.  Only grouped convolutions fall back to the reference op chain on library kernels.  There is no CPU path.
 """
 from __future__ import annotations
 
@@ -93,7 +96,7 @@ class _DispatchMonitor:
     GETA moves d_quant / q_m / t_quant every step through raw ``.data`` writes (geta.py:571-772) and walks the bit width
     from the conversion value (32 in train.py:247-250) down to ~4-8 bits (geta.py:895-900).  Whether a layer's codes fit the
     int8 tensor-core pipe therefore changes DURING training, and asking the device each step would synchronise every
-    layer.  Instead, roughly once per training step one tiny kernel (``qvit_quant_sat_levels``) evaluates all saturation
+    layer.  Instead, once per training step (detected as a layer running again) one tiny kernel (``qvit_quant_sat_levels``) evaluates all saturation
     codes through a pointer table, the result and the flag word are copied to pinned memory asynchronously, and the copy is
     consumed by whichever forward() first finds its event complete.  A layer takes the int8 path only while both codes
     are <= MARGIN (120 < 127): one step of lag cannot push a code past 127, so the int8 kernels never have to clamp; above
@@ -108,8 +111,8 @@ class _DispatchMonitor:
         self.device = device
         self.mods = []                 # weak references, slot = index
         self.sat = []                  # [2 * n] python floats (weight, activation), lagged
-        self.calls = 0
-        self.n_live = 0                # registered modules still alive (a refresh is due every n_live forward calls)
+        self.seen = set()              # slots that ran since the last refresh was launched
+        self.n_live = 0                # registered modules still alive
         self.pending = None            # CUDA event of the read-back in flight
         self.key = None
         self.ptab = self.dev_sat = self.host_sat = None
@@ -153,7 +156,6 @@ class _DispatchMonitor:
         w.zero_()                                                      # stream-ordered after the copy: later bits are kept
         self.pending = torch.cuda.Event()
         self.pending.record()
-        self.calls = 0
 
     def _consume(self) -> int:
         self.pending = None
@@ -172,7 +174,7 @@ class _DispatchMonitor:
         bits, self.sticky = self.sticky, 0
         return bits
 
-    def tick(self):
+    def tick(self, slot: int = -1):
         if torch.cuda.is_current_stream_capturing():
             return
         if self.pending is not None and self.pending.query():
@@ -183,15 +185,19 @@ class _DispatchMonitor:
             if bits & ops._lib.QVIT_FLAG_NAN_GRAD:
                 self.sticky &= ~ops._lib.QVIT_FLAG_NAN_GRAD
                 raise NanInGradientError("Error: NaN appears in gradient! (reported by the fused quantizer backward)")
-        self.calls += 1
-        if self.pending is None and self.calls >= max(1, self.n_live):
-            self._launch()
+        # a refresh is due once per training step: a step boundary is a layer calling again before the read-back was renewed
+        # (robust against modules that are registered but not part of the running model)
+        if slot in self.seen:
+            self.seen.clear()
+            if self.pending is None:
+                self._launch()
+        self.seen.add(slot)
 
     def int8_ok(self, mod) -> bool:
         slot = mod.__dict__.get("_mon_slot")
         if slot is None or slot[0] is not self or self.mods[slot[1]]() is not mod:
             slot = mod.__dict__["_mon_slot"] = (self, self.register(mod))
-        self.tick()
+        self.tick(slot[1])
         i = slot[1]
         return self.sat[2 * i] <= self.MARGIN and 0 <= self.sat[2 * i + 1] <= self.MARGIN
 
@@ -347,6 +353,78 @@ class QuantLinearFunction(torch.autograd.Function):
             check_nan_flags()
         return (None if grad_x is None else grad_x.view(ctx.x_shape), grad_w, grad_b, s_a[0:1], s_a[1:2],
                 s_a[2:3] if ctx.nl else None, s_w[0:1], s_w[1:2], s_w[2:3] if ctx.nl else None, None, None)
+
+
+class _LinearF32Function(torch.autograd.Function):
+    """F.linear on fp32 operands as fp32-equivalent tensor-core GEMMs (ops.matmul_f32_tc), forward and backward."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        x2 = x.reshape(-1, w.shape[1]).contiguous()
+        ctx.save_for_backward(x2, w)
+        ctx.x_shape, ctx.has_bias = x.shape, bias is not None
+        return ops.matmul_f32_tc(x2, w.detach().contiguous(), None if bias is None else bias.detach()).reshape(*x.shape[:-1], w.shape[0])
+
+    @staticmethod
+    def backward(ctx, g):
+        x2, w = ctx.saved_tensors
+        g2 = g.reshape(-1, w.shape[0]).contiguous()
+        gx = ops.matmul_f32_tc(g2, w.detach().contiguous(), b_transposed=True).view(ctx.x_shape) if ctx.needs_input_grad[0] else None
+        gw = ops.matmul_f32_tc(g2, x2, a_transposed=True, b_transposed=True) if ctx.needs_input_grad[1] else None
+        return gx, gw, (g2.sum(0) if ctx.has_bias else None)
+
+
+class WideQuantLinearFunction(torch.autograd.Function):
+    """QuantizeLinear (QL:495-499) for quantizers whose codes do NOT fit the int8 pipe - more than 8 bits (GETA starts at 16 or
+    32 bits and walks down, train.py:247-250 / geta.py:895-900) or weight-only mode - still on the tensor cores.
+
+    forward : fake-quant values from the fused quantizer kernels, then F.linear as an fp32-equivalent tcgen05 GEMM (both fp32
+              operands split exactly into three bf16 planes, six plane products, fp32 accumulation - ops.matmul_f32_tc).
+    backward: the two gradient GEMMs the same way, then ONE fused kernel per quantizer (STE mask + step-size / range /
+              exponent reductions), exactly as on the int8 path.  a_q is None in weight-only mode (QL:497)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, d_a, qm_a, t_a, d_w, qm_w, t_w, clip_a, clip_w):
+        K, N = weight.shape[1], weight.shape[0]
+        x2 = x.reshape(-1, K).contiguous()
+        wv = ops.fake_quantize_sym(weight.detach(), d_w, qm_w, t_w)
+        xv = x2 if d_a is None else ops.fake_quantize_sym(x2, d_a, qm_a, t_a)
+        y = ops.matmul_f32_tc(xv, wv, None if bias is None else bias.detach())
+        ctx.clip_a, ctx.clip_w, ctx.has_bias = clip_a, clip_w, bias is not None
+        ctx.x_shape, ctx.has_a, ctx.nl_a, ctx.nl_w = x.shape, d_a is not None, t_a is not None, t_w is not None
+        saved = [x2, weight, xv, wv, d_w, qm_w] + ([t_w] if t_w is not None else []) + \
+                ([d_a, qm_a] + ([t_a] if t_a is not None else []) if d_a is not None else [])
+        ctx.save_for_backward(*saved)
+        return y.reshape(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, g):
+        sv = list(ctx.saved_tensors)
+        x2, weight, xv, wv, d_w, qm_w = sv[:6]
+        sv = sv[6:]
+        t_w = sv.pop(0) if ctx.nl_w else None
+        d_a = qm_a = t_a = None
+        if ctx.has_a:
+            d_a, qm_a = sv.pop(0), sv.pop(0)
+            t_a = sv.pop(0) if ctx.nl_a else None
+        N = weight.shape[0]
+        g2 = g.reshape(-1, N).contiguous()
+        flags = _flags_for(g.device)
+        need_x = ctx.needs_input_grad[0] or ctx.has_a
+        grad_xq = ops.matmul_f32_tc(g2, wv, b_transposed=True) if need_x else None          # g @ w_q        [M, K]
+        grad_wq = ops.matmul_f32_tc(g2, xv, a_transposed=True, b_transposed=True)            # g^T @ x_q      [N, K]
+        if not ctx.has_a:
+            grad_x, s_a = grad_xq, None
+        else:
+            grad_x, s_a = ops.sym_backward(x2, grad_xq, d_a, qm_a, t_a, ctx.clip_a, want_grad_x=ctx.needs_input_grad[0], flags=flags)
+        grad_w, s_w = ops.sym_backward(weight.detach(), grad_wq, d_w, qm_w, t_w, ctx.clip_w, flags=flags)
+        grad_b = g2.sum(0) if ctx.has_bias else None
+        if EAGER_NAN_CHECK:
+            check_nan_flags()
+        gx = grad_x.view(ctx.x_shape) if (grad_x is not None and ctx.needs_input_grad[0]) else None
+        return (gx, grad_w, grad_b,
+                None if s_a is None else s_a[0:1], None if s_a is None else s_a[1:2], s_a[2:3] if (s_a is not None and ctx.nl_a) else None,
+                s_w[0:1], s_w[1:2], s_w[2:3] if ctx.nl_w else None, None, None)
 
 
 def _get_quantizer(qtype: QuantizationType):
@@ -505,6 +583,20 @@ class QuantizeMixin:
         ok = _monitor_for(self.weight.device).int8_ok(self)
         return ok and not self.__dict__.get("_force_wide", False)      # (_force_wide: tests compare the two paths)
 
+    def _wide_autograd(self, x2d_or_nd: torch.Tensor, weight2d: torch.Tensor, bias) -> torch.Tensor:
+        """Training forward on the wide path (DGE keeps the reference op chain: its backward is its own formula)."""
+        if self.quant_type == QuantizationType.DGE or x2d_or_nd.dtype != torch.float32:
+            w = self.quantize_weight(weight2d)
+            x = self.quantize_act(x2d_or_nd)
+            return _LinearF32Function.apply(x, w, bias) if x.dtype == torch.float32 else F.linear(x, w, bias)
+        d_w, q_w, t_w = self._wt_qparams()
+        if self.quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION:
+            d_a, q_a, t_a = self._act_qparams()
+        else:
+            d_a = q_a = t_a = None
+        return WideQuantLinearFunction.apply(x2d_or_nd, weight2d, bias, d_a, q_a, t_a, d_w, q_w, t_w,
+                                             _clip_pair(self.act_clip_val), _clip_pair(self.weight_clip_val))
+
     def _weight_codes(self, c: _QuantCache) -> torch.Tensor:
         """[out, pad16(K)] int8 codes, K = in_features or C*kh*kw ordered (c, kh, kw) = weight.reshape(O, -1)."""
         if c.w_codes is None:
@@ -598,10 +690,7 @@ class QuantizeLinear(QuantizeMixin, nn.Linear):
                 d_w, q_w, t_w = self._wt_qparams()
                 return QuantLinearFunction.apply(input_, self.weight, self.bias, d_a, q_a, t_a, d_w, q_w, t_w,
                                                  _clip_pair(self.act_clip_val), _clip_pair(self.weight_clip_val))
-            weight = self.quantize_weight(self.weight)
-            if self.quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION:
-                input_ = self.quantize_act(input_)
-            return F.linear(input_, weight, self.bias)
+            return self._wide_autograd(input_, self.weight, self.bias)
         c = self._refresh_cache()
         if self._int8_ok(c) and input_.dtype == torch.float32:
             K, N = self.in_features, self.out_features
@@ -611,11 +700,12 @@ class QuantizeLinear(QuantizeMixin, nn.Linear):
             y = ops.gemm_i8(a_codes, self._weight_codes(c), K, N, out_kind=ops.QVIT_OUT_F32, scale_a=d_a,
                             scale_w=self.d_quant_wt, bias=self.bias, flags=flags)
             return y.reshape(*input_.shape[:-1], N)
-        # wide path: codes do not fit int8 (or weight-only mode) -> fused quantizer kernels + library fp32 GEMM
-        x = input_
+        # wide path: codes do not fit int8 (or weight-only mode) -> fused quantizer kernels + fp32-equivalent tensor-core GEMM
+        x = input_.reshape(-1, self.in_features)
         if self.quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION:
-            x = ops.fake_quantize_sym(input_, *self._act_qparams())
-        return F.linear(x, self._weight_fake(c), self.bias)
+            x = ops.fake_quantize_sym(x, *self._act_qparams())
+        y = ops.matmul_f32_tc(x.float(), self._weight_fake(c), self.bias)
+        return y.reshape(*input_.shape[:-1], self.out_features).to(input_.dtype)
 
 
 class QuantizeConv2d(QuantizeMixin, nn.Conv2d):
@@ -648,14 +738,34 @@ class QuantizeConv2d(QuantizeMixin, nn.Conv2d):
     def forward(self, input_: torch.Tensor) -> torch.Tensor:
         """QL:575-587."""
         ops._lib.require_cuda(input_, self.weight)
+        plain = (self.groups == 1 and input_.dim() == 4 and not isinstance(self.padding, str) and self.padding_mode == "zeros"
+                 and input_.dtype == torch.float32)
         if self._needs_autograd(input_):
-            weight = self.quantize_weight(self.weight)
-            if self.quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION:
-                input_ = self.quantize_act(input_)
-            return F.conv2d(input_, weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+            if not plain:                      # grouped / exotic convolutions: the reference op chain on library kernels
+                weight = self.quantize_weight(self.weight)
+                if self.quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION:
+                    input_ = self.quantize_act(input_)
+                return F.conv2d(input_, weight, self.bias, self.stride, self.padding, self.dilation, self.groups)
+            # conv = im2col + QuantizeLinear on the patch matrix, through the same autograd Functions as QuantizeLinear: the
+            # quantizers are elementwise, so quantizing the unfolded matrix gives the same values, and the step-size / range
+            # sums over the duplicated elements equal the reference's sums over x against the folded gradient (padding zeros
+            # contribute nothing).  F.unfold / its backward (col2im) are data movement, not arithmetic.
+            B, O = input_.shape[0], self.out_channels
+            cols = F.unfold(input_, self.kernel_size, self.dilation, self.padding, self.stride)        # [B, C*kh*kw, L]
+            L = cols.shape[-1]
+            OH = (input_.shape[2] + 2 * self.padding[0] - self.dilation[0] * (self.kernel_size[0] - 1) - 1) // self.stride[0] + 1
+            cols2 = cols.transpose(1, 2).reshape(B * L, -1)
+            w2 = self.weight.reshape(O, -1)
+            if self._int8_train_ok():
+                d_a, q_a, t_a = self._act_qparams()
+                d_w, q_w, t_w = self._wt_qparams()
+                y2 = QuantLinearFunction.apply(cols2, w2, self.bias, d_a, q_a, t_a, d_w, q_w, t_w,
+                                               _clip_pair(self.act_clip_val), _clip_pair(self.weight_clip_val))
+            else:
+                y2 = self._wide_autograd(cols2, w2, self.bias)
+            return y2.view(B, L, O).permute(0, 2, 1).reshape(B, O, OH, L // OH)
         c = self._refresh_cache()
-        if (self._int8_ok(c) and self.groups == 1 and input_.dtype == torch.float32 and input_.dim() == 4
-                and not isinstance(self.padding, str) and self.padding_mode == "zeros"):
+        if self._int8_ok(c) and plain:
             flags = _flags_for(input_.device)
             d_a, q_a, t_a = self._act_qparams()
             cols, OH, OW = ops.im2col_quantize_sym(input_, self.kernel_size, self.stride, self.padding, self.dilation,
@@ -671,6 +781,13 @@ class QuantizeConv2d(QuantizeMixin, nn.Conv2d):
         x = input_
         if self.quant_mode == QuantizationMode.WEIGHT_AND_ACTIVATION:
             x = ops.fake_quantize_sym(input_, *self._act_qparams())
+        if plain:                              # wide path: im2col + fp32-equivalent tensor-core GEMM
+            B, O = x.shape[0], self.out_channels
+            cols = F.unfold(x, self.kernel_size, self.dilation, self.padding, self.stride)
+            L = cols.shape[-1]
+            OH = (x.shape[2] + 2 * self.padding[0] - self.dilation[0] * (self.kernel_size[0] - 1) - 1) // self.stride[0] + 1
+            y2 = ops.matmul_f32_tc(cols.transpose(1, 2).reshape(B * L, -1), self._weight_fake(c).reshape(O, -1), self.bias)
+            return y2.view(B, L, O).permute(0, 2, 1).reshape(B, O, OH, L // OH)
         return F.conv2d(x, self._weight_fake(c), self.bias, self.stride, self.padding, self.dilation, self.groups)
 
 

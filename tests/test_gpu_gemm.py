@@ -358,3 +358,22 @@ def test_f16x2_output_planes(ops, M, N, K):
     # the unscaled value equals the plain fp32 epilogue exactly (a power-of-two column scale commutes with the rounding)
     y0 = ops.gemm_i8(a, w, K, N, out_kind=ops.QVIT_OUT_F32, scale_a=0.013, scale_w=0.021, bias=bias, acc_abs_max=49 * K)
     assert torch.equal(y / cs, y0)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 96, 200), (394, 768, 768), (33, 37, 27), (768, 3072, 394)])
+def test_matmul_f32_tc_matches_fp64(ops, M, N, K):
+    """ops.matmul_f32_tc: fp32-equivalent GEMM on the tensor cores (both operands as three exact bf16 planes, six plane
+    products) for the wide (> 8-bit / weight-only) path.  Bar: 2e-5 of max|ref| (a plain fp32 GEMM scores ~1e-6, TF32 ~5e-4)."""
+    g = torch.Generator().manual_seed(M * 7 + N)
+    a = (torch.randn(M, K, generator=g) * 0.7).cuda()
+    b = (torch.randn(N, K, generator=g) * 0.05).cuda()
+    bias = torch.randn(N, generator=g).cuda()
+    ref = a.double() @ b.double().t() + bias.double()
+    out = ops.matmul_f32_tc(a, b, bias)
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    print(f"matmul_f32_tc M={M} N={N} K={K}: max-norm error {err:.2e}")
+    assert out.shape == (M, N) and err <= 2e-5
+    # transposed operand forms used by the backward passes
+    out_t = ops.matmul_f32_tc(a.t().contiguous(), b.t().contiguous(), a_transposed=True, b_transposed=True)
+    err_t = float((out_t.double() - (ref - bias.double())).abs().max() / ref.abs().max())
+    assert err_t <= 2e-5

@@ -1,7 +1,8 @@
 // Developer micro-benchmark: issue / pipe throughput of the CUDA-core instructions the GEMM epilogue is made of (sm_100a).
-// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o pipes pipes.cu ; run on the GPU box.
+// Build: nvcc -cudart shared -gencode arch=compute_100a,code=sm_100a -O3 -o pipes.bin pipes.cu ; run on the GPU box.
 #include <cstdio>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 #define ITERS 4096
@@ -58,6 +59,23 @@ __global__ void __launch_bounds__(512, 1) k(float* out, float seed, int n_iter) 
       if (MODE == 14) { x[j] = fmaf(x[j], c0, c1); asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(x[j])); }  // FFMA + MUFU
       if (MODE == 15) u[j] = (uint32_t)__float2int_rn(x[j]) , x[j] += 1.0f;           // F2I (+FADD)
       if (MODE == 16) x[j] = x[j] + c0;                                                // FADD
+      if (MODE == 17 && (j & 1) == 0) {                                                // F2FP.F16.F32.PACK_AB (2 elements per instruction)
+        const __half2 h = __floats2half2_rn(x[j], x[j + 1]);
+        u[j] ^= *reinterpret_cast<const uint32_t*>(&h);
+        x[j] += 1.0f;
+      }
+      if (MODE == 18) {                                                                // HADD2.F32 (fp16 -> fp32)
+        const __half2 h = *reinterpret_cast<const __half2*>(&u[j]);
+        x[j] += __low2float(h);
+        u[j] += 0x3c01u;
+      }
+      if (MODE == 19) x[j] = fmaf(x[j], 1.0009765625f, 0.25f);                         // FFMA, immediate operands
+      if (MODE == 20 && (j & 1) == 0) {                                                // FADD2
+        unsigned long long p;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(p) : "f"(x[j]), "f"(x[j + 1]));
+        asm("add.rn.f32x2 %0, %0, %1;" : "+l"(p) : "l"(cc0));
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(x[j]), "=f"(x[j + 1]) : "l"(p));
+      }
     }
   }
   float s = 0;
@@ -105,5 +123,9 @@ int main() {
   run<10>("FFMA + FMNMX (pairs)", 1);
   run<11>("FFMA2 + FMNMX (pairs)", 1);
   run<14>("FFMA + MUFU (pairs)", 1);
+  run<17>("F2FP.F16 pack (+FADD, IADD; per element)", 1);
+  run<18>("HADD2.F32 unpack (+FADD, IADD)", 1);
+  run<19>("FFMA imm", 1);
+  run<20>("FADD2 (per fp32 add)", 1);
   return 0;
 }
