@@ -125,6 +125,14 @@ int qvit_ultra_conv_bn_act(const uint8_t* in_codes, int B, int H, int W, int C,
                            int out_levels, int pool, uint8_t* out_codes, float* out_f32,
                            qvit_stream_t stream);
 
+/* The same fused layer as an IMPLICIT GEMM on the tcgen05 int8 tensor-core pipe (M = output pixels, N = O, K = taps * C,
+ * unsigned activation codes x signed weight codes -> int32 in TMEM), for C in {16, 32, 64, 128}, stride 1.  w_packed: int8
+ * [O_pad, K_pad], k = (ky * kw + kx) * C + c (the [O, kh, kw, C] codes flattened), O_pad = O rounded up to 16, K_pad = kh*kw*C
+ * rounded up to 128, zero padded.  Weights stay resident in shared memory while a persistent CTA walks its pixel tiles; the
+ * im2col tile is gathered in shared memory, never in HBM.  Codes are identical to qvit_ultra_conv_bn_act.   */
+int qvit_ultra_conv_tc(const uint8_t* in_codes, int B, int H, int W, int C, const int8_t* w_packed, int O, int kh, int kw,
+                       int pad, float acc_scale, const float* bn_scale, const float* bn_bias, int out_levels, int pool,
+                       uint8_t* out_codes, float* out_f32, qvit_stream_t stream);
 /* ------------------------------------------------------------------ BN fold / pack (one-time)
  * mode 0: nn.BatchNorm2d eval  scale = gamma/sqrt(var+eps),   bias = beta - mean*scale   (MM:74.. + F.batch_norm)
  * mode 1: export fold          scale = gamma/(sqrt(var)+eps), bias = beta - mean/(sqrt(var)+eps)*gamma (QZ:34-46) */

@@ -4,7 +4,9 @@ MM:71-125): 8 x [Conv2d_Q 3x3 -> nn.BatchNorm2d(eval) -> activation_quantize_fn(
 One-time preparation (K1' + K5): weight codes via the fused tanh/max/round kernels, re-laid out as
 [O, kh, kw, C] int8; BatchNorm folded to per-channel (scale, bias) with the nn.BatchNorm2d formula
 (eps inside the sqrt; ``fold="export"`` selects quantization.py:34-46 instead).
-Per image: every layer is ONE kernel (integer conv on activation codes + BN + clamp/round + pool on codes),
+Per image: every layer is ONE kernel (integer conv on activation codes + BN + clamp/round + pool on codes) - layers 1..8
+as implicit GEMMs on the tcgen05 int8 tensor-core pipe (weights resident in shared memory, im2col tile gathered in shared
+memory, int32 accumulators in TMEM), layer 0 (3 input channels) on the CUDA-core dp4a kernel -,
 NHWC uint8 codes between layers, and the whole chain is replayed from a CUDA graph (batch-1 latency is
 launch-bound: 0.4 GOP, 105 KB of weights).
 
@@ -27,7 +29,11 @@ ULTRANET_LAYERS = [(0, 1, True), (4, 5, True), (8, 9, True), (12, 13, True), (16
 
 class UltraNetEngine:
     def __init__(self, state_dict: Dict[str, torch.Tensor], w_bit: int = 4, a_bit: int = 4, bn_eps: float = 1e-5,
-                 input_bits: Optional[int] = 8, fold: str = "torch", device="cuda"):
+                 input_bits: Optional[int] = 8, fold: str = "torch", device="cuda", conv: str = "tc"):
+        """conv: "tc" = layers with 16 / 32 / 64 / 128 input channels (L1..L8) as implicit GEMMs on the tcgen05 int8 pipe
+        (qvit_ultra_conv_tc), "simt" = every layer on the CUDA-core dp4a kernel (layer 0 with its 3 input channels always)."""
+        if conv not in ("tc", "simt"):
+            raise ValueError("conv must be 'tc' or 'simt'")
         self.device = torch.device(device)
         if self.device.type != "cuda":
             raise RuntimeError("UltraNetEngine runs on CUDA (sm_100a) only - there is no CPU fallback")
@@ -49,6 +55,9 @@ class UltraNetEngine:
                                                     bn_eps, mode=0 if fold == "torch" else 1)
             else:
                 L["scale"], L["bias"] = None, (None if L["conv_bias"] is None else L["conv_bias"].float().contiguous())
+            kh, kw = w.shape[2], w.shape[3]
+            L["kh"], L["kw"] = kh, kw
+            L["w_tc"] = ops.pack_conv_weights_tc(L["codes_ohwi"]) if (conv == "tc" and ops.ultra_conv_tc_supported(L["C"], L["O"], kh, kw)) else None
             self.layers.append(L)
         if input_bits is not None:
             # layer-0 input channels padded 3 -> 4 so the dp4a kernel reads whole words
@@ -81,12 +90,18 @@ class UltraNetEngine:
             taps.append(h)
         acc_scale = 1.0 / (self.a_levels * self.w_levels)
         for L in self.layers[1:-1]:
-            h = ops.ultra_conv_bn_act(h, L["codes_ohwi"], L["pad"], acc_scale, L["scale"], L["bias"], self.a_levels, L["pool"])
+            h = self._layer(L, h, acc_scale)
             if taps is not None:
                 taps.append(h)
-        last = self.layers[-1]
-        return ops.ultra_conv_bn_act(h, last["codes_ohwi"], last["pad"], acc_scale, None, last["bias"], self.a_levels, False,
-                                     f32_out=True)
+        return self._layer(self.layers[-1], h, acc_scale, f32_out=True)
+
+    def _layer(self, L: dict, h: torch.Tensor, acc_scale: float, f32_out: bool = False) -> torch.Tensor:
+        scale = None if f32_out else L["scale"]
+        pool = False if f32_out else L["pool"]
+        if L["w_tc"] is not None:
+            return ops.ultra_conv_tc(h, L["w_tc"], L["O"], L["kh"], L["kw"], L["pad"], acc_scale, scale, L["bias"], self.a_levels, pool,
+                                     f32_out=f32_out)
+        return ops.ultra_conv_bn_act(h, L["codes_ohwi"], L["pad"], acc_scale, scale, L["bias"], self.a_levels, pool, f32_out=f32_out)
 
     __call__ = forward
 

@@ -17,7 +17,7 @@ from ._lib import (QVIT_ACT_GELU, QVIT_ACT_NONE, QVIT_ACT_RELU, QVIT_GEMM_AUTO, 
                    QVIT_OUT_BF16, QVIT_OUT_F16X2, QVIT_OUT_F32, QVIT_OUT_I8, QVIT_OUT_I32, QVIT_OUT_NONE)
 
 __all__ = ["pad16", "quantize_sym", "fake_quantize_sym", "sym_backward", "absmax", "im2col_quantize_sym", "gemm_i8",
-           "layernorm_quantize", "attention_f32", "attention_f32_supported", "split3_bf16", "codes_to_bf16_t", "gemm_bf16_split", "matmul_f32_tc", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "bn_fold",
+           "layernorm_quantize", "attention_f32", "attention_f32_supported", "split3_bf16", "codes_to_bf16_t", "gemm_bf16_split", "matmul_f32_tc", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "ultra_conv_tc", "pack_conv_weights_tc", "ultra_conv_tc_supported", "bn_fold",
            "bn_act_quantize_int", "pack_int4", "unpack_int4", "new_flags", "QVIT_OUT_I32", "QVIT_OUT_F32",
            "QVIT_OUT_BF16", "QVIT_OUT_I8", "QVIT_OUT_NONE", "QVIT_OUT_F16X2", "attention_f16x2", "split2_f16", "f16x2_exponent", "QVIT_ACT_NONE", "QVIT_ACT_GELU", "QVIT_ACT_RELU", "QVIT_GEMM_AUTO",
            "QVIT_GEMM_TCGEN05", "QVIT_GEMM_SIMT"]
@@ -511,6 +511,48 @@ def ultra_conv_bn_act(in_codes: torch.Tensor, w_codes_ohwi: torch.Tensor, pad: i
                                                  float(acc_scale), _lib.ptr(bn_scale), _lib.ptr(bn_bias), int(out_levels),
                                                  1 if pool else 0, _lib.ptr(oc), _lib.ptr(of), _lib.stream()),
                "qvit_ultra_conv_bn_act")
+    return out
+
+
+def pack_conv_weights_tc(w_codes_ohwi: torch.Tensor) -> torch.Tensor:
+    """[O, kh, kw, C] int8 weight codes -> the [O_pad, K_pad] operand of ultra_conv_tc (flattened (tap, channel) order, O padded to
+    16 and K to 128 with zeros).  One-time, per model."""
+    O = w_codes_ohwi.shape[0]
+    flat = w_codes_ohwi.reshape(O, -1)
+    K = flat.shape[1]
+    out = torch.zeros(((O + 15) // 16 * 16, (K + 127) // 128 * 128), dtype=torch.int8, device=w_codes_ohwi.device)
+    out[:O, :K] = flat
+    return out
+
+
+def ultra_conv_tc_supported(C: int, O: int, kh: int, kw: int) -> bool:
+    K_pad = (kh * kw * C + 127) // 128 * 128
+    return C in (16, 32, 64, 128) and O <= 256 and (K_pad // 128) * ((O + 15) // 16 * 16 + 128) * 128 + 2048 <= 227 * 1024
+
+
+def ultra_conv_tc(in_codes: torch.Tensor, w_packed: torch.Tensor, O: int, kh: int, kw: int, pad: int, acc_scale: float,
+                  bn_scale: Optional[torch.Tensor], bn_bias: Optional[torch.Tensor], out_levels: int, pool: bool,
+                  f32_out: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """One fused integer UltraNet layer as an implicit GEMM on tcgen05 (include/qvit_b200.h: qvit_ultra_conv_tc).
+    in_codes [B,H,W,C] uint8, w_packed from pack_conv_weights_tc.  Same outputs as ultra_conv_bn_act."""
+    _lib.require_cuda(in_codes, w_packed)
+    if in_codes.dtype != torch.uint8 or w_packed.dtype != torch.int8:
+        raise TypeError("ultra_conv_tc: uint8 activations and int8 weights expected")
+    in_codes = in_codes.contiguous()
+    B, H, W, Cc = in_codes.shape
+    OH, OW = H + 2 * pad - kh + 1, W + 2 * pad - kw + 1
+    dev = in_codes.device
+    if f32_out:
+        if out is None:
+            out = torch.empty((B, O, OH, OW), dtype=torch.float32, device=dev)
+        oc, of = None, out
+    else:
+        if out is None:
+            out = torch.empty((B, OH // 2, OW // 2, O) if pool else (B, OH, OW, O), dtype=torch.uint8, device=dev)
+        oc, of = out, None
+    _lib.check(_lib.lib().qvit_ultra_conv_tc(_lib.ptr(in_codes), B, H, W, Cc, _lib.ptr(w_packed), int(O), kh, kw, int(pad),
+                                             float(acc_scale), _lib.ptr(bn_scale), _lib.ptr(bn_bias), int(out_levels),
+                                             1 if pool else 0, _lib.ptr(oc), _lib.ptr(of), _lib.stream()), "qvit_ultra_conv_tc")
     return out
 
 

@@ -735,6 +735,21 @@ class QuantizeConv2d(QuantizeMixin, nn.Conv2d):
             initialize_quant_layer(q, num_bits=num_bits, quant_type=quant_type, quant_mode=quant_mode)
         return q
 
+    def _patch_matrix(self, x: torch.Tensor):
+        """im2col of an NCHW tensor -> ([B * OH * OW, C * kh * kw] fp32 with K ordered (c, kh, kw), OH * OW, OH), autograd-aware.
+        Non-overlapping patches (the ViT patch embedding, vit_model.py:94-103) are a pure permutation: one strided copy for the
+        whole batch; everything else goes through F.unfold (one im2col launch per image)."""
+        B, Cc, Hh, Ww = x.shape
+        kh, kw = self.kernel_size
+        if self.stride == self.kernel_size and self.padding == (0, 0) and self.dilation == (1, 1) and Hh % kh == 0 and Ww % kw == 0:
+            OH, OW = Hh // kh, Ww // kw
+            cols2 = x.reshape(B, Cc, OH, kh, OW, kw).permute(0, 2, 4, 1, 3, 5).reshape(B * OH * OW, Cc * kh * kw)
+            return cols2, OH * OW, OH
+        cols = F.unfold(x, self.kernel_size, self.dilation, self.padding, self.stride)                 # [B, C*kh*kw, L]
+        L = cols.shape[-1]
+        OH = (Hh + 2 * self.padding[0] - self.dilation[0] * (kh - 1) - 1) // self.stride[0] + 1
+        return cols.transpose(1, 2).reshape(B * L, -1), L, OH
+
     def forward(self, input_: torch.Tensor) -> torch.Tensor:
         """QL:575-587."""
         ops._lib.require_cuda(input_, self.weight)
@@ -751,10 +766,7 @@ class QuantizeConv2d(QuantizeMixin, nn.Conv2d):
             # sums over the duplicated elements equal the reference's sums over x against the folded gradient (padding zeros
             # contribute nothing).  F.unfold / its backward (col2im) are data movement, not arithmetic.
             B, O = input_.shape[0], self.out_channels
-            cols = F.unfold(input_, self.kernel_size, self.dilation, self.padding, self.stride)        # [B, C*kh*kw, L]
-            L = cols.shape[-1]
-            OH = (input_.shape[2] + 2 * self.padding[0] - self.dilation[0] * (self.kernel_size[0] - 1) - 1) // self.stride[0] + 1
-            cols2 = cols.transpose(1, 2).reshape(B * L, -1)
+            cols2, L, OH = self._patch_matrix(input_)
             w2 = self.weight.reshape(O, -1)
             if self._int8_train_ok():
                 d_a, q_a, t_a = self._act_qparams()
@@ -783,10 +795,8 @@ class QuantizeConv2d(QuantizeMixin, nn.Conv2d):
             x = ops.fake_quantize_sym(input_, *self._act_qparams())
         if plain:                              # wide path: im2col + fp32-equivalent tensor-core GEMM
             B, O = x.shape[0], self.out_channels
-            cols = F.unfold(x, self.kernel_size, self.dilation, self.padding, self.stride)
-            L = cols.shape[-1]
-            OH = (x.shape[2] + 2 * self.padding[0] - self.dilation[0] * (self.kernel_size[0] - 1) - 1) // self.stride[0] + 1
-            y2 = ops.matmul_f32_tc(cols.transpose(1, 2).reshape(B * L, -1), self._weight_fake(c).reshape(O, -1), self.bias)
+            cols2, L, OH = self._patch_matrix(x)
+            y2 = ops.matmul_f32_tc(cols2, self._weight_fake(c).reshape(O, -1), self.bias)
             return y2.view(B, L, O).permute(0, 2, 1).reshape(B, O, OH, L // OH)
         return F.conv2d(x, self._weight_fake(c), self.bias, self.stride, self.padding, self.dilation, self.groups)
 

@@ -415,3 +415,34 @@ def test_ultranet_cuda_graph(golden):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(ys, eager)
+
+
+@pytest.mark.parametrize("batch", [1, 3])
+def test_ultranet_tensor_core_conv_equals_cuda_core_conv(golden, batch):
+    """qvit_ultra_conv_tc (implicit GEMM on tcgen05 kind::i8, TMEM accumulators) against the CUDA-core dp4a kernel on every layer it
+    serves (L1..L8: C in {16, 32, 64}; 3x3 with / without pooling, and the 1x1 head with fp32 output): the integer
+    accumulators are exact on both pipes and the epilogue arithmetic is the same sequence, so the codes must be IDENTICAL -
+    on the reference's own layer inputs (golden taps) and on random codes for a ragged batch."""
+    from quantized_vit_b200 import ops
+    from quantized_vit_b200.engine import UltraNetEngine
+    g = golden("ultranet")
+    eng = UltraNetEngine(fixtures.ultranet_state_dict(), input_bits=8, conv="tc")
+    gen = torch.Generator().manual_seed(batch)
+    for i in range(1, 9):
+        L = eng.layers[i]
+        assert L["w_tc"] is not None, f"layer {i} is not on the tensor-core path"
+        prev = _t(g[f"tap{i - 1}.codes"]).permute(0, 2, 3, 1).contiguous().cuda()
+        if batch > 1:
+            prev = torch.randint(0, 16, (batch, prev.shape[1] - (i % 2), prev.shape[2] - 1 + (i % 2), prev.shape[3]), generator=gen,
+                                 dtype=torch.int64).to(torch.uint8).cuda()
+            if L["pool"]:                                      # pooled layers need even maps like the real network
+                prev = prev[:, : prev.shape[1] // 2 * 2, : prev.shape[2] // 2 * 2].contiguous()
+        last = i == 8
+        args = (L["pad"], 1.0 / (15 * 7), None if last else L["scale"], L["bias"], 15, False if last else L["pool"])
+        want = ops.ultra_conv_bn_act(prev, L["codes_ohwi"], *args, f32_out=last)
+        got = ops.ultra_conv_tc(prev, L["w_tc"], L["O"], L["kh"], L["kw"], *args, f32_out=last)
+        assert got.shape == want.shape
+        assert torch.equal(got, want), f"layer {i}: {int((got != want).sum())} of {want.numel()} outputs differ"
+    # and the whole network through either path
+    x = fixtures.ultranet_input(1).cuda()
+    assert torch.equal(eng(x), UltraNetEngine(fixtures.ultranet_state_dict(), input_bits=8, conv="simt")(x))

@@ -34,11 +34,11 @@ def main():
     crit = torch.nn.CrossEntropyLoss()
 
     def step():
-        model.zero_grad(set_to_none=True)
+        red.zero_grad()                      # persistent bucket views: no flatten / unflatten copies
         loss = crit(model(xs), ys) / 1.0
-        loss.backward()
+        loss.backward()                      # bucket all-reduces are launched from the backward hooks
         red.reduce()
-        parallel.clip_gradients_(model.parameters(), 1.0)
+        red.clip_(1.0)
         return loss
 
     for _ in range(2):

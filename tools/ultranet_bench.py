@@ -7,21 +7,45 @@ from quantized_vit_b200.engine import UltraNetEngine
 from quantized_vit_b200.engine.synthetic import ultranet_state_dict
 
 sd = ultranet_state_dict()
-eng = UltraNetEngine(sd, input_bits=8)
 out = {}
-for B in (1, 64):
-    x = torch.round(torch.rand(B, 3, 160, 320, device="cuda") * 255) / 255
-    xs, ys, g = eng.capture(B)
-    xs.copy_(x)
-    for _ in range(10):
-        g.replay()
-    ts = []
-    for _ in range(200 if B == 1 else 30):
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    med = statistics.median(ts)
-    out[f"batch{B}"] = {"latency_us": med * 1e3, "img_per_s": B / med * 1e3}
+for conv in ("tc", "simt"):
+    eng = UltraNetEngine(sd, input_bits=8, conv=conv)
+    for B in (1, 64, 256):
+        x = torch.round(torch.rand(B, 3, 160, 320, device="cuda") * 255) / 255
+        xs, ys, g = eng.capture(B)
+        xs.copy_(x)
+        for _ in range(10):
+            g.replay()
+        ts = []
+        for _ in range(200 if B == 1 else 20):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); g.replay(); e1.record(); torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1))
+        med = statistics.median(ts)
+        out[f"{conv}_batch{B}"] = {"latency_us": med * 1e3, "img_per_s": B / med * 1e3, "tops": B * 2 * UltraNetEngine.macs_per_image() / med / 1e9}
+if "--layers" in sys.argv:      # per-layer device time at batch 256 (eager, CUDA events around each launch)
+    from quantized_vit_b200 import ops
+    eng = UltraNetEngine(sd, input_bits=8, conv="tc")
+    x = torch.round(torch.rand(256, 3, 160, 320, device="cuda") * 255) / 255
+    taps = []
+    eng(x, taps=taps)
+    acc_scale = 1.0 / (15 * 7)
+    for i in range(1, 9):
+        L = eng.layers[i]
+        prev = taps[i - 1]
+        last = i == 8
+        for name, fn in (("tc", lambda: eng._layer(L, prev, acc_scale, f32_out=last)),
+                         ("simt", lambda: ops.ultra_conv_bn_act(prev, L["codes_ohwi"], L["pad"], acc_scale, None if last else L["scale"], L["bias"], 15,
+                                                                False if last else L["pool"], f32_out=last))):
+            for _ in range(3):
+                fn()
+            ts = []
+            for _ in range(10):
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record(); fn(); e1.record(); torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            macs = 256 * L["C"] * L["O"] * L["kh"] * L["kw"] * prev.shape[1] * prev.shape[2]
+            out[f"layer{i}_{name}_b256"] = {"us": statistics.median(ts) * 1e3, "tops": 2 * macs / statistics.median(ts) / 1e9}
 from oracle import ref_models
 torch.set_num_threads(os.cpu_count())
 sdc = {k: v.cpu() for k, v in sd.items()}
