@@ -133,6 +133,12 @@ int qvit_ultra_conv_bn_act(const uint8_t* in_codes, int B, int H, int W, int C,
 int qvit_ultra_conv_tc(const uint8_t* in_codes, int B, int H, int W, int C, const int8_t* w_packed, int O, int kh, int kw,
                        int pad, float acc_scale, const float* bn_scale, const float* bn_bias, int out_levels, int pool,
                        uint8_t* out_codes, float* out_f32, qvit_stream_t stream);
+/* QuantizeConv2d.forward (QL:575-587) as the same implicit GEMM on SIGNED int8 activation codes in NHWC [B, H, W, C], C in
+ * {16, 32, 64, 128}, any stride / symmetric padding / dilation, groups == 1: out fp32 NCHW [B, O, OH, OW] =
+ * acc * |*scale_a| * |*scale_w| + bias[o].  w_packed as for qvit_ultra_conv_tc ([O, kh, kw, C] codes flattened and padded). */
+int qvit_conv2d_i8_tc(const int8_t* a_codes_nhwc, int B, int H, int W, int C, const int8_t* w_packed, int O, int kh, int kw,
+                      int sh, int sw, int pad, int dh, int dw, const float* scale_a, const float* scale_w, const float* bias,
+                      float* out_nchw, qvit_stream_t stream);
 /* ------------------------------------------------------------------ BN fold / pack (one-time)
  * mode 0: nn.BatchNorm2d eval  scale = gamma/sqrt(var+eps),   bias = beta - mean*scale   (MM:74.. + F.batch_norm)
  * mode 1: export fold          scale = gamma/(sqrt(var)+eps), bias = beta - mean/(sqrt(var)+eps)*gamma (QZ:34-46) */

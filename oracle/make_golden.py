@@ -151,6 +151,11 @@ def golden_layers():
     run_conv("conv_3x3_w4a4", 3, 8, 3, 2, 1, 1, 1, False, 4, 4, L, WA, xc, 12)
     run_conv("conv_3x3_w4a8_dil", 4, 8, 3, 1, 2, 2, 1, True, 4, 8, L, WA, torch.randn(1, 4, 13, 11, generator=_gen(311)), 13)
     run_conv("conv_groups_wo", 4, 8, 3, 1, 1, 1, 2, True, 8, None, L, WO, torch.randn(1, 4, 9, 9, generator=_gen(312)), 14)
+    # channel counts the implicit-GEMM tensor-core conv serves (C in {16, 32, 64, 128}): plain, strided, dilated
+    run_conv("conv_c32_3x3_w4a4", 32, 48, 3, 1, 1, 1, 1, True, 4, 4, L, WA, torch.randn(2, 32, 19, 23, generator=_gen(313)), 15)
+    run_conv("conv_c16_s2_w4a8", 16, 40, 3, 2, 1, 1, 1, False, 4, 8, L, WA, torch.randn(3, 16, 17, 12, generator=_gen(314)), 16)
+    run_conv("conv_c64_dil2_w8a8", 64, 64, 3, 1, 2, 2, 1, True, 8, 8, L, WA, torch.randn(1, 64, 14, 14, generator=_gen(315)), 17)
+    run_conv("conv_c16_1x1_w4a4", 16, 36, 1, 1, 0, 1, 1, True, 4, 4, L, WA, torch.randn(2, 16, 10, 20, generator=_gen(316)), 18)
     out["cases"] = np.array(names)
     np.savez_compressed(os.path.join(OUT, "geta_layers.npz"), **out)
 

@@ -50,6 +50,7 @@ PROTOTYPES = {
     "qvit_conv2d_f32_wcodes": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _f, _p, _p, _p]),
     "qvit_ultra_conv_bn_act": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _f, _p, _p, _i, _i, _p, _p, _p]),
     "qvit_ultra_conv_tc": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _f, _p, _p, _i, _i, _p, _p, _p]),
+    "qvit_conv2d_i8_tc": (_i, [_p, _i, _i, _i, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p]),
     "qvit_bn_fold": (_i, [_p, _p, _p, _p, _f, _i, _i, _p, _p, _p]),
     "qvit_bn_act_quantize_int": (_i, [_p, _p, _p, _p, _i, C.c_double, _i, _i, _i, _i, _i, _p, _p, _p]),
     "qvit_pack_int4": (_i, [_p, _i64, _p, _p]),

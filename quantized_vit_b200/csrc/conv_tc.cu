@@ -33,7 +33,10 @@ struct Params {
   const float* bn_bias;
   uint8_t* out_codes;
   float* out_f32;
+  const float* scale_a;      // optional (1,) device scalars multiplied into acc_scale (|.| taken): GETA's d_quant_act / d_quant_wt
+  const float* scale_w;
   int B, H, W, C, O, O_pad, kh, kw, pad, K, K_pad;
+  int sh, sw, dh, dw, a_signed;
   int OH, OW, pool, out_levels, linear, tiles_per_img, tiles_x, total_tiles, tmem_cols;
   float acc_scale;
 };
@@ -96,7 +99,10 @@ __global__ void __launch_bounds__(ctc::kThreads, 1) ultra_conv_tc_kernel(const c
   const int taps = p.kh * p.kw;
   const int cp = p.C >> 4;                                           // 16-byte pieces per (pixel, tap): 1, 2, 4 or 8
   const int cp_shift = 31 - __clz(cp);
-  const uint32_t idesc = ptx::make_idesc_i8(kTileM, p.O_pad, false, true);
+  const uint32_t idesc = ptx::make_idesc_i8(kTileM, p.O_pad, p.a_signed != 0, true);
+  float acc_scale = p.acc_scale;
+  if (p.scale_a) acc_scale *= fabsf(__ldg(p.scale_a));
+  if (p.scale_w) acc_scale *= fabsf(__ldg(p.scale_w));
   uint32_t phase = 0;
 
   for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
@@ -125,7 +131,7 @@ __global__ void __launch_bounds__(ctc::kThreads, 1) ultra_conv_tc_kernel(const c
         int oy, ox;
         pixel(r, oy, ox);
         const int ky = tap / p.kw, kx = tap - ky * p.kw;
-        const int iy = oy + ky - p.pad, ix = ox + kx - p.pad;
+        const int iy = oy * p.sh + ky * p.dh - p.pad, ix = ox * p.sw + kx * p.dw - p.pad;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (oy >= 0 && iy >= 0 && iy < p.H && ix >= 0 && ix < p.W)
           v = ldg16(p.in + (((int64_t)b * p.H + iy) * p.W + ix) * p.C + c16 * 16);
@@ -167,7 +173,7 @@ __global__ void __launch_bounds__(ctc::kThreads, 1) ultra_conv_tc_kernel(const c
             for (int j = 0; j < 16; ++j) {
               const int o = o0 + j;
               if (o < p.O) {
-                float yv = (float)(int32_t)acc[j] * p.acc_scale;
+                float yv = (float)(int32_t)acc[j] * acc_scale;
                 if (p.bn_scale) yv *= __ldg(p.bn_scale + o);
                 if (p.bn_bias) yv += __ldg(p.bn_bias + o);
                 p.out_f32[(((int64_t)b * p.O + o) * p.OH + oy) * p.OW + ox] = yv;
@@ -180,7 +186,7 @@ __global__ void __launch_bounds__(ctc::kThreads, 1) ultra_conv_tc_kernel(const c
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           const int o = o0 + j;
-          float yv = (float)(int32_t)acc[j] * p.acc_scale;
+          float yv = (float)(int32_t)acc[j] * acc_scale;
           if (o < p.O) {
             if (p.bn_scale) yv *= __ldg(p.bn_scale + o);
             if (p.bn_bias) yv += __ldg(p.bn_bias + o);
@@ -230,20 +236,23 @@ using namespace qvit;
 // Fused UltraNet layer on the tensor cores.  in_codes: uint8 NHWC [B, H, W, C] (C % 16 == 0, C <= 128); w_packed: int8
 // [O_pad, K_pad] with k = (ky * kw + kx) * C + c, O_pad = O rounded up to 16, K_pad = kh * kw * C rounded up to 128, zero padded
 // (the [O, kh, kw, C] codes of the CUDA-core kernel, flattened and padded).  Stride 1.  Outputs as qvit_ultra_conv_bn_act.
-extern "C" int qvit_ultra_conv_tc(const uint8_t* in_codes, int B, int H, int W, int C, const int8_t* w_packed, int O, int kh, int kw,
-                                  int pad, float acc_scale, const float* bn_scale, const float* bn_bias, int out_levels, int pool,
-                                  uint8_t* out_codes, float* out_f32, qvit_stream_t stream) {
+static int conv_tc_launch(const void* in_codes, int a_signed, int B, int H, int W, int C, const int8_t* w_packed, int O, int kh, int kw,
+                          int sh, int sw, int pad, int dh, int dw, float acc_scale, const float* scale_a, const float* scale_w,
+                          const float* bn_scale, const float* bn_bias, int out_levels, int pool, uint8_t* out_codes, float* out_f32,
+                          qvit_stream_t stream) {
   QVIT_REQUIRE(in_codes && w_packed && (out_codes || out_f32), "qvit_ultra_conv_tc: null pointer");
-  QVIT_REQUIRE(B > 0 && H > 0 && W > 0 && O > 0 && kh > 0 && kw > 0 && pad >= 0, "qvit_ultra_conv_tc: bad geometry");
+  QVIT_REQUIRE(B > 0 && H > 0 && W > 0 && O > 0 && kh > 0 && kw > 0 && pad >= 0 && sh > 0 && sw > 0 && dh > 0 && dw > 0,
+               "qvit_ultra_conv_tc: bad geometry");
   QVIT_REQUIRE(C == 16 || C == 32 || C == 64 || C == 128, "qvit_ultra_conv_tc: C must be 16, 32, 64 or 128 (got %d)", C);
   QVIT_REQUIRE(O <= 256, "qvit_ultra_conv_tc: O <= 256");
   QVIT_REQUIRE((reinterpret_cast<uintptr_t>(in_codes) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
                "qvit_ultra_conv_tc: 16-byte aligned operands");
   ctc::Params p;
-  p.in = in_codes; p.wpk = w_packed; p.bn_scale = bn_scale; p.bn_bias = bn_bias; p.out_codes = out_codes; p.out_f32 = out_f32;
+  p.in = reinterpret_cast<const uint8_t*>(in_codes); p.wpk = w_packed; p.bn_scale = bn_scale;
+  p.scale_a = scale_a; p.scale_w = scale_w; p.sh = sh; p.sw = sw; p.dh = dh; p.dw = dw; p.a_signed = a_signed; p.bn_bias = bn_bias; p.out_codes = out_codes; p.out_f32 = out_f32;
   p.B = B; p.H = H; p.W = W; p.C = C; p.O = O; p.O_pad = (O + 15) / 16 * 16; p.kh = kh; p.kw = kw; p.pad = pad;
   p.K = kh * kw * C; p.K_pad = (p.K + 127) / 128 * 128;
-  p.OH = H + 2 * pad - kh + 1; p.OW = W + 2 * pad - kw + 1;
+  p.OH = (H + 2 * pad - dh * (kh - 1) - 1) / sh + 1; p.OW = (W + 2 * pad - dw * (kw - 1) - 1) / sw + 1;
   QVIT_REQUIRE(p.OH > 0 && p.OW > 0, "qvit_ultra_conv_tc: empty output");
   QVIT_REQUIRE(!pool || (out_codes && !out_f32), "qvit_ultra_conv_tc: pooling applies to the code output only");
   QVIT_REQUIRE(out_f32 || (out_levels >= 1 && out_levels <= 255), "qvit_ultra_conv_tc: out_levels in [1,255]");
@@ -282,4 +291,22 @@ extern "C" int qvit_ultra_conv_tc(const uint8_t* in_codes, int B, int H, int W, 
   const int grid = (int)(total < sm_count() ? total : sm_count());
   ultra_conv_tc_kernel<<<grid, ctc::kThreads, smem, (cudaStream_t)stream>>>(p);
   return check_launch("qvit_ultra_conv_tc");
+}
+
+extern "C" int qvit_ultra_conv_tc(const uint8_t* in_codes, int B, int H, int W, int C, const int8_t* w_packed, int O, int kh, int kw,
+                                  int pad, float acc_scale, const float* bn_scale, const float* bn_bias, int out_levels, int pool,
+                                  uint8_t* out_codes, float* out_f32, qvit_stream_t stream) {
+  return conv_tc_launch(in_codes, 0, B, H, W, C, w_packed, O, kh, kw, 1, 1, pad, 1, 1, acc_scale, nullptr, nullptr, bn_scale, bn_bias,
+                        out_levels, pool, out_codes, out_f32, stream);
+}
+
+// QuantizeConv2d.forward (quant_layers.py:575-587) as the same implicit GEMM: SIGNED int8 activation codes in NHWC [B, H, W, C]
+// (C in {16, 32, 64, 128}), weights packed as above, any stride / padding / dilation (symmetric padding, groups == 1);
+// y[b, o, oy, ox] = acc * |d_a| * |d_w| + bias[o] as fp32 NCHW.  No im2col matrix is materialised.
+extern "C" int qvit_conv2d_i8_tc(const int8_t* a_codes_nhwc, int B, int H, int W, int C, const int8_t* w_packed, int O, int kh, int kw,
+                                 int sh, int sw, int pad, int dh, int dw, const float* scale_a, const float* scale_w, const float* bias,
+                                 float* out_nchw, qvit_stream_t stream) {
+  QVIT_REQUIRE(out_nchw != nullptr, "qvit_conv2d_i8_tc: null output");
+  return conv_tc_launch(a_codes_nhwc, 1, B, H, W, C, w_packed, O, kh, kw, sh, sw, pad, dh, dw, 1.0f, scale_a, scale_w, nullptr, bias, 1, 0,
+                        nullptr, out_nchw, stream);
 }

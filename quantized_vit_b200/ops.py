@@ -17,7 +17,7 @@ from ._lib import (QVIT_ACT_GELU, QVIT_ACT_NONE, QVIT_ACT_RELU, QVIT_GEMM_AUTO, 
                    QVIT_OUT_BF16, QVIT_OUT_F16X2, QVIT_OUT_F32, QVIT_OUT_I8, QVIT_OUT_I32, QVIT_OUT_NONE)
 
 __all__ = ["pad16", "quantize_sym", "fake_quantize_sym", "sym_backward", "absmax", "im2col_quantize_sym", "gemm_i8",
-           "layernorm_quantize", "attention_f32", "attention_f32_supported", "split3_bf16", "codes_to_bf16_t", "gemm_bf16_split", "matmul_f32_tc", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "ultra_conv_tc", "pack_conv_weights_tc", "ultra_conv_tc_supported", "bn_fold",
+           "layernorm_quantize", "attention_f32", "attention_f32_supported", "split3_bf16", "codes_to_bf16_t", "gemm_bf16_split", "matmul_f32_tc", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "ultra_conv_tc", "conv2d_i8_tc", "pack_conv_weights_tc", "ultra_conv_tc_supported", "bn_fold",
            "bn_act_quantize_int", "pack_int4", "unpack_int4", "new_flags", "QVIT_OUT_I32", "QVIT_OUT_F32",
            "QVIT_OUT_BF16", "QVIT_OUT_I8", "QVIT_OUT_NONE", "QVIT_OUT_F16X2", "attention_f16x2", "split2_f16", "f16x2_exponent", "QVIT_ACT_NONE", "QVIT_ACT_GELU", "QVIT_ACT_RELU", "QVIT_GEMM_AUTO",
            "QVIT_GEMM_TCGEN05", "QVIT_GEMM_SIMT"]
@@ -553,6 +553,26 @@ def ultra_conv_tc(in_codes: torch.Tensor, w_packed: torch.Tensor, O: int, kh: in
     _lib.check(_lib.lib().qvit_ultra_conv_tc(_lib.ptr(in_codes), B, H, W, Cc, _lib.ptr(w_packed), int(O), kh, kw, int(pad),
                                              float(acc_scale), _lib.ptr(bn_scale), _lib.ptr(bn_bias), int(out_levels),
                                              1 if pool else 0, _lib.ptr(oc), _lib.ptr(of), _lib.stream()), "qvit_ultra_conv_tc")
+    return out
+
+
+def conv2d_i8_tc(a_codes_nhwc: torch.Tensor, w_packed: torch.Tensor, O: int, kernel, stride, pad: int, dilation, scale_a, scale_w,
+                 bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """QuantizeConv2d as an implicit GEMM on tcgen05: signed int8 NHWC codes [B,H,W,C] x packed weight codes -> fp32 NCHW."""
+    _lib.require_cuda(a_codes_nhwc, w_packed)
+    if a_codes_nhwc.dtype != torch.int8 or not a_codes_nhwc.is_contiguous():
+        raise TypeError("conv2d_i8_tc: contiguous int8 NHWC codes expected")
+    B, H, W, Cc = a_codes_nhwc.shape
+    kh, kw = kernel
+    OH = (H + 2 * pad - dilation[0] * (kh - 1) - 1) // stride[0] + 1
+    OW = (W + 2 * pad - dilation[1] * (kw - 1) - 1) // stride[1] + 1
+    dev = a_codes_nhwc.device
+    out = torch.empty((B, O, OH, OW), dtype=torch.float32, device=dev)
+    sa, sw_ = _scalar_param(scale_a, dev, "scale_a"), _scalar_param(scale_w, dev, "scale_w")
+    b = None if bias is None else _f32c(bias.detach(), "bias")
+    _lib.check(_lib.lib().qvit_conv2d_i8_tc(_lib.ptr(a_codes_nhwc), B, H, W, Cc, _lib.ptr(w_packed), int(O), kh, kw, stride[0], stride[1],
+                                            int(pad), dilation[0], dilation[1], _lib.ptr(sa), _lib.ptr(sw_), _lib.ptr(b), _lib.ptr(out),
+                                            _lib.stream()), "qvit_conv2d_i8_tc")
     return out
 
 

@@ -445,7 +445,7 @@ class _QuantCache:
     OTO pruning replaces ``module.weight`` with a new sliced Parameter (operator.py:481-499) and optimizers may
     write through ``.data`` without bumping ``_version``; the key therefore includes data_ptr/shape, and
     ``train()`` / ``load_state_dict`` / ``invalidate_quant_cache()`` drop the cache."""
-    __slots__ = ("key", "w_codes", "w_sat", "a_sat", "w_q")
+    __slots__ = ("key", "w_codes", "w_sat", "a_sat", "w_q", "w_tc")
 
     def __init__(self):
         self.key = None
@@ -453,6 +453,7 @@ class _QuantCache:
         self.w_sat = None
         self.a_sat = None
         self.w_q = None
+        self.w_tc = None
 
 
 def _bit_width(d: float, qmax: float, t: float) -> int:
@@ -561,7 +562,7 @@ class QuantizeMixin:
         key = self._cache_key()
         if c.key == key:
             return c
-        c.key, c.w_codes, c.w_q = key, None, None
+        c.key, c.w_codes, c.w_q, c.w_tc = key, None, None, None
         d, q, t = self._wt_qparams()
         c.w_sat = self._sat_level(d, q, t)
         c.a_sat = None
@@ -777,6 +778,20 @@ class QuantizeConv2d(QuantizeMixin, nn.Conv2d):
                 y2 = self._wide_autograd(cols2, w2, self.bias)
             return y2.view(B, L, O).permute(0, 2, 1).reshape(B, O, OH, L // OH)
         c = self._refresh_cache()
+        if (self._int8_ok(c) and plain and self.padding[0] == self.padding[1]
+                and ops.ultra_conv_tc_supported(self.in_channels, self.out_channels, *self.kernel_size)):
+            # implicit GEMM on the tensor cores: NHWC int8 activation codes, packed weight codes resident in shared memory, the
+            # im2col tile gathered on chip - nothing of the kh*kw-fold im2col matrix ever exists in HBM
+            flags = _flags_for(input_.device)
+            d_a, q_a, t_a = self._act_qparams()
+            a = ops.quantize_sym(input_.permute(0, 2, 3, 1).contiguous(), d_a, q_a, t_a, flags=flags).view(
+                input_.shape[0], input_.shape[2], input_.shape[3], self.in_channels)
+            if c.w_tc is None:
+                wc = self._weight_codes(c)[:, : self.in_channels * self.kernel_size[0] * self.kernel_size[1]]
+                wc = wc.reshape(self.out_channels, self.in_channels, *self.kernel_size).permute(0, 2, 3, 1).contiguous()
+                c.w_tc = ops.pack_conv_weights_tc(wc)
+            return ops.conv2d_i8_tc(a, c.w_tc, self.out_channels, self.kernel_size, self.stride, self.padding[0], self.dilation, d_a,
+                                    self.d_quant_wt, self.bias)
         if self._int8_ok(c) and plain:
             flags = _flags_for(input_.device)
             d_a, q_a, t_a = self._act_qparams()
