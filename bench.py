@@ -306,8 +306,47 @@ def run_ours(args, rank: int, local_rank: int, world: int):
     gemm_ops = sum(o for _, o, _, _ in eng.gemm_events)
     n_gemm = len(eng.gemm_events)
     eng.gemm_events = None
+    gemm_top_per_image = eng.gemm_ops_per_image(IMG) / 1e12
 
     int8_burst, int8_sust = measure_int8_peak(dev) if rank == 0 else (None, None)
+
+    # secondary workloads (rank 0 of a single-GPU run only; short graph-replay timings, reported beside the headline):
+    # fixture B of SURVEY.md 8d (calibrated activation ranges: the fc1 epilogue's exact-redo rate depends on the data) and
+    # BASELINE config 4 (ViT-L/16 W4A8, 128 images per GPU)
+    extras = None
+    if world == 1 and not args.no_extras:
+        extras = {}
+
+        def graph_ms(engine, batch, steps=8):
+            xs_, ys_, g_ = engine.capture(batch, IMG)
+            xs_.copy_(torch.randn(batch, 3, IMG, IMG, generator=torch.Generator().manual_seed(3)).to(dev))
+            for _ in range(3):
+                g_.replay()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(steps):
+                g_.replay()
+            b.record()
+            torch.cuda.synchronize()
+            return a.elapsed_time(b) / steps
+        del eng
+        torch.cuda.empty_cache()
+        sd_b = vit_state_dict(**CFG, num_bits=4, calibrate_to=2.5, seed=0, device=dev)
+        eng_b = ViTInferenceEngine(sd_b, depth=CFG["depth"], num_heads=CFG["num_heads"], patch_size=CFG["patch"], device=dev)
+        t_b = graph_ms(eng_b, BATCH)
+        extras["vit_b16_w4a4_calibrated_ranges"] = {"ms_per_step": t_b, "img_per_s": BATCH / t_b * 1e3, "batch": BATCH,
+                                                    "note": "fixture B: q_m_act = 2.5 for every layer (activations spread over all 15 codes)"}
+        del eng_b, sd_b
+        torch.cuda.empty_cache()
+        cfg_l = dict(embed_dim=1024, depth=24, num_heads=16, patch=16, img=IMG, classes=1000)
+        sd_l = vit_state_dict(**cfg_l, num_bits=4, act_bits=8, calibrate_to=3.0, seed=0, device=dev)
+        eng_l = ViTInferenceEngine(sd_l, depth=24, num_heads=16, patch_size=16, device=dev)
+        t_l = graph_ms(eng_l, 128, steps=5)
+        extras["vit_l16_w4a8_batch128"] = {"ms_per_step": t_l, "img_per_s": 128 / t_l * 1e3, "batch": 128,
+                                           "gemm_tops": eng_l.gemm_ops_per_image(IMG) * 128 / (t_l * 1e-3) / 1e12,
+                                           "note": "BASELINE config 4 per-GPU share (batch 1024 = 128 x 8 GPUs)", "flags": int(eng_l.flags.item())}
+        del eng_l, sd_l
+        torch.cuda.empty_cache()
 
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
@@ -353,7 +392,7 @@ def run_ours(args, rank: int, local_rank: int, world: int):
                                          "(sustained; MEASURED_PEAKS.json has no int8 entry)" if int8_sust else
                                          "2 x bf16_tflops_sustained of MEASURED_PEAKS.json (derived; int8 measurement unavailable)")},
             "cpu_baseline": cpu, "clocks": clocks, "quantizer_flags": flags,
-            "gemm_top_per_image": eng.gemm_ops_per_image(IMG) / 1e12}
+            "gemm_top_per_image": gemm_top_per_image, "other_configs": extras}
     print(json.dumps(line), flush=True)
 
 
@@ -364,6 +403,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary workloads (fixture B, ViT-L/16 W4A8)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

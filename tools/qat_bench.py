@@ -26,7 +26,10 @@ def main():
         for m in model.modules():
             if hasattr(m, "q_m_act"):
                 m.q_m_act.fill_(2.5); m.d_quant_act.fill_(2.5 / 7)
-    red = parallel.GradientAllReducer(model.named_parameters())
+    use_graph = os.environ.get("QAT_GRAPH", "0") == "1"
+    # graph mode: forward + backward are replayed from ONE CUDA graph and the bucket all-reduces are issued after it (no NCCL
+    # call inside the capture: hook-launched collectives under stream capture hung the 2-rank run), so the hooks stay off
+    red = parallel.GradientAllReducer(model.named_parameters(), overlap=not use_graph)
     g = torch.Generator().manual_seed(1)
     x = torch.randn(global_batch, 3, 224, 224, generator=g)
     y = torch.randint(0, 1000, (global_batch,), generator=torch.Generator().manual_seed(2))
@@ -41,9 +44,33 @@ def main():
         red.clip_(1.0)
         return loss
 
-    for _ in range(2):
+    for _ in range(3):
         step()
     torch.cuda.synchronize()
+    if use_graph:
+        # at 16-32 images per GPU the eager step is bound by ~1500 kernel launches, not by the kernels
+        def fwd_bwd():
+            red.zero_grad()
+            loss = crit(model(xs), ys) / 1.0
+            loss.backward()
+            return loss
+        gs = torch.cuda.Stream()
+        gs.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(gs):
+            fwd_bwd()
+        torch.cuda.current_stream().wait_stream(gs)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            static_loss = fwd_bwd()
+
+        def step():                                   # noqa: F811
+            graph.replay()
+            red.reduce()
+            red.clip_(1.0)
+            return static_loss
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -62,7 +89,7 @@ def main():
         print(json.dumps({"config": "ViT-B/16 4-bit QAT fwd+bwd+allreduce+clip", "quant_type": qtype, "n_gpus": world,
                           "global_batch": global_batch, "ms_per_step": float(ms), "img_per_s": global_batch / float(ms) * 1e3,
                           "loss": float(loss), "grad_norm_after_clip": float(gn), "grad_d_quant_act_block0_qkv": dq,
-                          "nan_flags": flags,
+                          "nan_flags": flags, "cuda_graph": use_graph,
                           "gradient_planes": __import__("quantized_vit_b200.quantization.quant_layers", fromlist=["x"]).GRADIENT_PLANES}), flush=True)
     if world > 1:
         dist.destroy_process_group()
