@@ -171,6 +171,12 @@ class ViTInferenceEngine:
         # kernel at 3e-6 vs 1e-6 max-norm error (tensor-core accumulation rounding), i.e. 0-5 proj-input code flips per
         # 302 592 elements and Block against the CPU reference (tests/test_gpu_models.py); attention="sdpa" selects the library
         use_tc3x = self.attention == "tc3x" or (self.attention == "auto" and not bf16 and ops.attention_f32_supported(NT, hd))
+        if self.attention == "auto" and not bf16 and not use_tc3x and not self.__dict__.get("_warned_sdpa"):
+            # loud, once: the own tensor-core kernels cover head_dim == 64 and T <= 208 (every ViT-B/L/H at 224 x 224)
+            import warnings
+            warnings.warn(f"ViTInferenceEngine: attention geometry head_dim={hd}, tokens={NT} is outside the tcgen05 kernels' range "
+                          "(head_dim == 64, tokens <= 208); using the library fused attention (fp32) for this model", RuntimeWarning)
+            self.__dict__["_warned_sdpa"] = True
         cp = None
         if use_tc3x:
             # own kernel, reads the qkv matrix in place (vit_model.py:133-149); proj's quantize_act (QL:356-381) is fused
