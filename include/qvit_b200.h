@@ -264,6 +264,13 @@ int qvit_layernorm_quantize(const float* x, int64_t rows, int cols, const float*
                             float eps, const float* d, const float* q_m, const float* t,
                             int8_t* codes, int64_t ld_codes, float* ln_out /* optional fp32 copy */,
                             int32_t* flags, qvit_stream_t stream);
+/* LayerNorm forward with saved statistics, and its backward, for the caller of the QAT step (Block.norm1 / norm2, VIT:202-208):
+ * y = (x - mean) * rstd * gamma + beta; gx = rstd * (g' - mean(g') - xhat * mean(g' * xhat)), g' = gy * gamma; dgamma = sum gy * xhat,
+ * dbeta = sum gy (both overwritten).  cols must be a multiple of 128, <= 1024; all tensors fp32, 16-byte aligned.           */
+int qvit_layernorm_fwd(const float* x, int64_t rows, int cols, const float* gamma, const float* beta, float eps, float* y,
+                       float* mean, float* rstd, qvit_stream_t stream);
+int qvit_layernorm_bwd(const float* x, const float* gy, int64_t rows, int cols, const float* gamma, const float* mean,
+                       const float* rstd, float* gx, float* dgamma, float* dbeta, qvit_stream_t stream);
 /* bf16 -> codes (attention output feeding `proj`): same quantizer on bf16 input widened to fp32. */
 int qvit_quantize_sym_bf16(const void* x_bf16, int64_t rows, int64_t cols, int64_t ld_x,
                            const float* d, const float* q_m, const float* t,

@@ -324,6 +324,7 @@ attention_f16x2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       const bool rows_live = q0 + (warp & 3) * 32 < T;
       ptx::mbar_wait(o_done, (uint32_t)(t & 1));
       ptx::tc_fence_after();
+      if (prof && blockIdx.x == 0 && threadIdx.x == 0 && t < 16) prof[192 + t * 4 + 0] = clock64();
       uint32_t r[16];
       if (rows_live) {
         tmem_ld16(tmem + kOCol + lane_addr + (uint32_t)(cq * 16), r);
@@ -332,6 +333,7 @@ attention_f16x2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(o_free);                   // the accumulator may be overwritten by the next P V
+      if (prof && blockIdx.x == 0 && threadIdx.x == 0 && t < 16) prof[192 + t * 4 + 1] = clock64();
       const int tq = q0 + row;
       if (rows_live && tq < T) {
         float v[16];

@@ -11,6 +11,36 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 
+class _LayerNormFunction(torch.autograd.Function):
+    """nn.LayerNorm forward / backward on the fused kernels of csrc/layernorm.cu (one pass each; the library backward runs
+    three kernels and was 5 % of the QAT step)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        from .. import ops
+        y, mean, rstd = ops.layernorm_fwd(x, weight, bias, eps)
+        ctx.save_for_backward(x, weight, mean, rstd)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        from .. import ops
+        x, weight, mean, rstd = ctx.saved_tensors
+        gx, dg, db = ops.layernorm_bwd(x, gy, weight, mean, rstd)
+        return gx, dg, db, None
+
+
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm with the same parameters / state_dict; fp32 CUDA inputs whose width the kernels cover take the fused path."""
+
+    def forward(self, x):
+        from .. import ops
+        if (x.is_cuda and x.dtype == torch.float32 and self.elementwise_affine and self.bias is not None and len(self.normalized_shape) == 1
+                and ops.layernorm_supported(self.normalized_shape[0])):
+            return _LayerNormFunction.apply(x, self.weight, self.bias, self.eps)
+        return super().forward(x)
+
+
 class PatchEmbed(nn.Module):
     def __init__(self, img_size, patch_size, in_c, embed_dim):
         super().__init__()
@@ -47,8 +77,8 @@ class Mlp(nn.Module):
 class Block(nn.Module):
     def __init__(self, dim, num_heads, mlp_ratio=4.0):
         super().__init__()
-        self.norm1, self.attn = nn.LayerNorm(dim, eps=1e-6), ViTAttention(dim, num_heads)
-        self.norm2, self.mlp = nn.LayerNorm(dim, eps=1e-6), Mlp(dim, int(dim * mlp_ratio))
+        self.norm1, self.attn = LayerNorm(dim, eps=1e-6), ViTAttention(dim, num_heads)
+        self.norm2, self.mlp = LayerNorm(dim, eps=1e-6), Mlp(dim, int(dim * mlp_ratio))
 
     def forward(self, x):
         x = x + self.attn(self.norm1(x))
@@ -65,7 +95,7 @@ class VisionTransformer(nn.Module):
         self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
         self.pos_embed = nn.Parameter(torch.zeros(1, n + 1, embed_dim))
         self.blocks = nn.Sequential(*[Block(embed_dim, num_heads, mlp_ratio) for _ in range(depth)])
-        self.norm = nn.LayerNorm(embed_dim, eps=1e-6)
+        self.norm = LayerNorm(embed_dim, eps=1e-6)
         self.head = nn.Linear(embed_dim, num_classes)
         nn.init.trunc_normal_(self.pos_embed, std=0.02)
         nn.init.trunc_normal_(self.cls_token, std=0.02)

@@ -17,7 +17,7 @@ from ._lib import (QVIT_ACT_GELU, QVIT_ACT_NONE, QVIT_ACT_RELU, QVIT_GEMM_AUTO, 
                    QVIT_OUT_BF16, QVIT_OUT_F16X2, QVIT_OUT_F32, QVIT_OUT_I8, QVIT_OUT_I32, QVIT_OUT_NONE)
 
 __all__ = ["pad16", "quantize_sym", "fake_quantize_sym", "sym_backward", "absmax", "im2col_quantize_sym", "gemm_i8",
-           "layernorm_quantize", "attention_f32", "attention_f32_supported", "split3_bf16", "codes_to_bf16_t", "gemm_bf16_split", "matmul_f32_tc", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "ultra_conv_tc", "conv2d_i8_tc", "pack_conv_weights_tc", "ultra_conv_tc_supported", "bn_fold",
+           "layernorm_quantize", "layernorm_fwd", "layernorm_bwd", "layernorm_supported", "attention_f32", "attention_f32_supported", "split3_bf16", "codes_to_bf16_t", "gemm_bf16_split", "matmul_f32_tc", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "ultra_conv_tc", "conv2d_i8_tc", "pack_conv_weights_tc", "ultra_conv_tc_supported", "bn_fold",
            "bn_act_quantize_int", "pack_int4", "unpack_int4", "new_flags", "QVIT_OUT_I32", "QVIT_OUT_F32",
            "QVIT_OUT_BF16", "QVIT_OUT_I8", "QVIT_OUT_NONE", "QVIT_OUT_F16X2", "attention_f16x2", "split2_f16", "f16x2_exponent", "QVIT_ACT_NONE", "QVIT_ACT_GELU", "QVIT_ACT_RELU", "QVIT_GEMM_AUTO",
            "QVIT_GEMM_TCGEN05", "QVIT_GEMM_SIMT"]
@@ -163,6 +163,38 @@ def layernorm_quantize(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
                                                   _lib.ptr(d_), _lib.ptr(q_), _lib.ptr(t_), _lib.ptr(codes), ld,
                                                   _lib.ptr(ln), _lib.ptr(flags), _lib.stream()), "qvit_layernorm_quantize")
     return codes, ln
+
+
+def layernorm_supported(cols: int) -> bool:
+    return cols % 128 == 0 and 0 < cols <= 1024
+
+
+def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps: float):
+    """(y, mean, rstd) of LayerNorm over the last dim (training caller; the inference engine uses layernorm_quantize)."""
+    x = _f32c(x, "layernorm_fwd")
+    x2 = x.reshape(-1, x.shape[-1])
+    rows, cols = x2.shape
+    gamma, beta = _f32c(gamma.detach(), "gamma"), _f32c(beta.detach(), "beta")
+    y = torch.empty_like(x2)
+    mean = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rstd = torch.empty(rows, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().qvit_layernorm_fwd(_lib.ptr(x2), rows, cols, _lib.ptr(gamma), _lib.ptr(beta), float(eps), _lib.ptr(y),
+                                             _lib.ptr(mean), _lib.ptr(rstd), _lib.stream()), "qvit_layernorm_fwd")
+    return y.view(x.shape), mean, rstd
+
+
+def layernorm_bwd(x: torch.Tensor, gy: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor):
+    """(gx, dgamma, dbeta) of LayerNorm."""
+    x, gy = _f32c(x, "layernorm_bwd x"), _f32c(gy, "layernorm_bwd gy")
+    x2, g2 = x.reshape(-1, x.shape[-1]), gy.reshape(-1, x.shape[-1])
+    rows, cols = x2.shape
+    gamma = _f32c(gamma.detach(), "gamma")
+    gx = torch.empty_like(x2)
+    dg = torch.empty(cols, dtype=torch.float32, device=x.device)
+    db = torch.empty(cols, dtype=torch.float32, device=x.device)
+    _lib.check(_lib.lib().qvit_layernorm_bwd(_lib.ptr(x2), _lib.ptr(g2), rows, cols, _lib.ptr(gamma), _lib.ptr(mean), _lib.ptr(rstd),
+                                             _lib.ptr(gx), _lib.ptr(dg), _lib.ptr(db), _lib.stream()), "qvit_layernorm_bwd")
+    return gx.view(x.shape), dg, db
 
 
 def attention_f32(qkv: torch.Tensor, num_heads: int, scale: Optional[float] = None) -> torch.Tensor:

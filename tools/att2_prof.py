@@ -21,6 +21,6 @@ print("tile: start  S_ready  softmax_done  epi_done | control: PV issued   (cycl
 for t in range(12):
     print(f"{t:3d}: {p[4*t]-t0:7d} {p[4*t+1]-t0:7d} {p[4*t+2]-t0:7d} {p[4*t+3]-t0:7d} | {p[64+t]-t0:7d}   "
           f"softmax {p[4*t+2]-p[4*t+1]:5d}  epi {p[4*t+3]-p[4*t+2]:5d}  wait_S {p[4*t+1]-p[4*t]:5d} | "
-          f"ld {p[128+4*t]-p[4*t+1]:5d} max+bar {p[129+4*t]-p[128+4*t]:5d} exp+split+st {p[130+4*t]-p[129+4*t]:5d} bar2 {p[131+4*t]-p[130+4*t]:5d}")
+          f"ld {p[128+4*t]-p[4*t+1]:5d} max+bar {p[129+4*t]-p[128+4*t]:5d} exp+split+st {p[130+4*t]-p[129+4*t]:5d} bar2 {p[131+4*t]-p[130+4*t]:5d} | epi(t-1): wait_O {(p[192+4*(t-1)]-p[4*t+2]) if t else 0:5d} ldO {(p[193+4*(t-1)]-p[192+4*(t-1)]) if t else 0:5d} rest {(p[4*t+3]-p[193+4*(t-1)]) if t else 0:5d}")
 med, best = timeit(lambda: ops.attention_f16x2(planes, B, T, H, exps, d, qm, None), iters=10, graph=True)
 print(f"attention_f16x2 B={B}: {med*1e3:.1f} us (best {best*1e3:.1f})")
