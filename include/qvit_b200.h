@@ -308,6 +308,16 @@ int qvit_attention_f16x2(const void* planes, int64_t ld, int plane_off, int B, i
 int qvit_split2_f16(const float* x, int64_t rows, int cols, int64_t ldx, const int* col_exp, void* out, int64_t ld,
                     int plane_off, int32_t* flags, qvit_stream_t stream);
 
+/* Attention core of the QAT step (ViTAttention.forward under autograd, VIT:133-149; config 3).  qkv: fp32 [B, T, 3, H, 64] - the
+ * output of the qkv layer as it lies in memory; out / dout: fp32 [B, T, H, 64]; lse (saved by the forward) and dstat (workspace):
+ * fp32 [B, H, 256]; planes: workspace, fp16 [B * T, 2 * 3 * H * 64]; dqkv: fp32 like qkv, every element written.
+ * head_dim must be 64 and T <= 208 (QVIT_ERR_UNSUPPORTED otherwise).  Forward: two fp16 planes, 22 significant bits; backward:
+ * two bf16 planes, 16 significant bits (fp32 range), both with fp32 accumulation on tcgen05.                                  */
+int qvit_attention_train_fwd(const float* qkv, int B, int T, int H, int head_dim, float scale, void* planes, float* out,
+                             float* lse, qvit_stream_t stream);
+int qvit_attention_train_bwd(const float* qkv, const float* out, const float* dout, const float* lse, int B, int T, int H,
+                             int head_dim, float scale, float* dstat, float* dqkv, qvit_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

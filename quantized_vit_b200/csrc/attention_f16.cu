@@ -52,62 +52,13 @@ __host__ __device__ constexpr uint32_t idesc_f16(int M, int N, bool b_mn_major) 
   return (1u << 4) /*D = f32*/ | (0u << 7) /*A = f16*/ | (0u << 10) /*B = f16*/ | ((b_mn_major ? 1u : 0u) << 16) |
          ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
-__device__ __forceinline__ void mma_f16_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n"
-      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void mma_f16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}\n"
-      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(acc)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_3d(uint32_t dst, const void* tmap, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(tmap), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
-      : "memory");
-}
-template <int N>
-__device__ __forceinline__ void tmem_st(uint32_t taddr, const uint32_t* r);
-template <>
-__device__ __forceinline__ void tmem_st<16>(uint32_t taddr, const uint32_t* r) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
-      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
-template <>
-__device__ __forceinline__ void tmem_st<8>(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
-               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
-               : "memory");
-}
-template <>
-__device__ __forceinline__ void tmem_st<2>(uint32_t taddr, const uint32_t* r) {
-  asm volatile("tcgen05.st.sync.aligned.32x32b.x2.b32 [%0], {%1, %2};" ::"r"(taddr), "r"(r[0]), "r"(r[1]) : "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
-               : "r"(taddr)
-               : "memory");
-}
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+using ptx::mma_f16_ss;
+using ptx::mma_f16_ts;
+using ptx::tma_load_3d;
+using ptx::tmem_ld16;
+using ptx::tmem_ld4;
+using ptx::tmem_st;
+using ptx::tmem_st_wait;
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -152,11 +103,14 @@ __device__ __forceinline__ void split2_pair(f32x2 v, uint32_t& hi, uint32_t& lo)
 // head-major inside a part), as the qkv GEMM writes them.  s_scale = softmax scale * log2(e) * 2^-(sq + sk); o_scale = 2^-sv.
 // (17 warps are allocated as 20 - registers come in units of four warps - so 96 registers per thread is the ceiling; the
 // softmax below is written in column groups so that it fits)
+// kLse (training forward, attention_train.cu): also writes the base-2 log-sum-exp of every row of scaled scores,
+// lse[(b * H + h) * 256 + t] = max * s_scale + log2(sum 2^(s * s_scale - max * s_scale)), which the backward recomputes P from.
+template <bool kLse>
 __global__ void __launch_bounds__(a2::kThreads, 1)
 attention_f16x2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_kv, float* __restrict__ out,
                        int T, int H, int plane_off, int total_pairs, float s_scale, float o_scale, int8_t* __restrict__ codes,
                        int64_t ld_codes, const float* __restrict__ q_d, const float* __restrict__ q_qm, const float* __restrict__ q_t,
-                       int32_t* __restrict__ q_flags, long long* __restrict__ prof) {
+                       int32_t* __restrict__ q_flags, long long* __restrict__ prof, float* __restrict__ lse) {
   using namespace a2;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (ptx::smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -433,6 +387,8 @@ attention_f16x2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         if (prof && blockIdx.x == 0 && threadIdx.x == 0 && t < 16) prof[128 + t * 4 + 3] = clock64();
         const float rs = (red_sum[row] + red_sum[kMQ + row]) + (red_sum[2 * kMQ + row] + red_sum[3 * kMQ + row]);
         inv = __fdiv_rn(o_scale, rs);                            // O' / sum(p') * 2^-sv  (the 2^10 of p' cancels)
+        if (kLse && cq == 0 && q0 + row < T)
+          lse[((int64_t)blockIdx.x + (int64_t)(t / q_tiles) * gridDim.x) * 256 + q0 + row] = mx * s_scale + (log2f(rs) - kPScaleLog2);
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -503,9 +459,10 @@ static int make_tmap_planes(CUtensorMap* map, const void* base, int B, int T, in
 
 // softmax(q k^T * scale) v from the two-plane fp16 form of qkv.  planes: fp16 [B, T, ld], hi plane in columns [0, 3*H*64), lo
 // plane in [plane_off, plane_off + 3*H*64); exp_q / exp_k / exp_v: the powers of two the producer multiplied q / k / v by.
-extern "C" int qvit_attention_f16x2(const void* planes, int64_t ld, int plane_off, int B, int T, int H, int head_dim, float scale,
-                                    int exp_q, int exp_k, int exp_v, const float* d, const float* q_m, const float* t, int8_t* codes,
-                                    int64_t ld_codes, float* out, int32_t* flags, long long* prof, qvit_stream_t stream) {
+namespace qvit {
+int attention_f16x2_launch(const void* planes, int64_t ld, int plane_off, int B, int T, int H, int head_dim, float scale, int exp_q,
+                           int exp_k, int exp_v, const float* d, const float* q_m, const float* t, int8_t* codes, int64_t ld_codes,
+                           float* out, int32_t* flags, long long* prof, float* lse, cudaStream_t stream) {
   QVIT_REQUIRE(planes && (out || codes) && B > 0 && T > 0 && H > 0, "qvit_attention_f16x2: bad argument");
   QVIT_REQUIRE(!codes || (d && q_m && ld_codes >= (int64_t)H * head_dim && (ld_codes & 15) == 0 &&
                           (reinterpret_cast<uintptr_t>(codes) & 15) == 0),
@@ -527,7 +484,8 @@ extern "C" int qvit_attention_f16x2(const void* planes, int64_t ld, int plane_of
   }
   static bool attr_set[64] = {false};
   if (dev >= 0 && dev < 64 && !attr_set[dev]) {
-    cudaError_t e = cudaFuncSetAttribute(attention_f16x2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, a2::kSmem);
+    cudaError_t e = cudaFuncSetAttribute(attention_f16x2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, a2::kSmem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attention_f16x2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, a2::kSmem);
     if (e != cudaSuccess) {
       set_error("qvit_attention_f16x2: cudaFuncSetAttribute(%d): %s", a2::kSmem, cudaGetErrorString(e));
       return QVIT_ERR_CUDA;
@@ -544,13 +502,25 @@ extern "C" int qvit_attention_f16x2(const void* planes, int64_t ld, int plane_of
   const int grid = (int)(total_pairs < sm_count() ? total_pairs : sm_count());
   const float s_scale = ldexpf(scale * 1.4426950408889634f, -(exp_q + exp_k));
   const float o_scale = ldexpf(1.0f, -exp_v);
-  attention_f16x2_kernel<<<grid, a2::kThreads, a2::kSmem, (cudaStream_t)stream>>>(tm_q, tm_kv, out, T, H, plane_off, (int)total_pairs,
-                                                                                   s_scale, o_scale, codes, ld_codes, d, q_m, t, flags, prof);
+  if (lse)
+    attention_f16x2_kernel<true><<<grid, a2::kThreads, a2::kSmem, stream>>>(tm_q, tm_kv, out, T, H, plane_off, (int)total_pairs, s_scale,
+                                                                              o_scale, codes, ld_codes, d, q_m, t, flags, prof, lse);
+  else
+    attention_f16x2_kernel<false><<<grid, a2::kThreads, a2::kSmem, stream>>>(tm_q, tm_kv, out, T, H, plane_off, (int)total_pairs, s_scale,
+                                                                               o_scale, codes, ld_codes, d, q_m, t, flags, prof, nullptr);
   return check_launch("qvit_attention_f16x2");
+}
+}  // namespace qvit
+
+extern "C" int qvit_attention_f16x2(const void* planes, int64_t ld, int plane_off, int B, int T, int H, int head_dim, float scale,
+                                    int exp_q, int exp_k, int exp_v, const float* d, const float* q_m, const float* t, int8_t* codes,
+                                    int64_t ld_codes, float* out, int32_t* flags, long long* prof, qvit_stream_t stream) {
+  return attention_f16x2_launch(planes, ld, plane_off, B, T, H, head_dim, scale, exp_q, exp_k, exp_v, d, q_m, t, codes, ld_codes, out,
+                                flags, prof, nullptr, (cudaStream_t)stream);
 }
 
 // fp32 -> the two-plane fp16 form (x * 2^e = hi + lo), for callers that hold qkv in fp32: out fp16 [rows, ld], hi in columns
-// [0, cols), lo in [plane_off, plane_off + cols); exps: one power of two per column.
+// [0, cols), lo in [plane_off, plane_off + cols); col_exp: one power of two per column (NULL = no scaling).
 namespace qvit {
 __global__ void split2_f16_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ldx, const int* __restrict__ col_exp,
                                   __half* __restrict__ out, int64_t ld, int plane_off, int32_t* __restrict__ flags) {
@@ -560,7 +530,7 @@ __global__ void split2_f16_kernel(const float* __restrict__ x, int64_t rows, int
     const int64_t r = i / (cols / 2);
     const int c = (int)(i - r * (cols / 2)) * 2;
     const float2 v = *reinterpret_cast<const float2*>(x + r * ldx + c);
-    const float a = ldexpf(v.x, col_exp[c]), b = ldexpf(v.y, col_exp[c + 1]);
+    const float a = col_exp ? ldexpf(v.x, col_exp[c]) : v.x, b = col_exp ? ldexpf(v.y, col_exp[c + 1]) : v.y;
     const __half2 h2 = __floats2half2_rn(a, b);
     const float2 hf = __half22float2(h2);
     const __half2 l2 = __floats2half2_rn(a - hf.x, b - hf.y);
@@ -575,7 +545,7 @@ __global__ void split2_f16_kernel(const float* __restrict__ x, int64_t rows, int
 
 extern "C" int qvit_split2_f16(const float* x, int64_t rows, int cols, int64_t ldx, const int* col_exp, void* out, int64_t ld,
                                int plane_off, int32_t* flags, qvit_stream_t stream) {
-  QVIT_REQUIRE(x && out && col_exp && rows >= 0 && cols > 0 && (cols & 1) == 0 && (ldx & 1) == 0 && (ld & 1) == 0 && (plane_off & 1) == 0 &&
+  QVIT_REQUIRE(x && out && rows >= 0 && cols > 0 && (cols & 1) == 0 && (ldx & 1) == 0 && (ld & 1) == 0 && (plane_off & 1) == 0 &&
                    plane_off >= cols && ld >= plane_off + cols,
                "qvit_split2_f16: bad argument (cols, pitches and plane_off must be even, ld >= plane_off + cols)");
   if (rows == 0) return QVIT_OK;

@@ -51,6 +51,25 @@ class PatchEmbed(nn.Module):
         return self.proj(x).flatten(2).transpose(1, 2)          # vit_model.py:100
 
 
+class _AttentionCoreFunction(torch.autograd.Function):
+    """softmax(q k^T / sqrt(d)) v straight on the qkv layer's output (no permuted copies), forward and backward on the tcgen05
+    kernels of csrc/attention_train.cu."""
+
+    @staticmethod
+    def forward(ctx, qkv, num_heads):
+        from .. import ops
+        out, lse = ops.attention_train_fwd(qkv, num_heads)
+        ctx.save_for_backward(qkv, out, lse)
+        ctx.num_heads = num_heads
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        from .. import ops
+        qkv, out, lse = ctx.saved_tensors
+        return ops.attention_train_bwd(qkv, out, lse, g, ctx.num_heads), None
+
+
 class ViTAttention(nn.Module):
     def __init__(self, dim, num_heads):
         super().__init__()
@@ -60,7 +79,11 @@ class ViTAttention(nn.Module):
 
     def forward(self, x):
         B, N, C = x.shape
-        qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+        from .. import ops
+        qkv = self.qkv(x)
+        if qkv.is_cuda and qkv.dtype == torch.float32 and ops.attention_train_supported(N, C // self.num_heads):
+            return self.proj(_AttentionCoreFunction.apply(qkv, self.num_heads))
+        qkv = qkv.reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
         o = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])      # softmax(q k^T / sqrt(d)) v, vit_model.py:141-149
         return self.proj(o.transpose(1, 2).reshape(B, N, C))
 

@@ -17,7 +17,7 @@ from ._lib import (QVIT_ACT_GELU, QVIT_ACT_NONE, QVIT_ACT_RELU, QVIT_GEMM_AUTO, 
                    QVIT_OUT_BF16, QVIT_OUT_F16X2, QVIT_OUT_F32, QVIT_OUT_I8, QVIT_OUT_I32, QVIT_OUT_NONE)
 
 __all__ = ["pad16", "quantize_sym", "fake_quantize_sym", "sym_backward", "absmax", "im2col_quantize_sym", "gemm_i8",
-           "layernorm_quantize", "layernorm_fwd", "layernorm_bwd", "layernorm_supported", "attention_f32", "attention_f32_supported", "split3_bf16", "codes_to_bf16_t", "gemm_bf16_split", "matmul_f32_tc", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "ultra_conv_tc", "conv2d_i8_tc", "pack_conv_weights_tc", "ultra_conv_tc_supported", "bn_fold",
+           "layernorm_quantize", "layernorm_fwd", "layernorm_bwd", "layernorm_supported", "attention_train_supported", "attention_train_fwd", "attention_train_bwd", "attention_f32", "attention_f32_supported", "split3_bf16", "codes_to_bf16_t", "gemm_bf16_split", "matmul_f32_tc", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "ultra_conv_tc", "conv2d_i8_tc", "pack_conv_weights_tc", "ultra_conv_tc_supported", "bn_fold",
            "bn_act_quantize_int", "pack_int4", "unpack_int4", "new_flags", "QVIT_OUT_I32", "QVIT_OUT_F32",
            "QVIT_OUT_BF16", "QVIT_OUT_I8", "QVIT_OUT_NONE", "QVIT_OUT_F16X2", "attention_f16x2", "split2_f16", "f16x2_exponent", "QVIT_ACT_NONE", "QVIT_ACT_GELU", "QVIT_ACT_RELU", "QVIT_GEMM_AUTO",
            "QVIT_GEMM_TCGEN05", "QVIT_GEMM_SIMT"]
@@ -288,6 +288,39 @@ def attention_f16x2(planes: torch.Tensor, B: int, T: int, num_heads: int, exps, 
                                                int(exps[2]), _lib.ptr(d_), _lib.ptr(q_), _lib.ptr(t_), _lib.ptr(codes), ldc,
                                                _lib.ptr(ctx), _lib.ptr(flags), _lib.ptr(prof), _lib.stream()), "qvit_attention_f16x2")
     return codes, ctx
+
+
+def attention_train_supported(T: int, head_dim: int) -> bool:
+    return head_dim == 64 and 1 <= T <= 208
+
+
+def attention_train_fwd(qkv: torch.Tensor, num_heads: int, scale: Optional[float] = None):
+    """Training forward of the attention core on the output of the qkv layer ([B, T, 3 * H * 64] fp32, parts q | k | v, head-major
+    inside a part).  Returns (out [B, T, H * 64] fp32, lse [B, H, 256] fp32 - what attention_train_bwd needs)."""
+    qkv = _f32c(qkv, "attention_train_fwd")
+    B, T, D3 = qkv.shape
+    hd = D3 // (3 * num_heads)
+    sc = float(hd) ** -0.5 if scale is None else float(scale)
+    planes = torch.empty((B * T, 2 * D3), dtype=torch.float16, device=qkv.device)
+    out = torch.empty((B, T, D3 // 3), dtype=torch.float32, device=qkv.device)
+    lse = torch.empty((B, num_heads, 256), dtype=torch.float32, device=qkv.device)
+    _lib.check(_lib.lib().qvit_attention_train_fwd(_lib.ptr(qkv), B, T, num_heads, hd, sc, _lib.ptr(planes), _lib.ptr(out), _lib.ptr(lse),
+                                                   _lib.stream()), "qvit_attention_train_fwd")
+    return out, lse
+
+
+def attention_train_bwd(qkv: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, dout: torch.Tensor, num_heads: int,
+                        scale: Optional[float] = None) -> torch.Tensor:
+    """d loss / d qkv ([B, T, 3 * H * 64] fp32) from d loss / d out."""
+    qkv, out, dout = _f32c(qkv, "qkv"), _f32c(out, "out"), _f32c(dout, "dout")
+    B, T, D3 = qkv.shape
+    hd = D3 // (3 * num_heads)
+    sc = float(hd) ** -0.5 if scale is None else float(scale)
+    dstat = torch.empty((B, num_heads, 256), dtype=torch.float32, device=qkv.device)
+    dqkv = torch.empty_like(qkv)
+    _lib.check(_lib.lib().qvit_attention_train_bwd(_lib.ptr(qkv), _lib.ptr(out), _lib.ptr(dout), _lib.ptr(lse), B, T, num_heads, hd, sc,
+                                                   _lib.ptr(dstat), _lib.ptr(dqkv), _lib.stream()), "qvit_attention_train_bwd")
+    return dqkv
 
 
 def attention_f32_supported(T: int, head_dim: int) -> bool:

@@ -2,6 +2,7 @@
 Reference = the same op sequence as the reference module in float64 on a deliberately sharp softmax (scores up to
 +-70).  Bar: max|delta| <= 6e-6 * max|ref|; measured 3e-6 (the library fp32 kernel scores 1e-6 on the same input, a
 single-pass TF32 kernel ~5e-4, bf16 ~4e-3)."""
+import numpy as np
 import pytest
 import torch
 
@@ -105,3 +106,55 @@ def test_attention_f16x2_fused_quantizer(nonlinear):
     assert torch.equal(codes, want)
     codes_only, none = ops.attention_f16x2(planes, B, T, H, exps, d, qm, t)
     assert none is None and torch.equal(codes_only, want)
+
+
+def _attention_ref64(qkv, H, gout):
+    B, T, D3 = qkv.shape
+    x = qkv.double().requires_grad_(True)
+    q, k, v = x.reshape(B, T, 3, H, 64).permute(2, 0, 3, 1, 4)
+    p = torch.softmax(q @ k.transpose(-2, -1) * 64 ** -0.5, dim=-1)
+    o = (p @ v).transpose(1, 2).reshape(B, T, D3 // 3)
+    o.backward(gout.double())
+    lse2 = torch.logsumexp(q.detach() @ k.detach().transpose(-2, -1) * 64 ** -0.5, dim=-1) / np.log(2.0)
+    return o.detach(), x.grad, lse2
+
+
+@pytest.mark.parametrize("B,T,H,gscale", [(3, 197, 4, 1.0), (2, 208, 2, 1e-5), (5, 50, 2, 30.0), (1, 129, 12, 1.0), (37, 197, 12, 1e-3)])
+def test_attention_train_forward_backward(B, T, H, gscale):
+    """csrc/attention_train.cu against float64 autograd of ViTAttention's core (vit_model.py:141-149): forward at the fp32 level,
+    backward at the 16-bit operand level (stated tolerance 1e-4 of the largest gradient; gradients of any magnitude)."""
+    from quantized_vit_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    qkv = (torch.randn(B, T, 3 * H * 64, generator=g) * 1.5).cuda()
+    qkv[:, :, : H * 64] *= 2.0                                   # peaked rows: |s| up to ~ 20
+    gout = (torch.randn(B, T, H * 64, generator=g) * gscale).cuda()
+    o_ref, dqkv_ref, lse_ref = _attention_ref64(qkv, H, gout)
+    out, lse = ops.attention_train_fwd(qkv, H)
+    assert float((out.double() - o_ref).abs().max()) <= 3e-6 * float(o_ref.abs().max())
+    assert float((lse[:, :, :T].double() - lse_ref).abs().max()) <= 2e-5
+    dqkv = ops.attention_train_bwd(qkv, out, lse, gout, H)
+    D = H * 64
+    for part, name in enumerate(("dq", "dk", "dv")):
+        got, want = dqkv[:, :, part * D:(part + 1) * D].double(), dqkv_ref[:, :, part * D:(part + 1) * D]
+        err = float((got - want).abs().max() / want.abs().max())
+        assert err <= 1e-4, f"{name}: {err:.2e}"
+
+
+def test_attention_module_uses_train_kernels():
+    """ViTAttention of the drop-in model (engine/vit_module.py) under autograd against the SDPA formulation it replaces."""
+    from quantized_vit_b200.engine.vit_module import ViTAttention
+    torch.manual_seed(3)
+    att = ViTAttention(128, 2).cuda()
+    x = torch.randn(4, 197, 128, device="cuda", requires_grad=True)
+    y = att(x)
+    y.square().sum().backward()
+    gx, gw = x.grad.clone(), att.qkv.weight.grad.clone()
+    x.grad = None
+    att.zero_grad()
+    qkv = att.qkv(x).reshape(4, 197, 3, 2, 64).permute(2, 0, 3, 1, 4)
+    o = torch.nn.functional.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])
+    y2 = att.proj(o.transpose(1, 2).reshape(4, 197, 128))
+    y2.square().sum().backward()
+    assert float((y - y2).detach().abs().max()) <= 1e-5 * float(y2.detach().abs().max())
+    assert float((gx - x.grad).abs().max()) <= 2e-4 * float(x.grad.abs().max())
+    assert float((gw - att.qkv.weight.grad).abs().max()) <= 2e-4 * float(att.qkv.weight.grad.abs().max())
