@@ -317,6 +317,9 @@ int qvit_attention_train_fwd(const float* qkv, int B, int T, int H, int head_dim
                              float* lse, qvit_stream_t stream);
 int qvit_attention_train_bwd(const float* qkv, const float* out, const float* dout, const float* lse, int B, int T, int H,
                              int head_dim, float scale, float* dstat, float* dqkv, qvit_stream_t stream);
+/* same; additionally records cycle stamps of the first CTA's first 8 tiles into prof (int64 [256]; NULL = off).  Diagnostic. */
+int qvit_attention_train_bwd_prof(const float* qkv, const float* out, const float* dout, const float* lse, int B, int T, int H,
+                                  int head_dim, float scale, float* dstat, float* dqkv, long long* prof, qvit_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -126,8 +126,12 @@ attention_f16x2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   const uint32_t o_done = bar0 + 72u, o_free = bar0 + 80u;
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + kOffBar + 128);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int D3 = 3 * H * kHd, D = H * kHd;
+  // warp index / TMEM base as values the compiler can SEE are warp-uniform (shuffle from lane 0): the control warp below then
+  // keeps descriptors in uniform registers and issues each tcgen05.mma as one instruction.  (Under a plain `lane == 0` guard
+  // every MMA sat in an ELECT / R2UR.BROADCAST loop; tools/ubench/mma_rate.cu: 134 -> 83 cycles per issued MMA, and the 39
+  // N = 64 P V MMAs of a tile are issue-bound.)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+  const int D = H * kHd;
   const int q_tiles = (T + kMQ - 1) / kMQ;
   const int n_pairs = ((int)blockIdx.x < total_pairs) ? (total_pairs - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
   const int nt = n_pairs * q_tiles;
@@ -156,33 +160,45 @@ attention_f16x2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == kComputeWarps) {
-    // ------------------------------------------------------------------------------------------ control thread
-    if (lane == 0 && nt > 0) {
-      ptx::prefetch_tmap(&tm_q);
-      ptx::prefetch_tmap(&tm_kv);
+    // ------------------------------------------------------------------------------------------ control warp (converged; one
+    // elected lane issues the copies and the MMAs)
+    if (nt > 0) {
+      if (lane == 0) {
+        ptx::prefetch_tmap(&tm_q);
+        ptx::prefetch_tmap(&tm_kv);
+      }
       auto pair_idx = [&](int i) { return (int)blockIdx.x + i * (int)gridDim.x; };
       auto load_q = [&](int t) {
         const int pr = pair_idx(t / q_tiles), b = pr / H, h = pr % H, qt = t % q_tiles, s = t & 1;
         const uint32_t dst = base + kOffQ + (uint32_t)(s * 2 * kQPlane);
-        ptx::mbar_expect_tx(q_full(s), 2u * kQPlane);
-        tma_load_3d(dst, &tm_q, q_full(s), h * kHd, qt * kMQ, b);
-        tma_load_3d(dst + kQPlane, &tm_q, q_full(s), plane_off + h * kHd, qt * kMQ, b);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(q_full(s), 2u * kQPlane);
+          tma_load_3d(dst, &tm_q, q_full(s), h * kHd, qt * kMQ, b);
+          tma_load_3d(dst + kQPlane, &tm_q, q_full(s), plane_off + h * kHd, qt * kMQ, b);
+        }
+        __syncwarp();
       };
       auto load_k = [&](int i) {
         const int pr = pair_idx(i), b = pr / H, h = pr % H;
-        ptx::mbar_expect_tx(k_full, 2u * kKVPlane);
-        tma_load_3d(base + kOffK, &tm_kv, k_full, D + h * kHd, 0, b);
-        tma_load_3d(base + kOffK + kKVPlane, &tm_kv, k_full, plane_off + D + h * kHd, 0, b);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(k_full, 2u * kKVPlane);
+          tma_load_3d(base + kOffK, &tm_kv, k_full, D + h * kHd, 0, b);
+          tma_load_3d(base + kOffK + kKVPlane, &tm_kv, k_full, plane_off + D + h * kHd, 0, b);
+        }
+        __syncwarp();
       };
       auto load_v = [&](int i) {
         const int pr = pair_idx(i), b = pr / H, h = pr % H, s = i & 1;
         const uint32_t dst = base + kOffV + (uint32_t)(s * 2 * kKVPlane);
-        ptx::mbar_expect_tx(v_full(s), 2u * kKVPlane);
-        tma_load_3d(dst, &tm_kv, v_full(s), 2 * D + h * kHd, 0, b);
-        tma_load_3d(dst + kKVPlane, &tm_kv, v_full(s), plane_off + 2 * D + h * kHd, 0, b);
+        if (ptx::elect_one()) {
+          ptx::mbar_expect_tx(v_full(s), 2u * kKVPlane);
+          tma_load_3d(dst, &tm_kv, v_full(s), 2 * D + h * kHd, 0, b);
+          tma_load_3d(dst + kKVPlane, &tm_kv, v_full(s), plane_off + 2 * D + h * kHd, 0, b);
+        }
+        __syncwarp();
       };
       // S_t = Q K^T: cross terms first (small), then hi * hi; 4 k-steps of 16 head-dim values (32 B inside the swizzle atom)
       auto issue_s = [&](int t) {
@@ -194,17 +210,20 @@ attention_f16x2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         const uint32_t kh = base + kOffK, kl = kh + kKVPlane;
         const uint32_t d = tmem + (uint32_t)(s ? kSB1 : 0);
         constexpr uint32_t idesc = idesc_f16(kMQ, kNK, false);
-        uint32_t acc = 0;
+        if (ptx::elect_one()) {
+          uint32_t acc = 0;
 #pragma unroll
-        for (int term = 0; term < 3; ++term) {
-          const uint32_t a_base = term == 0 ? ql : qh, b_base = term == 1 ? kl : kh;
+          for (int term = 0; term < 3; ++term) {
+            const uint64_t da = ptx::make_kmajor_sw128_desc(term == 0 ? ql : qh), db = ptx::make_kmajor_sw128_desc(term == 1 ? kl : kh);
 #pragma unroll
-          for (int ks = 0; ks < kHd / 16; ++ks) {
-            mma_f16_ss(d, ptx::make_kmajor_sw128_desc(a_base + ks * 32), ptx::make_kmajor_sw128_desc(b_base + ks * 32), idesc, acc);
-            acc = 1;
+            for (int ks = 0; ks < kHd / 16; ++ks) {
+              mma_f16_ss(d, da + 2 * ks, db + 2 * ks, idesc, acc);
+              acc = 1;
+            }
           }
+          ptx::mma_commit(s_done(s));
         }
-        ptx::mma_commit(s_done(s));
+        __syncwarp();
       };
       // O_t = P V: A = the packed-fp16 P planes in TMEM, B = the V planes as they lie in memory ([key][head dim], i.e. MN-major:
       // 8-key groups of 1024 B); 13 k-steps of 16 keys, three terms each into the one accumulator
@@ -218,16 +237,18 @@ attention_f16x2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
         const uint32_t pa = tmem + (uint32_t)(s ? kSB1 : 0);
         const uint32_t d = tmem + kOCol;
         constexpr uint32_t idesc = idesc_f16(kMQ, kHd, true);
-        uint32_t acc = 0;
-#pragma unroll 1
-        for (int ks = 0; ks < kNK / 16; ++ks) {
-          const uint64_t bh = ptx::make_kmajor_sw128_desc(vh + ks * 2048), bl = ptx::make_kmajor_sw128_desc(vl + ks * 2048);
-          mma_f16_ts(d, pa + (uint32_t)(kPCols + ks * 8), bh, idesc, acc);     // P_lo V_hi
-          mma_f16_ts(d, pa + (uint32_t)(ks * 8), bl, idesc, 1u);               // P_hi V_lo
-          mma_f16_ts(d, pa + (uint32_t)(ks * 8), bh, idesc, 1u);               // P_hi V_hi
-          acc = 1;
+        if (ptx::elect_one()) {
+          const uint64_t bh0 = ptx::make_kmajor_sw128_desc(vh), bl0 = ptx::make_kmajor_sw128_desc(vl);
+#pragma unroll
+          for (int ks = 0; ks < kNK / 16; ++ks) {
+            const uint64_t bh = bh0 + (uint64_t)(ks * 128), bl = bl0 + (uint64_t)(ks * 128);
+            mma_f16_ts(d, pa + (uint32_t)(kPCols + ks * 8), bh, idesc, ks ? 1u : 0u);   // P_lo V_hi
+            mma_f16_ts(d, pa + (uint32_t)(ks * 8), bl, idesc, 1u);                      // P_hi V_lo
+            mma_f16_ts(d, pa + (uint32_t)(ks * 8), bh, idesc, 1u);                      // P_hi V_hi
+          }
+          ptx::mma_commit(o_done);
         }
-        ptx::mma_commit(o_done);
+        __syncwarp();
       };
       auto last_of_pair = [&](int t) { return (t % q_tiles) == q_tiles - 1; };
 
@@ -245,7 +266,7 @@ attention_f16x2_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_co
       }
       for (int t = 0; t < nt; ++t) {
         issue_pv(t);
-        if (prof && blockIdx.x == 0 && t < 16) prof[64 + t] = clock64();
+        if (prof && blockIdx.x == 0 && t < 16 && lane == 0) prof[64 + t] = clock64();
         if (t + 2 < nt || last_of_pair(t)) {
           ptx::mbar_wait(o_done, (uint32_t)(t & 1));             // P V of tile t complete: its S/P buffer and (end of pair) V slot are free
           const int i = t / q_tiles;

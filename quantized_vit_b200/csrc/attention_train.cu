@@ -12,9 +12,9 @@
 //   products sits in TMEM with the lane = the output row, TS-mode MMAs as in the forward.)
 // Operands are converted in the kernel from fp32 to TWO bf16 planes (hi + lo = 16 significant bits, fp32 range - gradients need
 // no scaling) written in the 128B-swizzled layout the MMAs read; each product is lo*hi' + hi*lo' + hi*hi' with fp32 accumulation.
-// The key / query columns are walked in chunks of 64: S and dP of a chunk (2 x 64 TMEM columns, double-buffered) are turned into
+// The key / query columns are walked in chunks of 64: S and dP of a chunk (2 x 64 TMEM columns, three buffers) are turned into
 // the bf16 planes of P and dS in place, and the second products accumulate over the chunks into out1 / out2 (2 x 64 columns).
-//   control warp    one thread issues every MMA
+//   control warp    converged, one elected lane issues every MMA
 //   16 compute warps (thread = row, four warps share a row's 64 chunk columns): operand conversion, P / dS, epilogue
 #include <cuda_bf16.h>
 
@@ -41,8 +41,13 @@ constexpr int kOffC = kOffR + 4 * kRPlane;                 // C1 hi, C1 lo, C2 h
 constexpr int kOffStat = kOffC + 4 * kCPlane;              // L[256], D[256] of the item (pass 1)
 constexpr int kOffBar = kOffStat + 2 * kStat * 4;
 constexpr int kSmem = kOffBar + 256 + 1024;
+#ifndef QVIT_ATT_PREFETCH
+#define QVIT_ATT_PREFETCH 1
+#endif
+constexpr bool kPrefetchRows = QVIT_ATT_PREFETCH != 0;
+constexpr int kBufs = 3;               // chunk buffers in TMEM
 constexpr int kBufCols = 128;          // one chunk buffer: S / P planes [0, 64), dP / dS planes [64, 128)
-constexpr int kOut1 = 256, kOut2 = 320;
+constexpr int kOut1 = kBufs * kBufCols, kOut2 = kOut1 + 64;      // 384, 448: all 512 columns are in use
 
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool b_mn_major) {
   return (1u << 4) /*D = f32*/ | (1u << 7) /*A = bf16*/ | (1u << 10) /*B = bf16*/ | ((b_mn_major ? 1u : 0u) << 16) |
@@ -64,26 +69,37 @@ __device__ __forceinline__ float ex2_approx(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// fp32 rows [valid_rows, 64] (pitch row_stride) -> the hi / lo bf16 planes of an operand tile: 128-byte rows, 16-byte pieces
-// XOR-swizzled with the row number (what a SWIZZLE_128B tensor map would have written); rows past valid_rows are zero
-__device__ __forceinline__ void load_planes(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int64_t row_stride, int valid_rows,
-                                            int total_rows, int tid) {
-  for (int idx = tid; idx < total_rows * 8; idx += 32 * kComputeWarps) {
-    const int r = idx >> 3, ch = idx & 7;
-    float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+// One 16-byte piece (8 values) of an operand row -> the hi / lo bf16 planes of the tile: 128-byte rows, 16-byte pieces XOR-swizzled
+// with the row number (what a SWIZZLE_128B tensor map would have written)
+__device__ __forceinline__ void store_piece(uint8_t* hi, uint8_t* lo, int r, int ch, const float4& a, const float4& b) {
+  uint4 h, l;
+  split2_bf16(a.x, a.y, h.x, l.x);
+  split2_bf16(a.z, a.w, h.y, l.y);
+  split2_bf16(b.x, b.y, h.z, l.z);
+  split2_bf16(b.z, b.w, h.w, l.w);
+  const int off = r * 128 + ((ch ^ (r & 7)) << 4);
+  *reinterpret_cast<uint4*>(hi + off) = h;
+  *reinterpret_cast<uint4*>(lo + off) = l;
+}
+// fp32 rows [valid_rows, 64] (pitch row_stride) -> planes of total_rows (<= 256) rows, rows past valid_rows zero.  All global loads
+// of the thread are issued before the first conversion: one memory latency per call.
+__device__ __forceinline__ void load_planes_c(uint8_t* hi, uint8_t* lo, const float* __restrict__ src, int64_t row_stride, int valid_rows,
+                                              int total_rows, int tid) {
+  float4 v[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int idx = tid + k * 32 * kComputeWarps, r = idx >> 3, ch = idx & 7;
+    v[2 * k] = v[2 * k + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < valid_rows) {
       const float4* p = reinterpret_cast<const float4*>(src + (int64_t)r * row_stride + ch * 8);
-      a = __ldg(p);
-      b = __ldg(p + 1);
+      v[2 * k] = __ldg(p);
+      v[2 * k + 1] = __ldg(p + 1);
     }
-    uint4 h, l;
-    split2_bf16(a.x, a.y, h.x, l.x);
-    split2_bf16(a.z, a.w, h.y, l.y);
-    split2_bf16(b.x, b.y, h.z, l.z);
-    split2_bf16(b.z, b.w, h.w, l.w);
-    const int off = r * 128 + ((ch ^ (r & 7)) << 4);
-    *reinterpret_cast<uint4*>(hi + off) = h;
-    *reinterpret_cast<uint4*>(lo + off) = l;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int idx = tid + k * 32 * kComputeWarps, r = idx >> 3, ch = idx & 7;
+    if (r < total_rows) store_piece(hi, lo, r, ch, v[2 * k], v[2 * k + 1]);
   }
 }
 }  // namespace ab
@@ -91,7 +107,8 @@ __device__ __forceinline__ void load_planes(uint8_t* hi, uint8_t* lo, const floa
 // qkv fp32 [B, T, 3, H, 64]; dout fp32 [B, T, H, 64]; lse / dstat fp32 [B, H, 256] (finite beyond T); dqkv fp32 like qkv
 __global__ void __launch_bounds__(ab::kThreads, 1)
 attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ dout, const float* __restrict__ lse,
-                     const float* __restrict__ dstat, float* __restrict__ dqkv, int T, int H, int total_items, float scale) {
+                     const float* __restrict__ dstat, float* __restrict__ dqkv, int T, int H, int total_items, float scale,
+                     long long* __restrict__ prof) {
   using namespace ab;
   using ptx::mma_f16_ss;
   using ptx::mma_f16_ts;
@@ -103,16 +120,21 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ do
   const uint32_t bar0 = base + kOffBar;
   const uint32_t ops_ready = bar0, mma_done = bar0 + 8u, out_done = bar0 + 16u;
   auto sdp_done = [&](int b) { return bar0 + 24u + 8u * b; };
-  auto pds_ready = [&](int b) { return bar0 + 40u + 8u * b; };
+  auto pds_ready = [&](int b) { return bar0 + 48u + 8u * b; };
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + kOffBar + 128);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp-uniform values the compiler can SEE are uniform (shuffle from lane 0): the MMA-issuing code below then keeps its
+  // descriptors in uniform registers and issues each tcgen05.mma directly.  (With a plain `lane == 0` guard every MMA was wrapped
+  // in an elect / broadcast loop: tools/ubench/mma_rate.cu, 134 -> 83 cycles per issued MMA.)
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+  const int lane = threadIdx.x & 31;
   const int D = H * kHd;
   const int64_t D3 = 3 * (int64_t)D;
   const int Tc = (T + 15) & ~15;
   const int n_chunks = (Tc + 63) >> 6;
   const int r_tiles = (T + kMR - 1) / kMR;
   const int n_items = ((int)blockIdx.x < total_items) ? (total_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int n_tiles = n_items * r_tiles;
   const int half_grid = ((int)gridDim.x + 1) >> 1;
   // item -> (pair, pass); consecutive items of a CTA alternate between the passes (pass 1 is the longer one)
   auto decode = [&](int i, int& pair, int& pass) {
@@ -125,7 +147,7 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ do
     ptx::mbar_init(ops_ready, kComputeWarps);
     ptx::mbar_init(mma_done, 1);
     ptx::mbar_init(out_done, 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < kBufs; ++i) {
       ptx::mbar_init(sdp_done(i), 1);
       ptx::mbar_init(pds_ready(i), kComputeWarps);
     }
@@ -138,80 +160,92 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ do
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   if (warp == kComputeWarps) {
-    // ------------------------------------------------------------------------------------------ control thread
-    if (lane == 0) {
-      const uint32_t r1h = base + kOffR, r1l = r1h + kRPlane, r2h = r1l + kRPlane, r2l = r2h + kRPlane;
-      const uint32_t c1h = base + kOffC, c1l = c1h + kCPlane, c2h = c1l + kCPlane, c2l = c2h + kCPlane;
-      uint32_t ph_ops = 0, ph_mma = 0, ph_pds[2] = {0, 0};
-      // S and dP of chunk c into buffer b: [128 rows] x [width columns], K = 64 head-dim values in 4 steps, three terms each
-      auto issue_sdp = [&](int c, int b) {
-        const int width = min(64, Tc - 64 * c);
-        const uint32_t idesc = idesc_rt(width, false);
-        const uint32_t coff = (uint32_t)c * 8192u;
+    // ------------------------------------------------------------------------------------------ control warp (converged; one
+    // elected lane issues)
+    const uint32_t r1h = base + kOffR, r1l = r1h + kRPlane, r2h = r1l + kRPlane, r2l = r2h + kRPlane;
+    const uint32_t c1h = base + kOffC, c1l = c1h + kCPlane, c2h = c1l + kCPlane, c2l = c2h + kCPlane;
+    uint32_t ph_ops = 0, ph_mma = 0, ph_pds = 0;
+    // S and dP of chunk c into buffer b: [128 rows] x [width columns], K = 64 head-dim values in 4 steps, three terms each
+    auto issue_sdp = [&](int c, int b) {
+      const int width = min(64, Tc - 64 * c);
+      const uint32_t idesc = idesc_rt(width, false);
+      const uint32_t coff = (uint32_t)c * 8192u;
 #pragma unroll
-        for (int which = 0; which < 2; ++which) {
-          const uint32_t ah = which ? r2h : r1h, al = which ? r2l : r1l, bh = (which ? c2h : c1h) + coff, bl = (which ? c2l : c1l) + coff;
-          const uint32_t d = tmem + (uint32_t)(b * kBufCols + which * 64);
-          uint32_t acc = 0;
+      for (int which = 0; which < 2; ++which) {
+        const uint32_t ah = which ? r2h : r1h, al = which ? r2l : r1l, bh = (which ? c2h : c1h) + coff, bl = (which ? c2l : c1l) + coff;
+        const uint32_t d = tmem + (uint32_t)(b * kBufCols + which * 64);
+        const uint64_t dah = ptx::make_kmajor_sw128_desc(ah), dal = ptx::make_kmajor_sw128_desc(al);
+        const uint64_t dbh = ptx::make_kmajor_sw128_desc(bh), dbl = ptx::make_kmajor_sw128_desc(bl);
 #pragma unroll
-          for (int term = 0; term < 3; ++term) {
-            const uint32_t a_base = term == 0 ? al : ah, b_base = term == 1 ? bl : bh;
+        for (int ks = 0; ks < kHd / 16; ++ks) mma_f16_ss(d, dal + 2 * ks, dbh + 2 * ks, idesc, ks ? 1u : 0u);   // lo * hi'
 #pragma unroll
-            for (int ks = 0; ks < kHd / 16; ++ks) {
-              mma_f16_ss(d, ptx::make_kmajor_sw128_desc(a_base + ks * 32), ptx::make_kmajor_sw128_desc(b_base + ks * 32), idesc, acc);
-              acc = 1;
-            }
-          }
+        for (int ks = 0; ks < kHd / 16; ++ks) mma_f16_ss(d, dah + 2 * ks, dbl + 2 * ks, idesc, 1u);             // hi * lo'
+#pragma unroll
+        for (int ks = 0; ks < kHd / 16; ++ks) mma_f16_ss(d, dah + 2 * ks, dbh + 2 * ks, idesc, 1u);             // hi * hi'
+      }
+      ptx::mma_commit(sdp_done(b));
+    };
+    // out1 += dS_c C1_c (and out2 += P_c C2_c): A = the packed bf16 planes in TMEM (hi words [0, 32), lo words [32, 64) of the
+    // 64-column half), B = the column operand's rows as they lie in memory ([token][head dim] = MN-major, 2048 B per 16 tokens)
+    auto issue_out = [&](int c, int b, bool two, uint32_t acc0) {
+      const int ksteps = min(64, Tc - 64 * c) >> 4;
+      constexpr uint32_t idesc = idesc_bf16(kMR, kHd, true);
+      const uint32_t coff = (uint32_t)c * 8192u;
+      for (int which = 0; which < (two ? 2 : 1); ++which) {
+        const uint32_t pa = tmem + (uint32_t)(b * kBufCols + (which ? 0 : 64));     // out1 <- dS (second half), out2 <- P (first half)
+        const uint64_t dh0 = ptx::make_kmajor_sw128_desc((which ? c2h : c1h) + coff), dl0 = ptx::make_kmajor_sw128_desc((which ? c2l : c1l) + coff);
+        const uint32_t d = tmem + (uint32_t)(which ? kOut2 : kOut1);
+        uint32_t acc = acc0;
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t dh = dh0 + (uint64_t)(ks * 128), dl = dl0 + (uint64_t)(ks * 128);
+          mma_f16_ts(d, pa + (uint32_t)(32 + ks * 8), dh, idesc, acc);     // lo * hi'
+          mma_f16_ts(d, pa + (uint32_t)(ks * 8), dl, idesc, 1u);           // hi * lo'
+          mma_f16_ts(d, pa + (uint32_t)(ks * 8), dh, idesc, 1u);           // hi * hi'
+          acc = 1;
         }
-        ptx::mma_commit(sdp_done(b));
-      };
-      // out1 += dS_c C1_c (and out2 += P_c C2_c): A = the packed bf16 planes in TMEM (hi words [0, 32), lo words [32, 64) of the
-      // 64-column half), B = the column operand's rows as they lie in memory ([token][head dim] = MN-major, 2048 B per 16 tokens)
-      auto issue_out = [&](int c, int b, bool two, uint32_t acc0) {
-        const int ksteps = min(64, Tc - 64 * c) >> 4;
-        constexpr uint32_t idesc = idesc_bf16(kMR, kHd, true);
-        const uint32_t coff = (uint32_t)c * 8192u;
-        for (int which = 0; which < (two ? 2 : 1); ++which) {
-          const uint32_t pa = tmem + (uint32_t)(b * kBufCols + (which ? 0 : 64));     // out1 <- dS (second half), out2 <- P (first half)
-          const uint32_t bh = (which ? c2h : c1h) + coff, bl = (which ? c2l : c1l) + coff;
-          const uint32_t d = tmem + (uint32_t)(which ? kOut2 : kOut1);
-          uint32_t acc = acc0;
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t dh = ptx::make_kmajor_sw128_desc(bh + ks * 2048), dl = ptx::make_kmajor_sw128_desc(bl + ks * 2048);
-            mma_f16_ts(d, pa + (uint32_t)(32 + ks * 8), dh, idesc, acc);     // lo * hi'
-            mma_f16_ts(d, pa + (uint32_t)(ks * 8), dl, idesc, 1u);           // hi * lo'
-            mma_f16_ts(d, pa + (uint32_t)(ks * 8), dh, idesc, 1u);           // hi * hi'
-            acc = 1;
-          }
+      }
+    };
+    for (int it = 0; it < n_items; ++it) {
+      int pair, pass;
+      decode(it, pair, pass);
+      for (int rt = 0; rt < r_tiles; ++rt) {
+        const int tt = it * r_tiles + rt;
+        long long* pc = (prof && blockIdx.x == 0 && tt < 8 && lane == 0) ? prof + tt * 32 : nullptr;
+        if (pc) pc[0] = clock64();
+        ptx::mbar_wait(ops_ready, ph_ops);
+        ph_ops ^= 1;
+        ptx::tc_fence_after();
+        if (pc) pc[1] = clock64();
+        if (ptx::elect_one()) {
+          for (int c = 0; c < kBufs && c < n_chunks; ++c) issue_sdp(c, c);
         }
-      };
-      for (int it = 0; it < n_items; ++it) {
-        int pair, pass;
-        decode(it, pair, pass);
-        for (int rt = 0; rt < r_tiles; ++rt) {
-          ptx::mbar_wait(ops_ready, ph_ops);
-          ph_ops ^= 1;
+        __syncwarp();
+        if (pc) pc[2] = clock64();
+        for (int c = 0; c < n_chunks; ++c) {
+          const int b = c % kBufs;
+          ptx::mbar_wait(pds_ready(b), (ph_pds >> b) & 1u);
+          ph_pds ^= 1u << b;
           ptx::tc_fence_after();
-          issue_sdp(0, 0);
-          if (n_chunks > 1) issue_sdp(1, 1);
-          for (int c = 0; c < n_chunks; ++c) {
-            const int b = c & 1;
-            ptx::mbar_wait(pds_ready(b), ph_pds[b]);
-            ph_pds[b] ^= 1;
-            ptx::tc_fence_after();
+          if (pc && c < 4) pc[3 + c * 3] = clock64();
+          if (ptx::elect_one()) {
             issue_out(c, b, pass == 1, c > 0 ? 1u : 0u);
-            if (c + 2 < n_chunks) {
-              ptx::mma_commit(mma_done);                  // the planes of buffer b have been consumed: refill it with chunk c + 2
-              ptx::mbar_wait(mma_done, ph_mma);
-              ph_mma ^= 1;
-              issue_sdp(c + 2, b);
-            }
+            if (c + kBufs < n_chunks) ptx::mma_commit(mma_done);
+            if (c == n_chunks - 1) ptx::mma_commit(out_done);
           }
-          ptx::mma_commit(out_done);
+          __syncwarp();
+          if (pc && c < 4) pc[4 + c * 3] = clock64();
+          if (c + kBufs < n_chunks) {
+            ptx::mbar_wait(mma_done, ph_mma);               // the planes of buffer b have been consumed: refill it with chunk c + kBufs
+            ph_mma ^= 1;
+            if (pc && c < 2) pc[5 + c * 3] = clock64();
+            if (ptx::elect_one()) issue_sdp(c + kBufs, b);
+            __syncwarp();
+          }
         }
+        if (pc) pc[15] = clock64();
       }
     }
   } else {
@@ -221,121 +255,169 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ do
     const int cq = warp >> 2;
     const uint32_t lane_addr = ((uint32_t)((warp & 3) * 32)) << 16;
     const float s2 = scale * 1.4426950408889634f;
-    uint32_t ph_sdp[2] = {0, 0}, ph_out = 0;
-    for (int it = 0; it < n_items; ++it) {
+    uint32_t ph_sdp = 0, ph_out = 0;
+    // row operands of tile g: the global loads (into registers: issued one tile ahead, before the wait for the current tile's last
+    // MMAs) and, once those MMAs - the last readers of the old planes - are done, the conversion into the planes
+    auto r_issue = [&](int g, float4 (&pf)[8]) {
+      int pair, pass;
+      decode(g / r_tiles, pair, pass);
+      const int bi = pair / H, h = pair % H, r0 = (g % r_tiles) * kMR, vr = min(kMR, T - r0);
+      const float* qb = qkv + ((int64_t)bi * T + r0) * D3 + h * kHd;
+      const float* s1 = pass == 0 ? qb : qb + D;                                                       // q tile | k tile
+      const float* s2p = pass == 0 ? dout + ((int64_t)bi * T + r0) * D + h * kHd : qb + 2 * D;         // dO tile | v tile
+      const int64_t st2 = pass == 0 ? (int64_t)D : D3;
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int idx = tid + k * 32 * kComputeWarps, r = idx >> 3, ch = idx & 7;
+        pf[2 * k] = pf[2 * k + 1] = pf[4 + 2 * k] = pf[5 + 2 * k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (r < vr) {
+          const float4* p1 = reinterpret_cast<const float4*>(s1 + (int64_t)r * D3 + ch * 8);
+          const float4* p2 = reinterpret_cast<const float4*>(s2p + (int64_t)r * st2 + ch * 8);
+          pf[2 * k] = __ldg(p1);
+          pf[2 * k + 1] = __ldg(p1 + 1);
+          pf[4 + 2 * k] = __ldg(p2);
+          pf[5 + 2 * k] = __ldg(p2 + 1);
+        }
+      }
+    };
+    auto r_store = [&](const float4 (&pf)[8]) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int idx = tid + k * 32 * kComputeWarps, r = idx >> 3, ch = idx & 7;
+        store_piece(gen + kOffR, gen + kOffR + kRPlane, r, ch, pf[2 * k], pf[2 * k + 1]);
+        store_piece(gen + kOffR + 2 * kRPlane, gen + kOffR + 3 * kRPlane, r, ch, pf[4 + 2 * k], pf[5 + 2 * k]);
+      }
+    };
+    if (kPrefetchRows && n_tiles > 0) {
+      float4 pf[8];
+      r_issue(0, pf);
+      r_store(pf);
+    }
+#pragma unroll 1
+    for (int g = 0; g < n_tiles; ++g) {
+      const int it = g / r_tiles, rt = g - it * r_tiles;
       int pair, pass;
       decode(it, pair, pass);
       const int bi = pair / H, h = pair % H;
-      const float* qb = qkv + (int64_t)bi * T * D3 + h * kHd;               // q rows; k at + D, v at + 2 D
-      const float* gb = dout + (int64_t)bi * T * D + h * kHd;
       const float* Lg = lse + (int64_t)pair * kStat;
       const float* Dg = dstat + (int64_t)pair * kStat;
-      for (int rt = 0; rt < r_tiles; ++rt) {
-        const int r0 = rt * kMR;
-        const bool rows_live = r0 + (warp & 3) * 32 < T;
-        // ---- operands (the MMAs of the previous tile have completed: every warp waited for out_done in its epilogue)
-        if (rt == 0) {
-          if (pass == 0) {
-            load_planes(gen + kOffC, gen + kOffC + kCPlane, qb + D, D3, T, Tc, tid);                       // C1 = k
-            load_planes(gen + kOffC + 2 * kCPlane, gen + kOffC + 3 * kCPlane, qb + 2 * D, D3, T, Tc, tid); // C2 = v
-          } else {
-            load_planes(gen + kOffC, gen + kOffC + kCPlane, qb, D3, T, Tc, tid);                           // C1 = q
-            load_planes(gen + kOffC + 2 * kCPlane, gen + kOffC + 3 * kCPlane, gb, D, T, Tc, tid);          // C2 = dO
-            if (tid < kStat) {
-              Ls[tid] = __ldg(Lg + tid);
-              Ds[tid] = __ldg(Dg + tid);
-            }
-          }
-        }
-        const int vr = min(kMR, T - r0);
+      const int r0 = rt * kMR;
+      const bool rows_live = r0 + (warp & 3) * 32 < T;
+      long long* pk = (prof && blockIdx.x == 0 && tid == 0 && g < 8) ? prof + g * 32 + 16 : nullptr;
+      if (pk) pk[0] = clock64();
+      // ---- operands (the MMAs of the previous tile have completed: every warp waited for out_done in its epilogue)
+      if (!kPrefetchRows) {
+        float4 pf[8];
+        r_issue(g, pf);
+        r_store(pf);
+      }
+      if (rt == 0) {
+        const float* qb = qkv + (int64_t)bi * T * D3 + h * kHd;             // q rows; k at + D, v at + 2 D
+        const float* gb = dout + (int64_t)bi * T * D + h * kHd;
         if (pass == 0) {
-          load_planes(gen + kOffR, gen + kOffR + kRPlane, qb + (int64_t)r0 * D3, D3, vr, kMR, tid);                    // R1 = q tile
-          load_planes(gen + kOffR + 2 * kRPlane, gen + kOffR + 3 * kRPlane, gb + (int64_t)r0 * D, D, vr, kMR, tid);    // R2 = dO tile
+          load_planes_c(gen + kOffC, gen + kOffC + kCPlane, qb + D, D3, T, Tc, tid);                       // C1 = k
+          load_planes_c(gen + kOffC + 2 * kCPlane, gen + kOffC + 3 * kCPlane, qb + 2 * D, D3, T, Tc, tid); // C2 = v
         } else {
-          load_planes(gen + kOffR, gen + kOffR + kRPlane, qb + D + (int64_t)r0 * D3, D3, vr, kMR, tid);                // R1 = k tile
-          load_planes(gen + kOffR + 2 * kRPlane, gen + kOffR + 3 * kRPlane, qb + 2 * D + (int64_t)r0 * D3, D3, vr, kMR, tid);  // R2 = v tile
+          load_planes_c(gen + kOffC, gen + kOffC + kCPlane, qb, D3, T, Tc, tid);                           // C1 = q
+          load_planes_c(gen + kOffC + 2 * kCPlane, gen + kOffC + 3 * kCPlane, gb, D, T, Tc, tid);          // C2 = dO
+          if (tid < kStat) {
+            Ls[tid] = __ldg(Lg + tid);
+            Ds[tid] = __ldg(Dg + tid);
+          }
         }
-        ptx::fence_proxy_async_smem();
-        if (rt == 0 && pass == 1) asm volatile("bar.sync 5, 512;" ::: "memory");     // Ls / Ds visible to every compute warp
-        __syncwarp();
-        if (lane == 0) ptx::mbar_arrive(ops_ready);
-        float l_row = 0.f, d_row = 0.f;
-        if (pass == 0) {
-          l_row = __ldg(Lg + r0 + row);
-          d_row = __ldg(Dg + r0 + row);
-        }
-        // ---- chunks
+      }
+      ptx::fence_proxy_async_smem();
+      if (rt == 0 && pass == 1) asm volatile("bar.sync 5, 512;" ::: "memory");     // Ls / Ds visible to every compute warp
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(ops_ready);
+      if (pk) pk[1] = clock64();
+      float l_row = 0.f, d_row = 0.f;
+      if (pass == 0) {
+        l_row = __ldg(Lg + r0 + row);
+        d_row = __ldg(Dg + r0 + row);
+      }
+      // ---- chunks
 #pragma unroll 1
-        for (int c = 0; c < n_chunks; ++c) {
-          const int b = c & 1;
-          const int width = min(64, Tc - 64 * c);
-          const uint32_t buf = tmem + lane_addr + (uint32_t)(b * kBufCols);
-          ptx::mbar_wait(sdp_done(b), ph_sdp[b]);
-          ph_sdp[b] ^= 1;
-          ptx::tc_fence_after();
-          const bool active = rows_live && cq * 16 < width;
-          uint32_t s[16], g[16];
-          if (active) {
-            ptx::tmem_ld16(buf + (uint32_t)(cq * 16), s);
-            ptx::tmem_ld16(buf + (uint32_t)(64 + cq * 16), g);
-            ptx::tmem_ld_wait();
-          }
-          ptx::tc_fence_before();
-          // every warp of the lane quarter has read its S / dP columns before the planes overwrite them
-          if (rows_live) asm volatile("bar.sync %0, 128;" ::"r"(1 + (warp & 3)) : "memory");
-          ptx::tc_fence_after();
-          if (active) {
-            uint32_t ph[8], pl[8], dh[8], dl[8];
-            const int cb = c * 64 + cq * 16;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              float l0 = l_row, l1 = l_row, e0 = d_row, e1 = d_row;
-              if (pass == 1) {
-                l0 = Ls[cb + 2 * j];
-                l1 = Ls[cb + 2 * j + 1];
-                e0 = Ds[cb + 2 * j];
-                e1 = Ds[cb + 2 * j + 1];
-              }
-              const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * j]), s2, -l0));
-              const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * j + 1]), s2, -l1));
-              const float ds0 = p0 * (__uint_as_float(g[2 * j]) - e0), ds1 = p1 * (__uint_as_float(g[2 * j + 1]) - e1);
-              split2_bf16(p0, p1, ph[j], pl[j]);
-              split2_bf16(ds0, ds1, dh[j], dl[j]);
-            }
-            ptx::tmem_st<8>(buf + (uint32_t)(cq * 8), ph);
-            ptx::tmem_st<8>(buf + (uint32_t)(32 + cq * 8), pl);
-            ptx::tmem_st<8>(buf + (uint32_t)(64 + cq * 8), dh);
-            ptx::tmem_st<8>(buf + (uint32_t)(96 + cq * 8), dl);
-            ptx::tmem_st_wait();
-          }
-          ptx::tc_fence_before();
-          __syncwarp();
-          if (lane == 0) ptx::mbar_arrive(pds_ready(b));
+      for (int c = 0; c < n_chunks; ++c) {
+        const int b = c % kBufs;
+        const int width = min(64, Tc - 64 * c);
+        const uint32_t buf = tmem + lane_addr + (uint32_t)(b * kBufCols);
+        ptx::mbar_wait(sdp_done(b), (ph_sdp >> b) & 1u);
+        ph_sdp ^= 1u << b;
+        ptx::tc_fence_after();
+        if (pk && c < 4) pk[2 + c * 3] = clock64();
+        const bool active = rows_live && cq * 16 < width;
+        uint32_t s[16], gq[16];
+        if (active) {
+          ptx::tmem_ld16(buf + (uint32_t)(cq * 16), s);
+          ptx::tmem_ld16(buf + (uint32_t)(64 + cq * 16), gq);
+          ptx::tmem_ld_wait();
         }
-        // ---- epilogue
+        ptx::tc_fence_before();
+        // every warp of the lane quarter has read its S / dP columns before the planes overwrite them
+        if (rows_live) asm volatile("bar.sync %0, 128;" ::"r"(1 + (warp & 3)) : "memory");
+        ptx::tc_fence_after();
+        if (pk && c < 4) pk[3 + c * 3] = clock64();
+        if (active) {
+          uint32_t ph[8], pl[8], dh[8], dl[8];
+          const int cb = c * 64 + cq * 16;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float l0 = l_row, l1 = l_row, e0 = d_row, e1 = d_row;
+            if (pass == 1) {
+              l0 = Ls[cb + 2 * j];
+              l1 = Ls[cb + 2 * j + 1];
+              e0 = Ds[cb + 2 * j];
+              e1 = Ds[cb + 2 * j + 1];
+            }
+            const float p0 = ex2_approx(fmaf(__uint_as_float(s[2 * j]), s2, -l0));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(s[2 * j + 1]), s2, -l1));
+            const float ds0 = p0 * (__uint_as_float(gq[2 * j]) - e0), ds1 = p1 * (__uint_as_float(gq[2 * j + 1]) - e1);
+            split2_bf16(p0, p1, ph[j], pl[j]);
+            split2_bf16(ds0, ds1, dh[j], dl[j]);
+          }
+          ptx::tmem_st<8>(buf + (uint32_t)(cq * 8), ph);
+          ptx::tmem_st<8>(buf + (uint32_t)(32 + cq * 8), pl);
+          ptx::tmem_st<8>(buf + (uint32_t)(64 + cq * 8), dh);
+          ptx::tmem_st<8>(buf + (uint32_t)(96 + cq * 8), dl);
+          ptx::tmem_st_wait();
+        }
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(pds_ready(b));
+        if (pk && c < 4) pk[4 + c * 3] = clock64();
+      }
+      // ---- next tile's row operands on their way while the last MMAs finish, then the epilogue
+      {
+        float4 pf[8];
+        const bool more = kPrefetchRows && g + 1 < n_tiles;
+        if (more) r_issue(g + 1, pf);
         ptx::mbar_wait(out_done, ph_out);
         ph_out ^= 1;
         ptx::tc_fence_after();
-        const int t = r0 + row;
-        if (rows_live) {
-          uint32_t o1[16], o2[16];
-          ptx::tmem_ld16(tmem + lane_addr + (uint32_t)(kOut1 + cq * 16), o1);
-          if (pass == 1) ptx::tmem_ld16(tmem + lane_addr + (uint32_t)(kOut2 + cq * 16), o2);
-          ptx::tmem_ld_wait();
-          if (t < T) {
-            float* dst = dqkv + ((int64_t)bi * T + t) * D3 + (pass == 0 ? 0 : D) + h * kHd + cq * 16;
+        if (pk) pk[14] = clock64();
+        if (more) r_store(pf);                              // every MMA that read the old planes has completed
+      }
+      const int t = r0 + row;
+      if (rows_live) {
+        uint32_t o1[16], o2[16];
+        ptx::tmem_ld16(tmem + lane_addr + (uint32_t)(kOut1 + cq * 16), o1);
+        if (pass == 1) ptx::tmem_ld16(tmem + lane_addr + (uint32_t)(kOut2 + cq * 16), o2);
+        ptx::tmem_ld_wait();
+        if (t < T) {
+          float* dst = dqkv + ((int64_t)bi * T + t) * D3 + (pass == 0 ? 0 : D) + h * kHd + cq * 16;
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-              stg_v4_b32(dst + 4 * j, __float_as_uint(__uint_as_float(o1[4 * j]) * scale), __float_as_uint(__uint_as_float(o1[4 * j + 1]) * scale),
-                         __float_as_uint(__uint_as_float(o1[4 * j + 2]) * scale), __float_as_uint(__uint_as_float(o1[4 * j + 3]) * scale));
-            if (pass == 1) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) stg_v4_b32(dst + D + 4 * j, o2[4 * j], o2[4 * j + 1], o2[4 * j + 2], o2[4 * j + 3]);
-            }
+          for (int j = 0; j < 16; ++j) o1[j] = __float_as_uint(__uint_as_float(o1[j]) * scale);
+          stg_v8_b32(dst, o1);
+          stg_v8_b32(dst + 8, o1 + 8);
+          if (pass == 1) {
+            stg_v8_b32(dst + D, o2);
+            stg_v8_b32(dst + D + 8, o2 + 8);
           }
         }
-        ptx::tc_fence_before();
       }
+      ptx::tc_fence_before();
+      if (pk) pk[15] = clock64();
     }
   }
 
@@ -373,6 +455,8 @@ __global__ void attention_dstat_kernel(const float* __restrict__ out, const floa
 
 using namespace qvit;
 
+extern "C" int qvit_attention_train_bwd_prof(const float* qkv, const float* out, const float* dout, const float* lse, int B, int T, int H,
+                                             int head_dim, float scale, float* dstat, float* dqkv, long long* prof, qvit_stream_t stream);
 extern "C" int qvit_split2_f16(const float* x, int64_t rows, int cols, int64_t ldx, const int* col_exp, void* out, int64_t ld,
                                int plane_off, int32_t* flags, qvit_stream_t stream);
 
@@ -408,6 +492,12 @@ extern "C" int qvit_attention_train_fwd(const float* qkv, int B, int T, int H, i
 // dout = d loss / d out (fp32 [B, T, H, 64]).  dstat: workspace fp32 [B, H, 256].
 extern "C" int qvit_attention_train_bwd(const float* qkv, const float* out, const float* dout, const float* lse, int B, int T, int H,
                                         int head_dim, float scale, float* dstat, float* dqkv, qvit_stream_t stream) {
+  return qvit_attention_train_bwd_prof(qkv, out, dout, lse, B, T, H, head_dim, scale, dstat, dqkv, nullptr, stream);
+}
+
+// same, with the cycle stamps of CTA 0's first 8 tiles (prof: int64 [256]; tools/att_bwd_prof.py prints the timeline)
+extern "C" int qvit_attention_train_bwd_prof(const float* qkv, const float* out, const float* dout, const float* lse, int B, int T, int H,
+                                             int head_dim, float scale, float* dstat, float* dqkv, long long* prof, qvit_stream_t stream) {
   QVIT_REQUIRE(qkv && out && dout && lse && dstat && dqkv, "qvit_attention_train_bwd: null pointer");
   int rc = train_shape_ok("qvit_attention_train_bwd", B, T, H, head_dim);
   if (rc) return rc;
@@ -437,6 +527,6 @@ extern "C" int qvit_attention_train_bwd(const float* qkv, const float* out, cons
   const int64_t items = 2 * (int64_t)B * H;
   QVIT_REQUIRE(items < (1ll << 30), "qvit_attention_train_bwd: problem too large");
   const int grid = (int)(items < sm_count() ? items : sm_count());
-  attention_bwd_kernel<<<grid, ab::kThreads, ab::kSmem, s>>>(qkv, dout, lse, dstat, dqkv, T, H, (int)items, scale);
+  attention_bwd_kernel<<<grid, ab::kThreads, ab::kSmem, s>>>(qkv, dout, lse, dstat, dqkv, T, H, (int)items, scale, prof);
   return check_launch("qvit_attention_train_bwd");
 }

@@ -310,7 +310,7 @@ def attention_train_fwd(qkv: torch.Tensor, num_heads: int, scale: Optional[float
 
 
 def attention_train_bwd(qkv: torch.Tensor, out: torch.Tensor, lse: torch.Tensor, dout: torch.Tensor, num_heads: int,
-                        scale: Optional[float] = None) -> torch.Tensor:
+                        scale: Optional[float] = None, prof: Optional[torch.Tensor] = None) -> torch.Tensor:
     """d loss / d qkv ([B, T, 3 * H * 64] fp32) from d loss / d out."""
     qkv, out, dout = _f32c(qkv, "qkv"), _f32c(out, "out"), _f32c(dout, "dout")
     B, T, D3 = qkv.shape
@@ -318,8 +318,9 @@ def attention_train_bwd(qkv: torch.Tensor, out: torch.Tensor, lse: torch.Tensor,
     sc = float(hd) ** -0.5 if scale is None else float(scale)
     dstat = torch.empty((B, num_heads, 256), dtype=torch.float32, device=qkv.device)
     dqkv = torch.empty_like(qkv)
-    _lib.check(_lib.lib().qvit_attention_train_bwd(_lib.ptr(qkv), _lib.ptr(out), _lib.ptr(dout), _lib.ptr(lse), B, T, num_heads, hd, sc,
-                                                   _lib.ptr(dstat), _lib.ptr(dqkv), _lib.stream()), "qvit_attention_train_bwd")
+    _lib.check(_lib.lib().qvit_attention_train_bwd_prof(_lib.ptr(qkv), _lib.ptr(out), _lib.ptr(dout), _lib.ptr(lse), B, T, num_heads, hd,
+                                                        sc, _lib.ptr(dstat), _lib.ptr(dqkv), _lib.ptr(prof), _lib.stream()),
+               "qvit_attention_train_bwd")
     return dqkv
 
 
