@@ -251,6 +251,13 @@ int qvit_gemm_i8(const void* a, int64_t lda, int a_unsigned,
  *   B = [N, ldb >= Kp] bf16, Kp = K rounded up to 64; epilogue as qvit_gemm_i8 with QVIT_OUT_F32 / QVIT_ACT_NONE. */
 int qvit_split3_bf16(const float* x, int64_t rows, int64_t cols, int64_t ld_x, int transpose, void* out, int64_t plane_cols,
                      qvit_stream_t stream);
+
+/* Both forms of the gradient operand of a QAT linear layer, and its bias gradient, from one read of g (fp32 [rows, cols], pitch
+ * ld_g): rows_out = bf16 [rows, 3 * row_plane_cols] (as qvit_split3_bf16 transpose = 0; NULL = not needed), trans_out = bf16
+ * [cols, 3 * trans_plane_cols] (as transpose = 1), colsum[c] = sum over rows of g[:, c] (NULL = not needed; summed in a fixed order).
+ * partial: workspace fp32 [ceil(trans_plane_cols / 256), cols], required with colsum.  Plane widths: multiples of 64.          */
+int qvit_grad_prep(const float* g, int64_t rows, int64_t cols, int64_t ld_g, void* rows_out, int64_t row_plane_cols, void* trans_out,
+                   int64_t trans_plane_cols, float* partial, float* colsum, qvit_stream_t stream);
 int qvit_codes_to_bf16_t(const int8_t* codes, int64_t rows, int64_t cols, int64_t ld, void* out, int64_t out_cols,
                          qvit_stream_t stream);
 int qvit_gemm_bf16_split(const void* a_planes, int64_t lda, int planes, const void* b, int64_t ldb, int M, int N, int K,

@@ -71,6 +71,7 @@ PROTOTYPES = {
     "qvit_attention_train_fwd": (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
     "qvit_attention_train_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p]),
     "qvit_attention_train_bwd_prof": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
+    "qvit_grad_prep": (_i, [_p, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _p]),
     "qvit_attention_f32": (_i, [_p, _i, _i, _i, _i, _f, _p, _p]),
     "qvit_attention_quantize_sym": (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "qvit_attention_f32_debug": (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _i, _p]),

@@ -564,12 +564,56 @@ __global__ void split2_f16_kernel(const float* __restrict__ x, int64_t rows, int
 }
 }  // namespace qvit
 
+namespace qvit {
+// 8 values per thread (two 16-byte loads, one 16-byte store per plane); needs cols, pitches and plane_off multiples of 8 and
+// 16-byte aligned bases
+__global__ void __launch_bounds__(256) split2_f16_v8_kernel(const float* __restrict__ x, int64_t rows, int cols, int64_t ldx,
+                                                             const int* __restrict__ col_exp, __half* __restrict__ out, int64_t ld,
+                                                             int plane_off, int32_t* __restrict__ flags) {
+  const int pieces = cols / 8;
+  const int64_t n = rows * (int64_t)pieces;
+  int fl = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / pieces;
+    const int c = (int)(i - r * pieces) * 8;
+    const float4 a = ldg_stream4(x + r * ldx + c), b = ldg_stream4(x + r * ldx + c + 4);
+    float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    if (col_exp) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = ldexpf(v[j], col_exp[c + j]);
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __half2 h2 = __floats2half2_rn(v[2 * j], v[2 * j + 1]);
+      const float2 hf = __half22float2(h2);
+      const __half2 l2 = __floats2half2_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+      if (!(fabsf(hf.x) <= 65504.0f) || !(fabsf(hf.y) <= 65504.0f)) fl |= kFlagOverflow;
+      hi[j] = *reinterpret_cast<const uint32_t*>(&h2);
+      lo[j] = *reinterpret_cast<const uint32_t*>(&l2);
+    }
+    stg_v4_b32(out + r * ld + c, hi[0], hi[1], hi[2], hi[3]);
+    stg_v4_b32(out + r * ld + plane_off + c, lo[0], lo[1], lo[2], lo[3]);
+  }
+  fl = warp_or(fl);
+  if (fl && flags && (threadIdx.x & 31) == 0) atomicOr(flags, fl);
+}
+}  // namespace qvit
+
 extern "C" int qvit_split2_f16(const float* x, int64_t rows, int cols, int64_t ldx, const int* col_exp, void* out, int64_t ld,
                                int plane_off, int32_t* flags, qvit_stream_t stream) {
   QVIT_REQUIRE(x && out && rows >= 0 && cols > 0 && (cols & 1) == 0 && (ldx & 1) == 0 && (ld & 1) == 0 && (plane_off & 1) == 0 &&
                    plane_off >= cols && ld >= plane_off + cols,
                "qvit_split2_f16: bad argument (cols, pitches and plane_off must be even, ld >= plane_off + cols)");
   if (rows == 0) return QVIT_OK;
+  if ((cols & 7) == 0 && (ldx & 7) == 0 && (ld & 7) == 0 && (plane_off & 7) == 0 &&
+      ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const int64_t n8 = rows * (int64_t)(cols / 8);
+    const int blocks8 = (int)((n8 + 255) / 256 < 16 * 148 ? (n8 + 255) / 256 : 16 * 148);
+    split2_f16_v8_kernel<<<blocks8, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, col_exp, reinterpret_cast<__half*>(out), ld, plane_off,
+                                                                   flags);
+    return check_launch("qvit_split2_f16");
+  }
   const int64_t n = rows * (int64_t)(cols / 2);
   const int blocks = (int)((n + 255) / 256 < 8 * 148 ? (n + 255) / 256 : 8 * 148);
   split2_f16_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(x, rows, cols, ldx, col_exp, reinterpret_cast<__half*>(out), ld, plane_off, flags);

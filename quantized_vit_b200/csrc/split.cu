@@ -78,6 +78,79 @@ split3_transpose_kernel(const float* __restrict__ x, int64_t R, int C, int64_t l
   }
 }
 
+// Both forms of the gradient operand and the bias gradient from ONE read of g [R, C]: the row planes [R, 3 * Cp] (A operand of
+// grad_x_q = g @ w_q), the transposed planes [C, 3 * Rp] (A operand of grad_w_q = g^T @ x_q) and per-block column sums
+// partial[blockIdx.y, c] over the block's kPrepTiles x 64 rows (summed by colsum_reduce_kernel in a fixed order: the bias
+// gradient is reproducible run to run).  Tile = 64 rows x 32 columns through shared memory.
+constexpr int kPrepTiles = 4;
+__global__ void __launch_bounds__(256)
+grad_prep_kernel(const float* __restrict__ x, int64_t R, int C, int64_t ld_x, int Cp, __nv_bfloat16* __restrict__ rows_out, int64_t Rp,
+                 __nv_bfloat16* __restrict__ trans_out, float* __restrict__ partial) {
+  __shared__ float tile[64][33];
+  const int c0 = blockIdx.x * 32;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;      // 8 warps
+  float csum[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int rt = 0; rt < kPrepTiles; ++rt) {
+    const int64_t r0 = ((int64_t)blockIdx.y * kPrepTiles + rt) * 64;
+    if (r0 >= Rp) break;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int64_t r = r0 + wy * 8 + i;
+      const int c = c0 + lane;
+      tile[wy * 8 + i][lane] = (r < R && c < C) ? __ldcs(x + r * ld_x + c) : 0.0f;
+    }
+    __syncthreads();
+    // transposed planes + column sums: this warp owns 4 columns, the lane 2 rows
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int cl = wy * 4 + i;
+      const int c = c0 + cl;
+      const float a = tile[2 * lane][cl], b = tile[2 * lane + 1][cl];
+      csum[i] += a + b;
+      if (c < C) {
+        uint32_t p1, p2, p3;
+        split3_pair_bf16(a, b, p1, p2, p3);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(trans_out + (int64_t)c * (3 * Rp) + r0) + lane;   // r0 is a multiple of 64
+        dst[0] = p1;
+        dst[Rp / 2] = p2;
+        dst[Rp] = p3;
+      }
+    }
+    // row planes: thread = (row, 8-column piece); bank = (row + column) mod 32 is distinct across the warp
+    if (rows_out) {
+      const int r = threadIdx.x >> 2, pc = (threadIdx.x & 3) * 8;
+      if (r0 + r < R && c0 + pc < Cp) {
+        uint4 p1, p2, p3;
+        split3_pair_bf16(tile[r][pc], tile[r][pc + 1], p1.x, p2.x, p3.x);
+        split3_pair_bf16(tile[r][pc + 2], tile[r][pc + 3], p1.y, p2.y, p3.y);
+        split3_pair_bf16(tile[r][pc + 4], tile[r][pc + 5], p1.z, p2.z, p3.z);
+        split3_pair_bf16(tile[r][pc + 6], tile[r][pc + 7], p1.w, p2.w, p3.w);
+        __nv_bfloat16* dst = rows_out + (r0 + r) * (3ll * Cp) + c0 + pc;
+        *reinterpret_cast<uint4*>(dst) = p1;
+        *reinterpret_cast<uint4*>(dst + Cp) = p2;
+        *reinterpret_cast<uint4*>(dst + 2 * Cp) = p3;
+      }
+    }
+    __syncthreads();
+  }
+  if (partial) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float s = warp_sum(csum[i]);
+      const int c = c0 + wy * 4 + i;
+      if (lane == 0 && c < C) partial[(int64_t)blockIdx.y * C + c] = s;
+    }
+  }
+}
+
+__global__ void colsum_reduce_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  float s = 0.f;
+  for (int i = 0; i < nblk; ++i) s += partial[(int64_t)i * C + c];
+  out[c] = s;
+}
+
 // codes [R, C] int8 (pitch ld) -> out [C, Rp] bf16 (transposed); columns >= R are zero
 __global__ void __launch_bounds__(256)
 codes_transpose_bf16_kernel(const int8_t* __restrict__ codes, int64_t R, int C, int64_t ld, int64_t Rp,
@@ -133,6 +206,28 @@ int qvit_split3_bf16(const float* x, int64_t rows, int64_t cols, int64_t ld_x, i
     split3_transpose_kernel<<<grid, 256, 0, s>>>(x, rows, (int)cols, ld_x, plane_cols, reinterpret_cast<__nv_bfloat16*>(out));
   }
   return check_launch("qvit_split3_bf16");
+}
+
+int qvit_grad_prep(const float* g, int64_t rows, int64_t cols, int64_t ld_g, void* rows_out, int64_t row_plane_cols, void* trans_out,
+                   int64_t trans_plane_cols, float* partial, float* colsum, qvit_stream_t stream) {
+  QVIT_REQUIRE(g && trans_out && rows > 0 && cols > 0 && ld_g >= cols, "qvit_grad_prep: bad argument");
+  QVIT_REQUIRE(trans_plane_cols % 64 == 0 && trans_plane_cols >= rows && (reinterpret_cast<uintptr_t>(trans_out) & 15) == 0,
+               "qvit_grad_prep: trans_plane_cols must be a multiple of 64, >= rows");
+  QVIT_REQUIRE(!rows_out || (row_plane_cols % 64 == 0 && row_plane_cols >= cols && (reinterpret_cast<uintptr_t>(rows_out) & 15) == 0),
+               "qvit_grad_prep: row_plane_cols must be a multiple of 64, >= cols");
+  QVIT_REQUIRE((colsum == nullptr) == (partial == nullptr), "qvit_grad_prep: colsum needs the partial workspace (and vice versa)");
+  QVIT_REQUIRE(cols < (1ll << 31) && rows < (1ll << 40), "qvit_grad_prep: too large");
+  cudaStream_t s = (cudaStream_t)stream;
+  const int64_t cp = rows_out ? row_plane_cols : (cols + 63) / 64 * 64;
+  const int64_t tiles_y = trans_plane_cols / 64;
+  dim3 grid((unsigned)(cp / 32), (unsigned)((tiles_y + kPrepTiles - 1) / kPrepTiles));
+  QVIT_REQUIRE(grid.y <= 65535u, "qvit_grad_prep: too many rows");
+  grad_prep_kernel<<<grid, 256, 0, s>>>(g, rows, (int)cols, ld_g, (int)cp, reinterpret_cast<__nv_bfloat16*>(rows_out), trans_plane_cols,
+                                        reinterpret_cast<__nv_bfloat16*>(trans_out), partial);
+  int rc = check_launch("qvit_grad_prep");
+  if (rc || !colsum) return rc;
+  colsum_reduce_kernel<<<(unsigned)((cols + 255) / 256), 256, 0, s>>>(partial, (int)grid.y, (int)cols, colsum);
+  return check_launch("qvit_grad_prep (colsum)");
 }
 
 int qvit_codes_to_bf16_t(const int8_t* codes, int64_t rows, int64_t cols, int64_t ld, void* out, int64_t out_cols,

@@ -17,7 +17,7 @@ from ._lib import (QVIT_ACT_GELU, QVIT_ACT_NONE, QVIT_ACT_RELU, QVIT_GEMM_AUTO, 
                    QVIT_OUT_BF16, QVIT_OUT_F16X2, QVIT_OUT_F32, QVIT_OUT_I8, QVIT_OUT_I32, QVIT_OUT_NONE)
 
 __all__ = ["pad16", "quantize_sym", "fake_quantize_sym", "sym_backward", "absmax", "im2col_quantize_sym", "gemm_i8",
-           "layernorm_quantize", "layernorm_fwd", "layernorm_bwd", "layernorm_supported", "attention_train_supported", "attention_train_fwd", "attention_train_bwd", "attention_f32", "attention_f32_supported", "split3_bf16", "codes_to_bf16_t", "gemm_bf16_split", "matmul_f32_tc", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "ultra_conv_tc", "conv2d_i8_tc", "pack_conv_weights_tc", "ultra_conv_tc_supported", "bn_fold",
+           "layernorm_quantize", "layernorm_fwd", "layernorm_bwd", "layernorm_supported", "attention_train_supported", "attention_train_fwd", "attention_train_bwd", "attention_f32", "attention_f32_supported", "split3_bf16", "grad_prep", "codes_to_bf16_t", "gemm_bf16_split", "matmul_f32_tc", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "ultra_conv_tc", "conv2d_i8_tc", "pack_conv_weights_tc", "ultra_conv_tc_supported", "bn_fold",
            "bn_act_quantize_int", "pack_int4", "unpack_int4", "new_flags", "QVIT_OUT_I32", "QVIT_OUT_F32",
            "QVIT_OUT_BF16", "QVIT_OUT_I8", "QVIT_OUT_NONE", "QVIT_OUT_F16X2", "attention_f16x2", "split2_f16", "f16x2_exponent", "QVIT_ACT_NONE", "QVIT_ACT_GELU", "QVIT_ACT_RELU", "QVIT_GEMM_AUTO",
            "QVIT_GEMM_TCGEN05", "QVIT_GEMM_SIMT"]
@@ -416,6 +416,23 @@ def split3_bf16(x: torch.Tensor, transpose: bool = False) -> torch.Tensor:
     _lib.check(_lib.lib().qvit_split3_bf16(_lib.ptr(x), R, Cc, x.stride(0), 1 if transpose else 0, _lib.ptr(out), pc, _lib.stream()),
                "qvit_split3_bf16")
     return out
+
+
+def grad_prep(g: torch.Tensor, want_rows: bool = True, want_colsum: bool = True):
+    """One pass over the output gradient g [M, N] of a QAT linear layer: (row planes [M, 3*pad64(N)] | None, transposed planes
+    [N, 3*pad64(M)], column sums [N] | None) - the operands of the two gradient GEMMs and the bias gradient."""
+    g = _f32c(g, "grad_prep")
+    M, N = g.shape
+    mp, np_ = _pad64(M), _pad64(N)
+    rows = torch.empty((M, 3 * np_), dtype=torch.bfloat16, device=g.device) if want_rows else None
+    trans = torch.empty((N, 3 * mp), dtype=torch.bfloat16, device=g.device)
+    partial = colsum = None
+    if want_colsum:
+        partial = torch.empty(((mp // 64 + 3) // 4, N), dtype=torch.float32, device=g.device)
+        colsum = torch.empty((N,), dtype=torch.float32, device=g.device)
+    _lib.check(_lib.lib().qvit_grad_prep(_lib.ptr(g), M, N, g.stride(0), _lib.ptr(rows), np_, _lib.ptr(trans), mp, _lib.ptr(partial),
+                                         _lib.ptr(colsum), _lib.stream()), "qvit_grad_prep")
+    return rows, trans, colsum
 
 
 def codes_to_bf16_t(codes: torch.Tensor, cols: int) -> torch.Tensor:

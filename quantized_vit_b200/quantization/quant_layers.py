@@ -333,22 +333,23 @@ class QuantLinearFunction(torch.autograd.Function):
         if TENSOR_CORE_BACKWARD and K % 4 == 0:
             # grad_x_q = g @ w_q = |d_w| * (g1 + g2 + g3) @ codes_w   and   grad_w_q = g^T @ x_q = |d_a| * (g^T planes) @ codes_a:
             # exact 3-way bf16 split of g, integer codes as bf16, tcgen05 kind::f16 with fp32 accumulation
-            grad_xq = ops.gemm_bf16_split(ops.split3_bf16(g2), ops.codes_to_bf16_t(w_codes, K), N, planes=GRADIENT_PLANES, scale=d_w) \
+            # (both plane forms of g and the bias gradient come from one pass over g: ops.grad_prep)
+            g_rows, g_trans, grad_b = ops.grad_prep(g2, want_rows=need_act, want_colsum=ctx.has_bias)
+            grad_xq = ops.gemm_bf16_split(g_rows, ops.codes_to_bf16_t(w_codes, K), N, planes=GRADIENT_PLANES, scale=d_w) \
                 if need_act else None
-            grad_wq = ops.gemm_bf16_split(ops.split3_bf16(g2, transpose=True), ops.codes_to_bf16_t(a_codes, K), M,
-                                          planes=GRADIENT_PLANES, scale=d_a)
+            grad_wq = ops.gemm_bf16_split(g_trans, ops.codes_to_bf16_t(a_codes, K), M, planes=GRADIENT_PLANES, scale=d_a)
         else:
             # fake-quant values from the saved codes: value = code * |d| (exactly what the reference forward produced)
             x_q = a_codes[:, :K].to(torch.float32) * d_a.detach().abs()
             w_q = w_codes[:, :K].to(torch.float32) * d_w.detach().abs()
             grad_xq = g2 @ w_q if need_act else None
             grad_wq = g2.t() @ x_q
+            grad_b = g2.sum(0) if ctx.has_bias else None
         if grad_xq is None:
             grad_x, s_a = None, torch.zeros(3, dtype=torch.float32, device=g.device)
         else:
             grad_x, s_a = ops.sym_backward(x2, grad_xq, d_a, qm_a, t_a, ctx.clip_a, want_grad_x=ctx.needs_input_grad[0], flags=flags)
         grad_w, s_w = ops.sym_backward(weight.detach(), grad_wq, d_w, qm_w, t_w, ctx.clip_w, flags=flags)
-        grad_b = g2.sum(0) if ctx.has_bias else None
         if EAGER_NAN_CHECK:
             check_nan_flags()
         return (None if grad_x is None else grad_x.view(ctx.x_shape), grad_w, grad_b, s_a[0:1], s_a[1:2],

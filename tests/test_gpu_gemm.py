@@ -377,3 +377,17 @@ def test_matmul_f32_tc_matches_fp64(ops, M, N, K):
     out_t = ops.matmul_f32_tc(a.t().contiguous(), b.t().contiguous(), a_transposed=True, b_transposed=True)
     err_t = float((out_t.double() - (ref - bias.double())).abs().max() / ref.abs().max())
     assert err_t <= 2e-5
+
+
+@pytest.mark.parametrize("M,N", [(394, 768), (197 * 3, 2304), (70, 100), (25216, 768)])
+def test_grad_prep_matches_separate_kernels(M, N):
+    """qvit_grad_prep (one pass over g) against qvit_split3_bf16 in both forms (bit-identical planes) and the fp64 column sums."""
+    from quantized_vit_b200 import ops
+    g = (torch.randn(M, N, generator=torch.Generator().manual_seed(M + N)) * 1e-3).cuda()
+    rows, trans, colsum = ops.grad_prep(g)
+    assert torch.equal(rows.view(torch.int16), ops.split3_bf16(g).view(torch.int16))
+    assert torch.equal(trans.view(torch.int16), ops.split3_bf16(g, transpose=True).view(torch.int16))
+    ref = g.double().sum(0)
+    assert float((colsum.double() - ref).abs().max()) <= 2e-6 * float(g.abs().sum(0).max())
+    rows2, trans2, colsum2 = ops.grad_prep(g, want_rows=False, want_colsum=False)
+    assert rows2 is None and colsum2 is None and torch.equal(trans2.view(torch.int16), trans.view(torch.int16))
