@@ -65,6 +65,10 @@ class GradientAllReducer:
       shards; without them the shards are assumed equal and the collective averages.
     * Parameters that received no gradient on this rank stay ``None`` when ``keep_none`` (the autograd graph is the same on
       every data-parallel rank, so all ranks agree on which those are); their slice of the buffer travels as zeros.
+    * Under CUDA-graph capture (forward + backward replayed from one graph) no collective is captured: the hook of a bucket's
+      last parameter records an EXTERNAL event instead, and ``reduce()`` after ``graph.replay()`` makes a side stream wait for
+      each bucket's event before launching its all-reduce there - the exchange still overlaps the rest of the replayed
+      backward, and NCCL never runs inside a capture.
     Must run BEFORE gradient clipping (reference order utils.py:291-292)."""
 
     def __init__(self, named_params: Iterable[Tuple[str, torch.nn.Parameter]], bucket_bytes: int = 64 << 20, group=None,
@@ -105,6 +109,9 @@ class GradientAllReducer:
         self._seen = [set() for _ in self._all]
         self._work = [None] * len(self._all)
         self._scale = None
+        self._events = None          # per-bucket external events recorded by a captured backward
+        self._graph_seen = None
+        self._comm = None
         self._hooks = []
         if overlap and hasattr(torch.Tensor, "register_post_accumulate_grad_hook"):
             for params in self._all:
@@ -162,7 +169,15 @@ class GradientAllReducer:
             return
         self._seen[bi].add(pi)
         if len(self._seen[bi]) == len(self._all[bi]):
-            self._launch(bi)                 # the whole bucket is final: its all-reduce runs under the rest of backward
+            if p.is_cuda and torch.cuda.is_current_stream_capturing():
+                if self._events is None:
+                    self._events = [None] * len(self._all)
+                    self._comm = torch.cuda.Stream(device=p.device)
+                if self._events[bi] is None:
+                    self._events[bi] = torch.cuda.Event(external=True)
+                self._events[bi].record()    # becomes an event-record node of the graph: fires on every replay
+            else:
+                self._launch(bi)             # the whole bucket is final: its all-reduce runs under the rest of backward
 
     def reduce(self) -> int:
         """Finish the step's gradient exchange in place; returns the number of collectives issued."""
@@ -173,6 +188,20 @@ class GradientAllReducer:
             return 0
         none_mask = [[(p.grad is None) for p in params] for params in self._all]
         n = 0
+        graph_mode = self._events is not None and not any(self._seen)
+        if self._events is not None and any(self._seen):     # the step that was captured: remember which parameters it touched
+            self._graph_seen = [set(s) for s in self._seen]
+        if graph_mode:
+            # a replayed step: hooks did not run; every bucket's all-reduce goes to the side stream behind the bucket's event
+            cur = torch.cuda.current_stream()
+            for bi in range(len(self._all)):
+                if self._events[bi] is not None:
+                    self._comm.wait_event(self._events[bi])
+                else:
+                    self._comm.wait_stream(cur)
+                with torch.cuda.stream(self._comm):
+                    self._seen[bi] = set(self._graph_seen[bi]) if self._graph_seen is not None else set(range(len(self._all[bi])))
+                    self._launch(bi)
         for bi in range(len(self._all)):
             self._launch(bi)
         for bi, params in enumerate(self._all):

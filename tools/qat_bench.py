@@ -26,10 +26,12 @@ def main():
         for m in model.modules():
             if hasattr(m, "q_m_act"):
                 m.q_m_act.fill_(2.5); m.d_quant_act.fill_(2.5 / 7)
-    use_graph = os.environ.get("QAT_GRAPH", "0") == "1"
+    use_graph = os.environ.get("QAT_GRAPH", "0") in ("1", "2")
     # graph mode: forward + backward are replayed from ONE CUDA graph and the bucket all-reduces are issued after it (no NCCL
     # call inside the capture: hook-launched collectives under stream capture hung the 2-rank run), so the hooks stay off
-    red = parallel.GradientAllReducer(model.named_parameters(), overlap=not use_graph)
+    # (QAT_GRAPH=2: the bucket hooks stay on and record external events inside the capture; the all-reduces are launched after
+    # graph.replay() on a side stream behind those events, overlapping the rest of the replayed backward)
+    red = parallel.GradientAllReducer(model.named_parameters(), overlap=(not use_graph) or os.environ.get("QAT_GRAPH") == "2")
     g = torch.Generator().manual_seed(1)
     x = torch.randn(global_batch, 3, 224, 224, generator=g)
     y = torch.randint(0, 1000, (global_batch,), generator=torch.Generator().manual_seed(2))
@@ -59,6 +61,7 @@ def main():
         with torch.cuda.stream(gs):
             fwd_bwd()
         torch.cuda.current_stream().wait_stream(gs)
+        red.reduce()                                  # drain what the warm-up's hooks launched
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
             static_loss = fwd_bwd()
@@ -89,7 +92,7 @@ def main():
         print(json.dumps({"config": "ViT-B/16 4-bit QAT fwd+bwd+allreduce+clip", "quant_type": qtype, "n_gpus": world,
                           "global_batch": global_batch, "ms_per_step": float(ms), "img_per_s": global_batch / float(ms) * 1e3,
                           "loss": float(loss), "grad_norm_after_clip": float(gn), "grad_d_quant_act_block0_qkv": dq,
-                          "nan_flags": flags, "cuda_graph": use_graph,
+                          "nan_flags": flags, "cuda_graph": int(os.environ.get("QAT_GRAPH", "0")),
                           "gradient_planes": __import__("quantized_vit_b200.quantization.quant_layers", fromlist=["x"]).GRADIENT_PLANES}), flush=True)
     if world > 1:
         dist.destroy_process_group()
