@@ -288,6 +288,30 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ do
         store_piece(gen + kOffR + 2 * kRPlane, gen + kOffR + 3 * kRPlane, r, ch, pf[4 + 2 * k], pf[5 + 2 * k]);
       }
     };
+    // L2 prefetch of the NEXT tile's operands (one 128-byte line per thread and operand row half), issued at the start of a tile:
+    // the bursts of register loads above then hit L2 instead of queueing on HBM behind every other CTA's burst
+    auto l2_prefetch = [&](int g) {
+      int pair, pass;
+      decode(g / r_tiles, pair, pass);
+      const int bi = pair / H, h = pair % H, rt = g % r_tiles, r0 = rt * kMR, vr = min(kMR, T - r0);
+      const float* qb = qkv + (int64_t)bi * T * D3 + h * kHd;
+      const float* gb = dout + (int64_t)bi * T * D + h * kHd;
+      {
+        const int op = tid >> 8, r = (tid & 255) >> 1, half = tid & 1;
+        const float* src = op == 0 ? (pass == 0 ? qb : qb + D) : (pass == 0 ? gb : qb + 2 * D);
+        const int64_t st = (op == 1 && pass == 0) ? (int64_t)D : D3;
+        if (r < vr) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (int64_t)(r0 + r) * st + half * 32));
+      }
+      if (rt == 0) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const int idx = tid + k * 32 * kComputeWarps, op = idx >= 2 * kNC ? 1 : 0, rem = idx - op * 2 * kNC, r = rem >> 1, half = rem & 1;
+          const float* src = op == 0 ? (pass == 0 ? qb + D : qb) : (pass == 0 ? qb + 2 * D : gb);
+          const int64_t st = (op == 1 && pass == 1) ? (int64_t)D : D3;
+          if (idx < 4 * kNC && r < T) asm volatile("prefetch.global.L2 [%0];" ::"l"(src + (int64_t)r * st + half * 32));
+        }
+      }
+    };
     if (kPrefetchRows && n_tiles > 0) {
       float4 pf[8];
       r_issue(0, pf);
@@ -314,12 +338,10 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ do
       if (rt == 0) {
         const float* qb = qkv + (int64_t)bi * T * D3 + h * kHd;             // q rows; k at + D, v at + 2 D
         const float* gb = dout + (int64_t)bi * T * D + h * kHd;
-        if (pass == 0) {
-          load_planes_c(gen + kOffC, gen + kOffC + kCPlane, qb + D, D3, T, Tc, tid);                       // C1 = k
-          load_planes_c(gen + kOffC + 2 * kCPlane, gen + kOffC + 3 * kCPlane, qb + 2 * D, D3, T, Tc, tid); // C2 = v
-        } else {
-          load_planes_c(gen + kOffC, gen + kOffC + kCPlane, qb, D3, T, Tc, tid);                           // C1 = q
-          load_planes_c(gen + kOffC + 2 * kCPlane, gen + kOffC + 3 * kCPlane, gb, D, T, Tc, tid);          // C2 = dO
+        // C1 = k | q, C2 = v | dO  (two rounds of eight 16-byte loads per thread: sixteen at once do not stay in registers)
+        load_planes_c(gen + kOffC, gen + kOffC + kCPlane, pass == 0 ? qb + D : qb, D3, T, Tc, tid);
+        load_planes_c(gen + kOffC + 2 * kCPlane, gen + kOffC + 3 * kCPlane, pass == 0 ? qb + 2 * D : gb, pass == 0 ? D3 : (int64_t)D, T, Tc, tid);
+        if (pass == 1) {
           if (tid < kStat) {
             Ls[tid] = __ldg(Lg + tid);
             Ds[tid] = __ldg(Dg + tid);
@@ -330,6 +352,7 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ do
       if (rt == 0 && pass == 1) asm volatile("bar.sync 5, 512;" ::: "memory");     // Ls / Ds visible to every compute warp
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(ops_ready);
+      if (g + 1 < n_tiles) l2_prefetch(g + 1);
       if (pk) pk[1] = clock64();
       float l_row = 0.f, d_row = 0.f;
       if (pass == 0) {
@@ -388,16 +411,21 @@ attention_bwd_kernel(const float* __restrict__ qkv, const float* __restrict__ do
         if (pk && c < 4) pk[4 + c * 3] = clock64();
       }
       // ---- next tile's row operands on their way while the last MMAs finish, then the epilogue
-      {
+      if (kPrefetchRows) {
+        // (unconditional: after the last tile the same rows are fetched and stored once more - a branch around the loads makes the
+        // compiler keep them in local memory, and the store to it waits for the data right here)
         float4 pf[8];
-        const bool more = kPrefetchRows && g + 1 < n_tiles;
-        if (more) r_issue(g + 1, pf);
+        r_issue(min(g + 1, n_tiles - 1), pf);
         ptx::mbar_wait(out_done, ph_out);
-        ph_out ^= 1;
         ptx::tc_fence_after();
         if (pk) pk[14] = clock64();
-        if (more) r_store(pf);                              // every MMA that read the old planes has completed
+        r_store(pf);                                        // every MMA that read the old planes has completed
+      } else {
+        ptx::mbar_wait(out_done, ph_out);
+        ptx::tc_fence_after();
+        if (pk) pk[14] = clock64();
       }
+      ph_out ^= 1;
       const int t = r0 + row;
       if (rows_live) {
         uint32_t o1[16], o2[16];

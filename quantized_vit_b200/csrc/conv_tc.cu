@@ -69,7 +69,7 @@ __global__ void __launch_bounds__(ctc::kThreads, 1) ultra_conv_tc_kernel(const c
   const uint32_t bar = a_sm + (uint32_t)(chunks * kTileM * 128);
   uint8_t* gen = smem_raw + (base - ptx::smem_u32(smem_raw));
   volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(gen + (bar - base) + 16);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // (visibly warp-uniform)
 
   if (threadIdx.x == 0) {
     ptx::mbar_init(bar, 1);
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(ctc::kThreads, 1) ultra_conv_tc_kernel(const c
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 
   const int taps = p.kh * p.kw;
   const int cp = p.C >> 4;                                           // 16-byte pieces per (pixel, tap): 1, 2, 4 or 8
@@ -142,16 +142,21 @@ __global__ void __launch_bounds__(ctc::kThreads, 1) ultra_conv_tc_kernel(const c
     ptx::fence_proxy_async_smem();                                    // generic-proxy writes -> visible to the tensor core
     ptx::tc_fence_before();                                           // (previous tile's TMEM reads are complete)
     __syncthreads();
-    if (threadIdx.x == 128) {
+    if (warp == 4) {
+      // converged warp, one elected lane issues: the descriptors stay in uniform registers and every MMA is one instruction
+      // (a `threadIdx.x == 128` guard wraps each in an elect / broadcast loop, tools/ubench/mma_rate.cu)
       ptx::tc_fence_after();
-      uint32_t acc = 0;
-      for (int kb = 0; kb < p.K; kb += 32) {                          // 32 bytes of K per MMA; chunks beyond K hold zeros (skipped)
-        const uint32_t ch = (uint32_t)(kb >> 7), within = (uint32_t)(kb & 127);
-        ptx::mma_i8<1>(tmem, ptx::make_kmajor_sw128_desc(a_sm + ch * kTileM * 128 + within),
-                       ptx::make_kmajor_sw128_desc(w_sm + ch * (uint32_t)p.O_pad * 128 + within), idesc, acc);
-        acc = 1;
+      if (ptx::elect_one()) {
+        uint32_t acc = 0;
+        for (int kb = 0; kb < p.K; kb += 32) {                        // 32 bytes of K per MMA; chunks beyond K hold zeros (skipped)
+          const uint32_t ch = (uint32_t)(kb >> 7), within = (uint32_t)(kb & 127);
+          ptx::mma_i8<1>(tmem, ptx::make_kmajor_sw128_desc(a_sm + ch * kTileM * 128 + within),
+                         ptx::make_kmajor_sw128_desc(w_sm + ch * (uint32_t)p.O_pad * 128 + within), idesc, acc);
+          acc = 1;
+        }
+        ptx::mma_commit(bar);
       }
-      ptx::mma_commit(bar);
+      __syncwarp();
     }
     // every thread waits for the MMAs: the gather of the next tile overwrites the operand tile they read
     ptx::mbar_wait(bar, phase);
