@@ -19,6 +19,9 @@ def main():
     if len(sys.argv) > 3:                    # optional: bf16 planes of the gradient operand (3 = exact, 2 = 16 significant bits)
         from quantized_vit_b200.quantization import quant_layers
         quant_layers.GRADIENT_PLANES = int(sys.argv[3])
+    if os.environ.get("QVIT_CG"):            # A/B switch: 1 = single-CTA tiles everywhere (qvit_gemm_set_cta_group)
+        from quantized_vit_b200 import _lib
+        _lib.lib().qvit_gemm_set_cta_group(int(os.environ["QVIT_CG"]))
     torch.manual_seed(0)
     model = VisionTransformer(num_classes=1000)
     model = model_to_quantize_model(model, num_bits=4, quant_type=qtype, quant_mode="weight_and_activation").cuda().train()
