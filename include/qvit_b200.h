@@ -75,6 +75,16 @@ int qvit_sym_backward(const float* x, const float* g, int64_t n,
                       float clip_lo, float clip_hi,
                       float* grad_x, float* grad_scalars, int32_t* flags, qvit_stream_t stream);
 
+/* The same two kernels with Mlp.forward's nn.GELU (VIT:173) fused in, for the QAT step of the layer BEHIND the GELU (fc2):
+ * codes = quantize_act(gelu(x)) from the pre-activation x (contiguous, n elements; the fp32 activation is never written), and the
+ * backward that recomputes gelu(pre), applies the STE mask / scalar-gradient sums of qvit_sym_backward to it and writes the
+ * gradient with respect to the PRE-activation (x gelu'(pre)).                                                                   */
+int qvit_gelu_quantize_sym(const float* x, int64_t n, const float* d, const float* q_m, const float* t, int8_t* codes,
+                           int32_t* flags, qvit_stream_t stream);
+int qvit_gelu_sym_backward(const float* pre, const float* g, int64_t n, const float* d, const float* q_m, const float* t,
+                           float clip_lo, float clip_hi, float* grad_pre, float* grad_scalars, int32_t* flags,
+                           qvit_stream_t stream);
+
 /* max|x| over n elements -> out[0] (initialize_quant_layer, QL:423: q_m = max|W|).  out is overwritten. */
 int qvit_absmax(const float* x, int64_t n, float* out, qvit_stream_t stream);
 

@@ -59,6 +59,16 @@ __device__ __forceinline__ void bwd_elem(float x, float g, const BwdParams& p, f
   if (p.nonlinear) st += gs * dt;
 }
 
+// d gelu(x) / dx = Phi(x) + x * phi(x)   (what autograd derives for nn.GELU(), vit_model.py:173)
+__device__ __forceinline__ float gelu_grad(float x) {
+  const float cdf = 0.5f * (1.0f + erff(x * 0.7071067811865476f));
+  return fmaf(x * 0.3989422804014327f, expf(-0.5f * x * x), cdf);
+}
+
+// GELU: x is the PRE-activation of a GELU that feeds the quantizer (fc2 of the Mlp): the quantizer's input is recomputed as
+// gelu(x), and the gradient written is the one with respect to the pre-activation (STE mask, then gelu'): the fp32 activation
+// and its gradient never exist in HBM
+template <bool GELU>
 __global__ void __launch_bounds__(kBwdThreads)
 sym_backward_kernel(const float* __restrict__ x, const float* __restrict__ g, int64_t n, const float* __restrict__ d,
                     const float* __restrict__ qm, const float* __restrict__ t, float clip_lo, float clip_hi,
@@ -69,27 +79,31 @@ sym_backward_kernel(const float* __restrict__ x, const float* __restrict__ g, in
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   const bool aligned = (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) |
                           reinterpret_cast<uintptr_t>(grad_x)) & 15) == 0);
+  auto elem = [&](float xv, float gv, float& o) {
+    bwd_elem(GELU ? gelu_erf(xv) : xv, gv, p, clip_lo, clip_hi, o, sd, sq, st);
+    if (GELU) o *= gelu_grad(xv);
+  };
   if (aligned) {
     const int64_t n4 = n >> 2;
     for (int64_t i = tid; i < n4; i += stride) {
       const float4 xv = ldg_stream4(x + 4 * i);
       const float4 gv = ldg_stream4(g + 4 * i);
       float4 o;
-      bwd_elem(xv.x, gv.x, p, clip_lo, clip_hi, o.x, sd, sq, st);
-      bwd_elem(xv.y, gv.y, p, clip_lo, clip_hi, o.y, sd, sq, st);
-      bwd_elem(xv.z, gv.z, p, clip_lo, clip_hi, o.z, sd, sq, st);
-      bwd_elem(xv.w, gv.w, p, clip_lo, clip_hi, o.w, sd, sq, st);
+      elem(xv.x, gv.x, o.x);
+      elem(xv.y, gv.y, o.y);
+      elem(xv.z, gv.z, o.z);
+      elem(xv.w, gv.w, o.w);
       if (grad_x) reinterpret_cast<float4*>(grad_x)[i] = o;
     }
     for (int64_t i = n4 * 4 + tid; i < n; i += stride) {
       float o;
-      bwd_elem(x[i], g[i], p, clip_lo, clip_hi, o, sd, sq, st);
+      elem(x[i], g[i], o);
       if (grad_x) grad_x[i] = o;
     }
   } else {
     for (int64_t i = tid; i < n; i += stride) {
       float o;
-      bwd_elem(x[i], g[i], p, clip_lo, clip_hi, o, sd, sq, st);
+      elem(x[i], g[i], o);
       if (grad_x) grad_x[i] = o;
     }
   }
@@ -130,7 +144,20 @@ extern "C" int qvit_sym_backward(const float* x, const float* g, int64_t n, cons
   int64_t blocks = (n + kBwdThreads * 8 - 1) / (kBwdThreads * 8);
   const int64_t cap = (int64_t)sm_count() * 4;
   if (blocks > cap) blocks = cap;
-  sym_backward_kernel<<<(int)blocks, kBwdThreads, 0, (cudaStream_t)stream>>>(x, g, n, d, q_m, t, clip_lo, clip_hi, grad_x,
-                                                                            grad_scalars, flags);
+  sym_backward_kernel<false><<<(int)blocks, kBwdThreads, 0, (cudaStream_t)stream>>>(x, g, n, d, q_m, t, clip_lo, clip_hi, grad_x,
+                                                                                   grad_scalars, flags);
   return check_launch("qvit_sym_backward");
+}
+
+extern "C" int qvit_gelu_sym_backward(const float* pre, const float* g, int64_t n, const float* d, const float* q_m, const float* t,
+                                      float clip_lo, float clip_hi, float* grad_pre, float* grad_scalars, int32_t* flags,
+                                      qvit_stream_t stream) {
+  QVIT_REQUIRE(pre && g && d && q_m && grad_scalars && n >= 0, "qvit_gelu_sym_backward: bad argument");
+  if (n == 0) return QVIT_OK;
+  int64_t blocks = (n + kBwdThreads * 8 - 1) / (kBwdThreads * 8);
+  const int64_t cap = (int64_t)sm_count() * 4;
+  if (blocks > cap) blocks = cap;
+  sym_backward_kernel<true><<<(int)blocks, kBwdThreads, 0, (cudaStream_t)stream>>>(pre, g, n, d, q_m, t, clip_lo, clip_hi, grad_pre,
+                                                                                  grad_scalars, flags);
+  return check_launch("qvit_gelu_sym_backward");
 }

@@ -25,6 +25,9 @@ static inline int stream_grid(int64_t work_items, int per_block, int ctas_per_sm
 // ------------------------------------------------------------------------------------------------
 // flat fp32 -> int8 codes, n % 512 handled by a scalar tail
 // ------------------------------------------------------------------------------------------------
+// GELU: the codes of quantize_act(gelu(x)) - Mlp.forward's nn.GELU (vit_model.py:173) fused into fc2's activation quantizer
+// for the QAT step (the fp32 activation is never written; the backward recomputes it, backward.cu)
+template <bool GELU>
 __global__ void __launch_bounds__(kThreads)
 quantize_sym_flat_kernel(const float* __restrict__ x, int64_t n, const float* __restrict__ d,
                          const float* __restrict__ qm, const float* __restrict__ t,
@@ -41,6 +44,10 @@ quantize_sym_flat_kernel(const float* __restrict__ x, int64_t n, const float* __
     float4 v[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) v[j] = ldg_stream4(src + j * 128 + lane * 4);
+    if (GELU) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) v[j] = make_float4(gelu_erf(v[j].x), gelu_erf(v[j].y), gelu_erf(v[j].z), gelu_erf(v[j].w));
+    }
     uint32_t* dst = reinterpret_cast<uint32_t*>(codes + w * kWarpElems);
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
@@ -49,7 +56,7 @@ quantize_sym_flat_kernel(const float* __restrict__ x, int64_t n, const float* __
   }
   // tail (< 512 elements): first warp of block 0
   if (warp_global == 0) {
-    for (int64_t i = full * kWarpElems + lane; i < n; i += 32) codes[i] = (int8_t)sym_code(x[i], p, fl);
+    for (int64_t i = full * kWarpElems + lane; i < n; i += 32) codes[i] = (int8_t)sym_code(GELU ? gelu_erf(x[i]) : x[i], p, fl);
   }
   fl = warp_or(fl);
   if (fl && flags && lane == 0) atomicOr(flags, fl);
@@ -388,13 +395,23 @@ int qvit_quantize_sym(const float* x, int64_t rows, int64_t cols, int64_t ld_x, 
                     ((reinterpret_cast<uintptr_t>(codes) & 3) == 0);
   if (flat) {
     const int64_t n = rows * cols;
-    quantize_sym_flat_kernel<<<stream_grid(n, kBlockElems), kThreads, 0, s>>>(x, n, d, q_m, t, codes, flags);
+    quantize_sym_flat_kernel<false><<<stream_grid(n, kBlockElems), kThreads, 0, s>>>(x, n, d, q_m, t, codes, flags);
   } else {
     const int64_t n = rows * ld_codes;
     quantize_sym_rows_kernel<<<stream_grid(n, kThreads * 4), kThreads, 0, s>>>(x, rows, cols, ld_x, d, q_m, t, codes,
                                                                              ld_codes, flags);
   }
   return check_launch("qvit_quantize_sym");
+}
+
+int qvit_gelu_quantize_sym(const float* x, int64_t n, const float* d, const float* q_m, const float* t, int8_t* codes, int32_t* flags,
+                           qvit_stream_t stream) {
+  QVIT_REQUIRE(x && d && q_m && codes && n >= 0, "qvit_gelu_quantize_sym: bad argument");
+  QVIT_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(codes) & 3) == 0,
+               "qvit_gelu_quantize_sym: x must be 16-byte and codes 4-byte aligned");
+  if (n == 0) return QVIT_OK;
+  quantize_sym_flat_kernel<true><<<stream_grid(n, kBlockElems), kThreads, 0, (cudaStream_t)stream>>>(x, n, d, q_m, t, codes, flags);
+  return check_launch("qvit_gelu_quantize_sym");
 }
 
 int qvit_fake_quantize_sym(const float* x, int64_t n, const float* d, const float* q_m, const float* t, float* out,

@@ -94,7 +94,10 @@ class Mlp(nn.Module):
         self.fc1, self.act, self.fc2 = nn.Linear(dim, hidden), nn.GELU(), nn.Linear(hidden, dim)
 
     def forward(self, x):
-        return self.fc2(self.act(self.fc1(x)))
+        h = self.fc1(x)
+        if getattr(self.fc2, "fuses_pre_act", False) and getattr(self.act, "approximate", None) == "none":
+            return self.fc2(h, pre_act="gelu")       # QuantizeLinear: GELU fused into fc2's quantizer kernels (forward and backward)
+        return self.fc2(self.act(h))
 
 
 class Block(nn.Module):

@@ -55,9 +55,23 @@ def new_flags(device) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------------------ GETA quantizers
 def quantize_sym(x: torch.Tensor, d, q_m, t=None, ld_codes: Optional[int] = None, flags: Optional[torch.Tensor] = None,
-                 out: Optional[torch.Tensor] = None) -> torch.Tensor:
+                 out: Optional[torch.Tensor] = None, gelu: bool = False) -> torch.Tensor:
     """int8 codes of SymQuantizerLinear/NonLinear.forward (QL:136-161 / QL:40-69) for x viewed as [rows, cols]
-    (cols = last dim).  Returns [rows, ld_codes] int8, padding columns zero."""
+    (cols = last dim).  Returns [rows, ld_codes] int8, padding columns zero.  gelu=True: the codes of gelu(x) (nn.GELU of
+    Mlp.forward fused into the quantizer; fp32, cols a multiple of 16, ld_codes == cols)."""
+    if gelu:
+        x = _f32c(x, "quantize_sym")
+        x2 = x.reshape(-1, x.shape[-1])
+        rows, cols = x2.shape
+        if (ld_codes is not None and int(ld_codes) != cols) or out is not None or cols % 4:
+            raise ValueError("quantize_sym(gelu=True): contiguous codes only (ld_codes == cols, cols % 4 == 0)")
+        dev = x2.device
+        d_, q_ = _scalar_param(d, dev, "d_quant"), _scalar_param(q_m, dev, "q_m")
+        t_ = None if t is None else _scalar_param(t, dev, "t_quant")
+        out = torch.empty((rows, cols), dtype=torch.int8, device=dev)
+        _lib.check(_lib.lib().qvit_gelu_quantize_sym(_lib.ptr(x2), x2.numel(), _lib.ptr(d_), _lib.ptr(q_), _lib.ptr(t_), _lib.ptr(out),
+                                                     _lib.ptr(flags), _lib.stream()), "qvit_gelu_quantize_sym")
+        return out
     if x.dtype == torch.bfloat16:
         _lib.require_cuda(x)
         x2 = x.reshape(-1, x.shape[-1]) if x.dim() > 1 else x.reshape(1, -1)
@@ -96,8 +110,9 @@ def fake_quantize_sym(x: torch.Tensor, d, q_m, t=None) -> torch.Tensor:
 
 
 def sym_backward(x: torch.Tensor, g: torch.Tensor, d, q_m, t=None, clip: Tuple[float, float] = (-2.0, 2.0),
-                 want_grad_x: bool = True, flags: Optional[torch.Tensor] = None):
-    """One fused pass: (grad_x | None, scalars[3] = grad_d, grad_qm, grad_t).  QL:163-205 / QL:71-125."""
+                 want_grad_x: bool = True, flags: Optional[torch.Tensor] = None, gelu: bool = False):
+    """One fused pass: (grad_x | None, scalars[3] = grad_d, grad_qm, grad_t).  QL:163-205 / QL:71-125.
+    gelu=True: x is the pre-activation of a GELU in front of the quantizer; grad_x is the gradient w.r.t. that pre-activation."""
     x = _f32c(x, "sym_backward x")
     g = _f32c(g, "sym_backward g")
     if g.shape != x.shape:
@@ -107,9 +122,9 @@ def sym_backward(x: torch.Tensor, g: torch.Tensor, d, q_m, t=None, clip: Tuple[f
     t_ = None if t is None else _scalar_param(t, dev, "t_quant")
     grad_x = torch.empty_like(x) if want_grad_x else None
     scalars = torch.zeros(3, dtype=torch.float32, device=dev)
-    _lib.check(_lib.lib().qvit_sym_backward(_lib.ptr(x), _lib.ptr(g), x.numel(), _lib.ptr(d_), _lib.ptr(q_), _lib.ptr(t_),
-                                            float(clip[0]), float(clip[1]), _lib.ptr(grad_x), _lib.ptr(scalars),
-                                            _lib.ptr(flags), _lib.stream()), "qvit_sym_backward")
+    fn = _lib.lib().qvit_gelu_sym_backward if gelu else _lib.lib().qvit_sym_backward
+    _lib.check(fn(_lib.ptr(x), _lib.ptr(g), x.numel(), _lib.ptr(d_), _lib.ptr(q_), _lib.ptr(t_), float(clip[0]), float(clip[1]),
+                  _lib.ptr(grad_x), _lib.ptr(scalars), _lib.ptr(flags), _lib.stream()), "qvit_sym_backward")
     return grad_x, scalars
 
 

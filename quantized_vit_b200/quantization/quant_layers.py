@@ -303,11 +303,17 @@ class QuantLinearFunction(torch.autograd.Function):
               range / exponent gradient reductions (K6).  Saved for backward: x, W and the int8 codes (1 B/element)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, d_a, qm_a, t_a, d_w, qm_w, t_w, clip_a, clip_w):
+    def forward(ctx, x, weight, bias, d_a, qm_a, t_a, d_w, qm_w, t_w, clip_a, clip_w, *extra):
+        pre_gelu = bool(extra[0]) if extra else False
+        ctx.n_extra = len(extra)
         K, N = weight.shape[1], weight.shape[0]
         x2 = x.reshape(-1, K).contiguous()
         flags = _flags_for(x.device)
-        a_codes = ops.quantize_sym(x2, d_a, qm_a, t_a, ld_codes=ops.pad16(K), flags=flags)
+        # pre_gelu: x is the PRE-activation of the nn.GELU in front of this layer (Mlp.forward, vit_model.py:173): the quantizer
+        # kernel applies it, the backward kernel recomputes it - the fp32 activation and its gradient never exist in HBM
+        ctx.pre_gelu = bool(pre_gelu)
+        a_codes = ops.quantize_sym(x2, d_a, qm_a, t_a, flags=flags, gelu=True) if ctx.pre_gelu else \
+            ops.quantize_sym(x2, d_a, qm_a, t_a, ld_codes=ops.pad16(K), flags=flags)
         w_codes = ops.quantize_sym(weight.detach(), d_w, qm_w, t_w, ld_codes=ops.pad16(K), flags=flags)
         y = ops.gemm_i8(a_codes, w_codes, K, N, out_kind=ops.QVIT_OUT_F32, scale_a=d_a, scale_w=d_w,
                         bias=None if bias is None else bias.detach(), flags=flags)
@@ -348,12 +354,13 @@ class QuantLinearFunction(torch.autograd.Function):
         if grad_xq is None:
             grad_x, s_a = None, torch.zeros(3, dtype=torch.float32, device=g.device)
         else:
-            grad_x, s_a = ops.sym_backward(x2, grad_xq, d_a, qm_a, t_a, ctx.clip_a, want_grad_x=ctx.needs_input_grad[0], flags=flags)
+            grad_x, s_a = ops.sym_backward(x2, grad_xq, d_a, qm_a, t_a, ctx.clip_a, want_grad_x=ctx.needs_input_grad[0], flags=flags,
+                                           gelu=ctx.pre_gelu)
         grad_w, s_w = ops.sym_backward(weight.detach(), grad_wq, d_w, qm_w, t_w, ctx.clip_w, flags=flags)
         if EAGER_NAN_CHECK:
             check_nan_flags()
         return (None if grad_x is None else grad_x.view(ctx.x_shape), grad_w, grad_b, s_a[0:1], s_a[1:2],
-                s_a[2:3] if ctx.nl else None, s_w[0:1], s_w[1:2], s_w[2:3] if ctx.nl else None, None, None)
+                s_a[2:3] if ctx.nl else None, s_w[0:1], s_w[1:2], s_w[2:3] if ctx.nl else None, None, None) + (None,) * ctx.n_extra
 
 
 class _LinearF32Function(torch.autograd.Function):
@@ -683,16 +690,29 @@ class QuantizeLinear(QuantizeMixin, nn.Linear):
             initialize_quant_layer(q, num_bits=num_bits, quant_type=quant_type, quant_mode=quant_mode)
         return q
 
-    def forward(self, input_: torch.Tensor) -> torch.Tensor:
-        """QL:495-499."""
+    fuses_pre_act = True     # forward(x, pre_act="gelu"): the caller's nn.GELU in front of this layer is applied here
+
+    def forward(self, input_: torch.Tensor, pre_act: Optional[str] = None) -> torch.Tensor:
+        """QL:495-499.  ``pre_act="gelu"`` (extension, used by the drop-in ViT's Mlp): ``input_`` is the pre-activation of the
+        exact-erf GELU in front of this layer; on the int8 QAT path it is fused into the quantizer kernels, elsewhere it is
+        simply applied first."""
         ops._lib.require_cuda(input_, self.weight)
+        if pre_act not in (None, "gelu"):
+            raise ValueError(f"QuantizeLinear: unsupported pre_act {pre_act!r}")
         if self._needs_autograd(input_):
             if self._int8_train_ok() and input_.dtype == torch.float32:
                 d_a, q_a, t_a = self._act_qparams()
                 d_w, q_w, t_w = self._wt_qparams()
+                fuse = pre_act == "gelu" and self.in_features % 16 == 0
+                if pre_act and not fuse:
+                    input_ = F.gelu(input_)
                 return QuantLinearFunction.apply(input_, self.weight, self.bias, d_a, q_a, t_a, d_w, q_w, t_w,
-                                                 _clip_pair(self.act_clip_val), _clip_pair(self.weight_clip_val))
+                                                 _clip_pair(self.act_clip_val), _clip_pair(self.weight_clip_val), fuse)
+            if pre_act:
+                input_ = F.gelu(input_)
             return self._wide_autograd(input_, self.weight, self.bias)
+        if pre_act:
+            input_ = F.gelu(input_)
         c = self._refresh_cache()
         if self._int8_ok(c) and input_.dtype == torch.float32:
             K, N = self.in_features, self.out_features
