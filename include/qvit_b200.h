@@ -287,7 +287,8 @@ int qvit_layernorm_quantize(const float* x, int64_t rows, int cols, const float*
 int qvit_layernorm_fwd(const float* x, int64_t rows, int cols, const float* gamma, const float* beta, float eps, float* y,
                        float* mean, float* rstd, qvit_stream_t stream);
 int qvit_layernorm_bwd(const float* x, const float* gy, int64_t rows, int cols, const float* gamma, const float* mean,
-                       const float* rstd, float* gx, float* dgamma, float* dbeta, qvit_stream_t stream);
+                       const float* rstd, const float* add /* optional: gradient reaching x over the residual path */, float* gx,
+                       float* dgamma, float* dbeta, qvit_stream_t stream);
 /* bf16 -> codes (attention output feeding `proj`): same quantizer on bf16 input widened to fp32. */
 int qvit_quantize_sym_bf16(const void* x_bf16, int64_t rows, int64_t cols, int64_t ld_x,
                            const float* d, const float* q_m, const float* t,

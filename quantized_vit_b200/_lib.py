@@ -69,7 +69,7 @@ PROTOTYPES = {
     "qvit_gemm_bf16_split": (_i, [_p, _i64, _i, _p, _i64, _i, _i, _i, _p, _i64, C.POINTER(Epilogue), _p]),
     "qvit_layernorm_quantize": (_i, [_p, _i64, _i, _p, _p, _f, _p, _p, _p, _p, _i64, _p, _p, _p]),
     "qvit_layernorm_fwd": (_i, [_p, _i64, _i, _p, _p, _f, _p, _p, _p, _p]),
-    "qvit_layernorm_bwd": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _p]),
+    "qvit_layernorm_bwd": (_i, [_p, _p, _i64, _i, _p, _p, _p, _p, _p, _p, _p, _p]),
     "qvit_attention_train_fwd": (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
     "qvit_attention_train_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p]),
     "qvit_attention_train_bwd_prof": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p]),

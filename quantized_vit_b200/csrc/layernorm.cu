@@ -67,7 +67,8 @@ template <int V>
 __global__ void __launch_bounds__(kLnThreads) layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gy, int64_t rows,
                                                                     const float* __restrict__ gamma, const float* __restrict__ mean_in,
                                                                     const float* __restrict__ rstd_in, float* __restrict__ gx,
-                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta) {
+                                                                    float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                    const float* __restrict__ add) {
   constexpr int cols = V * 128;
   __shared__ float red[kLnThreads / 32][128];                    // one 128-column slice at a time
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -96,10 +97,17 @@ __global__ void __launch_bounds__(kLnThreads) layernorm_bwd_kernel(const float* 
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       float4 o;
-      o.x = rstd * (gp[j].x - c1 - xh[j].x * c2);
-      o.y = rstd * (gp[j].y - c1 - xh[j].y * c2);
-      o.z = rstd * (gp[j].z - c1 - xh[j].z * c2);
-      o.w = rstd * (gp[j].w - c1 - xh[j].w * c2);
+      o.x = __fmul_rn(rstd, gp[j].x - c1 - xh[j].x * c2);
+      o.y = __fmul_rn(rstd, gp[j].y - c1 - xh[j].y * c2);
+      o.z = __fmul_rn(rstd, gp[j].z - c1 - xh[j].z * c2);
+      o.w = __fmul_rn(rstd, gp[j].w - c1 - xh[j].w * c2);
+      if (add) {                                             // gradient arriving over the residual connection (same rounding as a separate add)
+        const float4 a = ldg_stream4(add + r * cols + j * 128 + lane * 4);
+        o.x = __fadd_rn(a.x, o.x);
+        o.y = __fadd_rn(a.y, o.y);
+        o.z = __fadd_rn(a.z, o.z);
+        o.w = __fadd_rn(a.w, o.w);
+      }
       reinterpret_cast<float4*>(gx + r * cols)[j * 32 + lane] = o;
     }
   }
@@ -151,16 +159,17 @@ extern "C" int qvit_layernorm_fwd(const float* x, int64_t rows, int cols, const 
   return check_launch("qvit_layernorm_fwd");
 }
 
-// gx, dgamma, dbeta of LayerNorm from x, grad_output and the saved statistics (dgamma / dbeta are overwritten).
+// gx, dgamma, dbeta of LayerNorm from x, grad_output and the saved statistics (dgamma / dbeta are overwritten).  add (optional,
+// like x): a gradient that reaches x over another path (the residual connection around the block) - gx = add + LayerNorm'(gy).
 extern "C" int qvit_layernorm_bwd(const float* x, const float* gy, int64_t rows, int cols, const float* gamma, const float* mean,
-                                  const float* rstd, float* gx, float* dgamma, float* dbeta, qvit_stream_t stream) {
+                                  const float* rstd, const float* add, float* gx, float* dgamma, float* dbeta, qvit_stream_t stream) {
   QVIT_REQUIRE(x && gy && gamma && mean && rstd && gx && dgamma && dbeta && rows >= 0, "qvit_layernorm_bwd: null pointer");
   if (cols <= 0 || cols % 128 != 0 || cols > 1024) {
     set_error("qvit_layernorm_bwd: cols must be a multiple of 128, <= 1024 (got %d)", cols);
     return QVIT_ERR_UNSUPPORTED;
   }
   QVIT_REQUIRE(((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(gy) | reinterpret_cast<uintptr_t>(gx) |
-                 reinterpret_cast<uintptr_t>(gamma)) & 15) == 0, "qvit_layernorm_bwd: 16-byte aligned tensors");
+                 reinterpret_cast<uintptr_t>(gamma) | reinterpret_cast<uintptr_t>(add)) & 15) == 0, "qvit_layernorm_bwd: 16-byte aligned tensors");
   cudaStream_t s = (cudaStream_t)stream;
   if (cudaMemsetAsync(dgamma, 0, sizeof(float) * cols, s) != cudaSuccess || cudaMemsetAsync(dbeta, 0, sizeof(float) * cols, s) != cudaSuccess) {
     set_error("qvit_layernorm_bwd: cudaMemsetAsync failed");
@@ -168,7 +177,7 @@ extern "C" int qvit_layernorm_bwd(const float* x, const float* gy, int64_t rows,
   }
   if (rows == 0) return QVIT_OK;
   const int g = ln_grid(rows, 2);   // the wide instances hold one block per SM (150-190 registers); fewer blocks = fewer column atomics
-#define QVIT_LNB(V) case V: layernorm_bwd_kernel<V><<<g, kLnThreads, 0, s>>>(x, gy, rows, gamma, mean, rstd, gx, dgamma, dbeta); break;
+#define QVIT_LNB(V) case V: layernorm_bwd_kernel<V><<<g, kLnThreads, 0, s>>>(x, gy, rows, gamma, mean, rstd, gx, dgamma, dbeta, add); break;
   switch (cols / 128) { QVIT_LNB(1) QVIT_LNB(2) QVIT_LNB(3) QVIT_LNB(4) QVIT_LNB(5) QVIT_LNB(6) QVIT_LNB(7) QVIT_LNB(8) }
 #undef QVIT_LNB
   return check_launch("qvit_layernorm_bwd");

@@ -30,15 +30,45 @@ class _LayerNormFunction(torch.autograd.Function):
         return gx, dg, db, None
 
 
+class _ResidualLayerNormFunction(torch.autograd.Function):
+    """(x, LayerNorm(x)): the block input handed through for the residual connection together with its normalised form, so that
+    the backward sees BOTH gradients reaching x and sums them inside the LayerNorm backward kernel (no separate add kernel)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        from .. import ops
+        y, mean, rstd = ops.layernorm_fwd(x, weight, bias, eps)
+        ctx.save_for_backward(x, weight, mean, rstd)
+        return x.view_as(x), y
+
+    @staticmethod
+    def backward(ctx, g_pass, gy):
+        from .. import ops
+        x, weight, mean, rstd = ctx.saved_tensors
+        if gy is None:
+            return g_pass, None, None, None
+        gx, dg, db = ops.layernorm_bwd(x, gy, weight, mean, rstd, add=g_pass)
+        return gx, dg, db, None
+
+
 class LayerNorm(nn.LayerNorm):
     """nn.LayerNorm with the same parameters / state_dict; fp32 CUDA inputs whose width the kernels cover take the fused path."""
 
-    def forward(self, x):
+    def _fused_ok(self, x):
         from .. import ops
-        if (x.is_cuda and x.dtype == torch.float32 and self.elementwise_affine and self.bias is not None and len(self.normalized_shape) == 1
-                and ops.layernorm_supported(self.normalized_shape[0])):
+        return (x.is_cuda and x.dtype == torch.float32 and self.elementwise_affine and self.bias is not None
+                and len(self.normalized_shape) == 1 and ops.layernorm_supported(self.normalized_shape[0]))
+
+    def forward(self, x):
+        if self._fused_ok(x):
             return _LayerNormFunction.apply(x, self.weight, self.bias, self.eps)
         return super().forward(x)
+
+    def with_passthrough(self, x):
+        """(x', LayerNorm(x)) with x' == x: use x' for the residual connection (see _ResidualLayerNormFunction)."""
+        if self._fused_ok(x) and torch.is_grad_enabled() and (x.requires_grad or self.weight.requires_grad):
+            return _ResidualLayerNormFunction.apply(x, self.weight, self.bias, self.eps)
+        return x, self.forward(x)
 
 
 class PatchEmbed(nn.Module):
@@ -70,6 +100,15 @@ class _AttentionCoreFunction(torch.autograd.Function):
         return ops.attention_train_bwd(qkv, out, lse, g, ctx.num_heads), None
 
 
+def _linear_plus(layer, x, residual):
+    """residual + layer(x); inside the layer's GEMM epilogue when it is a QuantizeLinear."""
+    if residual is None:
+        return layer(x)
+    if getattr(layer, "fuses_pre_act", False):
+        return layer(x, residual=residual)
+    return residual + layer(x)
+
+
 class ViTAttention(nn.Module):
     def __init__(self, dim, num_heads):
         super().__init__()
@@ -77,15 +116,18 @@ class ViTAttention(nn.Module):
         self.qkv = nn.Linear(dim, dim * 3, bias=True)
         self.proj = nn.Linear(dim, dim)
 
-    def forward(self, x):
+    def forward(self, x, residual=None):
+        """residual: the block input; `residual + proj(...)` (vit_model.py:206) happens in proj's GEMM epilogue when it can."""
         B, N, C = x.shape
         from .. import ops
         qkv = self.qkv(x)
         if qkv.is_cuda and qkv.dtype == torch.float32 and ops.attention_train_supported(N, C // self.num_heads):
-            return self.proj(_AttentionCoreFunction.apply(qkv, self.num_heads))
-        qkv = qkv.reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
-        o = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])      # softmax(q k^T / sqrt(d)) v, vit_model.py:141-149
-        return self.proj(o.transpose(1, 2).reshape(B, N, C))
+            o = _AttentionCoreFunction.apply(qkv, self.num_heads)
+        else:
+            qkv = qkv.reshape(B, N, 3, self.num_heads, C // self.num_heads).permute(2, 0, 3, 1, 4)
+            o = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])  # softmax(q k^T / sqrt(d)) v, vit_model.py:141-149
+            o = o.transpose(1, 2).reshape(B, N, C)
+        return _linear_plus(self.proj, o, residual)
 
 
 class Mlp(nn.Module):
@@ -93,11 +135,12 @@ class Mlp(nn.Module):
         super().__init__()
         self.fc1, self.act, self.fc2 = nn.Linear(dim, hidden), nn.GELU(), nn.Linear(hidden, dim)
 
-    def forward(self, x):
+    def forward(self, x, residual=None):
         h = self.fc1(x)
         if getattr(self.fc2, "fuses_pre_act", False) and getattr(self.act, "approximate", None) == "none":
-            return self.fc2(h, pre_act="gelu")       # QuantizeLinear: GELU fused into fc2's quantizer kernels (forward and backward)
-        return self.fc2(self.act(h))
+            # QuantizeLinear: GELU fused into fc2's quantizer kernels (forward and backward), residual into its GEMM epilogue
+            return self.fc2(h, pre_act="gelu", residual=residual)
+        return _linear_plus(self.fc2, self.act(h), residual)
 
 
 class Block(nn.Module):
@@ -107,8 +150,12 @@ class Block(nn.Module):
         self.norm2, self.mlp = LayerNorm(dim, eps=1e-6), Mlp(dim, int(dim * mlp_ratio))
 
     def forward(self, x):
-        x = x + self.attn(self.norm1(x))
-        return x + self.mlp(self.norm2(x))
+        # x + attn(norm1(x)); x + mlp(norm2(x))  (vit_model.py:206-207): the additions run in the proj / fc2 GEMM epilogues and
+        # the two gradients that meet at each block input are summed inside the LayerNorm backward kernel
+        xp, y = self.norm1.with_passthrough(x)
+        x = self.attn(y, residual=xp)
+        xp, y = self.norm2.with_passthrough(x)
+        return self.mlp(y, residual=xp)
 
 
 class VisionTransformer(nn.Module):

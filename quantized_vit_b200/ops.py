@@ -198,9 +198,14 @@ def layernorm_fwd(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, eps:
     return y.view(x.shape), mean, rstd
 
 
-def layernorm_bwd(x: torch.Tensor, gy: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor):
-    """(gx, dgamma, dbeta) of LayerNorm."""
+def layernorm_bwd(x: torch.Tensor, gy: torch.Tensor, gamma: torch.Tensor, mean: torch.Tensor, rstd: torch.Tensor,
+                  add: Optional[torch.Tensor] = None):
+    """(gx, dgamma, dbeta) of LayerNorm; ``add``: a gradient reaching x over the residual path, summed into gx in the same pass."""
     x, gy = _f32c(x, "layernorm_bwd x"), _f32c(gy, "layernorm_bwd gy")
+    if add is not None:
+        add = _f32c(add, "layernorm_bwd add")
+        if add.shape != x.shape:
+            raise ValueError("layernorm_bwd: add must have the shape of x")
     x2, g2 = x.reshape(-1, x.shape[-1]), gy.reshape(-1, x.shape[-1])
     rows, cols = x2.shape
     gamma = _f32c(gamma.detach(), "gamma")
@@ -208,7 +213,7 @@ def layernorm_bwd(x: torch.Tensor, gy: torch.Tensor, gamma: torch.Tensor, mean: 
     dg = torch.empty(cols, dtype=torch.float32, device=x.device)
     db = torch.empty(cols, dtype=torch.float32, device=x.device)
     _lib.check(_lib.lib().qvit_layernorm_bwd(_lib.ptr(x2), _lib.ptr(g2), rows, cols, _lib.ptr(gamma), _lib.ptr(mean), _lib.ptr(rstd),
-                                             _lib.ptr(gx), _lib.ptr(dg), _lib.ptr(db), _lib.stream()), "qvit_layernorm_bwd")
+                                             _lib.ptr(add), _lib.ptr(gx), _lib.ptr(dg), _lib.ptr(db), _lib.stream()), "qvit_layernorm_bwd")
     return gx.view(x.shape), dg, db
 
 

@@ -305,7 +305,8 @@ class QuantLinearFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, d_a, qm_a, t_a, d_w, qm_w, t_w, clip_a, clip_w, *extra):
         pre_gelu = bool(extra[0]) if extra else False
-        ctx.n_extra = len(extra)
+        residual = extra[1] if len(extra) > 1 else None        # fp32 [..., N]: added in the GEMM epilogue (Block.forward's x + ...)
+        ctx.n_extra, ctx.has_res = len(extra), residual is not None
         K, N = weight.shape[1], weight.shape[0]
         x2 = x.reshape(-1, K).contiguous()
         flags = _flags_for(x.device)
@@ -316,7 +317,8 @@ class QuantLinearFunction(torch.autograd.Function):
             ops.quantize_sym(x2, d_a, qm_a, t_a, ld_codes=ops.pad16(K), flags=flags)
         w_codes = ops.quantize_sym(weight.detach(), d_w, qm_w, t_w, ld_codes=ops.pad16(K), flags=flags)
         y = ops.gemm_i8(a_codes, w_codes, K, N, out_kind=ops.QVIT_OUT_F32, scale_a=d_a, scale_w=d_w,
-                        bias=None if bias is None else bias.detach(), flags=flags)
+                        bias=None if bias is None else bias.detach(), flags=flags,
+                        residual=None if residual is None else residual.detach().reshape(-1, N))
         ctx.clip_a, ctx.clip_w, ctx.has_bias, ctx.nl = clip_a, clip_w, bias is not None, t_a is not None
         ctx.x_shape = x.shape
         saved = [x2, weight, d_a, qm_a, d_w, qm_w, a_codes, w_codes] + ([t_a, t_w] if t_a is not None else [])
@@ -360,7 +362,8 @@ class QuantLinearFunction(torch.autograd.Function):
         if EAGER_NAN_CHECK:
             check_nan_flags()
         return (None if grad_x is None else grad_x.view(ctx.x_shape), grad_w, grad_b, s_a[0:1], s_a[1:2],
-                s_a[2:3] if ctx.nl else None, s_w[0:1], s_w[1:2], s_w[2:3] if ctx.nl else None, None, None) + (None,) * ctx.n_extra
+                s_a[2:3] if ctx.nl else None, s_w[0:1], s_w[1:2], s_w[2:3] if ctx.nl else None, None, None) + \
+            ((None, g if ctx.has_res else None) + (None,) * (ctx.n_extra - 2) if ctx.n_extra >= 2 else (None,) * ctx.n_extra)
 
 
 class _LinearF32Function(torch.autograd.Function):
@@ -692,27 +695,33 @@ class QuantizeLinear(QuantizeMixin, nn.Linear):
 
     fuses_pre_act = True     # forward(x, pre_act="gelu"): the caller's nn.GELU in front of this layer is applied here
 
-    def forward(self, input_: torch.Tensor, pre_act: Optional[str] = None) -> torch.Tensor:
-        """QL:495-499.  ``pre_act="gelu"`` (extension, used by the drop-in ViT's Mlp): ``input_`` is the pre-activation of the
-        exact-erf GELU in front of this layer; on the int8 QAT path it is fused into the quantizer kernels, elsewhere it is
-        simply applied first."""
+    def forward(self, input_: torch.Tensor, pre_act: Optional[str] = None, residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """QL:495-499.  Extensions used by the drop-in ViT: ``pre_act="gelu"`` - ``input_`` is the pre-activation of the exact-erf
+        GELU in front of this layer (fused into the quantizer kernels on the int8 QAT path, simply applied first elsewhere);
+        ``residual`` - returns ``residual + layer(input_)`` (in the GEMM epilogue on the int8 QAT path)."""
         ops._lib.require_cuda(input_, self.weight)
         if pre_act not in (None, "gelu"):
             raise ValueError(f"QuantizeLinear: unsupported pre_act {pre_act!r}")
-        if self._needs_autograd(input_):
-            if self._int8_train_ok() and input_.dtype == torch.float32:
-                d_a, q_a, t_a = self._act_qparams()
-                d_w, q_w, t_w = self._wt_qparams()
-                fuse = pre_act == "gelu" and self.in_features % 16 == 0
-                if pre_act and not fuse:
-                    input_ = F.gelu(input_)
-                return QuantLinearFunction.apply(input_, self.weight, self.bias, d_a, q_a, t_a, d_w, q_w, t_w,
-                                                 _clip_pair(self.act_clip_val), _clip_pair(self.weight_clip_val), fuse)
-            if pre_act:
+        if self._needs_autograd(input_) and input_.dtype == torch.float32 and self._int8_train_ok():
+            d_a, q_a, t_a = self._act_qparams()
+            d_w, q_w, t_w = self._wt_qparams()
+            fuse = pre_act == "gelu" and self.in_features % 16 == 0
+            if pre_act and not fuse:
                 input_ = F.gelu(input_)
-            return self._wide_autograd(input_, self.weight, self.bias)
+            res_ok = residual is not None and residual.dtype == torch.float32 and residual.is_cuda and \
+                tuple(residual.shape) == tuple(input_.shape[:-1]) + (self.out_features,)
+            y = QuantLinearFunction.apply(input_, self.weight, self.bias, d_a, q_a, t_a, d_w, q_w, t_w,
+                                          _clip_pair(self.act_clip_val), _clip_pair(self.weight_clip_val), fuse,
+                                          residual if res_ok else None)
+            return y if (residual is None or res_ok) else residual + y
         if pre_act:
             input_ = F.gelu(input_)
+        y = self._forward_plain(input_)
+        return y if residual is None else residual + y
+
+    def _forward_plain(self, input_: torch.Tensor) -> torch.Tensor:
+        if self._needs_autograd(input_):
+            return self._wide_autograd(input_, self.weight, self.bias)
         c = self._refresh_cache()
         if self._int8_ok(c) and input_.dtype == torch.float32:
             K, N = self.in_features, self.out_features
