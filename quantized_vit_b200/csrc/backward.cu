@@ -59,12 +59,6 @@ __device__ __forceinline__ void bwd_elem(float x, float g, const BwdParams& p, f
   if (p.nonlinear) st += gs * dt;
 }
 
-// d gelu(x) / dx = Phi(x) + x * phi(x)   (what autograd derives for nn.GELU(), vit_model.py:173)
-__device__ __forceinline__ float gelu_grad(float x) {
-  const float cdf = 0.5f * (1.0f + erff(x * 0.7071067811865476f));
-  return fmaf(x * 0.3989422804014327f, expf(-0.5f * x * x), cdf);
-}
-
 // GELU: x is the PRE-activation of a GELU that feeds the quantizer (fc2 of the Mlp): the quantizer's input is recomputed as
 // gelu(x), and the gradient written is the one with respect to the pre-activation (STE mask, then gelu'): the fp32 activation
 // and its gradient never exist in HBM
@@ -80,8 +74,14 @@ sym_backward_kernel(const float* __restrict__ x, const float* __restrict__ g, in
   const bool aligned = (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(g) |
                           reinterpret_cast<uintptr_t>(grad_x)) & 15) == 0);
   auto elem = [&](float xv, float gv, float& o) {
-    bwd_elem(GELU ? gelu_erf(xv) : xv, gv, p, clip_lo, clip_hi, o, sd, sq, st);
-    if (GELU) o *= gelu_grad(xv);
+    if (GELU) {       // d gelu / dx = Phi(x) + x * phi(x): what autograd derives for nn.GELU() (vit_model.py:173)
+      float y, dy;
+      gelu_erf_grad(xv, y, dy);
+      bwd_elem(y, gv, p, clip_lo, clip_hi, o, sd, sq, st);
+      o *= dy;
+    } else {
+      bwd_elem(xv, gv, p, clip_lo, clip_hi, o, sd, sq, st);
+    }
   };
   if (aligned) {
     const int64_t n4 = n >> 2;

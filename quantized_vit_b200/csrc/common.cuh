@@ -113,6 +113,30 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(-t, h, r);                      // t == |x| wherever h is not negligible (|x| <= 5.94)
 }
 
+// gelu(x) exactly as gelu_erf computes it, plus d gelu / dx = Phi(x) + x * phi(x) from the SAME h = 0.5 * erfc(|x| / sqrt(2)):
+// Phi(x) = 1 - h (x >= 0) or h (x < 0); phi(x) = exp2(-x^2 * log2(e) / 2) / sqrt(2 pi).  One polynomial and two MUFU.EX2
+// instead of erff + expf (the fused GELU + quantizer backward was compute-bound at 2 x its HBM time with those).
+__device__ __forceinline__ void gelu_erf_grad(float x, float& y, float& dy) {
+  const float t = fminf(fabsf(x), 5.939696788787842f);
+  float p = -2.2758645172871184e-06f;
+  p = fmaf(p, t, 3.296791692264378e-05f);
+  p = fmaf(p, t, -0.0001572782639414072f);
+  p = fmaf(p, t, -0.00020248025248292834f);
+  p = fmaf(p, t, 0.007142783608287573f);
+  p = fmaf(p, t, -0.052546434104442596f);
+  p = fmaf(p, t, -0.45919305086135864f);
+  p = fmaf(p, t, -1.1511069536209106f);
+  p = fmaf(p, t, -0.9999999403953552f);
+  float h, e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(h) : "f"(p));
+  float r;
+  asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(x), "f"(0.0f));
+  y = fmaf(-t, h, r);
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.7213475204444817f));
+  const float cdf = (x >= 0.0f) ? 1.0f - h : h;
+  dy = fmaf(x * 0.3989422804014327f, e, cdf);          // (NaN x: y and dy are NaN)
+}
+
 // ---- packed fp32 pairs: FFMA2 / FADD2 / FMUL2 of sm_100 process two elements per issue slot ------------------------
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float a, float b) {
