@@ -281,6 +281,11 @@ int qvit_layernorm_quantize(const float* x, int64_t rows, int cols, const float*
                             float eps, const float* d, const float* q_m, const float* t,
                             int8_t* codes, int64_t ld_codes, float* ln_out /* optional fp32 copy */,
                             int32_t* flags, qvit_stream_t stream);
+/* Token sequence of the ViT (cat(cls_token, x) + pos_embed, VIT:295-305) from the patch-embedding output: h[b, 0, :] = cls + pos[0],
+ * h[b, 1 + p, :] = tok[b * P + p, :] + pos[1 + p, :].  tok fp32 [B * P, D], pos fp32 [P + 1, D], cls fp32 [D], h fp32 [B, P + 1, D];
+ * D a multiple of 4, 16-byte aligned tensors.                                                                                   */
+int qvit_embed_assemble(const float* tok, const float* pos, const float* cls, int B, int P, int D, float* h, qvit_stream_t stream);
+
 /* LayerNorm forward with saved statistics, and its backward, for the caller of the QAT step (Block.norm1 / norm2, VIT:202-208):
  * y = (x - mean) * rstd * gamma + beta; gx = rstd * (g' - mean(g') - xhat * mean(g' * xhat)), g' = gy * gamma; dgamma = sum gy * xhat,
  * dbeta = sum gy (both overwritten).  cols must be a multiple of 128, <= 1024; all tensors fp32, 16-byte aligned.           */

@@ -42,6 +42,7 @@ PROTOTYPES = {
     "qvit_sym_backward": (_i, [_p, _p, _i64, _p, _p, _p, _f, _f, _p, _p, _p, _p]),
     "qvit_gelu_quantize_sym": (_i, [_p, _i64, _p, _p, _p, _p, _p, _p]),
     "qvit_gelu_sym_backward": (_i, [_p, _p, _i64, _p, _p, _p, _f, _f, _p, _p, _p, _p]),
+    "qvit_embed_assemble": (_i, [_p, _p, _p, _i, _i, _i, _p, _p]),
     "qvit_absmax": (_i, [_p, _i64, _p, _p]),
     "qvit_im2col_quantize_sym": (_i, [_p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _i64, _p, _p]),
     "qvit_ultra_tanh_absmax": (_i, [_p, _i64, _p, _p]),

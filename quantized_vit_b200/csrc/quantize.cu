@@ -283,6 +283,22 @@ layernorm_quantize_kernel(const float* __restrict__ x, int64_t rows, const float
   if (fl && flags && lane == 0) atomicOr(flags, fl);
 }
 
+// h[b, 0, :] = cls + pos[0]; h[b, 1 + p, :] = tok[b * P + p, :] + pos[1 + p]   (cat(cls_token, x) + pos_embed, vit_model.py:295-305)
+__global__ void __launch_bounds__(kThreads)
+embed_assemble_kernel(const float* __restrict__ tok, const float* __restrict__ pos, const float* __restrict__ cls, int B, int P, int D4,
+                      float* __restrict__ h) {
+  const int64_t n4 = (int64_t)B * (P + 1) * D4;
+  const int64_t row4 = (int64_t)(P + 1) * D4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t b = i / row4, r = i - b * row4;                 // r = token * D4 + column group
+    const float4 pe = __ldg(reinterpret_cast<const float4*>(pos) + r);
+    float4 v;
+    if (r < D4) v = __ldg(reinterpret_cast<const float4*>(cls) + r);
+    else v = ldg_stream4(tok + (b * (int64_t)P * D4 + (r - D4)) * 4);
+    reinterpret_cast<float4*>(h)[i] = make_float4(v.x + pe.x, v.y + pe.y, v.z + pe.z, v.w + pe.w);
+  }
+}
+
 // generic width: one warp per row, three passes over the (L1/L2-resident) row
 __global__ void __launch_bounds__(kThreads)
 layernorm_quantize_generic_kernel(const float* __restrict__ x, int64_t rows, int cols, const float* __restrict__ gamma,
@@ -496,6 +512,15 @@ int qvit_layernorm_quantize(const float* x, int64_t rows, int cols, const float*
   }
 #undef QVIT_LN_CASE
   return check_launch("qvit_layernorm_quantize");
+}
+
+int qvit_embed_assemble(const float* tok, const float* pos, const float* cls, int B, int P, int D, float* h, qvit_stream_t stream) {
+  QVIT_REQUIRE(tok && pos && cls && h && B > 0 && P > 0 && D > 0 && D % 4 == 0, "qvit_embed_assemble: bad argument (D must be a multiple of 4)");
+  QVIT_REQUIRE(((reinterpret_cast<uintptr_t>(tok) | reinterpret_cast<uintptr_t>(pos) | reinterpret_cast<uintptr_t>(cls) |
+                 reinterpret_cast<uintptr_t>(h)) & 15) == 0, "qvit_embed_assemble: 16-byte aligned tensors");
+  const int64_t n4 = (int64_t)B * (P + 1) * (D / 4);
+  embed_assemble_kernel<<<stream_grid(n4, kThreads * 4), kThreads, 0, (cudaStream_t)stream>>>(tok, pos, cls, B, P, D / 4, h);
+  return check_launch("qvit_embed_assemble");
 }
 
 int qvit_absmax(const float* x, int64_t n, float* out, qvit_stream_t stream) {

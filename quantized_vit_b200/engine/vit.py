@@ -230,9 +230,12 @@ class ViTInferenceEngine:
                                                flags=self.flags)
         tok = self._gemm(cols, pe, out_kind=ops.QVIT_OUT_F32)                     # [B*OH*OW, D]
         NT = OH * OW + 1
-        h = torch.empty((B, NT, D), dtype=torch.float32, device=x.device)
-        h[:, 0] = self.cls[0, 0] + self.pos[0, 0]                                 # vit_model.py:295-305
-        torch.add(tok.view(B, OH * OW, D), self.pos[:, 1:], out=h[:, 1:])
+        if D % 4 == 0:
+            h = ops.embed_assemble(tok, self.pos, self.cls, B)                    # cat(cls, x) + pos_embed, vit_model.py:295-305
+        else:
+            h = torch.empty((B, NT, D), dtype=torch.float32, device=x.device)
+            h[:, 0] = self.cls[0, 0] + self.pos[0, 0]
+            torch.add(tok.view(B, OH * OW, D), self.pos[:, 1:], out=h[:, 1:])
         h2 = h.view(B * NT, D)
         if taps is not None:
             taps["embed"] = h.clone()

@@ -17,7 +17,7 @@ from ._lib import (QVIT_ACT_GELU, QVIT_ACT_NONE, QVIT_ACT_RELU, QVIT_GEMM_AUTO, 
                    QVIT_OUT_BF16, QVIT_OUT_F16X2, QVIT_OUT_F32, QVIT_OUT_I8, QVIT_OUT_I32, QVIT_OUT_NONE)
 
 __all__ = ["pad16", "quantize_sym", "fake_quantize_sym", "sym_backward", "absmax", "im2col_quantize_sym", "gemm_i8",
-           "layernorm_quantize", "layernorm_fwd", "layernorm_bwd", "layernorm_supported", "attention_train_supported", "attention_train_fwd", "attention_train_bwd", "attention_f32", "attention_f32_supported", "split3_bf16", "grad_prep", "codes_to_bf16_t", "gemm_bf16_split", "matmul_f32_tc", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "ultra_conv_tc", "conv2d_i8_tc", "pack_conv_weights_tc", "ultra_conv_tc_supported", "bn_fold",
+           "layernorm_quantize", "embed_assemble", "layernorm_fwd", "layernorm_bwd", "layernorm_supported", "attention_train_supported", "attention_train_fwd", "attention_train_bwd", "attention_f32", "attention_f32_supported", "split3_bf16", "grad_prep", "codes_to_bf16_t", "gemm_bf16_split", "matmul_f32_tc", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "ultra_conv_tc", "conv2d_i8_tc", "pack_conv_weights_tc", "ultra_conv_tc_supported", "bn_fold",
            "bn_act_quantize_int", "pack_int4", "unpack_int4", "new_flags", "QVIT_OUT_I32", "QVIT_OUT_F32",
            "QVIT_OUT_BF16", "QVIT_OUT_I8", "QVIT_OUT_NONE", "QVIT_OUT_F16X2", "attention_f16x2", "split2_f16", "f16x2_exponent", "QVIT_ACT_NONE", "QVIT_ACT_GELU", "QVIT_ACT_RELU", "QVIT_GEMM_AUTO",
            "QVIT_GEMM_TCGEN05", "QVIT_GEMM_SIMT"]
@@ -178,6 +178,19 @@ def layernorm_quantize(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor,
                                                   _lib.ptr(d_), _lib.ptr(q_), _lib.ptr(t_), _lib.ptr(codes), ld,
                                                   _lib.ptr(ln), _lib.ptr(flags), _lib.stream()), "qvit_layernorm_quantize")
     return codes, ln
+
+
+def embed_assemble(tok: torch.Tensor, pos: torch.Tensor, cls: torch.Tensor, B: int) -> torch.Tensor:
+    """cat(cls_token, x) + pos_embed (vit_model.py:295-305) in one pass: tok [B * P, D] fp32 -> h [B, P + 1, D] fp32."""
+    tok, pos, cls = _f32c(tok, "embed_assemble tok"), _f32c(pos, "pos_embed"), _f32c(cls, "cls_token")
+    D = tok.shape[-1]
+    P = tok.shape[0] // B
+    if pos.numel() != (P + 1) * D or cls.numel() != D or tok.shape[0] != B * P:
+        raise ValueError("embed_assemble: shapes do not match (tok [B*P, D], pos [P+1, D], cls [D])")
+    h = torch.empty((B, P + 1, D), dtype=torch.float32, device=tok.device)
+    _lib.check(_lib.lib().qvit_embed_assemble(_lib.ptr(tok), _lib.ptr(pos), _lib.ptr(cls), B, P, D, _lib.ptr(h), _lib.stream()),
+               "qvit_embed_assemble")
+    return h
 
 
 def layernorm_supported(cols: int) -> bool:
