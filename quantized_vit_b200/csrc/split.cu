@@ -151,28 +151,43 @@ __global__ void colsum_reduce_kernel(const float* __restrict__ partial, int nblk
   out[c] = s;
 }
 
-// codes [R, C] int8 (pitch ld) -> out [C, Rp] bf16 (transposed); columns >= R are zero
+// codes [R, C] int8 (pitch ld) -> out [C, Rp] bf16 (transposed); columns >= R are zero.
+// Tile = 64 rows (r) x 128 columns (c) through shared memory: a warp reads one 128-byte row segment per instruction (4 bytes per
+// lane) and writes 64-byte runs of one output row (lane = r, then r + 32: bank = (33 r + c / 4) mod 32 is distinct across lanes).
 __global__ void __launch_bounds__(256)
 codes_transpose_bf16_kernel(const int8_t* __restrict__ codes, int64_t R, int C, int64_t ld, int64_t Rp,
                             __nv_bfloat16* __restrict__ out) {
-  __shared__ float tile[64][33];
+  __shared__ __align__(16) int8_t tile[64][132];
   const int64_t r0 = (int64_t)blockIdx.y * 64;
-  const int c0 = blockIdx.x * 32;
-  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 128;
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;      // 8 warps
+  const bool vec = ((ld & 3) == 0) && ((reinterpret_cast<uintptr_t>(codes) & 3) == 0);
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
-    const int64_t r = r0 + wy * 8 + i;
-    const int c = c0 + lane;
-    tile[wy * 8 + i][lane] = (r < R && c < C) ? (float)codes[r * ld + c] : 0.0f;
+    const int rl = wy * 8 + i;
+    const int64_t r = r0 + rl;
+    const int c = c0 + lane * 4;
+    uint32_t w = 0;
+    if (r < R) {
+      if (vec && c + 4 <= C) {
+        w = __ldg(reinterpret_cast<const uint32_t*>(codes + r * ld + c));
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (c + j < C) w |= (uint32_t)(uint8_t)codes[r * ld + c + j] << (8 * j);
+      }
+    }
+    *reinterpret_cast<uint32_t*>(&tile[rl][lane * 4]) = w;
   }
   __syncthreads();
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int cl = wy * 4 + i;
+#pragma unroll 4
+  for (int i = 0; i < 16; ++i) {
+    const int cl = wy * 16 + i;                                  // output row inside the tile
     const int c = c0 + cl;
-    if (c >= C) continue;
-    const __nv_bfloat162 v = __floats2bfloat162_rn(tile[2 * lane][cl], tile[2 * lane + 1][cl]);
-    reinterpret_cast<uint32_t*>(out + (int64_t)c * Rp + r0)[lane] = *reinterpret_cast<const uint32_t*>(&v);
+    if (c >= C) break;
+    __nv_bfloat16* dst = out + (int64_t)c * Rp + r0;             // r0 + 63 < Rp (Rp is a multiple of 64)
+    dst[lane] = __float2bfloat16_rn((float)tile[lane][cl]);
+    dst[lane + 32] = __float2bfloat16_rn((float)tile[lane + 32][cl]);
   }
 }
 
@@ -235,7 +250,7 @@ int qvit_codes_to_bf16_t(const int8_t* codes, int64_t rows, int64_t cols, int64_
   QVIT_REQUIRE(codes && out && rows > 0 && cols > 0 && ld >= cols, "qvit_codes_to_bf16_t: bad argument");
   QVIT_REQUIRE(out_cols % 64 == 0 && out_cols >= rows && (reinterpret_cast<uintptr_t>(out) & 3) == 0,
                "qvit_codes_to_bf16_t: out_cols must be a multiple of 64 and >= rows");
-  dim3 grid((unsigned)((cols + 31) / 32), (unsigned)(out_cols / 64));
+  dim3 grid((unsigned)((cols + 127) / 128), (unsigned)(out_cols / 64));
   QVIT_REQUIRE(grid.y <= 65535u, "qvit_codes_to_bf16_t: too many rows");
   codes_transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(codes, rows, (int)cols, ld, out_cols,
                                                                      reinterpret_cast<__nv_bfloat16*>(out));
