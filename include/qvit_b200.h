@@ -264,7 +264,7 @@ int qvit_split3_bf16(const float* x, int64_t rows, int64_t cols, int64_t ld_x, i
 
 /* Both forms of the gradient operand of a QAT linear layer, and its bias gradient, from one read of g (fp32 [rows, cols], pitch
  * ld_g): rows_out = bf16 [rows, 3 * row_plane_cols] (as qvit_split3_bf16 transpose = 0; NULL = not needed), trans_out = bf16
- * [cols, 3 * trans_plane_cols] (as transpose = 1), colsum[c] = sum over rows of g[:, c] (NULL = not needed; summed in a fixed order).
+ * [cols, 3 * trans_plane_cols] (as transpose = 1; NULL = not needed), colsum[c] = sum over rows of g[:, c] (NULL = not needed; summed in a fixed order).
  * partial: workspace fp32 [ceil(trans_plane_cols / 256), cols], required with colsum.  Plane widths: multiples of 64.          */
 int qvit_grad_prep(const float* g, int64_t rows, int64_t cols, int64_t ld_g, void* rows_out, int64_t row_plane_cols, void* trans_out,
                    int64_t trans_plane_cols, float* partial, float* colsum, qvit_stream_t stream);
@@ -272,6 +272,16 @@ int qvit_codes_to_bf16_t(const int8_t* codes, int64_t rows, int64_t cols, int64_
                          qvit_stream_t stream);
 int qvit_gemm_bf16_split(const void* a_planes, int64_t lda, int planes, const void* b, int64_t ldb, int M, int N, int K,
                          float* out, int64_t ldo, const qvit_epilogue_t* epi, qvit_stream_t stream);
+
+/* grad_w_q = g^T x_q without a transposed copy of either operand: out[N_out, K_in] (fp32) = |scale| * sum_p G_p^T X, G = `planes`
+ * bf16 planes of g side by side ([tokens, planes * plane_cols] row-major, as qvit_split3_bf16 / qvit_grad_prep write the row form),
+ * X = bf16 [tokens, ld_x >= K_in] (qvit_codes_to_bf16); both are read as MN-major tcgen05 operands.  Plain fp32 output
+ * (scale_const / scale_a / scale_w of the epilogue apply; no activation, no residual).                                            */
+int qvit_gemm_bf16_split_t(const void* g_planes, int64_t ld_g, int planes, int64_t plane_cols, const void* x, int64_t ld_x,
+                           int64_t tokens, int N_out, int K_in, float* out, int64_t ldo, const qvit_epilogue_t* epi,
+                           qvit_stream_t stream);
+/* int8 codes [rows, ld] -> bf16 [rows, out_cols] (same orientation, columns >= cols zero; out_cols a multiple of 64). */
+int qvit_codes_to_bf16(const int8_t* codes, int64_t rows, int64_t cols, int64_t ld, void* out, int64_t out_cols, qvit_stream_t stream);
 
 /* ------------------------------------------------------------------ glue fused with the quantizer
  * ("next" rows of SURVEY.md section 8f, built on the same quantizer device function)

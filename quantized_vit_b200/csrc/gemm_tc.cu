@@ -233,7 +233,8 @@ __device__ __forceinline__ long long global_ns() {
 #define QVIT_PROF(slot) do { (void)prof; (void)prof_tile; } while (0)
 #endif
 
-// KIND 0: int8 x int8 -> int32 (tcgen05 kind::i8).  KIND 1: bf16 x bf16 -> fp32 (kind::f16) for the QAT gradient GEMMs:
+// KIND 0: int8 x int8 -> int32 (tcgen05 kind::i8).  KIND 2: as KIND 1 with BOTH operands MN-major (grad_w = g^T x straight from
+// the row-major gradient planes and codes, gemm_tc_launch_bf16_split_t).  KIND 1: bf16 x bf16 -> fp32 (kind::f16) for the QAT gradient GEMMs:
 // the fp32 gradient operand arrives as three exact bf16 planes concatenated along K, the integer codes as one bf16
 // plane that is re-read for every A plane (`b_wrap` k-blocks), i.e. D = (A1 + A2 + A3) * B^T with fp32 accumulation.
 template <int BN, int OUT, int CG, int KIND, int SPEC>
@@ -242,7 +243,7 @@ __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_res,
                   const EpiParams ep, const int K, const uint32_t idesc, const int tma_store, const int res_tma,
-                  const int mma_only_flags, const int b_wrap, const int ksplit) {
+                  const int mma_only_flags, const int b_wrap, const int ksplit, const int aux) {
   using S = GemmSmem<BN, CG>;
   constexpr int kStages = S::kStages;
   constexpr int kTmemCols = 2 * BN;   // 256 or 512: a power of two >= 32
@@ -338,6 +339,18 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               // benchmark mode: operands stay whatever the first kStages loads brought in - measures the tensor-core
               // issue rate with no L2 / HBM traffic at all
               if (rank == 0) ptx::mbar_arrive(full_bar(stage));
+            } else if (KIND == 2) {
+              // both operands MN-major (grad_w = g^T x read from the row-major g planes and codes): a k-block is 64 rows of the
+              // contraction (tokens); each 64-element atom along M / N is one [64 x 64] box (8 KiB) of the row-major matrices.
+              // aux = columns of one g plane; k-block kb = (plane kb / b_wrap, token block kb % b_wrap)
+              const int tb = (kb % b_wrap) * 64, pl = kb / b_wrap;
+              ptx::mbar_expect_tx(full_bar(stage), S::kStageBytes);
+#pragma unroll
+              for (int j = 0; j < kBM / 64; ++j)
+                ptx::tma_load_2d(a_dst + j * 8192, &tmap_a, full_bar(stage), (pl * aux + a_row + 64 * j) * 2, tb);
+#pragma unroll
+              for (int j = 0; j < BN / 64; ++j)
+                ptx::tma_load_2d(b_dst + j * 8192, &tmap_w, full_bar(stage), (w_row + 64 * j) * 2, tb);
             } else if (CG == 1) {
               ptx::mbar_expect_tx(full_bar(stage), S::kStageBytes);
               ptx::tma_load_2d(a_dst, &tmap_a, full_bar(stage), kb * kBK, a_row);
@@ -389,6 +402,9 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               if (KIND == 0)
                 ptx::mma_i8<CG>(d_tmem, a_desc + (uint64_t)(k * (kUmmaK >> 4)), b_desc + (uint64_t)(k * (kUmmaK >> 4)), idesc,
                                 (uint32_t)(kPre || kb != kb0 || k != 0));
+              else if (KIND == 2)   // MN-major: 16 contraction rows = 2048 B per step; atoms along M / N every 8192 B (LBO)
+                ptx::mma_bf16<CG>(d_tmem, ptx::make_mnmajor_sw128_desc(a_src + k * 2048, 8192), ptx::make_mnmajor_sw128_desc(a_src + S::kABytes + k * 2048, 8192),
+                                  idesc, (uint32_t)(kb != kb0 || k != 0));
               else
                 ptx::mma_bf16<CG>(d_tmem, a_desc + (uint64_t)(k * (kUmmaK >> 4)), b_desc + (uint64_t)(k * (kUmmaK >> 4)), idesc,
                                   (uint32_t)(kb != kb0 || k != 0));
@@ -567,7 +583,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
               for (int j = 0; j < 32; ++j) w[j % (kChunkBytes / 4)] = r[j];      // kChunkBytes/4 == 32 here
             } else {
               f32x2 y[16];
-              epi_math32<KIND == 1, SPEC>(ep, r, scale, bias_sm + (uint32_t)(cq * 128), bias_sm + 256u + (uint32_t)(cq * 128), y);
+              epi_math32<KIND != 0, SPEC>(ep, r, scale, bias_sm + (uint32_t)(cq * 128), bias_sm + 256u + (uint32_t)(cq * 128), y);
               if (use_res_tma) {
                 ptx::mbar_wait(res_bar(ew), res_phase);
                 res_phase ^= 1u;
@@ -681,7 +697,7 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
           if (OUT != QVIT_OUT_F16X2) {
             if (redo && ts != 2) {
               slab_free();
-              epi_chunk_generic<OUT, KIND == 1, kPre>(ep, nq, t_row + (uint32_t)(c * 32), scale, m, n0, row_ok,
+              epi_chunk_generic<OUT, KIND != 0, kPre>(ep, nq, t_row + (uint32_t)(c * 32), scale, m, n0, row_ok,
                                                       ts ? slab + row_off : 0u, sw, byte0, &fl);
               if (kPre && !hot) fill_magic(t_row + (uint32_t)(c * 32));   // (hot chunks were re-initialised right after their load)
             }
@@ -858,7 +874,7 @@ struct TcMaps {
 
 template <int BN, int OUT, int CG, int KIND = 0, int SPEC = 0>
 static int launch_tc(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsigned, int max_ctas, cudaStream_t s,
-                     int b_wrap = 1 << 30, int ksplit = 1) {
+                     int b_wrap = 1 << 30, int ksplit = 1, int aux = 0) {
   using S = GemmSmem<BN, CG>;
   static bool attr_set[64] = {false};
   int dev = 0;
@@ -875,7 +891,8 @@ static int launch_tc(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsign
   int grid = m_tiles * n_tiles * CG * ksplit;
   if (grid > max_ctas) grid = max_ctas;
   if (CG == 2) grid &= ~1;
-  const uint32_t idesc = KIND == 0 ? ptx::make_idesc_i8(kBM * CG, BN, !a_unsigned, true) : ptx::make_idesc_bf16_f32(kBM * CG, BN);
+  const uint32_t idesc = KIND == 0 ? ptx::make_idesc_i8(kBM * CG, BN, !a_unsigned, true)
+                                   : (ptx::make_idesc_bf16_f32(kBM * CG, BN) | (KIND == 2 ? (3u << 15) : 0u));   // bits 15 / 16: A / B MN-major
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(kGemmThreads);
@@ -889,7 +906,7 @@ static int launch_tc(const TcMaps& tm, const EpiParams& ep, int K, bool a_unsign
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_i8_tc_kernel<BN, OUT, CG, KIND, SPEC>, tm.a, tm.w, tm.out, tm.res, ep, K, idesc,
-                                     (tm.tma_store && g_skip_store) ? 2 : tm.tma_store, tm.res_tma, g_mma_only | (g_profile << 1) | (g_force_path == 1 ? 4 : 0) | (g_force_path == 2 ? 8 : 0), b_wrap, ksplit);
+                                     (tm.tma_store && g_skip_store) ? 2 : tm.tma_store, tm.res_tma, g_mma_only | (g_profile << 1) | (g_force_path == 1 ? 4 : 0) | (g_force_path == 2 ? 8 : 0), b_wrap, ksplit, aux);
   if (e != cudaSuccess) {
     set_error("gemm_i8_tc_kernel launch: %s", cudaGetErrorString(e));
     return QVIT_ERR_CUDA;
@@ -1034,6 +1051,47 @@ int gemm_tc_launch_bf16_split(const void* a, int64_t lda, int planes, const void
   }
   if (bn == 256) return launch_tc<256, QVIT_OUT_F32, 1, 1>(tm, ep, k_bytes, false, sms, s, b_wrap, ksplit);
   return launch_tc<128, QVIT_OUT_F32, 1, 1>(tm, ep, k_bytes, false, sms, s, b_wrap, ksplit);
+}
+
+// D[N_out, K_in] (fp32) = scale * sum_p G_p^T X : G = `planes` bf16 planes of the output gradient side by side ([tokens, planes *
+// plane_cols], row-major as qvit_split3_bf16 / qvit_grad_prep write them), X = bf16 [tokens, >= K_in] (the activation codes);
+// both are read as MN-major operands - no transposed copy of either exists.  ep.M = N_out, ep.N = K_in.
+int gemm_tc_launch_bf16_split_t(const void* g, int64_t ldg, int planes, int64_t plane_cols, const void* x, int64_t ldx, int64_t tokens,
+                                const EpiParams& ep, cudaStream_t s) {
+  const int M = ep.M, N = ep.N;
+  const int sms = sm_count();
+  TcMaps tm;
+  // byte views of the row-major matrices; boxes of [128 B = 64 columns] x [64 rows]; rows >= tokens and columns past the end are zero filled
+  int rc = make_tmap_bytes(&tm.a, g, tokens, (int64_t)2 * planes * plane_cols, ldg * 2, 64);
+  if (rc) return rc;
+  rc = make_tmap_bytes(&tm.w, x, tokens, (int64_t)2 * ((N + 7) / 8 * 8), ldx * 2, 64);
+  if (rc) return rc;
+  if ((reinterpret_cast<uintptr_t>(ep.out) & 15) || ((ep.ldo * 4) & 15)) {
+    set_error("qvit_gemm_bf16_split_t: output must be 16-byte aligned with a pitch that is a multiple of 4 floats");
+    return QVIT_ERR_UNSUPPORTED;
+  }
+  const int b_wrap = (int)((tokens + 63) / 64);      // k-blocks (64 tokens) per plane
+  const int k_blocks = planes * b_wrap;
+  const int k_bytes = k_blocks * kBK;
+  const int64_t tiles256 = (int64_t)((M + kBM - 1) / kBM) * ((N + 255) / 256);
+  const int64_t tiles128 = (int64_t)((M + kBM - 1) / kBM) * ((N + 127) / 128);
+  int bn = (N <= 128 || tiles256 < sms) ? 128 : 256;
+  int ksplit = 1;
+  if (k_blocks >= 64 && !ep.bias && !ep.residual && !ep.col_scale && ep.act == QVIT_ACT_NONE) {   // as in gemm_tc_launch_bf16_split
+    if (N > 128 && tiles256 * 2 <= sms && tiles256 * 4 >= sms) { ksplit = 2; bn = 256; }
+    else if (tiles128 * 2 <= sms) { ksplit = 2; bn = 128; }
+  }
+  tm.tma_store = 1;
+  tm.res = tm.a;
+  tm.res_tma = 0;
+  rc = make_tmap_out(&tm.out, ep.out, M, N, ep.ldo, QVIT_OUT_F32, out_box_bytes(bn, QVIT_OUT_F32), 32);
+  if (rc) return rc;
+  if (ksplit > 1 && cudaMemset2DAsync(ep.out, (size_t)ep.ldo * 4, 0, (size_t)N * 4, (size_t)M, s) != cudaSuccess) {
+    set_error("qvit_gemm_bf16_split_t: cudaMemset2DAsync failed");
+    return QVIT_ERR_CUDA;
+  }
+  if (bn == 256) return launch_tc<256, QVIT_OUT_F32, 1, 2>(tm, ep, k_bytes, false, sms, s, b_wrap, ksplit, (int)plane_cols);
+  return launch_tc<128, QVIT_OUT_F32, 1, 2>(tm, ep, k_bytes, false, sms, s, b_wrap, ksplit, (int)plane_cols);
 }
 
 }  // namespace qvit

@@ -107,7 +107,7 @@ grad_prep_kernel(const float* __restrict__ x, int64_t R, int C, int64_t ld_x, in
       const int c = c0 + cl;
       const float a = tile[2 * lane][cl], b = tile[2 * lane + 1][cl];
       csum[i] += a + b;
-      if (c < C) {
+      if (trans_out && c < C) {
         uint32_t p1, p2, p3;
         split3_pair_bf16(a, b, p1, p2, p3);
         uint32_t* dst = reinterpret_cast<uint32_t*>(trans_out + (int64_t)c * (3 * Rp) + r0) + lane;   // r0 is a multiple of 64
@@ -191,8 +191,38 @@ codes_transpose_bf16_kernel(const int8_t* __restrict__ codes, int64_t R, int C, 
   }
 }
 
+// codes [R, C] int8 (pitch ld) -> out [R, Cp] bf16 (same orientation); columns >= C are zero.  16 codes per thread.
+__global__ void __launch_bounds__(256)
+codes_to_bf16_kernel(const int8_t* __restrict__ codes, int64_t R, int C, int64_t ld, int Cp, __nv_bfloat16* __restrict__ out) {
+  const int pieces = Cp / 16;
+  const int64_t total = R * pieces;
+  const bool vec = ((ld & 15) == 0) && ((reinterpret_cast<uintptr_t>(codes) & 15) == 0);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / pieces;
+    const int c0 = (int)(i - r * pieces) * 16;
+    int8_t v[16];
+    if (vec && c0 + 16 <= C) {
+      *reinterpret_cast<uint4*>(v) = __ldg(reinterpret_cast<const uint4*>(codes + r * ld + c0));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = (c0 + j < C) ? codes[r * ld + c0 + j] : (int8_t)0;
+    }
+    uint32_t w[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const __nv_bfloat162 p = __floats2bfloat162_rn((float)v[2 * j], (float)v[2 * j + 1]);
+      w[j] = *reinterpret_cast<const uint32_t*>(&p);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + r * (int64_t)Cp + c0);
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
 int gemm_tc_launch_bf16_split(const void* a, int64_t lda, int planes, const void* b, int64_t ldb, const struct EpiParams& ep, int K,
                               cudaStream_t s);
+int gemm_tc_launch_bf16_split_t(const void* g, int64_t ldg, int planes, int64_t plane_cols, const void* x, int64_t ldx, int64_t tokens,
+                                const struct EpiParams& ep, cudaStream_t s);
 
 }  // namespace qvit
 
@@ -225,9 +255,9 @@ int qvit_split3_bf16(const float* x, int64_t rows, int64_t cols, int64_t ld_x, i
 
 int qvit_grad_prep(const float* g, int64_t rows, int64_t cols, int64_t ld_g, void* rows_out, int64_t row_plane_cols, void* trans_out,
                    int64_t trans_plane_cols, float* partial, float* colsum, qvit_stream_t stream) {
-  QVIT_REQUIRE(g && trans_out && rows > 0 && cols > 0 && ld_g >= cols, "qvit_grad_prep: bad argument");
+  QVIT_REQUIRE(g && (trans_out || rows_out) && rows > 0 && cols > 0 && ld_g >= cols, "qvit_grad_prep: bad argument");
   QVIT_REQUIRE(trans_plane_cols % 64 == 0 && trans_plane_cols >= rows && (reinterpret_cast<uintptr_t>(trans_out) & 15) == 0,
-               "qvit_grad_prep: trans_plane_cols must be a multiple of 64, >= rows");
+               "qvit_grad_prep: trans_plane_cols must be a multiple of 64, >= rows (also without trans_out: it sizes the row blocks)");
   QVIT_REQUIRE(!rows_out || (row_plane_cols % 64 == 0 && row_plane_cols >= cols && (reinterpret_cast<uintptr_t>(rows_out) & 15) == 0),
                "qvit_grad_prep: row_plane_cols must be a multiple of 64, >= cols");
   QVIT_REQUIRE((colsum == nullptr) == (partial == nullptr), "qvit_grad_prep: colsum needs the partial workspace (and vice versa)");
@@ -255,6 +285,55 @@ int qvit_codes_to_bf16_t(const int8_t* codes, int64_t rows, int64_t cols, int64_
   codes_transpose_bf16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(codes, rows, (int)cols, ld, out_cols,
                                                                      reinterpret_cast<__nv_bfloat16*>(out));
   return check_launch("qvit_codes_to_bf16_t");
+}
+
+int qvit_codes_to_bf16(const int8_t* codes, int64_t rows, int64_t cols, int64_t ld, void* out, int64_t out_cols, qvit_stream_t stream) {
+  QVIT_REQUIRE(codes && out && rows > 0 && cols > 0 && ld >= cols, "qvit_codes_to_bf16: bad argument");
+  QVIT_REQUIRE(out_cols % 64 == 0 && out_cols >= cols && (reinterpret_cast<uintptr_t>(out) & 15) == 0,
+               "qvit_codes_to_bf16: out_cols must be a multiple of 64 and >= cols");
+  const int64_t total = rows * (out_cols / 16);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 8;
+  if (blocks > cap) blocks = cap;
+  codes_to_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(codes, rows, (int)cols, ld, (int)out_cols,
+                                                                     reinterpret_cast<__nv_bfloat16*>(out));
+  return check_launch("qvit_codes_to_bf16");
+}
+
+int qvit_gemm_bf16_split_t(const void* g_planes, int64_t ld_g, int planes, int64_t plane_cols, const void* x, int64_t ld_x, int64_t tokens,
+                           int N_out, int K_in, float* out, int64_t ldo, const qvit_epilogue_t* epi, qvit_stream_t stream) {
+  QVIT_REQUIRE(g_planes && x && out && epi, "qvit_gemm_bf16_split_t: null pointer");
+  QVIT_REQUIRE(tokens > 0 && N_out > 0 && K_in > 0 && planes >= 1 && planes <= 3 && ldo >= K_in, "qvit_gemm_bf16_split_t: bad shape");
+  QVIT_REQUIRE(plane_cols % 64 == 0 && plane_cols >= N_out && ld_g >= (int64_t)planes * plane_cols && (ld_g % 8) == 0 && (ld_x % 8) == 0 &&
+                   ld_x >= K_in, "qvit_gemm_bf16_split_t: plane_cols a multiple of 64 >= N_out, ld_g >= planes * plane_cols, pitches multiples of 8");
+  QVIT_REQUIRE(((reinterpret_cast<uintptr_t>(g_planes) | reinterpret_cast<uintptr_t>(x)) & 15) == 0, "qvit_gemm_bf16_split_t: alignment");
+  QVIT_REQUIRE(epi->out_kind == QVIT_OUT_F32 && epi->act == QVIT_ACT_NONE && !epi->residual, "qvit_gemm_bf16_split_t: plain fp32 output only");
+  QVIT_REQUIRE(tokens < (1ll << 31) - 64 && (int64_t)planes * plane_cols * 2 < (1ll << 31), "qvit_gemm_bf16_split_t: too large");
+  int dev = 0, maj = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&maj, cudaDevAttrComputeCapabilityMajor, dev);
+  if (maj != 10) {
+    set_error("qvit_gemm_bf16_split_t: needs sm_100");
+    return QVIT_ERR_UNSUPPORTED;
+  }
+  EpiParams ep;
+  ep.out_kind = QVIT_OUT_F32;
+  ep.act = QVIT_ACT_NONE;
+  ep.scale_const = epi->scale_const;
+  ep.acc_abs_max = 0;
+  ep.scale_a = epi->scale_a;
+  ep.scale_w = epi->scale_w;
+  ep.col_scale = epi->col_scale;
+  ep.bias = epi->bias;
+  ep.residual = nullptr;
+  ep.ld_res = 0;
+  ep.next_d = ep.next_qm = ep.next_t = nullptr;
+  ep.flags = epi->flags;
+  ep.out = out;
+  ep.ldo = ldo;
+  ep.M = N_out;
+  ep.N = K_in;
+  return gemm_tc_launch_bf16_split_t(g_planes, ld_g, planes, plane_cols, x, ld_x, tokens, ep, (cudaStream_t)stream);
 }
 
 int qvit_gemm_bf16_split(const void* a_planes, int64_t lda, int planes, const void* b, int64_t ldb, int M, int N, int K,

@@ -293,6 +293,19 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   return d;
 }
 
+// MN-major operand (the MN index is the contiguous one): rows of 128 bytes = 64 MN elements of ONE k index, 8-row groups of
+// 1024 B along K (SBO), further 64-element atoms along MN every `lbo_bytes` (LBO); a 16-row k-step advances the start address
+// by 2048 B.  Verified against a host product in tools/ubench/mnmajor_check.cu (the swapped LBO / SBO assignment is wrong).
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
 // instruction descriptor for kind::i8: S32 accumulate, K-major A and B
 __host__ __device__ constexpr uint32_t make_idesc_i8(int M, int N, bool a_signed, bool b_signed) {
   return (2u << 4) | ((a_signed ? 1u : 0u) << 7) | ((b_signed ? 1u : 0u) << 10) | ((uint32_t)(N >> 3) << 17) |

@@ -17,7 +17,7 @@ from ._lib import (QVIT_ACT_GELU, QVIT_ACT_NONE, QVIT_ACT_RELU, QVIT_GEMM_AUTO, 
                    QVIT_OUT_BF16, QVIT_OUT_F16X2, QVIT_OUT_F32, QVIT_OUT_I8, QVIT_OUT_I32, QVIT_OUT_NONE)
 
 __all__ = ["pad16", "quantize_sym", "fake_quantize_sym", "sym_backward", "absmax", "im2col_quantize_sym", "gemm_i8",
-           "layernorm_quantize", "embed_assemble", "layernorm_fwd", "layernorm_bwd", "layernorm_supported", "attention_train_supported", "attention_train_fwd", "attention_train_bwd", "attention_f32", "attention_f32_supported", "split3_bf16", "grad_prep", "codes_to_bf16_t", "gemm_bf16_split", "matmul_f32_tc", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "ultra_conv_tc", "conv2d_i8_tc", "pack_conv_weights_tc", "ultra_conv_tc_supported", "bn_fold",
+           "layernorm_quantize", "embed_assemble", "layernorm_fwd", "layernorm_bwd", "layernorm_supported", "attention_train_supported", "attention_train_fwd", "attention_train_bwd", "attention_f32", "attention_f32_supported", "split3_bf16", "grad_prep", "codes_to_bf16", "gemm_bf16_split_t", "codes_to_bf16_t", "gemm_bf16_split", "matmul_f32_tc", "ultra_weight_codes", "ultra_act", "uniform_quantize", "ultra_bn_act_pool_nchw", "conv2d_f32_wcodes", "ultra_conv_bn_act", "ultra_conv_tc", "conv2d_i8_tc", "pack_conv_weights_tc", "ultra_conv_tc_supported", "bn_fold",
            "bn_act_quantize_int", "pack_int4", "unpack_int4", "new_flags", "QVIT_OUT_I32", "QVIT_OUT_F32",
            "QVIT_OUT_BF16", "QVIT_OUT_I8", "QVIT_OUT_NONE", "QVIT_OUT_F16X2", "attention_f16x2", "split2_f16", "f16x2_exponent", "QVIT_ACT_NONE", "QVIT_ACT_GELU", "QVIT_ACT_RELU", "QVIT_GEMM_AUTO",
            "QVIT_GEMM_TCGEN05", "QVIT_GEMM_SIMT"]
@@ -451,14 +451,16 @@ def split3_bf16(x: torch.Tensor, transpose: bool = False) -> torch.Tensor:
     return out
 
 
-def grad_prep(g: torch.Tensor, want_rows: bool = True, want_colsum: bool = True):
+def grad_prep(g: torch.Tensor, want_rows: bool = True, want_colsum: bool = True, want_trans: bool = True):
     """One pass over the output gradient g [M, N] of a QAT linear layer: (row planes [M, 3*pad64(N)] | None, transposed planes
-    [N, 3*pad64(M)], column sums [N] | None) - the operands of the two gradient GEMMs and the bias gradient."""
+    [N, 3*pad64(M)] | None, column sums [N] | None) - the operands of the two gradient GEMMs and the bias gradient."""
     g = _f32c(g, "grad_prep")
     M, N = g.shape
     mp, np_ = _pad64(M), _pad64(N)
+    if not (want_rows or want_trans):
+        raise ValueError("grad_prep: nothing to produce")
     rows = torch.empty((M, 3 * np_), dtype=torch.bfloat16, device=g.device) if want_rows else None
-    trans = torch.empty((N, 3 * mp), dtype=torch.bfloat16, device=g.device)
+    trans = torch.empty((N, 3 * mp), dtype=torch.bfloat16, device=g.device) if want_trans else None
     partial = colsum = None
     if want_colsum:
         partial = torch.empty(((mp // 64 + 3) // 4, N), dtype=torch.float32, device=g.device)
@@ -476,6 +478,36 @@ def codes_to_bf16_t(codes: torch.Tensor, cols: int) -> torch.Tensor:
     _lib.check(_lib.lib().qvit_codes_to_bf16_t(_lib.ptr(codes), R, int(cols), codes.stride(0), _lib.ptr(out), out.shape[1], _lib.stream()),
                "qvit_codes_to_bf16_t")
     return out
+
+
+def codes_to_bf16(codes: torch.Tensor, cols: int) -> torch.Tensor:
+    """int8 codes [R, >=cols] -> bf16 [R, pad64(cols)] (same orientation, zero padded)."""
+    _lib.require_cuda(codes)
+    R = codes.shape[0]
+    out = torch.empty((R, _pad64(cols)), dtype=torch.bfloat16, device=codes.device)
+    _lib.check(_lib.lib().qvit_codes_to_bf16(_lib.ptr(codes), R, int(cols), codes.stride(0), _lib.ptr(out), out.shape[1], _lib.stream()),
+               "qvit_codes_to_bf16")
+    return out
+
+
+def gemm_bf16_split_t(g_planes: torch.Tensor, x_bf16: torch.Tensor, N_out: int, K_in: int, planes: int = 3, scale=None) -> torch.Tensor:
+    """out[N_out, K_in] fp32 = |scale| * sum_p G_p^T @ X: the weight-gradient GEMM straight from the ROW planes of the output
+    gradient ([tokens, 3*pad64(N_out)]) and the bf16 codes [tokens, >= K_in] - both read as MN-major tcgen05 operands."""
+    _lib.require_cuda(g_planes, x_bf16)
+    tokens = g_planes.shape[0]
+    if x_bf16.shape[0] != tokens:
+        raise ValueError("gemm_bf16_split_t: operand row counts differ")
+    out = torch.empty((N_out, (K_in + 3) // 4 * 4), dtype=torch.float32, device=g_planes.device)
+    epi = _lib.Epilogue()
+    epi.out_kind, epi.act, epi.scale_const = QVIT_OUT_F32, QVIT_ACT_NONE, 1.0
+    keep = None
+    if scale is not None:
+        keep = _scalar_param(scale, g_planes.device, "scale")
+        epi.scale_a = keep.data_ptr()
+    _lib.check(_lib.lib().qvit_gemm_bf16_split_t(_lib.ptr(g_planes), g_planes.stride(0), planes, g_planes.shape[1] // 3, _lib.ptr(x_bf16),
+                                                 x_bf16.stride(0), tokens, int(N_out), int(K_in), _lib.ptr(out), out.stride(0),
+                                                 C.byref(epi), _lib.stream()), "qvit_gemm_bf16_split_t")
+    return out if out.shape[1] == K_in else out[:, :K_in]
 
 
 def gemm_bf16_split(a_planes: torch.Tensor, b: torch.Tensor, K: int, planes: int = 3, scale=None,

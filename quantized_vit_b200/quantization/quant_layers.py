@@ -59,6 +59,7 @@ class QuantizationMode(Enum):          # QL:27-29
 _flag_words = {}
 EAGER_NAN_CHECK = False
 TENSOR_CORE_BACKWARD = True     # QAT gradient GEMMs on tcgen05 (exact bf16 split); False = library fp32 GEMMs
+MN_MAJOR_WEIGHT_GRADIENT = True   # grad_w = g^T x_q from the row planes / codes as MN-major operands (no transposed copies)
 GRADIENT_PLANES = 3             # bf16 planes of the gradient operand: 3 = exact fp32 (default), 2 = 16 significant bits
                                 # (relative error <= 2^-17 per element, ~1e-5 on the result, a third less tensor-core work)
 
@@ -342,10 +343,16 @@ class QuantLinearFunction(torch.autograd.Function):
             # grad_x_q = g @ w_q = |d_w| * (g1 + g2 + g3) @ codes_w   and   grad_w_q = g^T @ x_q = |d_a| * (g^T planes) @ codes_a:
             # exact 3-way bf16 split of g, integer codes as bf16, tcgen05 kind::f16 with fp32 accumulation
             # (both plane forms of g and the bias gradient come from one pass over g: ops.grad_prep)
-            g_rows, g_trans, grad_b = ops.grad_prep(g2, want_rows=need_act, want_colsum=ctx.has_bias)
+            if MN_MAJOR_WEIGHT_GRADIENT:
+                # the weight-gradient GEMM reads the ROW planes of g and the codes as MN-major operands: no transposed copy of
+                # either is made (the transposed planes were 6 of the 16 bytes per element grad_prep moved)
+                g_rows, _, grad_b = ops.grad_prep(g2, want_rows=True, want_colsum=ctx.has_bias, want_trans=False)
+                grad_wq = ops.gemm_bf16_split_t(g_rows, ops.codes_to_bf16(a_codes, K), N, K, planes=GRADIENT_PLANES, scale=d_a)
+            else:
+                g_rows, g_trans, grad_b = ops.grad_prep(g2, want_rows=need_act, want_colsum=ctx.has_bias)
+                grad_wq = ops.gemm_bf16_split(g_trans, ops.codes_to_bf16_t(a_codes, K), M, planes=GRADIENT_PLANES, scale=d_a)
             grad_xq = ops.gemm_bf16_split(g_rows, ops.codes_to_bf16_t(w_codes, K), N, planes=GRADIENT_PLANES, scale=d_w) \
                 if need_act else None
-            grad_wq = ops.gemm_bf16_split(g_trans, ops.codes_to_bf16_t(a_codes, K), M, planes=GRADIENT_PLANES, scale=d_a)
         else:
             # fake-quant values from the saved codes: value = code * |d| (exactly what the reference forward produced)
             x_q = a_codes[:, :K].to(torch.float32) * d_a.detach().abs()

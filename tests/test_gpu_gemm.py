@@ -391,3 +391,24 @@ def test_grad_prep_matches_separate_kernels(M, N):
     assert float((colsum.double() - ref).abs().max()) <= 2e-6 * float(g.abs().sum(0).max())
     rows2, trans2, colsum2 = ops.grad_prep(g, want_rows=False, want_colsum=False)
     assert rows2 is None and colsum2 is None and torch.equal(trans2.view(torch.int16), trans.view(torch.int16))
+
+
+@pytest.mark.parametrize("T,N,K", [(394, 768, 768), (1000, 2304, 768), (197 * 5, 96, 3072), (333, 1000, 200), (6304, 768, 768)])
+def test_weight_gradient_gemm_from_mn_major_operands(T, N, K):
+    """qvit_gemm_bf16_split_t (g^T x from the ROW planes of g and the bf16 codes, both MN-major tcgen05 operands) against float64
+    and against the transposed-copy formulation it replaces (same plane products: equal to fp32 summation order)."""
+    from quantized_vit_b200 import ops
+    gen = torch.Generator().manual_seed(T + N + K)
+    g = (torch.randn(T, N, generator=gen) * 1e-3).cuda()
+    codes = torch.randint(-7, 8, (T, ops.pad16(K)), generator=gen, dtype=torch.int8).cuda()
+    codes[:, K:] = 0
+    scale = torch.tensor([0.0371])
+    ref = (g.double().t() @ codes[:, :K].double()) * float(scale)
+    rows, trans, _ = ops.grad_prep(g, want_colsum=False)
+    new = ops.gemm_bf16_split_t(rows, ops.codes_to_bf16(codes, K), N, K, scale=scale)
+    old = ops.gemm_bf16_split(trans, ops.codes_to_bf16_t(codes, K), T, scale=scale)
+    assert new.shape == (N, K)
+    assert torch.equal(ops.codes_to_bf16(codes, K)[:, :K].float(), codes[:, :K].float())
+    err = float((new.double() - ref).abs().max() / ref.abs().max())
+    assert err <= 1e-5, err
+    assert float((new - old).abs().max()) <= 2e-6 * float(old.abs().max())
