@@ -143,6 +143,56 @@ grad_prep_kernel(const float* __restrict__ x, int64_t R, int C, int64_t ld_x, in
   }
 }
 
+// Row planes + per-block column sums WITHOUT the transposed planes (the weight-gradient GEMM reads the row planes MN-major): no
+// shared-memory tile, every thread streams 8 columns of its rows (32-byte loads, three 16-byte stores) and keeps the 8 column
+// sums in registers.  Block = 32 column groups (256 columns) x 8 row lanes over kPrepTiles * 64 = 256 rows.
+__global__ void __launch_bounds__(256)
+grad_rows_kernel(const float* __restrict__ x, int64_t R, int C, int64_t ld_x, int Cp, __nv_bfloat16* __restrict__ rows_out,
+                 float* __restrict__ partial) {
+  __shared__ float red[8][257];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c0 = blockIdx.x * 256 + tx * 8;
+  const int64_t r0 = (int64_t)blockIdx.y * (kPrepTiles * 64);
+  const bool vec = ((ld_x & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) && c0 + 8 <= C;
+  float cs[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c0 < Cp) {
+    for (int64_t r = r0 + ty; r < r0 + kPrepTiles * 64 && r < R; r += 8) {
+      float v[8];
+      const float* src = x + r * ld_x + c0;
+      if (vec) {
+        const float4 a = ldg_stream4(src), b = ldg_stream4(src + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (c0 + j < C) ? src[j] : 0.0f;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cs[j] += v[j];
+      uint4 p1, p2, p3;
+      split3_pair_bf16(v[0], v[1], p1.x, p2.x, p3.x);
+      split3_pair_bf16(v[2], v[3], p1.y, p2.y, p3.y);
+      split3_pair_bf16(v[4], v[5], p1.z, p2.z, p3.z);
+      split3_pair_bf16(v[6], v[7], p1.w, p2.w, p3.w);
+      __nv_bfloat16* dst = rows_out + r * (3ll * Cp) + c0;
+      *reinterpret_cast<uint4*>(dst) = p1;
+      *reinterpret_cast<uint4*>(dst + Cp) = p2;
+      *reinterpret_cast<uint4*>(dst + 2 * Cp) = p3;
+    }
+  }
+  if (partial) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) red[ty][tx * 8 + j] = cs[j];
+    __syncthreads();
+    const int c = blockIdx.x * 256 + threadIdx.x;
+    if (c < C) {
+      float sum = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) sum += red[i][threadIdx.x];
+      partial[(int64_t)blockIdx.y * C + c] = sum;
+    }
+  }
+}
+
 __global__ void colsum_reduce_kernel(const float* __restrict__ partial, int nblk, int C, float* __restrict__ out) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
@@ -267,6 +317,10 @@ int qvit_grad_prep(const float* g, int64_t rows, int64_t cols, int64_t ld_g, voi
   const int64_t tiles_y = trans_plane_cols / 64;
   dim3 grid((unsigned)(cp / 32), (unsigned)((tiles_y + kPrepTiles - 1) / kPrepTiles));
   QVIT_REQUIRE(grid.y <= 65535u, "qvit_grad_prep: too many rows");
+  if (!trans_out) {
+    grid.x = (unsigned)((cp + 255) / 256);
+    grad_rows_kernel<<<grid, 256, 0, s>>>(g, rows, (int)cols, ld_g, (int)cp, reinterpret_cast<__nv_bfloat16*>(rows_out), partial);
+  } else
   grad_prep_kernel<<<grid, 256, 0, s>>>(g, rows, (int)cols, ld_g, (int)cp, reinterpret_cast<__nv_bfloat16*>(rows_out), trans_plane_cols,
                                         reinterpret_cast<__nv_bfloat16*>(trans_out), partial);
   int rc = check_launch("qvit_grad_prep");

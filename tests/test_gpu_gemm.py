@@ -391,6 +391,9 @@ def test_grad_prep_matches_separate_kernels(M, N):
     assert float((colsum.double() - ref).abs().max()) <= 2e-6 * float(g.abs().sum(0).max())
     rows2, trans2, colsum2 = ops.grad_prep(g, want_rows=False, want_colsum=False)
     assert rows2 is None and colsum2 is None and torch.equal(trans2.view(torch.int16), trans.view(torch.int16))
+    rows3, trans3, colsum3 = ops.grad_prep(g, want_trans=False)          # the streaming kernel (no transposed planes)
+    assert trans3 is None and torch.equal(rows3.view(torch.int16), rows.view(torch.int16))
+    assert float((colsum3.double() - ref).abs().max()) <= 2e-6 * float(g.abs().sum(0).max())
 
 
 @pytest.mark.parametrize("T,N,K", [(394, 768, 768), (1000, 2304, 768), (197 * 5, 96, 3072), (333, 1000, 200), (6304, 768, 768)])
