@@ -278,8 +278,9 @@ int qvit_gemm_bf16_split(const void* a_planes, int64_t lda, int planes, const vo
  * X = bf16 [tokens, ld_x >= K_in] (qvit_codes_to_bf16); both are read as MN-major tcgen05 operands.  Plain fp32 output
  * (scale_const / scale_a / scale_w of the epilogue apply; no activation, no residual).                                            */
 int qvit_gemm_bf16_split_t(const void* g_planes, int64_t ld_g, int planes, int64_t plane_cols, const void* x, int64_t ld_x,
-                           int64_t tokens, int N_out, int K_in, float* out, int64_t ldo, const qvit_epilogue_t* epi,
-                           qvit_stream_t stream);
+                           int64_t tokens, int N_out, int K_in, float* out, int64_t ldo,
+                           float* workspace /* optional, fp32 [N_out, ldo]: lets small outputs split the contraction four ways */,
+                           const qvit_epilogue_t* epi, qvit_stream_t stream);
 /* int8 codes [rows, ld] -> bf16 [rows, out_cols] (same orientation, columns >= cols zero; out_cols a multiple of 64). */
 int qvit_codes_to_bf16(const int8_t* codes, int64_t rows, int64_t cols, int64_t ld, void* out, int64_t out_cols, qvit_stream_t stream);
 

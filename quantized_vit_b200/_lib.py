@@ -74,7 +74,7 @@ PROTOTYPES = {
     "qvit_attention_train_fwd": (_i, [_p, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
     "qvit_attention_train_bwd": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p]),
     "qvit_attention_train_bwd_prof": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
-    "qvit_gemm_bf16_split_t": (_i, [_p, _i64, _i, _i64, _p, _i64, _i64, _i, _i, _p, _i64, _p, _p]),
+    "qvit_gemm_bf16_split_t": (_i, [_p, _i64, _i, _i64, _p, _i64, _i64, _i, _i, _p, _i64, _p, _p, _p]),
     "qvit_codes_to_bf16": (_i, [_p, _i64, _i64, _i64, _p, _i64, _p]),
     "qvit_grad_prep": (_i, [_p, _i64, _i64, _i64, _p, _i64, _p, _i64, _p, _p, _p]),
     "qvit_attention_f32": (_i, [_p, _i, _i, _i, _i, _f, _p, _p]),

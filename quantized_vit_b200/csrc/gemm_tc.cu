@@ -720,7 +720,11 @@ gemm_i8_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_const
             ptx::fence_proxy_async_smem();                   // generic-proxy writes -> visible to the TMA engine
             __syncwarp();
             if (lane == 0) {
-              if (ksplit > 1) ptx::tma_reduce_add_2d(&tmap_out, slab, box_n0, row0);   // split-K partials add up in global memory
+              // split-K partials add up in global memory.  Every destination receives exactly TWO partials (a + b is order
+              // independent, so the sum is reproducible): with a four-way split the upper two go to the workspace behind tmap_res
+              // and the host adds the two buffers afterwards
+              if (ksplit > 2 && (tile % ksplit) >= (ksplit >> 1)) ptx::tma_reduce_add_2d(&tmap_res, slab, box_n0, row0);
+              else if (ksplit > 1) ptx::tma_reduce_add_2d(&tmap_out, slab, box_n0, row0);
               else ptx::tma_store_2d(&tmap_out, slab, box_n0, row0);
               if (OUT == QVIT_OUT_F16X2) ptx::tma_store_2d(&tmap_out, slab + 2048u, box_n0 + (int)(ep.ldo >> 1), row0);
               ptx::tma_store_commit();
@@ -1056,8 +1060,17 @@ int gemm_tc_launch_bf16_split(const void* a, int64_t lda, int planes, const void
 // D[N_out, K_in] (fp32) = scale * sum_p G_p^T X : G = `planes` bf16 planes of the output gradient side by side ([tokens, planes *
 // plane_cols], row-major as qvit_split3_bf16 / qvit_grad_prep write them), X = bf16 [tokens, >= K_in] (the activation codes);
 // both are read as MN-major operands - no transposed copy of either exists.  ep.M = N_out, ep.N = K_in.
+__global__ void add_rows_inplace_kernel(float* __restrict__ out, int64_t ldo, const float* __restrict__ ws, int M, int N) {
+  const int64_t n = (int64_t)M * N;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / N, c = i - r * N;
+    out[r * ldo + c] = __fadd_rn(out[r * ldo + c], ws[r * ldo + c]);
+  }
+}
+
+// workspace (optional): fp32 like the output (same pitch); allows a four-way split of the contraction for outputs of few tiles
 int gemm_tc_launch_bf16_split_t(const void* g, int64_t ldg, int planes, int64_t plane_cols, const void* x, int64_t ldx, int64_t tokens,
-                                const EpiParams& ep, cudaStream_t s) {
+                                const EpiParams& ep, float* workspace, cudaStream_t s) {
   const int M = ep.M, N = ep.N;
   const int sms = sm_count();
   TcMaps tm;
@@ -1080,18 +1093,35 @@ int gemm_tc_launch_bf16_split_t(const void* g, int64_t ldg, int planes, int64_t 
   if (k_blocks >= 64 && !ep.bias && !ep.residual && !ep.col_scale && ep.act == QVIT_ACT_NONE) {   // as in gemm_tc_launch_bf16_split
     if (N > 128 && tiles256 * 2 <= sms && tiles256 * 4 >= sms) { ksplit = 2; bn = 256; }
     else if (tiles128 * 2 <= sms) { ksplit = 2; bn = 128; }
+    // still under half of the machine (proj: 36 tiles x 2 = 72 CTAs, measured 189 us for 89 GFLOP): four-way split, two
+    // partials into the output and two into the workspace (each pair sums order-independently), then out += workspace
+    const int64_t tiles = bn == 256 ? tiles256 : tiles128;
+    if (ksplit == 2 && workspace && tiles * 4 <= sms && k_blocks >= 128 && ((reinterpret_cast<uintptr_t>(workspace) & 15) == 0)) ksplit = 4;
   }
   tm.tma_store = 1;
   tm.res = tm.a;
   tm.res_tma = 0;
   rc = make_tmap_out(&tm.out, ep.out, M, N, ep.ldo, QVIT_OUT_F32, out_box_bytes(bn, QVIT_OUT_F32), 32);
   if (rc) return rc;
+  if (ksplit == 4) {
+    rc = make_tmap_out(&tm.res, workspace, M, N, ep.ldo, QVIT_OUT_F32, out_box_bytes(bn, QVIT_OUT_F32), 32);
+    if (rc) return rc;
+    if (cudaMemset2DAsync(workspace, (size_t)ep.ldo * 4, 0, (size_t)N * 4, (size_t)M, s) != cudaSuccess) {
+      set_error("qvit_gemm_bf16_split_t: cudaMemset2DAsync failed");
+      return QVIT_ERR_CUDA;
+    }
+  }
   if (ksplit > 1 && cudaMemset2DAsync(ep.out, (size_t)ep.ldo * 4, 0, (size_t)N * 4, (size_t)M, s) != cudaSuccess) {
     set_error("qvit_gemm_bf16_split_t: cudaMemset2DAsync failed");
     return QVIT_ERR_CUDA;
   }
-  if (bn == 256) return launch_tc<256, QVIT_OUT_F32, 1, 2>(tm, ep, k_bytes, false, sms, s, b_wrap, ksplit, (int)plane_cols);
-  return launch_tc<128, QVIT_OUT_F32, 1, 2>(tm, ep, k_bytes, false, sms, s, b_wrap, ksplit, (int)plane_cols);
+  rc = bn == 256 ? launch_tc<256, QVIT_OUT_F32, 1, 2>(tm, ep, k_bytes, false, sms, s, b_wrap, ksplit, (int)plane_cols)
+                 : launch_tc<128, QVIT_OUT_F32, 1, 2>(tm, ep, k_bytes, false, sms, s, b_wrap, ksplit, (int)plane_cols);
+  if (rc || ksplit != 4) return rc;
+  const int64_t n = (int64_t)M * N;
+  add_rows_inplace_kernel<<<(unsigned)((n + 255) / 256 < 8 * sms ? (n + 255) / 256 : 8 * sms), 256, 0, s>>>(
+      reinterpret_cast<float*>(ep.out), ep.ldo, workspace, M, N);
+  return check_launch("qvit_gemm_bf16_split_t (partial sums)");
 }
 
 }  // namespace qvit

@@ -272,7 +272,7 @@ codes_to_bf16_kernel(const int8_t* __restrict__ codes, int64_t R, int C, int64_t
 int gemm_tc_launch_bf16_split(const void* a, int64_t lda, int planes, const void* b, int64_t ldb, const struct EpiParams& ep, int K,
                               cudaStream_t s);
 int gemm_tc_launch_bf16_split_t(const void* g, int64_t ldg, int planes, int64_t plane_cols, const void* x, int64_t ldx, int64_t tokens,
-                                const struct EpiParams& ep, cudaStream_t s);
+                                const struct EpiParams& ep, float* workspace, cudaStream_t s);
 
 }  // namespace qvit
 
@@ -355,7 +355,7 @@ int qvit_codes_to_bf16(const int8_t* codes, int64_t rows, int64_t cols, int64_t 
 }
 
 int qvit_gemm_bf16_split_t(const void* g_planes, int64_t ld_g, int planes, int64_t plane_cols, const void* x, int64_t ld_x, int64_t tokens,
-                           int N_out, int K_in, float* out, int64_t ldo, const qvit_epilogue_t* epi, qvit_stream_t stream) {
+                           int N_out, int K_in, float* out, int64_t ldo, float* workspace, const qvit_epilogue_t* epi, qvit_stream_t stream) {
   QVIT_REQUIRE(g_planes && x && out && epi, "qvit_gemm_bf16_split_t: null pointer");
   QVIT_REQUIRE(tokens > 0 && N_out > 0 && K_in > 0 && planes >= 1 && planes <= 3 && ldo >= K_in, "qvit_gemm_bf16_split_t: bad shape");
   QVIT_REQUIRE(plane_cols % 64 == 0 && plane_cols >= N_out && ld_g >= (int64_t)planes * plane_cols && (ld_g % 8) == 0 && (ld_x % 8) == 0 &&
@@ -387,7 +387,7 @@ int qvit_gemm_bf16_split_t(const void* g_planes, int64_t ld_g, int planes, int64
   ep.ldo = ldo;
   ep.M = N_out;
   ep.N = K_in;
-  return gemm_tc_launch_bf16_split_t(g_planes, ld_g, planes, plane_cols, x, ld_x, tokens, ep, (cudaStream_t)stream);
+  return gemm_tc_launch_bf16_split_t(g_planes, ld_g, planes, plane_cols, x, ld_x, tokens, ep, workspace, (cudaStream_t)stream);
 }
 
 int qvit_gemm_bf16_split(const void* a_planes, int64_t lda, int planes, const void* b, int64_t ldb, int M, int N, int K,

@@ -504,9 +504,11 @@ def gemm_bf16_split_t(g_planes: torch.Tensor, x_bf16: torch.Tensor, N_out: int, 
     if scale is not None:
         keep = _scalar_param(scale, g_planes.device, "scale")
         epi.scale_a = keep.data_ptr()
+    # (small outputs: a workspace lets the kernel split the long contraction four ways with a reproducible sum)
+    ws = torch.empty_like(out) if out.numel() <= (1 << 20) else None
     _lib.check(_lib.lib().qvit_gemm_bf16_split_t(_lib.ptr(g_planes), g_planes.stride(0), planes, g_planes.shape[1] // 3, _lib.ptr(x_bf16),
                                                  x_bf16.stride(0), tokens, int(N_out), int(K_in), _lib.ptr(out), out.stride(0),
-                                                 C.byref(epi), _lib.stream()), "qvit_gemm_bf16_split_t")
+                                                 _lib.ptr(ws), C.byref(epi), _lib.stream()), "qvit_gemm_bf16_split_t")
     return out if out.shape[1] == K_in else out[:, :K_in]
 
 

@@ -414,4 +414,5 @@ def test_weight_gradient_gemm_from_mn_major_operands(T, N, K):
     assert torch.equal(ops.codes_to_bf16(codes, K)[:, :K].float(), codes[:, :K].float())
     err = float((new.double() - ref).abs().max() / ref.abs().max())
     assert err <= 1e-5, err
-    assert float((new - old).abs().max()) <= 2e-6 * float(old.abs().max())
+    # (both sit within 1e-5 of float64; they differ by fp32 summation order - the new kernel may split the contraction four ways)
+    assert float((new - old).abs().max()) <= 2e-5 * float(old.abs().max())
