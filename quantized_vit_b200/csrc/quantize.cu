@@ -188,34 +188,36 @@ im2col_quantize_kernel(const float* __restrict__ x, ConvGeom g, const float* __r
 }
 
 // Non-overlapping patches (kernel == stride, no padding, no dilation, kw % 4 == 0, W % 4 == 0): ViT PatchEmbed
-// (vit_model.py:94-100).  One thread = 4 consecutive pixels of one patch row = 4 consecutive K entries: a 128-bit
-// coalesced load along W and one coalesced 32-bit store along K.
+// (vit_model.py:94-100).  One WARP = one (image, channel, patch): its kh x kw pixels are kh runs of kw * 4 contiguous bytes in
+// the image and ONE run of kh * kw contiguous bytes in the patch matrix (K index = (c * kh + ki) * kw + kj), so lane j takes the
+// j-th group of 4 pixels: 128-bit loads in full 32-byte sectors, 128-byte coalesced stores.  (The first version gave every thread
+// 4 pixels of an image row: its 4-byte stores landed 16 bytes per patch row, half a sector at a time - 81 us for the 154 MB batch.)
 __global__ void __launch_bounds__(kThreads)
 patchify_quantize_kernel(const float* __restrict__ x, ConvGeom g, const float* __restrict__ d, const float* __restrict__ qm,
                          const float* __restrict__ t, int8_t* __restrict__ cols, int64_t ld_cols, int32_t* __restrict__ flags) {
   const SymParams p = load_sym_params(d, qm, t);
   const FastQ2 fq = make_fastq2(p);
   int fl = 0;
-  const int w4 = g.W / 4;                                  // float4 groups per image row
-  const int64_t total = (int64_t)g.B * g.C * g.H * w4;
-  const uint32_t hw4 = (uint32_t)(g.H * w4);               // groups per (image, channel) plane: 32-bit index math inside it
-  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    // (64-bit divisions cost ~100 instructions each and made this kernel instruction bound: one 64-bit divide, the
-    // rest in 32 bits)
-    const uint32_t plane = (uint32_t)(i / hw4), rem = (uint32_t)(i - (int64_t)plane * hw4);
-    const int ih = (int)(rem / (uint32_t)w4), xg = (int)(rem - (uint32_t)ih * (uint32_t)w4);
+  const int lane = threadIdx.x & 31;
+  const int kw4 = g.kw / 4;                                // float4 groups per patch row
+  const int groups = g.kh * kw4;                           // float4 groups per (channel, patch)
+  const int64_t total = (int64_t)g.B * g.C * g.OH * g.OW;  // warps' work items
+  const int64_t warp0 = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5), wstride = (int64_t)gridDim.x * (kThreads / 32);
+  const uint32_t per_plane = (uint32_t)(g.OH * g.OW);
+  for (int64_t w = warp0; w < total; w += wstride) {
+    const uint32_t plane = (uint32_t)(w / per_plane), rem = (uint32_t)(w - (int64_t)plane * per_plane);
     const int b = (int)(plane / (uint32_t)g.C), c = (int)(plane - (uint32_t)b * (uint32_t)g.C);
-    const int iw = xg * 4;
-    const int oh = ih / g.kh, ki = ih - oh * g.kh;
-    const int ow = iw / g.kw, kj = iw - ow * g.kw;
-    if (oh >= g.OH || ow >= g.OW) continue;                // pixels beyond the last full patch are not used
-    const float4 v = ldg_stream4(x + i * 4);
-    const int64_t row = ((int64_t)b * g.OH + oh) * g.OW + ow;
-    const int k = (c * g.kh + ki) * g.kw + kj;
-    *reinterpret_cast<uint32_t*>(cols + row * ld_cols + k) = sym_codes4_v2(v.x, v.y, v.z, v.w, p, fq, fl);
+    const int oh = (int)(rem / (uint32_t)g.OW), ow = (int)(rem - (uint32_t)oh * (uint32_t)g.OW);
+    const float* src = x + (((int64_t)b * g.C + c) * g.H + (int64_t)oh * g.kh) * g.W + ow * g.kw;
+    int8_t* dst = cols + (((int64_t)b * g.OH + oh) * g.OW + ow) * ld_cols + c * g.kh * g.kw;
+    for (int j = lane; j < groups; j += 32) {
+      const int ki = j / kw4, kj = (j - ki * kw4) * 4;
+      const float4 v = ldg_stream4(src + (int64_t)ki * g.W + kj);
+      *reinterpret_cast<uint32_t*>(dst + j * 4) = sym_codes4_v2(v.x, v.y, v.z, v.w, p, fq, fl);
+    }
   }
   fl = warp_or(fl);
-  if (fl && flags && (threadIdx.x & 31) == 0) atomicOr(flags, fl);
+  if (fl && flags && lane == 0) atomicOr(flags, fl);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -466,8 +468,8 @@ int qvit_im2col_quantize_sym(const float* x, int B, int C, int H, int W, int kh,
       (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
     if (ld_cols > g.K)      // K padding columns (none for ViT: K = 768)
       cudaMemsetAsync(cols, 0, (size_t)B * g.OH * g.OW * ld_cols, s);
-    const int64_t groups = (int64_t)B * C * H * (W / 4);
-    patchify_quantize_kernel<<<stream_grid(groups, kThreads * 4), kThreads, 0, s>>>(x, g, d, q_m, t, cols, ld_cols, flags);
+    const int64_t patches = (int64_t)B * C * g.OH * g.OW;   // one warp each
+    patchify_quantize_kernel<<<stream_grid(patches, kThreads / 32, 8), kThreads, 0, s>>>(x, g, d, q_m, t, cols, ld_cols, flags);
     return check_launch("qvit_im2col_quantize_sym(patchify)");
   }
   const int64_t words = (int64_t)B * g.OH * g.OW * (ld_cols / 4);
